@@ -1,0 +1,210 @@
+/*
+ * mksnap.h — C-ABI of libmksnap.so: the B200-native snapshot+hash engine that
+ * replaces the CPU arithmetic on makisu's build-context fingerprint and layer
+ * digest path.  Plain C, plain pointers and sizes; no torch / C++ types.
+ *
+ * The reference (uber/makisu @5fdc8f4) has NO FFI on this path: it is direct Go
+ * calls inside a CGO_ENABLED=0 binary (reference Makefile:46-49).  The entry
+ * points below are what a cgo shim would bind at the three seams SURVEY.md
+ * section 8(b) identifies; each one cites the reference code it replaces.  The Go-side
+ * stubs are shown in INTEGRATION.md.
+ *
+ * Model: a handle owns one CUDA device, its streams, a ring of pinned host
+ * arenas and device arena slots.  A *session* (begin ... finish) digests one
+ * build context / layer: the host packs file bytes into an arena in layer-tar
+ * order (512-byte aligned, zero padded -- i.e. the arena *is* the tar stream),
+ * describes what to hash with extent / range tables, and submits.  All
+ * arithmetic runs on the device; there is no CPU fallback: every call fails
+ * with MKSNAP_E_CUDA if no device is usable.
+ *
+ * Threading: one session per handle at a time, calls on a handle must be
+ * serialised by the caller (the reference calls these seams from one goroutine
+ * per build: lib/builder/build_plan.go:174, lib/stream/multi_writer.go:60);
+ * different handles may be used concurrently.  Every entry point does its own
+ * cudaSetDevice, so a goroutine may migrate between OS threads.
+ *
+ * Errors: 0 = ok, negative = MKSNAP_E_*; text via mksnap_last_error().  A Go
+ * wrapper maps them to fmt.Errorf("...: %s", err) like lib/builder/step/common.go:59.
+ */
+#ifndef MKSNAP_H
+#define MKSNAP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MKSNAP_ABI_VERSION 1
+
+enum {
+    MKSNAP_OK = 0,
+    MKSNAP_E_INVAL = -1,    /* bad argument / misuse */
+    MKSNAP_E_CUDA = -2,     /* CUDA runtime / driver failure, or no device */
+    MKSNAP_E_NOMEM = -3,    /* allocation failed */
+    MKSNAP_E_CAPACITY = -4, /* batch / table exceeds a configured capacity */
+    MKSNAP_E_STATE = -5,    /* call out of sequence */
+    MKSNAP_E_NCCL = -6      /* NCCL unavailable or failed */
+};
+
+typedef struct mksnap mksnap_t;
+
+/* Content-defined chunking parameters (no reference counterpart). */
+typedef struct {
+    uint32_t min_size;    /* default 4096   (must be >= 64)                     */
+    uint32_t normal_size; /* default 16384  (strict mask below, loose at/after) */
+    uint32_t max_size;    /* default 131072                                     */
+    uint32_t strict_bits; /* default 16: candidate iff gear32 < 2^(32-bits)     */
+    uint32_t loose_bits;  /* default 12                                         */
+} mksnap_cdc_params;
+
+typedef struct {
+    int32_t device;              /* CUDA ordinal                                      */
+    uint32_t n_host_arenas;      /* pinned staging arenas; 0 = device-resident use    */
+    uint64_t host_arena_bytes;   /* capacity of each pinned arena                     */
+    uint64_t device_arena_bytes; /* capacity of each device arena slot                */
+    uint32_t n_device_slots;     /* 0 = auto (2 if host arenas are used, else 1)      */
+    uint32_t reserved0;
+    uint64_t max_extents;        /* per submit                                        */
+    uint64_t max_chunks;         /* per session; 0 = device_arena_bytes/min_size+max_extents */
+    mksnap_cdc_params cdc;       /* all-zero = defaults                               */
+} mksnap_config;
+
+/* One contiguous piece of an arena.  Offsets are relative to the arena that is
+ * being submitted and must be multiples of 16. */
+#define MKSNAP_X_CRC 1u /* part of the CRC-32 context stream */
+#define MKSNAP_X_CDC 2u /* chunk + digest this extent as one file */
+typedef struct {
+    uint64_t arena_off;
+    uint64_t len;
+    /* MKSNAP_X_CRC: number of context-stream bytes that FOLLOW this extent's last
+     * byte (over the whole session, across submits).  The stream is the byte
+     * sequence the reference feeds to crc32 in lib/builder/step/add_copy_step.go:104-119,
+     * 194-238: seed+directive+args, then relpath / link target / file content
+     * per walked path, no separators. */
+    uint64_t crc_suffix;
+    uint32_t flags;
+    uint32_t reserved;
+} mksnap_extent;
+
+/* A byte range digested as ONE serial SHA-256 stream (replaces the tarDigester
+ * sha256.New() sink of lib/builder/step/common.go:44-55).  arena_off multiple of 16. */
+typedef struct {
+    uint64_t arena_off;
+    uint64_t len;
+} mksnap_range;
+
+typedef struct {
+    uint32_t crc_pure;      /* GF(2)-linear accumulator; use mksnap_ctx_crc32() */
+    uint32_t reserved;
+    uint64_t crc_bytes;     /* context-stream bytes seen */
+    uint64_t cdc_bytes;     /* bytes chunked             */
+    uint64_t n_files;       /* MKSNAP_X_CDC extents      */
+    uint64_t n_chunks;
+    uint64_t n_unique;      /* rows of the sorted-unique table */
+    uint8_t root[32];       /* fan-out-256 Merkle root of the table = layer content address */
+    uint64_t n_streams;     /* serial SHA-256 streams digested */
+} mksnap_result;
+
+typedef struct {
+    /* device time of the most recent submit, CUDA events on the compute stream */
+    float ms_total;
+    float ms_crc;     /* K0  crc32 extents          */
+    float ms_gear;    /* K1  gear candidate scan    */
+    float ms_select;  /* K1b cut selection          */
+    float ms_sha;     /* K2  per-chunk SHA-256      */
+    float ms_stream;  /* K4  serial-stream SHA-256  */
+    float ms_h2d;     /* host->device copy (copy stream) */
+    /* device time of the most recent finish */
+    float ms_sort;    /* K3  radix sort + unique    */
+    float ms_root;    /* Merkle root                */
+    float ms_gather;  /* NCCL all-gather + merge    */
+    uint64_t kernel_launches; /* kernels launched by this handle since create */
+    uint64_t h2d_bytes;       /* since create */
+    uint64_t d2h_bytes;       /* since create */
+} mksnap_stats_t;
+
+/* ---- lifetime --------------------------------------------------------- */
+int mksnap_abi_version(void);
+int mksnap_create(const mksnap_config *cfg, mksnap_t **out);
+void mksnap_destroy(mksnap_t *h);
+const char *mksnap_last_error(const mksnap_t *h); /* h may be NULL: create() errors */
+
+/* ---- session ---------------------------------------------------------- */
+/* Start digesting a new context/layer: clears the CRC accumulator and the
+ * chunk table.  Replaces crc32.NewIEEE() (add_copy_step.go:104) +
+ * sha256.New() (common.go:44-45). */
+int mksnap_begin(mksnap_t *h);
+
+/* Borrow a C-owned pinned host arena (cudaHostAlloc).  Blocks until one is
+ * free.  The caller writes file bytes into it (the Go side through
+ * unsafe.Slice; no Go-heap pointer crosses the boundary) and hands it back
+ * with mksnap_arena_submit. */
+int mksnap_arena_acquire(mksnap_t *h, void **host_ptr, uint64_t *capacity, int32_t *arena_id);
+
+/* Async: copy arena[0,used) host->device, then run CRC over MKSNAP_X_CRC
+ * extents, CDC + per-chunk SHA-256 over MKSNAP_X_CDC extents and one serial
+ * SHA-256 per range.  Returns once everything is enqueued; the arena becomes
+ * acquirable again when its copy has completed.  Replaces the io.Copy(checksum, fh)
+ * loop of add_copy_step.go:230-237 and the tario.WriteEntry -> ConcurrentMultiWriter
+ * fan-out of lib/tario/write.go:28-52 / lib/stream/multi_writer.go:35-66. */
+int mksnap_arena_submit(mksnap_t *h, int32_t arena_id, uint64_t used,
+                        const mksnap_extent *extents, uint64_t n_extents,
+                        const mksnap_range *ranges, uint64_t n_ranges);
+
+/* Device-resident variant: the bytes are already in device slot `slot`
+ * (written by mksnap_synth_fill, a previous upload, or a GPUDirect producer). */
+int mksnap_device_arena(mksnap_t *h, uint32_t slot, void **device_ptr, uint64_t *capacity);
+int mksnap_device_upload(mksnap_t *h, uint32_t slot, uint64_t dst_off, const void *src, uint64_t n);
+int mksnap_device_submit(mksnap_t *h, uint32_t slot, uint64_t used,
+                         const mksnap_extent *extents, uint64_t n_extents,
+                         const mksnap_range *ranges, uint64_t n_ranges);
+
+/* Finish the session: sort + unique the chunk digests, Merkle root, wait for
+ * the device, fill *out. */
+int mksnap_finish(mksnap_t *h, mksnap_result *out);
+
+/* cacheID arithmetic: the value checksum.Sum32() returns at
+ * add_copy_step.go:119 for a context stream of stream_len bytes whose pure
+ * accumulator is res->crc_pure. */
+uint32_t mksnap_ctx_crc32(const mksnap_result *res);
+
+/* ---- result tables (valid after mksnap_finish, until the next begin) ---- */
+/* chunk END offsets (exclusive; position in the concatenation of all submitted
+ * arenas) and digests, in (submit, extent, position) order. */
+int mksnap_get_chunks(mksnap_t *h, uint64_t *ends, uint8_t *digests, uint64_t capacity);
+/* sorted-unique 32-byte digest table */
+int mksnap_get_table(mksnap_t *h, uint8_t *table, uint64_t capacity_rows);
+/* serial-stream digests in (submit, range) order: the TarDigest bytes of
+ * lib/builder/step/common.go:86 (hex-encode and prefix "sha256:" on the host). */
+int mksnap_get_stream_digests(mksnap_t *h, uint8_t *digests, uint64_t capacity);
+
+/* ---- multi-GPU: one process per GPU, files sharded, one exchange step ---- */
+/* NCCL is dlopen()ed (libnccl.so.2); rank 0 creates the id, the host side
+ * distributes it (any out-of-band channel), every rank calls comm_init. */
+int mksnap_comm_unique_id(uint8_t id[128]);
+int mksnap_comm_init(mksnap_t *h, const uint8_t id[128], int32_t n_ranks, int32_t rank);
+/* After mksnap_finish on every rank: all-gather the per-rank sorted-unique
+ * tables (ncclAllGather of counts, then of padded rows), merge + unique on the
+ * device, XOR-combine the CRC partials.  *out is identical on every rank and
+ * equal to what a single GPU would produce for the whole context. */
+int mksnap_allgather_tables(mksnap_t *h, mksnap_result *out);
+
+/* ---- utilities --------------------------------------------------------- */
+/* Deterministic synthetic content, generated on the device into slot bytes
+ * [byte_off, byte_off+n) (multiples of 16): little-endian u64 word i (absolute
+ * word index in the slot) = mix64(seed + (i+1)*0x9E3779B97F4A7C15). */
+int mksnap_synth_fill(mksnap_t *h, uint32_t slot, uint64_t byte_off, uint64_t n, uint64_t seed);
+int mksnap_memset(mksnap_t *h, uint32_t slot, uint64_t byte_off, uint64_t n, int value);
+int mksnap_device_download(mksnap_t *h, uint32_t slot, uint64_t src_off, void *dst, uint64_t n);
+int mksnap_sync(mksnap_t *h);
+int mksnap_stats(mksnap_t *h, mksnap_stats_t *out);
+void mksnap_default_cdc(mksnap_cdc_params *p);
+/* the frozen Gear-32 table (for cross-checking against the oracle) */
+void mksnap_gear_table(uint32_t out[256]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,901 @@
+// mksnap_kernels.cuh — hand-written sm_100a kernels of the snapshot+hash path.
+//
+//   K0  k_crc32_extents   CRC-32/IEEE of the context stream      (HBM-read bound)
+//   K1  k_gear_scan       Gear-32 candidate scan                 (HBM-read bound)
+//   K1b k_select_cuts     min/normal/max cut selection per file  (latency, tiny)
+//   K2  k_sha256_ranges   SHA-256 of many byte ranges            (int-ALU bound)
+//       (the same kernel digests the serial layer-tar streams, K4, and the
+//        Merkle levels of the table root)
+//   K3  radix sort / unique of 256-bit digests                   (HBM, tiny)
+//
+// Reference arithmetic being replaced (all Go stdlib behind these call sites):
+//   hash/crc32   <- lib/builder/step/add_copy_step.go:104-119,230-237
+//   crypto/sha256<- lib/builder/step/common.go:44-55
+// Everything here is 32-bit integer / byte work: no tensor cores, no floats.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mk {
+
+// ------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------
+#define MK_CRC_POLY 0xEDB88320u
+#define MK_GOLDEN64 0x9E3779B97F4A7C15ull
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// (a*b) mod P in the reflected representation (bit 31 = x^0).
+__host__ __device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b)
+{
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 31; k >= 0; --k) {
+        acc ^= (0u - ((a >> k) & 1u)) & b;
+        b = (b >> 1) ^ ((0u - (b & 1u)) & MK_CRC_POLY);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ------------------------------------------------------------------------
+// synthetic content: word i (absolute u64 index in the slot) = mix64(seed+(i+1)*G)
+// ------------------------------------------------------------------------
+__global__ void k_synth_fill(uint64_t *dst, uint64_t word0, uint64_t nwords, uint64_t seed)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 2;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < nwords; i += stride) {
+        uint64_t a = mix64(seed + (word0 + i + 1) * MK_GOLDEN64);
+        if (i + 1 < nwords) {
+            uint64_t b = mix64(seed + (word0 + i + 2) * MK_GOLDEN64);
+            ulonglong2 v;
+            v.x = a;
+            v.y = b;
+            *reinterpret_cast<ulonglong2 *>(dst + i) = v; // dst 16-byte aligned, i even
+        } else {
+            dst[i] = a;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------
+// K0: CRC-32 of the context stream.
+//
+// The stream is a list of extents.  With pure(M) = M(x)*x^32 mod P (init 0, no
+// xorout) the CRC is GF(2)-linear:
+//     pure(stream) = XOR over pieces  pure(piece) * x^(8*bytes_after_piece)
+// so every piece is independent and the result is one 32-bit XOR reduction.
+// A warp owns a piece (<= PIECE bytes of one extent) and walks it in 512-byte
+// rows; lane l keeps four Horner chains, one per 32-bit component of its
+// coalesced uint4, chain step  acc = acc*x^4096 mod P  ^ word  done with four
+// byte-indexed table lookups.  The tables are replicated per lane in shared
+// memory ([4][256][32] words = 128 KiB) so every lookup is bank-conflict free.
+// ------------------------------------------------------------------------
+struct CrcExtent {
+    uint64_t off;    // byte offset in the slot, multiple of 16
+    uint64_t len;
+    uint64_t suffix; // stream bytes after this extent
+};
+
+constexpr uint32_t CRC_PIECE = 256u * 1024u; // bytes per warp-piece (multiple of 512)
+constexpr int CRC_THREADS = 1024;
+constexpr size_t CRC_SMEM = 4u * 256u * 32u * sizeof(uint32_t);
+
+struct CrcConsts {
+    uint32_t mulk[4][256]; // byte tables for a -> a*x^4096 mod P
+    uint32_t lane_c[128];  // x^(32 + 8*(508-16l-4c)) for (l,c)
+    uint32_t xp[32];       // x^(2^i), i = bit exponent
+};
+
+__device__ __forceinline__ uint32_t crc_step(const uint32_t *T, uint32_t a, uint32_t w)
+{
+    // T already includes the lane offset; table t, value v at T[(t*256+v)*32]
+    uint32_t r = T[((a & 0xFFu)) << 5];
+    r ^= T[(256u + ((a >> 8) & 0xFFu)) << 5];
+    r ^= T[(512u + ((a >> 16) & 0xFFu)) << 5];
+    r ^= T[(768u + (a >> 24)) << 5];
+    return r ^ w;
+}
+
+__global__ void __launch_bounds__(CRC_THREADS, 1)
+k_crc32_extents(const uint8_t *__restrict__ arena, const CrcExtent *__restrict__ ext,
+                const uint32_t *__restrict__ piece_base, uint32_t n_ext, uint32_t n_pieces,
+                const CrcConsts *__restrict__ cst, uint32_t *__restrict__ acc_out)
+{
+    extern __shared__ uint32_t s_tab[];
+    for (uint32_t i = threadIdx.x; i < 4u * 256u * 32u; i += blockDim.x)
+        s_tab[i] = (&cst->mulk[0][0])[i >> 5];
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t *T = s_tab + lane;
+    const uint32_t warps_per_cta = blockDim.x >> 5;
+    const uint32_t total_warps = gridDim.x * warps_per_cta;
+    uint32_t warp_acc = 0;
+
+    for (uint32_t piece = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); piece < n_pieces;
+         piece += total_warps) {
+        // extent lookup: largest e with piece_base[e] <= piece
+        uint32_t lo = 0, hi = n_ext;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(piece_base + mid) <= piece)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const CrcExtent e = ext[lo];
+        const uint64_t start = (uint64_t)(piece - __ldg(piece_base + lo)) * CRC_PIECE;
+        const uint64_t left = e.len - start;
+        const uint32_t valid = left < CRC_PIECE ? (uint32_t)left : CRC_PIECE;
+        const uint32_t rows = (valid + 511u) >> 9;
+        const uint8_t *base = arena + e.off + start + lane * 16u;
+
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        uint32_t r = 0;
+        // full rows, 4 loads in flight per lane
+        const uint32_t full_rows = valid >> 9;
+        for (; r + 4 <= full_rows; r += 4) {
+            uint4 w0 = ldg_stream(reinterpret_cast<const uint4 *>(base + (size_t)r * 512));
+            uint4 w1 = ldg_stream(reinterpret_cast<const uint4 *>(base + (size_t)(r + 1) * 512));
+            uint4 w2 = ldg_stream(reinterpret_cast<const uint4 *>(base + (size_t)(r + 2) * 512));
+            uint4 w3 = ldg_stream(reinterpret_cast<const uint4 *>(base + (size_t)(r + 3) * 512));
+            a0 = crc_step(T, a0, w0.x); a1 = crc_step(T, a1, w0.y); a2 = crc_step(T, a2, w0.z); a3 = crc_step(T, a3, w0.w);
+            a0 = crc_step(T, a0, w1.x); a1 = crc_step(T, a1, w1.y); a2 = crc_step(T, a2, w1.z); a3 = crc_step(T, a3, w1.w);
+            a0 = crc_step(T, a0, w2.x); a1 = crc_step(T, a1, w2.y); a2 = crc_step(T, a2, w2.z); a3 = crc_step(T, a3, w2.w);
+            a0 = crc_step(T, a0, w3.x); a1 = crc_step(T, a1, w3.y); a2 = crc_step(T, a2, w3.z); a3 = crc_step(T, a3, w3.w);
+        }
+        for (; r < rows; ++r) {
+            // remaining rows; the last one may be partial: bytes past `valid` count as zero
+            uint4 w = make_uint4(0, 0, 0, 0);
+            const int32_t nb = (int32_t)valid - (int32_t)(r * 512u + lane * 16u);
+            if (nb > 0) {
+                w = ldg_stream(reinterpret_cast<const uint4 *>(base + (size_t)r * 512));
+                if (nb < 16) {
+                    uint32_t m[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        int32_t bytes = nb - 4 * k;
+                        m[k] = bytes >= 4 ? 0xFFFFFFFFu : (bytes <= 0 ? 0u : (0xFFFFFFFFu >> (32 - 8 * bytes)));
+                    }
+                    w.x &= m[0]; w.y &= m[1]; w.z &= m[2]; w.w &= m[3];
+                }
+            }
+            a0 = crc_step(T, a0, w.x); a1 = crc_step(T, a1, w.y); a2 = crc_step(T, a2, w.z); a3 = crc_step(T, a3, w.w);
+        }
+        // fold the 128 chains of the warp: chain (l,c) ends 8*(508-16l-4c) bits before the row end
+        uint32_t c = crc_mulmod(a0, cst->lane_c[lane * 4 + 0]) ^ crc_mulmod(a1, cst->lane_c[lane * 4 + 1]) ^
+                     crc_mulmod(a2, cst->lane_c[lane * 4 + 2]) ^ crc_mulmod(a3, cst->lane_c[lane * 4 + 3]);
+#pragma unroll
+        for (int s = 16; s; s >>= 1)
+            c ^= __shfl_xor_sync(0xFFFFFFFFu, c, s);
+        // c = pure(piece || zero padding to the row end).  Shift it to its place in
+        // the stream: x^(8*(bytes after the piece) - 8*pad), exponent mod 2^32-1
+        // (x is primitive mod P, so x^(2^32-1) = 1).
+        const uint32_t M = 0xFFFFFFFFu;
+        const uint32_t pad = rows * 512u - valid;
+        const uint64_t after = e.suffix + (left - valid);
+        uint32_t E = (uint32_t)(((after % M) * 8ull) % M);
+        E = (uint32_t)(((uint64_t)E + M - 8ull * pad) % M);
+        uint32_t f = ((E >> lane) & 1u) ? cst->xp[lane] : 0x80000000u;
+#pragma unroll
+        for (int s = 16; s; s >>= 1)
+            f = crc_mulmod(f, __shfl_xor_sync(0xFFFFFFFFu, f, s));
+        warp_acc ^= crc_mulmod(c, f);
+    }
+    if (lane == 0 && warp_acc)
+        atomicXor(acc_out, warp_acc);
+}
+
+// ------------------------------------------------------------------------
+// K1: Gear-32 candidate scan.
+//   h_i = sum_{k<32} G[b_{i-k}] << k  (mod 2^32);  candidate iff h_i < 2^(32-bits)
+// The update h' = (h<<1)+G[b] is linear in h, so a lane that owns 16 coalesced
+// bytes computes its local prefix hashes L_0..L_15 from state 0 and then adds
+// the carry of the 32 preceding bytes:  h_i = L_i + (A << (i+1)),
+// A = Lfull[lane-1] + (Lfull[lane-2] << 16), exchanged with two warp shuffles
+// (rows chain through lanes 30/31 of the previous iteration).
+// A warp walks a 4 KiB stripe, a CTA a 32 KiB tile; hits are rare (2^-12) and
+// go to a per-tile shared-memory bitmap, which is then compacted *in order*
+// into a bump-allocated pool: pool entry = pos_in_tile | strict<<31.
+// ------------------------------------------------------------------------
+constexpr uint32_t GEAR_TILE = 32768;
+constexpr uint32_t GEAR_THREADS = 256;
+constexpr uint32_t GEAR_STRIPE = GEAR_TILE / (GEAR_THREADS / 32); // 4096
+
+struct TileRec {
+    uint32_t base;  // first pool entry of this tile
+    uint32_t count; // candidates in this tile
+};
+
+__device__ __forceinline__ uint32_t gear_lookup(const uint32_t *G, uint32_t byte)
+{
+    return G[byte << 5]; // G already includes the lane offset
+}
+
+#define MK_GEAR_BYTES(word, k0)                                  \
+    {                                                            \
+        h = (h << 1) + gear_lookup(G, (word) & 0xFFu);           \
+        L[(k0)] = h;                                             \
+        h = (h << 1) + gear_lookup(G, ((word) >> 8) & 0xFFu);    \
+        L[(k0) + 1] = h;                                         \
+        h = (h << 1) + gear_lookup(G, ((word) >> 16) & 0xFFu);   \
+        L[(k0) + 2] = h;                                         \
+        h = (h << 1) + gear_lookup(G, (word) >> 24);             \
+        L[(k0) + 3] = h;                                         \
+    }
+
+__device__ __forceinline__ uint32_t gear_full16(const uint32_t *G, uint4 w)
+{
+    uint32_t h = 0;
+    uint32_t L[16];
+    MK_GEAR_BYTES(w.x, 0) MK_GEAR_BYTES(w.y, 4) MK_GEAR_BYTES(w.z, 8) MK_GEAR_BYTES(w.w, 12)
+    return L[15];
+}
+
+__global__ void __launch_bounds__(GEAR_THREADS)
+k_gear_scan(const uint8_t *__restrict__ arena, uint64_t nbytes /* multiple of 16 */, uint32_t n_tiles,
+            const uint32_t *__restrict__ gear, uint32_t strict_lim, uint32_t loose_lim,
+            TileRec *__restrict__ tiles, uint32_t *__restrict__ pool, uint32_t pool_cap,
+            uint32_t *__restrict__ pool_count, uint32_t *__restrict__ err_flag)
+{
+    __shared__ uint32_t s_gear[256 * 32];
+    __shared__ uint32_t s_bmL[GEAR_TILE / 32];
+    __shared__ uint32_t s_bmS[GEAR_TILE / 32];
+    __shared__ uint32_t s_wsum[GEAR_THREADS / 32];
+    __shared__ uint32_t s_base;
+
+    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += blockDim.x)
+        s_gear[i] = __ldg(gear + (i >> 5));
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t *G = s_gear + lane;
+
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < GEAR_TILE / 32; i += blockDim.x) {
+            s_bmL[i] = 0;
+            s_bmS[i] = 0;
+        }
+        __syncthreads();
+
+        const uint64_t s0 = (uint64_t)tile * GEAR_TILE + (uint64_t)warp * GEAR_STRIPE;
+        // carry-in: Lfull of the two 16-byte words before the stripe
+        uint32_t p30 = 0, p31 = 0;
+        {
+            uint32_t lf = 0;
+            if (lane >= 30 && s0 >= 32) {
+                uint4 w = *reinterpret_cast<const uint4 *>(arena + s0 - 32 + (lane - 30) * 16);
+                lf = gear_full16(G, w);
+            }
+            p30 = __shfl_sync(0xFFFFFFFFu, lf, 30);
+            p31 = __shfl_sync(0xFFFFFFFFu, lf, 31);
+        }
+        uint4 wnext = make_uint4(0, 0, 0, 0);
+        {
+            const uint64_t a = s0 + lane * 16u;
+            if (a < nbytes)
+                wnext = ldg_stream(reinterpret_cast<const uint4 *>(arena + a));
+        }
+#pragma unroll 1
+        for (uint32_t r = 0; r < GEAR_STRIPE / 512; ++r) {
+            const uint4 w = wnext;
+            {
+                const uint64_t a = s0 + (uint64_t)(r + 1) * 512 + lane * 16u;
+                wnext = make_uint4(0, 0, 0, 0);
+                if (r + 1 < GEAR_STRIPE / 512 && a < nbytes)
+                    wnext = ldg_stream(reinterpret_cast<const uint4 *>(arena + a));
+            }
+            uint32_t h = 0;
+            uint32_t L[16];
+            MK_GEAR_BYTES(w.x, 0) MK_GEAR_BYTES(w.y, 4) MK_GEAR_BYTES(w.z, 8) MK_GEAR_BYTES(w.w, 12)
+            const uint32_t lfull = L[15];
+            uint32_t up1 = __shfl_up_sync(0xFFFFFFFFu, lfull, 1);
+            uint32_t up2 = __shfl_up_sync(0xFFFFFFFFu, lfull, 2);
+            if (lane == 0) { up1 = p31; up2 = p30; }
+            if (lane == 1) { up2 = p31; }
+            const uint32_t A = up1 + (up2 << 16);
+            uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                L[i] += A << (i + 1);
+                m = min(m, L[i]);
+            }
+            if (m < loose_lim) { // rare: ~2^-8 per lane-row
+                const uint32_t pos0 = warp * GEAR_STRIPE + r * 512 + lane * 16;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (L[i] < loose_lim) {
+                        const uint32_t pos = pos0 + i;
+                        atomicOr(&s_bmL[pos >> 5], 1u << (pos & 31));
+                        if (L[i] < strict_lim)
+                            atomicOr(&s_bmS[pos >> 5], 1u << (pos & 31));
+                    }
+                }
+            }
+            p30 = __shfl_sync(0xFFFFFFFFu, lfull, 30);
+            p31 = __shfl_sync(0xFFFFFFFFu, lfull, 31);
+        }
+        __syncthreads();
+
+        // ordered compaction of the tile bitmap: thread t owns words 4t..4t+3
+        uint32_t wl[4], cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            wl[k] = s_bmL[threadIdx.x * 4 + k];
+            cnt += __popc(wl[k]);
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, s);
+            if (lane >= s)
+                incl += v;
+        }
+        if (lane == 31)
+            s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < GEAR_THREADS / 32; ++k) {
+            const uint32_t v = s_wsum[k];
+            if (k < warp)
+                woff += v;
+            total += v;
+        }
+        if (threadIdx.x == 0) {
+            uint32_t b = total ? atomicAdd(pool_count, total) : 0u;
+            if (b + total > pool_cap || b + total < b) {
+                atomicExch(err_flag, 1u);
+                b = 0xFFFFFFFFu;
+            }
+            s_base = b;
+            TileRec tr;
+            tr.base = b;
+            tr.count = total;
+            tiles[tile] = tr;
+        }
+        __syncthreads();
+        const uint32_t base = s_base;
+        if (base != 0xFFFFFFFFu && cnt) {
+            uint32_t o = base + woff + incl - cnt;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t bits = wl[k];
+                const uint32_t sb = s_bmS[threadIdx.x * 4 + k];
+                while (bits) {
+                    const uint32_t b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    pool[o++] = ((threadIdx.x * 4 + k) * 32 + b) | (((sb >> b) & 1u) << 31);
+                }
+            }
+        }
+        __syncthreads(); // bitmaps are re-zeroed next iteration
+    }
+}
+
+// ------------------------------------------------------------------------
+// K1b: cut selection.  One thread per file walks the ordered candidates of the
+// tiles its file covers.  pass 0 counts chunks, pass 1 writes (start,len).
+// ------------------------------------------------------------------------
+struct CdcFile {
+    uint64_t off;
+    uint64_t len;
+};
+
+struct CdcParamsDev {
+    uint32_t min_size, normal_size, max_size, strict_lim, loose_lim;
+};
+
+struct SessionCounters {
+    unsigned long long n_chunks;   // chunks appended so far in this session
+    unsigned long long n_files;
+    unsigned long long cdc_bytes;
+    unsigned long long n_streams;
+    uint32_t batch_chunks;         // chunks of the batch being processed
+    uint32_t err;                  // 1 = candidate pool overflow, 2 = chunk table overflow
+    uint32_t crc_acc;              // XOR accumulator of K0
+    uint32_t work;                 // work-stealing counter of K2
+};
+
+template <int PASS>
+__global__ void __launch_bounds__(128)
+k_select_cuts(const CdcFile *__restrict__ files, uint32_t n_files, CdcParamsDev prm,
+              const TileRec *__restrict__ tiles, const uint32_t *__restrict__ pool,
+              uint32_t *__restrict__ counts, const uint32_t *__restrict__ bases,
+              SessionCounters *__restrict__ sc, uint64_t max_chunks, uint64_t stream_base,
+              uint64_t *__restrict__ chunk_start, uint64_t *__restrict__ chunk_len,
+              uint64_t *__restrict__ chunk_end_out)
+{
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_files)
+        return;
+    if (PASS == 1 && sc->err)
+        return;
+    const CdcFile fl = files[f];
+    uint64_t prev = fl.off;
+    const uint64_t end = fl.off + fl.len;
+    uint64_t out = 0;
+    if (PASS == 1)
+        out = sc->n_chunks + bases[f];
+    uint32_t n = 0;
+    while (prev < end) {
+        const uint64_t rem = end - prev;
+        uint64_t cut;
+        if (rem <= prm.min_size) {
+            cut = end;
+        } else {
+            const uint64_t limit_end = prev + (rem < prm.max_size ? rem : prm.max_size);
+            const uint64_t lo = prev + prm.min_size - 1;
+            const uint64_t normal_pos = prev + prm.normal_size - 1; // pos >= this: loose accepted
+            cut = 0;
+            for (uint64_t t = lo / GEAR_TILE; t * GEAR_TILE < limit_end && !cut; ++t) {
+                const TileRec tr = tiles[t];
+                const uint64_t tb = t * GEAR_TILE;
+                for (uint32_t j = 0; j < tr.count; ++j) {
+                    const uint32_t ent = __ldg(pool + tr.base + j);
+                    const uint64_t pos = tb + (ent & 0x7FFFFFFFu);
+                    if (pos < lo)
+                        continue;
+                    if (pos >= limit_end)
+                        break;
+                    if (pos >= normal_pos || (ent >> 31)) {
+                        cut = pos + 1;
+                        break;
+                    }
+                }
+            }
+            if (!cut)
+                cut = limit_end;
+        }
+        if (PASS == 1) {
+            if (out + n < max_chunks) {
+                chunk_start[out + n] = prev;
+                chunk_len[out + n] = cut - prev;
+                chunk_end_out[out + n] = stream_base + cut;
+            }
+        }
+        ++n;
+        prev = cut;
+    }
+    if (PASS == 0)
+        counts[f] = n;
+}
+
+// after the scan of counts: publish the batch chunk count / overflow
+__global__ void k_batch_begin(SessionCounters *sc, const uint32_t *counts, const uint32_t *bases, uint32_t n_files,
+                              uint64_t max_chunks, uint64_t cdc_bytes)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t total = n_files ? bases[n_files - 1] + counts[n_files - 1] : 0;
+        sc->batch_chunks = total;
+        sc->work = 0;
+        if (sc->n_chunks + total > max_chunks)
+            sc->err |= 2u;
+        sc->n_files += n_files;
+        sc->cdc_bytes += cdc_bytes;
+    }
+}
+
+__global__ void k_batch_end(SessionCounters *sc)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (!sc->err)
+            sc->n_chunks += sc->batch_chunks;
+        sc->batch_chunks = 0;
+        sc->work = 0;
+    }
+}
+
+// ------------------------------------------------------------------------
+// K2 / K4: SHA-256 of byte ranges.  One lane per range, one 64-byte block per
+// loop iteration; a lane that finishes its range pulls the next one from a
+// global counter, so a warp stays converged on "compress one block" no matter
+// how ragged the range lengths are.  Ranges start at arbitrary byte
+// alignment (cut points are content defined): five aligned 16-byte loads
+// cover the block, two select stages rotate by words and one PRMT per word
+// does the byte shift and the big-endian swap together.
+// ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+
+__device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16])
+{
+    constexpr uint32_t K[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+        0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+        0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+        0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+        0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+        0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+        0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+        0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        uint32_t wi;
+        if (i < 16) {
+            wi = w[i];
+        } else {
+            const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+            const uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
+            const uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
+            wi = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+            w[i & 15] = wi;
+        }
+        const uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+        const uint32_t ch = (e & f) ^ (~e & g);
+        const uint32_t t1 = h + S1 + ch + K[i] + wi;
+        const uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+        const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        h = g; g = f; f = e; e = d + t1;
+        d = c; c = b; b = a; a = t1 + S0 + mj;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d;
+    st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+constexpr int SHA_THREADS = 128;
+
+// mode 0: ranges from (start[], len[]) arrays, count read from *n_dev (or n_host if n_dev==nullptr)
+// mode 1: uniform ranges of `uni_len` bytes over [0, uni_total) of `data` (Merkle levels)
+__global__ void __launch_bounds__(SHA_THREADS)
+k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ start,
+                const uint64_t *__restrict__ len, const uint32_t *__restrict__ n_dev, uint64_t n_host,
+                const unsigned long long *__restrict__ first_dev, uint64_t first_host, /* index of range 0 in start/len/out */
+                uint64_t uni_len, uint64_t uni_total, uint8_t *__restrict__ out,
+                uint32_t *__restrict__ work_counter, const uint32_t *__restrict__ skip_if_err)
+{
+    if (skip_if_err && *skip_if_err)
+        return;
+    const uint64_t n = n_dev ? (uint64_t)*n_dev : n_host;
+    const uint64_t first = first_dev ? (uint64_t)*first_dev : first_host;
+    const uint32_t lane = threadIdx.x & 31;
+
+    uint32_t st[8];
+    const uint8_t *p = nullptr; // next block to read
+    uint64_t total = 0;         // range length
+    uint64_t done = 0;          // bytes already compressed
+    uint64_t my = 0;            // range index
+    uint32_t phase = 0;         // 0 idle, 1 data blocks, 2 needs extra length block
+    bool exhausted = false;
+
+    for (;;) {
+        // ---- refill idle lanes (warp-aggregated fetch) ----
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, phase == 0 && !exhausted);
+        if (need) {
+            uint32_t basei = 0;
+            const uint32_t leader = __ffs(need) - 1;
+            if (lane == leader)
+                basei = atomicAdd(work_counter, __popc(need));
+            basei = __shfl_sync(0xFFFFFFFFu, basei, leader);
+            if (phase == 0 && !exhausted) {
+                const uint64_t idx = (uint64_t)basei + __popc(need & ((1u << lane) - 1u));
+                if (idx < n) {
+                    my = first + idx;
+                    if (start) {
+                        p = data + start[my];
+                        total = len[my];
+                    } else {
+                        const uint64_t o = idx * uni_len;
+                        p = data + o;
+                        total = uni_total - o < uni_len ? uni_total - o : uni_len;
+                    }
+                    done = 0;
+                    phase = 1;
+                    st[0] = 0x6a09e667; st[1] = 0xbb67ae85; st[2] = 0x3c6ef372; st[3] = 0xa54ff53a;
+                    st[4] = 0x510e527f; st[5] = 0x9b05688c; st[6] = 0x1f83d9ab; st[7] = 0x5be0cd19;
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, phase != 0))
+            break;
+        if (phase == 0)
+            continue;
+
+        uint32_t w[16];
+        const uint64_t rem = total - done;
+        bool last = false;
+        if (phase == 2) {
+#pragma unroll
+            for (int i = 0; i < 14; ++i)
+                w[i] = 0;
+            w[14] = (uint32_t)((total * 8) >> 32);
+            w[15] = (uint32_t)(total * 8);
+            last = true;
+        } else {
+            // aligned 80-byte window covering [p, p+64)
+            const uint32_t a = (uint32_t)((uintptr_t)p & 15u);
+            const uint4 *q = reinterpret_cast<const uint4 *>(p - a);
+            uint32_t x[20];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                // only touch 16-byte words that intersect [p, p+min(rem,64))
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if ((uint64_t)(16 * k) < (uint64_t)a + (rem < 64 ? rem : 64))
+                    v = __ldg(q + k);
+                x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+            }
+            uint32_t y[18];
+#pragma unroll
+            for (int i = 0; i < 18; ++i)
+                y[i] = (a & 8u) ? x[i + 2] : x[i];
+            uint32_t z[17];
+#pragma unroll
+            for (int i = 0; i < 17; ++i)
+                z[i] = (a & 4u) ? y[i + 1] : y[i];
+            const uint32_t sel = 0x0123u + 0x1111u * (a & 3u);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                w[i] = __byte_perm(z[i], z[i + 1], sel);
+            if (rem < 64) {
+                // final data block: keep `rem` bytes, append 0x80, zero the rest
+                const uint32_t rb = (uint32_t)rem;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int32_t k = (int32_t)rb - 4 * i; // valid bytes in this word
+                    uint32_t keep = k >= 4 ? 0xFFFFFFFFu : (k <= 0 ? 0u : ~(0xFFFFFFFFu >> (8 * k)));
+                    uint32_t v = w[i] & keep;
+                    if (k >= 0 && k < 4)
+                        v |= 0x80000000u >> (8 * k);
+                    w[i] = v;
+                }
+                if (rb < 56) {
+                    w[14] = (uint32_t)((total * 8) >> 32);
+                    w[15] = (uint32_t)(total * 8);
+                    last = true;
+                } else {
+                    phase = 2;
+                }
+            }
+        }
+        sha256_compress(st, w);
+        if (last) {
+            uint4 o0, o1;
+            o0.x = __byte_perm(st[0], 0, 0x0123); o0.y = __byte_perm(st[1], 0, 0x0123);
+            o0.z = __byte_perm(st[2], 0, 0x0123); o0.w = __byte_perm(st[3], 0, 0x0123);
+            o1.x = __byte_perm(st[4], 0, 0x0123); o1.y = __byte_perm(st[5], 0, 0x0123);
+            o1.z = __byte_perm(st[6], 0, 0x0123); o1.w = __byte_perm(st[7], 0, 0x0123);
+            uint4 *dst = reinterpret_cast<uint4 *>(out + my * 32);
+            dst[0] = o0;
+            dst[1] = o1;
+            phase = 0;
+        } else if (phase == 1) {
+            p += 64;
+            done += 64;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------
+// generic exclusive scan of u32 (block = 256 threads x 4 items)
+// ------------------------------------------------------------------------
+constexpr uint32_t SCAN_ITEMS = 1024;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t *s_w, uint32_t &total)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, s);
+        if (lane >= s)
+            incl += t;
+    }
+    if (lane == 31)
+        s_w[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    total = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; ++k) {
+        const uint32_t t = s_w[k];
+        if (k < warp)
+            woff += t;
+        total += t;
+    }
+    __syncthreads();
+    return woff + incl - v;
+}
+
+__global__ void __launch_bounds__(256) k_scan_reduce(const uint32_t *in, uint64_t n, uint32_t *sums)
+{
+    __shared__ uint32_t s_w[8];
+    const uint64_t b0 = (uint64_t)blockIdx.x * SCAN_ITEMS + threadIdx.x * 4;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (b0 + k < n)
+            v += in[b0 + k];
+    uint32_t total;
+    block_exclusive_scan_256(v, s_w, total);
+    if (threadIdx.x == 0)
+        sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) k_scan_apply(const uint32_t *in, uint64_t n, const uint32_t *block_off, uint32_t *out)
+{
+    __shared__ uint32_t s_w[8];
+    const uint64_t b0 = (uint64_t)blockIdx.x * SCAN_ITEMS + threadIdx.x * 4;
+    uint32_t x[4], v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        x[k] = b0 + k < n ? in[b0 + k] : 0;
+        v += x[k];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan_256(v, s_w, total) + (block_off ? block_off[blockIdx.x] : 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (b0 + k < n)
+            out[b0 + k] = ex;
+        ex += x[k];
+    }
+}
+
+// ------------------------------------------------------------------------
+// K3: LSD radix sort of (u64 key, u32 payload), 8 bits per pass, then unique.
+// key = first 8 digest bytes big-endian; ties beyond 64 bits are fixed up by
+// k_fix_ties so the final order is the full bytewise order.
+// ------------------------------------------------------------------------
+constexpr uint32_t SORT_THREADS = 256;
+constexpr uint32_t SORT_ITEMS = 16;
+constexpr uint32_t SORT_TILE = SORT_THREADS * SORT_ITEMS;
+
+__global__ void k_make_keys(const uint8_t *__restrict__ digests, uint64_t n, uint64_t *keys, uint32_t *idx)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const uint2 v = *reinterpret_cast<const uint2 *>(digests + i * 32);
+    keys[i] = ((uint64_t)__byte_perm(v.x, 0, 0x0123) << 32) | __byte_perm(v.y, 0, 0x0123);
+    idx[i] = (uint32_t)i;
+}
+
+// histogram: hist[digit * nblocks + block]
+__global__ void __launch_bounds__(SORT_THREADS)
+k_radix_hist(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint32_t *__restrict__ hist, uint32_t nblocks)
+{
+    __shared__ uint32_t s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t b0 = (uint64_t)blockIdx.x * SORT_TILE;
+    for (uint32_t k = 0; k < SORT_ITEMS; ++k) {
+        const uint64_t i = b0 + k * SORT_THREADS + threadIdx.x;
+        if (i < n)
+            atomicAdd(&s_h[(keys[i] >> shift) & 0xFF], 1u);
+    }
+    __syncthreads();
+    hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = s_h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_radix_scatter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, int shift,
+                const uint32_t *__restrict__ offs, uint32_t nblocks, uint64_t *__restrict__ keys_out,
+                uint32_t *__restrict__ vals_out)
+{
+    __shared__ uint32_t s_cnt[SORT_THREADS / 32][256];
+    __shared__ uint32_t s_run[256];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    s_run[threadIdx.x] = offs[(uint64_t)threadIdx.x * nblocks + blockIdx.x];
+    const uint64_t b0 = (uint64_t)blockIdx.x * SORT_TILE;
+    for (uint32_t k = 0; k < SORT_ITEMS; ++k) {
+        for (uint32_t j = threadIdx.x; j < (SORT_THREADS / 32) * 256; j += SORT_THREADS)
+            (&s_cnt[0][0])[j] = 0;
+        __syncthreads();
+        const uint64_t i = b0 + k * SORT_THREADS + threadIdx.x;
+        const bool ok = i < n;
+        uint64_t key = 0;
+        uint32_t val = 0, d = 0, rank = 0;
+        if (ok) {
+            key = keys[i];
+            val = vals[i];
+            d = (uint32_t)(key >> shift) & 0xFF;
+        }
+        const uint32_t okmask = __ballot_sync(0xFFFFFFFFu, ok);
+        if (ok) {
+            const uint32_t peers = __match_any_sync(okmask, d);
+            rank = __popc(peers & ((1u << lane) - 1u));
+            if (rank == 0)
+                s_cnt[warp][d] = __popc(peers);
+        }
+        __syncthreads();
+        if (ok) {
+            uint32_t before = 0;
+            for (uint32_t wq = 0; wq < warp; ++wq)
+                before += s_cnt[wq][d];
+            const uint32_t dst = s_run[d] + before + rank;
+            keys_out[dst] = key;
+            vals_out[dst] = val;
+        }
+        __syncthreads();
+        {
+            uint32_t add = 0;
+#pragma unroll
+            for (uint32_t wq = 0; wq < SORT_THREADS / 32; ++wq)
+                add += s_cnt[wq][threadIdx.x];
+            s_run[threadIdx.x] += add;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_gather_digests(const uint8_t *__restrict__ digests, const uint32_t *__restrict__ idx, uint64_t n,
+                                 uint8_t *__restrict__ out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i = t >> 1;
+    if (i >= n)
+        return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(digests + (uint64_t)idx[i] * 32);
+    reinterpret_cast<uint4 *>(out + i * 32)[t & 1] = src[t & 1];
+}
+
+__device__ __forceinline__ int digest_cmp(const uint8_t *a, const uint8_t *b)
+{
+    // bytewise order == order of big-endian words
+    const uint32_t *x = reinterpret_cast<const uint32_t *>(a), *y = reinterpret_cast<const uint32_t *>(b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t p = __byte_perm(x[k], 0, 0x0123), q = __byte_perm(y[k], 0, 0x0123);
+        if (p != q)
+            return p < q ? -1 : 1;
+    }
+    return 0;
+}
+
+// runs of equal 64-bit prefix: insertion sort on the full digest (linear when the run is all duplicates)
+__global__ void k_fix_ties(const uint64_t *__restrict__ keys, uint64_t n, uint8_t *__restrict__ d)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    if (i > 0 && keys[i - 1] == keys[i])
+        return; // not a run start
+    uint64_t e = i + 1;
+    while (e < n && keys[e] == keys[i])
+        ++e;
+    for (uint64_t j = i + 1; j < e; ++j) {
+        uint64_t k = j;
+        while (k > i && digest_cmp(d + (k - 1) * 32, d + k * 32) > 0) {
+            uint4 *a = reinterpret_cast<uint4 *>(d + (k - 1) * 32), *b = reinterpret_cast<uint4 *>(d + k * 32);
+            uint4 t0 = a[0], t1 = a[1];
+            a[0] = b[0]; a[1] = b[1];
+            b[0] = t0; b[1] = t1;
+            --k;
+        }
+    }
+}
+
+__global__ void k_unique_flags(const uint8_t *__restrict__ d, uint64_t n, uint32_t *__restrict__ flags)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    flags[i] = (i == 0 || digest_cmp(d + (i - 1) * 32, d + i * 32) != 0) ? 1u : 0u;
+}
+
+__global__ void k_compact_digests(const uint8_t *__restrict__ d, const uint32_t *__restrict__ flags,
+                                  const uint32_t *__restrict__ pos, uint64_t n, uint8_t *__restrict__ out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i = t >> 1;
+    if (i >= n || !flags[i])
+        return;
+    reinterpret_cast<uint4 *>(out + (uint64_t)pos[i] * 32)[t & 1] = reinterpret_cast<const uint4 *>(d + i * 32)[t & 1];
+}
+
+} // namespace mk

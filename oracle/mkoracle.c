@@ -1,0 +1,401 @@
+/*
+ * mkoracle.c — CPU ORACLE (test infrastructure only; see mkoracle.h).
+ *
+ * Scalar single-thread restatement of the arithmetic on the makisu
+ * snapshot+hash hot path.  Reference call sites (all under /root/reference):
+ *   CRC-32/IEEE   lib/builder/step/add_copy_step.go:104-119 (context cacheID),
+ *                 lib/builder/step/base_step.go:62-67, lib/builder/build_plan.go:96-97
+ *   SHA-256       lib/builder/step/common.go:44-55,86-87 (TarDigest, gzip digest),
+ *                 lib/docker/image/digester.go:35-55
+ * Both algorithms live in the Go standard library (go1.14, hash/crc32 and
+ * crypto/sha256), which is not vendored under /root/reference; the published
+ * algorithms (reflected CRC-32 poly 0xEDB88320; FIPS 180-4) are restated and
+ * pinned against the reference's own fixtures in tests/test_oracle_golden.py.
+ *
+ * Gear-32 CDC / chunk table / Merkle root: no reference counterpart
+ * ("parity unpinned"); this file is the normative statement of DESIGN.md section 3.
+ */
+#include "mkoracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+/* ======================================================================= */
+/* CRC-32/IEEE                                                             */
+/* ======================================================================= */
+
+#define CRC_POLY_REFLECTED 0xEDB88320u
+
+static uint32_t crc_tab[8][256];
+static int crc_tab_ready = 0;
+
+static void crc_init_tables(void)
+{
+    if (crc_tab_ready)
+        return;
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++)
+            c = (c & 1) ? (c >> 1) ^ CRC_POLY_REFLECTED : c >> 1;
+        crc_tab[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; i++)
+        for (int t = 1; t < 8; t++)
+            crc_tab[t][i] = (crc_tab[t - 1][i] >> 8) ^ crc_tab[0][crc_tab[t - 1][i] & 0xFF];
+    crc_tab_ready = 1;
+}
+
+/* register update without init/xorout handling (slicing-by-8) */
+static uint32_t crc_raw(uint32_t r, const uint8_t *p, size_t n)
+{
+    crc_init_tables();
+    while (n && ((uintptr_t)p & 7)) {
+        r = (r >> 8) ^ crc_tab[0][(r ^ *p++) & 0xFF];
+        n--;
+    }
+    while (n >= 8) {
+        uint32_t lo, hi;
+        memcpy(&lo, p, 4);
+        memcpy(&hi, p + 4, 4);
+        lo ^= r;
+        r = crc_tab[7][lo & 0xFF] ^ crc_tab[6][(lo >> 8) & 0xFF] ^
+            crc_tab[5][(lo >> 16) & 0xFF] ^ crc_tab[4][lo >> 24] ^
+            crc_tab[3][hi & 0xFF] ^ crc_tab[2][(hi >> 8) & 0xFF] ^
+            crc_tab[1][(hi >> 16) & 0xFF] ^ crc_tab[0][hi >> 24];
+        p += 8;
+        n -= 8;
+    }
+    while (n--)
+        r = (r >> 8) ^ crc_tab[0][(r ^ *p++) & 0xFF];
+    return r;
+}
+
+uint32_t mko_crc32_update(uint32_t crc, const uint8_t *p, size_t n)
+{
+    return crc_raw(crc ^ 0xFFFFFFFFu, p, n) ^ 0xFFFFFFFFu;
+}
+
+uint32_t mko_crc32_pure(const uint8_t *p, size_t n)
+{
+    return crc_raw(0, p, n);
+}
+
+/* Reflected representation: bit 31 is the x^0 coefficient, bit 0 is x^31. */
+uint32_t mko_crc32_mulmod(uint32_t a, uint32_t b)
+{
+    uint32_t acc = 0;
+    for (int k = 31; k >= 0; k--) { /* walk a from x^0 up to x^31 */
+        if ((a >> k) & 1)
+            acc ^= b;
+        b = (b & 1) ? (b >> 1) ^ CRC_POLY_REFLECTED : b >> 1; /* b *= x */
+    }
+    return acc;
+}
+
+uint32_t mko_crc32_xpow8n(uint64_t nbytes)
+{
+    uint32_t result = 0x80000000u; /* x^0 */
+    uint32_t sq = 0x00800000u;     /* x^8 */
+    while (nbytes) {
+        if (nbytes & 1)
+            result = mko_crc32_mulmod(result, sq);
+        sq = mko_crc32_mulmod(sq, sq);
+        nbytes >>= 1;
+    }
+    return result;
+}
+
+uint32_t mko_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b)
+{
+    return mko_crc32_mulmod(mko_crc32_xpow8n(len_b), crc_a) ^ crc_b;
+}
+
+/* ======================================================================= */
+/* SHA-256 (FIPS 180-4)                                                    */
+/* ======================================================================= */
+
+static const uint32_t SHA_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+static inline uint32_t rotr32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+
+static void sha256_block(uint32_t st[8], const uint8_t *p)
+{
+    uint32_t w[64];
+    for (int i = 0; i < 16; i++)
+        w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) |
+               ((uint32_t)p[4 * i + 2] << 8) | (uint32_t)p[4 * i + 3];
+    for (int i = 16; i < 64; i++) {
+        uint32_t s0 = rotr32(w[i - 15], 7) ^ rotr32(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        uint32_t s1 = rotr32(w[i - 2], 17) ^ rotr32(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3];
+    uint32_t e = st[4], f = st[5], g = st[6], h = st[7];
+    for (int i = 0; i < 64; i++) {
+        uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t t1 = h + S1 + ch + SHA_K[i] + w[i];
+        uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t2 = S0 + mj;
+        h = g; g = f; f = e; e = d + t1;
+        d = c; c = b; b = a; a = t1 + t2;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d;
+    st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+void mko_sha256_init(mko_sha256_ctx *c)
+{
+    static const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a,
+                                   0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    memcpy(c->h, iv, sizeof iv);
+    c->nbytes = 0;
+    c->fill = 0;
+}
+
+void mko_sha256_update(mko_sha256_ctx *c, const uint8_t *p, size_t n)
+{
+    c->nbytes += n;
+    if (c->fill) {
+        size_t take = 64 - c->fill;
+        if (take > n)
+            take = n;
+        memcpy(c->buf + c->fill, p, take);
+        c->fill += (uint32_t)take;
+        p += take;
+        n -= take;
+        if (c->fill < 64)
+            return;
+        sha256_block(c->h, c->buf);
+        c->fill = 0;
+    }
+    while (n >= 64) {
+        sha256_block(c->h, p);
+        p += 64;
+        n -= 64;
+    }
+    if (n) {
+        memcpy(c->buf, p, n);
+        c->fill = (uint32_t)n;
+    }
+}
+
+void mko_sha256_final(mko_sha256_ctx *c, uint8_t out[32])
+{
+    uint64_t bits = c->nbytes * 8;
+    uint8_t pad[72];
+    size_t padlen = (c->fill < 56) ? 56 - c->fill : 120 - c->fill;
+    memset(pad, 0, sizeof pad);
+    pad[0] = 0x80;
+    for (int i = 0; i < 8; i++)
+        pad[padlen + i] = (uint8_t)(bits >> (56 - 8 * i));
+    mko_sha256_update(c, pad, padlen + 8);
+    for (int i = 0; i < 8; i++) {
+        out[4 * i] = (uint8_t)(c->h[i] >> 24);
+        out[4 * i + 1] = (uint8_t)(c->h[i] >> 16);
+        out[4 * i + 2] = (uint8_t)(c->h[i] >> 8);
+        out[4 * i + 3] = (uint8_t)c->h[i];
+    }
+}
+
+void mko_sha256(const uint8_t *p, size_t n, uint8_t out[32])
+{
+    mko_sha256_ctx c;
+    mko_sha256_init(&c);
+    mko_sha256_update(&c, p, n);
+    mko_sha256_final(&c, out);
+}
+
+/* ======================================================================= */
+/* Gear-32 CDC (no reference counterpart)                   */
+/* ======================================================================= */
+
+static inline uint64_t mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+#define GOLDEN64 0x9E3779B97F4A7C15ull
+#define GEAR_SEED 0x6D616B697375ull /* "makisu" */
+
+void mko_gear_table(uint32_t out[256])
+{
+    for (uint64_t b = 0; b < 256; b++)
+        out[b] = (uint32_t)(mix64(GEAR_SEED + (b + 1) * GOLDEN64) >> 32);
+}
+
+void mko_cdc_default_params(mko_cdc_params *p)
+{
+    p->min_size = 4096;
+    p->normal_size = 16384;
+    p->max_size = 131072;
+    p->strict_bits = 16;
+    p->loose_bits = 12;
+}
+
+uint32_t mko_gear_at(const uint8_t *data, size_t i)
+{
+    uint32_t g[256];
+    mko_gear_table(g);
+    size_t start = i >= 31 ? i - 31 : 0;
+    uint32_t h = 0;
+    for (size_t k = start; k <= i; k++)
+        h = (h << 1) + g[data[k]];
+    return h;
+}
+
+size_t mko_cdc_cuts(const uint8_t *data, size_t len, const mko_cdc_params *p,
+                    uint64_t *ends, size_t cap)
+{
+    uint32_t g[256];
+    mko_gear_table(g);
+    const uint32_t strict_lim = 1u << (32 - p->strict_bits);
+    const uint32_t loose_lim = 1u << (32 - p->loose_bits);
+    size_t n = 0, prev = 0;
+    while (prev < len) {
+        size_t rem = len - prev;
+        size_t cut;
+        if (rem <= p->min_size) {
+            cut = len;
+        } else {
+            size_t limit = rem < p->max_size ? rem : p->max_size;
+            /* window of 32 bytes ending at the last byte of a min-size chunk */
+            uint32_t h = 0;
+            for (size_t k = prev + p->min_size - 32; k < prev + p->min_size; k++)
+                h = (h << 1) + g[data[k]];
+            size_t L = p->min_size;
+            cut = 0;
+            for (;;) {
+                uint32_t lim = L < p->normal_size ? strict_lim : loose_lim;
+                if (h < lim) {
+                    cut = prev + L;
+                    break;
+                }
+                if (L == limit)
+                    break;
+                h = (h << 1) + g[data[prev + L]];
+                L++;
+            }
+            if (!cut)
+                cut = prev + limit; /* forced at max, or end of file */
+        }
+        if (n < cap)
+            ends[n] = cut;
+        n++;
+        prev = cut;
+    }
+    return n;
+}
+
+/* ======================================================================= */
+/* chunk table                                                             */
+/* ======================================================================= */
+
+static int cmp_digest(const void *a, const void *b) { return memcmp(a, b, 32); }
+
+size_t mko_sort_unique_digests(uint8_t *d, size_t n)
+{
+    if (n == 0)
+        return 0;
+    qsort(d, n, 32, cmp_digest);
+    size_t m = 1;
+    for (size_t i = 1; i < n; i++)
+        if (memcmp(d + 32 * i, d + 32 * (m - 1), 32) != 0) {
+            if (i != m)
+                memcpy(d + 32 * m, d + 32 * i, 32);
+            m++;
+        }
+    return m;
+}
+
+void mko_merkle_root(const uint8_t *digests, size_t n, uint8_t out[32])
+{
+    if (n == 0) {
+        mko_sha256((const uint8_t *)"", 0, out);
+        return;
+    }
+    size_t cur_n = n;
+    const uint8_t *cur = digests;
+    uint8_t *owned = NULL;
+    for (;;) {
+        size_t next_n = (cur_n + 255) / 256;
+        uint8_t *next = (uint8_t *)malloc(next_n * 32);
+        for (size_t j = 0; j < next_n; j++) {
+            size_t cnt = cur_n - j * 256 < 256 ? cur_n - j * 256 : 256;
+            mko_sha256(cur + j * 256 * 32, cnt * 32, next + j * 32);
+        }
+        free(owned);
+        owned = next;
+        cur = next;
+        cur_n = next_n;
+        if (cur_n == 1)
+            break;
+    }
+    memcpy(out, cur, 32);
+    free(owned);
+}
+
+int mko_chunk_table(const uint8_t *arena, const uint64_t *offs, const uint64_t *lens,
+                    size_t n_files, const mko_cdc_params *p, uint64_t *cut_ends,
+                    uint8_t *digests, uint8_t *table, size_t cap,
+                    mko_table_summary *summary)
+{
+    /* pass 1: count */
+    size_t total = 0;
+    for (size_t f = 0; f < n_files; f++)
+        total += mko_cdc_cuts(arena + offs[f], lens[f], p, NULL, 0);
+    summary->n_chunks = total;
+    summary->n_unique = 0;
+    if ((cut_ends || digests || table) && total > cap)
+        return -1;
+    uint64_t *ends = cut_ends ? cut_ends : (uint64_t *)malloc((total ? total : 1) * 8);
+    uint8_t *dg = digests ? digests : (uint8_t *)malloc((total ? total : 1) * 32);
+    size_t k = 0;
+    for (size_t f = 0; f < n_files; f++) {
+        size_t c = mko_cdc_cuts(arena + offs[f], lens[f], p, ends + k, total - k);
+        uint64_t prev = 0;
+        for (size_t j = 0; j < c; j++) {
+            uint64_t e = ends[k + j];
+            mko_sha256(arena + offs[f] + prev, e - prev, dg + 32 * (k + j));
+            prev = e;
+            ends[k + j] = offs[f] + e; /* absolute arena offset */
+        }
+        k += c;
+    }
+    uint8_t *tb = table ? table : (uint8_t *)malloc((total ? total : 1) * 32);
+    memcpy(tb, dg, total * 32);
+    size_t uniq = mko_sort_unique_digests(tb, total);
+    summary->n_unique = uniq;
+    mko_merkle_root(tb, uniq, summary->root);
+    if (!table)
+        free(tb);
+    if (!digests)
+        free(dg);
+    if (!cut_ends)
+        free(ends);
+    return 0;
+}
+
+/* ======================================================================= */
+/* synthetic content                                                       */
+/* ======================================================================= */
+
+void mko_synth_fill(uint8_t *dst, uint64_t byte_off, uint64_t n, uint64_t seed)
+{
+    uint64_t w0 = byte_off / 8;
+    for (uint64_t i = 0; i < n / 8; i++) {
+        uint64_t v = mix64(seed + (w0 + i + 1) * GOLDEN64);
+        memcpy(dst + 8 * i, &v, 8);
+    }
+}

@@ -1,0 +1,167 @@
+"""-m gpu: the CUDA path (through the C-ABI) against the CPU oracle, bit exact.
+
+Reads like the reference's own tests where they exist:
+  reference lib/builder/step/copy_step_test.go:51-169 (TestCopyStepSetCacheID): same content => same
+  ID, changed content / order => different ID -- here additionally checked against the exact CRC value.
+"""
+import hashlib
+import zlib
+
+import numpy as np
+import pytest
+
+from tests.util import pack, crc_extents, cdc_extents, ranges
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from makisu_b200.abi import Engine
+    e = Engine(device=0, device_arena_bytes=256 << 20, n_host_arenas=2, host_arena_bytes=64 << 20,
+               max_extents=1 << 16)
+    yield e
+    e.close()
+
+
+def _rand(rng, n):
+    return rng.integers(0, 256, n, dtype=np.uint8)
+
+
+SIZES = [0, 1, 3, 15, 16, 17, 63, 64, 65, 511, 512, 513, 4095, 4096, 4097, 70000, 262143, 262144, 262145,
+         524288, 1000003, 3 * 262144 + 77]
+
+
+def test_crc32_ragged_extents(eng):
+    rng = np.random.default_rng(7)
+    segs = [_rand(rng, n) for n in SIZES]
+    arena, offs = pack(segs, file_align=16)
+    lens = [len(s) for s in segs]
+    order = list(rng.permutation(len(segs)))
+    ext, total = crc_extents(offs, lens, order)
+    eng.begin()
+    eng.device_upload(0, 0, arena)
+    eng.device_submit(0, arena.size, ext)
+    res = eng.finish()
+    want = zlib.crc32(b"".join(segs[i].tobytes() for i in order))
+    assert res.crc_bytes == total
+    assert eng.ctx_crc32(res) == want
+    # split over two submits (session accumulates, suffixes are global)
+    half = len(ext) // 2
+    eng.begin()
+    eng.device_submit(0, arena.size, ext[:half])
+    eng.device_submit(0, arena.size, ext[half:])
+    res2 = eng.finish()
+    assert eng.ctx_crc32(res2) == want
+    # relational properties of TestCopyStepSetCacheID: changed content => different id
+    arena2 = arena.copy()
+    arena2[offs[-1] + 5] ^= 1
+    eng.begin()
+    eng.device_upload(0, 0, arena2)
+    eng.device_submit(0, arena2.size, ext)
+    assert eng.ctx_crc32(eng.finish()) != want
+
+
+def test_crc32_empty_stream(eng):
+    eng.begin()
+    res = eng.finish()
+    assert eng.ctx_crc32(res) == zlib.crc32(b"") == 0
+    assert res.n_chunks == 0 and res.n_unique == 0
+    assert bytes(res.root) == hashlib.sha256(b"").digest()
+
+
+def test_sha256_streams(eng):
+    rng = np.random.default_rng(11)
+    sizes = [0, 1, 55, 56, 57, 63, 64, 65, 119, 120, 121, 128, 1000, 1024, 65536 + 3, 1 << 20]
+    segs = [_rand(rng, n) for n in sizes]
+    arena, offs = pack(segs, file_align=16)
+    eng.begin()
+    eng.device_upload(0, 0, arena)
+    eng.device_submit(0, arena.size, [], ranges(offs, sizes))
+    res = eng.finish()
+    got = eng.get_stream_digests(res.n_streams)
+    assert res.n_streams == len(sizes)
+    for s, g in zip(segs, got):
+        assert g.tobytes() == hashlib.sha256(s.tobytes()).digest()
+
+
+def _check_table(eng, oracle_lib, arena, offs, lens, via_host=False):
+    eng.begin()
+    ext = cdc_extents(offs, lens)
+    if via_host:
+        ptr, cap, aid = eng.arena_acquire()
+        import ctypes
+        ctypes.memmove(ptr, arena.ctypes.data, arena.size)
+        eng.arena_submit(aid, arena.size, ext)
+    else:
+        eng.device_upload(0, 0, arena)
+        eng.device_submit(0, arena.size, ext)
+    res = eng.finish()
+    want = oracle_lib.chunk_table(arena, offs, lens)
+    assert res.n_chunks == want["n_chunks"]
+    ends, dig = eng.get_chunks(res.n_chunks)
+    np.testing.assert_array_equal(ends, want["ends"])
+    np.testing.assert_array_equal(dig, want["digests"])
+    assert res.n_unique == want["n_unique"]
+    np.testing.assert_array_equal(eng.get_table(res.n_unique), want["table"])
+    assert bytes(res.root) == want["root"]
+    return res
+
+
+def test_chunk_table_random_files(eng, oracle_lib):
+    rng = np.random.default_rng(3)
+    lens = [0, 10, 4095, 4096, 4097, 8192, 40000, 131072, 131073, 300000, 1 << 20, 2500000, 31, 77]
+    segs = [_rand(rng, n) for n in lens]
+    arena, offs = pack(segs)
+    _check_table(eng, oracle_lib, arena, offs, lens)
+    _check_table(eng, oracle_lib, arena, offs, lens, via_host=True)
+
+
+def test_chunk_table_low_entropy_and_duplicates(eng, oracle_lib):
+    rng = np.random.default_rng(5)
+    zeros = np.zeros(700000, dtype=np.uint8)                       # no candidates: forced max cuts
+    ones = np.full(300001, 0xFF, dtype=np.uint8)
+    text = np.frombuffer((b"the quick brown fox jumps over the lazy dog\n" * 20000), dtype=np.uint8)
+    period = np.tile(_rand(rng, 37), 20000)                        # short period
+    blob = _rand(rng, 600000)
+    dup = np.concatenate([blob, blob, blob[:250000]])               # repeated content resynchronises
+    segs = [zeros, ones, text, period, blob, dup, blob.copy()]
+    lens = [len(s) for s in segs]
+    arena, offs = pack(segs)
+    res = _check_table(eng, oracle_lib, arena, offs, lens)
+    assert res.n_unique < res.n_chunks  # dedup happened
+
+
+def test_chunk_table_many_small_files(eng, oracle_lib):
+    rng = np.random.default_rng(9)
+    lens = [int(x) for x in rng.integers(0, 20000, 3000)]
+    segs = [_rand(rng, n) for n in lens]
+    arena, offs = pack(segs)
+    _check_table(eng, oracle_lib, arena, offs, lens)
+
+
+def test_everything_in_one_submit(eng, oracle_lib):
+    """CRC + CDC + a serial stream over the same arena, like a COPY step that is both fingerprinted and committed."""
+    rng = np.random.default_rng(21)
+    lens = [123456, 7, 999999, 512, 65536]
+    segs = [_rand(rng, n) for n in lens]
+    arena, offs = pack(segs)
+    from makisu_b200.abi import MKSNAP_X_CDC
+    ext, total = crc_extents(offs, lens, [4, 0, 1, 2, 3], flags_extra=[MKSNAP_X_CDC] * 5)
+    eng.begin()
+    eng.device_upload(0, 0, arena)
+    eng.device_submit(0, arena.size, ext, ranges([0], [arena.size]))
+    res = eng.finish()
+    assert eng.ctx_crc32(res) == zlib.crc32(b"".join(segs[i].tobytes() for i in [4, 0, 1, 2, 3]))
+    # CDC extents are reported in submit order: [4,0,1,2,3]
+    want = oracle_lib.chunk_table(arena, [offs[i] for i in [4, 0, 1, 2, 3]], [lens[i] for i in [4, 0, 1, 2, 3]])
+    assert bytes(res.root) == want["root"] and res.n_chunks == want["n_chunks"]
+    assert eng.get_stream_digests(1)[0].tobytes() == hashlib.sha256(arena.tobytes()).digest()
+
+
+def test_synth_fill_matches_oracle(eng, oracle_lib):
+    eng.begin()
+    eng.synth_fill(0, 4096, 1 << 20, 0xC2)
+    got = eng.device_download(0, 4096, 1 << 20)
+    np.testing.assert_array_equal(got, oracle_lib.synth_fill(4096, 1 << 20, 0xC2))
+    eng.finish()
