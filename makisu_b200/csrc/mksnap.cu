@@ -89,6 +89,8 @@ struct mksnap {
     SessionCounters *h_sc = nullptr; // pinned
 
     TileRec *d_tiles = nullptr;
+    CUtensorMap tm_main[MAX_SLOTS][3], tm_halo[MAX_SLOTS]; // per slot: arena viewed as [rows][128 B]
+    int gear_cfg = 1;                                       // index into the k_gear_scan instantiations
     uint32_t *d_pool = nullptr;
     uint32_t pool_cap = 0;
     uint32_t *d_pool_count = nullptr;
@@ -335,6 +337,41 @@ void mksnap_gear_table(uint32_t out[256]) { gear_table_host(out); }
 
 const char *mksnap_last_error(const mksnap_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+} // extern "C" (helpers below are C++)
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_row_map(mksnap *h, EncodeTiledFn enc, CUtensorMap *out, void *base, uint64_t n_rows, uint32_t box_rows)
+{
+    const cuuint64_t dims[2] = {128, n_rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {128, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(h, MKSNAP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu box=%u", (int)r,
+                    (unsigned long long)n_rows, box_rows);
+    return 0;
+}
+
+template <int W, int S> static int launch_gear(mksnap *h, uint32_t slot, int cfg_idx, uint32_t n_regions, cudaStream_t sk)
+{
+    using Cfg = GearCfg<W, S>;
+    const uint32_t n_tiles = (n_regions + W - 1) / W;
+    const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)h->sm_count);
+    k_gear_scan<W, S><<<grid, Cfg::THREADS, Cfg::SMEM, sk>>>(h->tm_main[slot][cfg_idx], h->tm_halo[slot], n_tiles, h->d_gear,
+                                                            h->prm.strict_lim, h->prm.loose_lim, h->d_tiles, h->d_pool,
+                                                            h->pool_cap, h->d_pool_count, &h->d_sc->err);
+    LAUNCH_OK(h);
+    return 0;
+}
+
+extern "C" {
+
 static int create_impl(mksnap *h)
 {
     const mksnap_config &c = h->cfg;
@@ -397,8 +434,30 @@ static int create_impl(mksnap *h)
     CK(h, cudaMemset(h->d_sc, 0, sizeof(SessionCounters)));
     CK(h, cudaHostAlloc(&h->h_sc, sizeof(SessionCounters), cudaHostAllocDefault));
 
-    const uint64_t n_tiles = c.device_arena_bytes / GEAR_TILE + 2;
+    const uint64_t n_tiles = c.device_arena_bytes / GEAR_TILE + 64; // one TileRec per 4 KiB region (+ tile round-up)
     CK(h, cudaMalloc(&h->d_tiles, n_tiles * sizeof(TileRec)));
+    {
+        EncodeTiledFn enc = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&enc, cudaEnableDefault, &qres));
+        if (!enc || qres != cudaDriverEntryPointSuccess)
+            return fail(h, MKSNAP_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+        const uint64_t n_rows = (c.device_arena_bytes + SLOT_SLACK) / 128;
+        for (uint32_t s = 0; s < h->n_slots; s++) {
+            int rc;
+            if ((rc = make_row_map(h, enc, &h->tm_main[s][0], h->d_slot[s], n_rows, GearCfg<8, 4>::BOX_ROWS)) ||
+                (rc = make_row_map(h, enc, &h->tm_main[s][1], h->d_slot[s], n_rows, GearCfg<12, 3>::BOX_ROWS)) ||
+                (rc = make_row_map(h, enc, &h->tm_main[s][2], h->d_slot[s], n_rows, GearCfg<16, 2>::BOX_ROWS)) ||
+                (rc = make_row_map(h, enc, &h->tm_halo[s], h->d_slot[s], n_rows, 1)))
+                return rc;
+        }
+        CK(h, cudaFuncSetAttribute(k_gear_scan<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<8, 4>::SMEM));
+        CK(h, cudaFuncSetAttribute(k_gear_scan<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<12, 3>::SMEM));
+        CK(h, cudaFuncSetAttribute(k_gear_scan<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<16, 2>::SMEM));
+        const char *e = getenv("MKSNAP_GEAR_CFG"); // tuning knob: 0 = 8 warps x 4 stages, 1 = 12x3, 2 = 16x2
+        if (e && e[0] >= '0' && e[0] <= '2')
+            h->gear_cfg = e[0] - '0';
+    }
     uint64_t pc = std::max<uint64_t>(1u << 20, c.device_arena_bytes / 128);
     if (pc > 0xFFFFFFF0ull)
         pc = 0xFFFFFFF0ull;
@@ -661,14 +720,13 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     }
     CK(h, cudaEventRecord(h->ev[1], sk));
     if (n_files) {
-        const uint64_t nbytes = (used + 15) & ~15ull;
-        const uint32_t n_tiles = (uint32_t)((nbytes + GEAR_TILE - 1) / GEAR_TILE);
+        const uint32_t n_regions = (uint32_t)((used + GEAR_TILE - 1) / GEAR_TILE);
         CK(h, cudaMemsetAsync(h->d_pool_count, 0, 4, sk));
-        const uint32_t grid = std::min<uint32_t>(n_tiles, h->sm_count * 6);
-        k_gear_scan<<<grid, GEAR_THREADS, 0, sk>>>(d_arena, nbytes, n_tiles, h->d_gear, h->prm.strict_lim,
-                                                    h->prm.loose_lim, h->d_tiles, h->d_pool, h->pool_cap,
-                                                    h->d_pool_count, &h->d_sc->err);
-        LAUNCH_OK(h);
+        int rc = h->gear_cfg == 0   ? launch_gear<8, 4>(h, slot, 0, n_regions, sk)
+                 : h->gear_cfg == 1 ? launch_gear<12, 3>(h, slot, 1, n_regions, sk)
+                                    : launch_gear<16, 2>(h, slot, 2, n_regions, sk);
+        if (rc)
+            return rc;
     }
     CK(h, cudaEventRecord(h->ev[2], sk));
     if (n_files) {

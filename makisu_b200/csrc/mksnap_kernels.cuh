@@ -13,6 +13,7 @@
 //   crypto/sha256<- lib/builder/step/common.go:44-55
 // Everything here is 32-bit integer / byte work: no tensor cores, no floats.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -41,6 +42,29 @@ __host__ __device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b)
         b = (b >> 1) ^ ((0u - (b & 1u)) & MK_CRC_POLY);
     }
     return acc;
+}
+
+// Table lookups: tables are replicated per lane ([value][32 lanes] words) so a warp-wide lookup
+// never bank-conflicts.  Address = lane_base + byte*128, built as PRMT (byte extract, ALU pipe) +
+// IMAD (FMA pipe) and fed to ld.shared directly: 3 issue slots per lookup instead of the 5 the
+// generic-pointer path costs.
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <int K> __device__ __forceinline__ uint32_t byte_of(uint32_t w)
+{
+    return __byte_perm(w, 0, 0x4440 + K); // zero-extended byte K
+}
+__device__ __forceinline__ uint32_t tab_addr(uint32_t lane_base, uint32_t byte)
+{
+    return byte * 128u + lane_base;
 }
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
@@ -101,14 +125,14 @@ struct CrcConsts {
     uint32_t xp[32];       // x^(2^i), i = bit exponent
 };
 
-__device__ __forceinline__ uint32_t crc_step(const uint32_t *T, uint32_t a, uint32_t w)
+__device__ __forceinline__ uint32_t crc_step(uint32_t T, uint32_t a, uint32_t w)
 {
-    // T already includes the lane offset; table t, value v at T[(t*256+v)*32]
-    uint32_t r = T[((a & 0xFFu)) << 5];
-    r ^= T[(256u + ((a >> 8) & 0xFFu)) << 5];
-    r ^= T[(512u + ((a >> 16) & 0xFFu)) << 5];
-    r ^= T[(768u + (a >> 24)) << 5];
-    return r ^ w;
+    // T = shared address of table 0 + lane*4; table t, value v at T + t*32768 + v*128
+    const uint32_t r0 = lds_u32(tab_addr(T, byte_of<0>(a)));
+    const uint32_t r1 = lds_u32(tab_addr(T + 32768u, byte_of<1>(a)));
+    const uint32_t r2 = lds_u32(tab_addr(T + 65536u, byte_of<2>(a)));
+    const uint32_t r3 = lds_u32(tab_addr(T + 98304u, byte_of<3>(a)));
+    return r0 ^ r1 ^ r2 ^ r3 ^ w;
 }
 
 __global__ void __launch_bounds__(CRC_THREADS, 1)
@@ -122,7 +146,7 @@ k_crc32_extents(const uint8_t *__restrict__ arena, const CrcExtent *__restrict__
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t *T = s_tab + lane;
+    const uint32_t T = smem_u32(s_tab) + lane * 4u;
     const uint32_t warps_per_cta = blockDim.x >> 5;
     const uint32_t total_warps = gridDim.x * warps_per_cta;
     uint32_t warp_acc = 0;
@@ -204,185 +228,274 @@ k_crc32_extents(const uint8_t *__restrict__ arena, const CrcExtent *__restrict__
 // ------------------------------------------------------------------------
 // K1: Gear-32 candidate scan.
 //   h_i = sum_{k<32} G[b_{i-k}] << k  (mod 2^32);  candidate iff h_i < 2^(32-bits)
-// The update h' = (h<<1)+G[b] is linear in h, so a lane that owns 16 coalesced
-// bytes computes its local prefix hashes L_0..L_15 from state 0 and then adds
-// the carry of the 32 preceding bytes:  h_i = L_i + (A << (i+1)),
-// A = Lfull[lane-1] + (Lfull[lane-2] << 16), exchanged with two warp shuffles
-// (rows chain through lanes 30/31 of the previous iteration).
-// A warp walks a 4 KiB stripe, a CTA a 32 KiB tile; hits are rare (2^-12) and
-// go to a per-tile shared-memory bitmap, which is then compacted *in order*
-// into a bump-allocated pool: pool entry = pos_in_tile | strict<<31.
+//
+// Data path: the arena is viewed as a [rows][128 B] tensor.  A producer warp streams
+// tiles of GEAR_WARPS*32 rows into shared memory with TMA (cp.async.bulk.tensor.2d,
+// SWIZZLE_128B) through a GEAR_STAGES-deep full/empty mbarrier ring; a second one-row
+// TMA brings the 128 bytes that precede the tile (the rolling-hash halo).
+// Each consumer thread owns ONE 128-byte row: it reads it with eight conflict-free
+// LDS.128 (chunk c of row r sits at c ^ (r&7)), and rolls the hash over its 128
+// bytes from state 0.  The update h' = 2h + G[b] is linear in h, so the state the
+// thread should have started from -- A = hash of the 32 bytes before its row, i.e.
+// the previous lane's final state, one warp shuffle away -- is added afterwards as
+// h_i += A << (i+1), which only matters for the first 31 positions.  A warp is
+// fully autonomous (its lane-0 carry comes from a 32-lane cooperative hash of the
+// preceding 32 bytes), so there is no block-level synchronisation at all.
+// Candidates are rare (2^-12 per byte): they are collected in per-lane register
+// bitmasks (lane l's mask = its own row), compacted in position order with one
+// warp scan, and bump-allocated into the pool: one TileRec per 4 KiB warp region,
+// pool entry = pos_in_region | strict<<31.
 // ------------------------------------------------------------------------
-constexpr uint32_t GEAR_TILE = 32768;
-constexpr uint32_t GEAR_THREADS = 256;
-constexpr uint32_t GEAR_STRIPE = GEAR_TILE / (GEAR_THREADS / 32); // 4096
+constexpr uint32_t GEAR_TILE = 4096; // bytes per TileRec region (= one warp x 32 rows x 128 B)
 
 struct TileRec {
-    uint32_t base;  // first pool entry of this tile
-    uint32_t count; // candidates in this tile
+    uint32_t base;  // first pool entry of this region
+    uint32_t count; // candidates in this region
 };
 
-__device__ __forceinline__ uint32_t gear_lookup(const uint32_t *G, uint32_t byte)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    return G[byte << 5]; // G already includes the lane offset
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int32_t x, int32_t y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
 
-#define MK_GEAR_BYTES(word, k0)                                  \
-    {                                                            \
-        h = (h << 1) + gear_lookup(G, (word) & 0xFFu);           \
-        L[(k0)] = h;                                             \
-        h = (h << 1) + gear_lookup(G, ((word) >> 8) & 0xFFu);    \
-        L[(k0) + 1] = h;                                         \
-        h = (h << 1) + gear_lookup(G, ((word) >> 16) & 0xFFu);   \
-        L[(k0) + 2] = h;                                         \
-        h = (h << 1) + gear_lookup(G, (word) >> 24);             \
-        L[(k0) + 3] = h;                                         \
+// roll 4 bytes of `word` into h, keeping every intermediate state in hv[k0..k0+3]
+#define MK_GEAR_BYTES(word, k0)                                     \
+    {                                                               \
+        const uint32_t g0 = lds_u32(tab_addr(G, byte_of<0>(word))); \
+        const uint32_t g1 = lds_u32(tab_addr(G, byte_of<1>(word))); \
+        const uint32_t g2 = lds_u32(tab_addr(G, byte_of<2>(word))); \
+        const uint32_t g3 = lds_u32(tab_addr(G, byte_of<3>(word))); \
+        h = h * 2u + g0;                                            \
+        hv[(k0)] = h;                                               \
+        h = h * 2u + g1;                                            \
+        hv[(k0) + 1] = h;                                           \
+        h = h * 2u + g2;                                            \
+        hv[(k0) + 2] = h;                                           \
+        h = h * 2u + g3;                                            \
+        hv[(k0) + 3] = h;                                           \
     }
 
-__device__ __forceinline__ uint32_t gear_full16(const uint32_t *G, uint4 w)
-{
-    uint32_t h = 0;
-    uint32_t L[16];
-    MK_GEAR_BYTES(w.x, 0) MK_GEAR_BYTES(w.y, 4) MK_GEAR_BYTES(w.z, 8) MK_GEAR_BYTES(w.w, 12)
-    return L[15];
-}
+template <int GEAR_WARPS, int GEAR_STAGES> struct GearCfg {
+    static constexpr uint32_t ROWS = GEAR_WARPS * 32;
+    static constexpr uint32_t TILE_BYTES = ROWS * 128;
+    static constexpr uint32_t BOX_ROWS = ROWS > 256 ? 128 : ROWS; // rows per TMA op (tensor-map box)
+    static constexpr uint32_t THREADS = (GEAR_WARPS + 1) * 32;
+    // shared layout (offsets from a 1024-aligned base)
+    static constexpr uint32_t OFF_TILES = 0;
+    static constexpr uint32_t OFF_HALO = OFF_TILES + GEAR_STAGES * TILE_BYTES;
+    static constexpr uint32_t OFF_GEAR = OFF_HALO + GEAR_STAGES * 1024;
+    static constexpr uint32_t OFF_BARS = OFF_GEAR + 256 * 32 * 4;
+    static constexpr uint32_t SMEM = OFF_BARS + 2 * GEAR_STAGES * 8 + 1024 /* alignment slack */;
+};
 
-__global__ void __launch_bounds__(GEAR_THREADS)
-k_gear_scan(const uint8_t *__restrict__ arena, uint64_t nbytes /* multiple of 16 */, uint32_t n_tiles,
-            const uint32_t *__restrict__ gear, uint32_t strict_lim, uint32_t loose_lim,
+template <int GEAR_WARPS, int GEAR_STAGES>
+__global__ void __launch_bounds__((GEAR_WARPS + 1) * 32, 1)
+k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
+            uint32_t n_tiles, const uint32_t *__restrict__ gear, uint32_t strict_lim, uint32_t loose_lim,
             TileRec *__restrict__ tiles, uint32_t *__restrict__ pool, uint32_t pool_cap,
             uint32_t *__restrict__ pool_count, uint32_t *__restrict__ err_flag)
 {
-    __shared__ uint32_t s_gear[256 * 32];
-    __shared__ uint32_t s_bmL[GEAR_TILE / 32];
-    __shared__ uint32_t s_bmS[GEAR_TILE / 32];
-    __shared__ uint32_t s_wsum[GEAR_THREADS / 32];
-    __shared__ uint32_t s_base;
-
-    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += blockDim.x)
-        s_gear[i] = __ldg(gear + (i >> 5));
+    using Cfg = GearCfg<GEAR_WARPS, GEAR_STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t *G = s_gear + lane;
+    const uint32_t bar_full = sbase + Cfg::OFF_BARS, bar_empty = bar_full + GEAR_STAGES * 8;
 
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i < GEAR_TILE / 32; i += blockDim.x) {
-            s_bmL[i] = 0;
-            s_bmS[i] = 0;
+    // lane-replicated gear table: value v of lane l at OFF_GEAR + v*128 + l*4
+    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += blockDim.x)
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + Cfg::OFF_GEAR + i * 4u), "r"(__ldg(gear + (i >> 5))));
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GEAR_STAGES; ++s) {
+            mbar_init(bar_full + s * 8, 1);
+            mbar_init(bar_empty + s * 8, GEAR_WARPS);
         }
-        __syncthreads();
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
-        const uint64_t s0 = (uint64_t)tile * GEAR_TILE + (uint64_t)warp * GEAR_STRIPE;
-        // carry-in: Lfull of the two 16-byte words before the stripe
-        uint32_t p30 = 0, p31 = 0;
-        {
-            uint32_t lf = 0;
-            if (lane >= 30 && s0 >= 32) {
-                uint4 w = *reinterpret_cast<const uint4 *>(arena + s0 - 32 + (lane - 30) * 16);
-                lf = gear_full16(G, w);
-            }
-            p30 = __shfl_sync(0xFFFFFFFFu, lf, 30);
-            p31 = __shfl_sync(0xFFFFFFFFu, lf, 31);
-        }
-        uint4 wnext = make_uint4(0, 0, 0, 0);
-        {
-            const uint64_t a = s0 + lane * 16u;
-            if (a < nbytes)
-                wnext = ldg_stream(reinterpret_cast<const uint4 *>(arena + a));
-        }
-#pragma unroll 1
-        for (uint32_t r = 0; r < GEAR_STRIPE / 512; ++r) {
-            const uint4 w = wnext;
-            {
-                const uint64_t a = s0 + (uint64_t)(r + 1) * 512 + lane * 16u;
-                wnext = make_uint4(0, 0, 0, 0);
-                if (r + 1 < GEAR_STRIPE / 512 && a < nbytes)
-                    wnext = ldg_stream(reinterpret_cast<const uint4 *>(arena + a));
-            }
-            uint32_t h = 0;
-            uint32_t L[16];
-            MK_GEAR_BYTES(w.x, 0) MK_GEAR_BYTES(w.y, 4) MK_GEAR_BYTES(w.z, 8) MK_GEAR_BYTES(w.w, 12)
-            const uint32_t lfull = L[15];
-            uint32_t up1 = __shfl_up_sync(0xFFFFFFFFu, lfull, 1);
-            uint32_t up2 = __shfl_up_sync(0xFFFFFFFFu, lfull, 2);
-            if (lane == 0) { up1 = p31; up2 = p30; }
-            if (lane == 1) { up2 = p31; }
-            const uint32_t A = up1 + (up2 << 16);
-            uint32_t m = 0xFFFFFFFFu;
+    if (warp == GEAR_WARPS) {
+        // ------------------------- TMA producer -------------------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t s = it % GEAR_STAGES;
+                if (it >= GEAR_STAGES)
+                    mbar_wait(bar_empty + s * 8, ((it / GEAR_STAGES) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(bar_full + s * 8, Cfg::TILE_BYTES + 128u);
+                const int32_t row0 = (int32_t)(tile * Cfg::ROWS);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+                for (uint32_t b = 0; b < Cfg::ROWS / Cfg::BOX_ROWS; ++b)
+                    tma_load_2d(sbase + Cfg::OFF_TILES + s * Cfg::TILE_BYTES + b * Cfg::BOX_ROWS * 128u, &tm_main, 0,
+                                row0 + (int32_t)(b * Cfg::BOX_ROWS), bar_full + s * 8);
+                tma_load_2d(sbase + Cfg::OFF_HALO + s * 1024u, &tm_halo, 0, row0 - 1, bar_full + s * 8);
+            }
+        }
+        return;
+    }
+
+    // ----------------------------- consumers -----------------------------
+    const uint32_t G = sbase + Cfg::OFF_GEAR + lane * 4u;
+    const uint32_t row = warp * 32u + lane;
+    const uint32_t swz = (row & 7u) << 4;
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % GEAR_STAGES;
+        const uint32_t sb = sbase + Cfg::OFF_TILES + s * Cfg::TILE_BYTES;
+        mbar_wait(bar_full + s * 8, (it / GEAR_STAGES) & 1u);
+
+        // carry into lane 0: hash of the 32 bytes before the warp's first row, one byte per lane
+        uint32_t a_warp;
+        {
+            uint32_t addr;
+            if (warp == 0) {
+                addr = sbase + Cfg::OFF_HALO + s * 1024u + 96u + lane; // one-row box lands unswizzled
+            } else {
+                const uint32_t pr = warp * 32u - 1u; // previous row, chunks 6 and 7
+                addr = sb + pr * 128u + (((6u + (lane >> 4)) ^ (pr & 7u)) << 4) + (lane & 15u);
+            }
+            uint32_t v = lds_u32(tab_addr(G, lds_u8(addr))) << (31u - lane);
+#pragma unroll
+            for (int sft = 16; sft; sft >>= 1)
+                v += __shfl_xor_sync(0xFFFFFFFFu, v, sft);
+            a_warp = v;
+        }
+
+        const uint32_t ra = sb + row * 128u;
+        uint32_t h = 0;
+        uint32_t L[32];                           // states of positions 0..31 (need the carry)
+        uint32_t mL0 = 0, mL1 = 0, mL2 = 0, mL3 = 0; // loose candidates, bit p of the row
+        uint32_t mS0 = 0, mS1 = 0, mS2 = 0, mS3 = 0; // strict candidates
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 w = lds_u128(ra + ((uint32_t)(c << 4) ^ swz));
+            uint32_t hv[16];
+            MK_GEAR_BYTES(w.x, 0) MK_GEAR_BYTES(w.y, 4) MK_GEAR_BYTES(w.z, 8) MK_GEAR_BYTES(w.w, 12)
+            if (c < 2) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    L[c * 16 + i] = hv[i];
+            } else {
+                uint32_t m = hv[0];
+#pragma unroll
+                for (int i = 1; i < 16; ++i)
+                    m = min(m, hv[i]);
+                if (m < loose_lim) { // ~0.4 % of lane-chunks
+                    uint32_t bl = 0, bs = 0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        bl |= (hv[i] < loose_lim ? 1u : 0u) << i;
+                        bs |= (hv[i] < strict_lim ? 1u : 0u) << i;
+                    }
+                    const uint32_t sh = (c & 1) * 16;
+                    if ((c >> 1) == 1) { mL1 |= bl << sh; mS1 |= bs << sh; }
+                    if ((c >> 1) == 2) { mL2 |= bl << sh; mS2 |= bs << sh; }
+                    if ((c >> 1) == 3) { mL3 |= bl << sh; mS3 |= bs << sh; }
+                }
+            }
+        }
+        // the stage is consumed: hand it back to the producer before the tail work
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(bar_empty + s * 8);
+
+        // positions 0..30 need the carry A = previous lane's final state
+        {
+            uint32_t A = __shfl_up_sync(0xFFFFFFFFu, h, 1);
+            if (lane == 0)
+                A = a_warp;
+            uint32_t m = L[31];
+#pragma unroll
+            for (int i = 0; i < 31; ++i) {
                 L[i] += A << (i + 1);
                 m = min(m, L[i]);
             }
-            if (m < loose_lim) { // rare: ~2^-8 per lane-row
-                const uint32_t pos0 = warp * GEAR_STRIPE + r * 512 + lane * 16;
+            if (m < loose_lim) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (L[i] < loose_lim) {
-                        const uint32_t pos = pos0 + i;
-                        atomicOr(&s_bmL[pos >> 5], 1u << (pos & 31));
-                        if (L[i] < strict_lim)
-                            atomicOr(&s_bmS[pos >> 5], 1u << (pos & 31));
-                    }
+                for (int i = 0; i < 32; ++i) {
+                    mL0 |= (L[i] < loose_lim ? 1u : 0u) << i;
+                    mS0 |= (L[i] < strict_lim ? 1u : 0u) << i;
                 }
             }
-            p30 = __shfl_sync(0xFFFFFFFFu, lfull, 30);
-            p31 = __shfl_sync(0xFFFFFFFFu, lfull, 31);
         }
-        __syncthreads();
 
-        // ordered compaction of the tile bitmap: thread t owns words 4t..4t+3
-        uint32_t wl[4], cnt = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            wl[k] = s_bmL[threadIdx.x * 4 + k];
-            cnt += __popc(wl[k]);
-        }
+        // ordered compaction: lane l's candidates precede lane l+1's
+        const uint32_t cnt = __popc(mL0) + __popc(mL1) + __popc(mL2) + __popc(mL3);
         uint32_t incl = cnt;
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, s);
-            if (lane >= s)
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, sft);
+            if (lane >= sft)
                 incl += v;
         }
-        if (lane == 31)
-            s_wsum[warp] = incl;
-        __syncthreads();
-        uint32_t woff = 0, total = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < GEAR_THREADS / 32; ++k) {
-            const uint32_t v = s_wsum[k];
-            if (k < warp)
-                woff += v;
-            total += v;
-        }
-        if (threadIdx.x == 0) {
-            uint32_t b = total ? atomicAdd(pool_count, total) : 0u;
-            if (b + total > pool_cap || b + total < b) {
-                atomicExch(err_flag, 1u);
-                b = 0xFFFFFFFFu;
-            }
-            s_base = b;
-            TileRec tr;
-            tr.base = b;
-            tr.count = total;
-            tiles[tile] = tr;
-        }
-        __syncthreads();
-        const uint32_t base = s_base;
-        if (base != 0xFFFFFFFFu && cnt) {
-            uint32_t o = base + woff + incl - cnt;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t bits = wl[k];
-                const uint32_t sb = s_bmS[threadIdx.x * 4 + k];
-                while (bits) {
-                    const uint32_t b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    pool[o++] = ((threadIdx.x * 4 + k) * 32 + b) | (((sb >> b) & 1u) << 31);
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0) {
+            if (total) {
+                base = atomicAdd(pool_count, total);
+                if (base + total > pool_cap || base + total < base) {
+                    atomicExch(err_flag, 1u);
+                    base = 0xFFFFFFFFu;
                 }
             }
+            TileRec tr;
+            tr.base = base;
+            tr.count = total;
+            tiles[(size_t)tile * GEAR_WARPS + warp] = tr;
         }
-        __syncthreads(); // bitmaps are re-zeroed next iteration
+        if (total) {
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (base != 0xFFFFFFFFu && cnt) {
+                uint32_t o = base + incl - cnt;
+                const uint32_t p0 = lane * 128u;
+#define MK_EMIT(ML, MS, WORD)                                              \
+    {                                                                      \
+        uint32_t bits = (ML);                                              \
+        while (bits) {                                                     \
+            const uint32_t b = __ffs(bits) - 1;                            \
+            bits &= bits - 1;                                              \
+            pool[o++] = (p0 + (WORD) * 32u + b) | ((((MS) >> b) & 1u) << 31); \
+        }                                                                  \
+    }
+                MK_EMIT(mL0, mS0, 0) MK_EMIT(mL1, mS1, 1) MK_EMIT(mL2, mS2, 2) MK_EMIT(mL3, mS3, 3)
+#undef MK_EMIT
+            }
+        }
     }
 }
 
