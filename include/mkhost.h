@@ -1,0 +1,88 @@
+/*
+ * mkhost.h — host side ABOVE the mksnap C-ABI, in C++ (libmkhost.so), C interface.
+ *
+ * The reference's host code on this path is Go; no Go toolchain exists in the build image, so the
+ * packer / walker / tar-header logic a cgo build would keep in Go is implemented here in C++ with the
+ * reference's names, argument meaning and error behaviour, and is what the tests drive.  It contains NO
+ * hashing: every digest comes from libmksnap (the GPU); without a device these calls fail.
+ *
+ *   mkhost_context_crc32      = addCopyStep.SetCacheID + calculateContextChecksum + checksumPathContents
+ *                               reference lib/builder/step/add_copy_step.go:102-122,153-184,194-238
+ *   mkhost_commit_copy_ops    = MemFS.AddLayerByCopyOps + commitLayer + tario.WriteEntry, digested on the GPU
+ *                               reference lib/snapshot/mem_fs.go:276-289,353-433,509-569, mem_layer.go:152-244,
+ *                               lib/tario/write.go:28-68, lib/builder/step/common.go:35-111
+ *   mkhost_encode_tar_header  = tario.WriteHeader + go1.14 archive/tar Writer.WriteHeader (USTAR / PAX)
+ *   mkhost_describe_*         = the same host logic without a GPU (entry order / stream order as text), so the
+ *                               CPU test-suite can diff it against the oracle.
+ */
+#ifndef MKHOST_H
+#define MKHOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "mksnap.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    const char *name;     /* as stored in tar.Header.Name (WriteHeader strips leading '/') */
+    const char *linkname;
+    int64_t mode;         /* perm | 04000 | 02000 | 01000, no type bits (FileInfoHeader) */
+    int64_t uid, gid;
+    int64_t size;
+    int64_t mtime_ns;     /* truncated to the second by tario.WriteHeader (write.go:61) */
+    char typeflag;        /* '0' reg, '1' link, '2' symlink, '5' dir, ... */
+} mkhost_tar_header;
+
+/* Returns the number of bytes written (512 for USTAR, 1536+ for PAX), 0 on error (cap too small /
+ * field not encodable). */
+size_t mkhost_encode_tar_header(const mkhost_tar_header *h, uint8_t *out, size_t cap);
+
+/* snapshot.CopyOperation (lib/snapshot/copy_op.go:29-80).  srcs are relative to src_root (leading '/'
+ * allowed, as TrimRoot produces them); dst is absolute or relative to work_dir. */
+typedef struct {
+    const char *src_root;
+    const char *const *srcs;
+    size_t n_srcs;
+    const char *work_dir;
+    const char *dst;
+    int32_t uid, gid;
+} mkhost_copy_op;
+
+typedef struct {
+    uint8_t tar_digest[32]; /* DigestPair.TarDigest bytes */
+    uint8_t root[32];       /* chunk-table content address */
+    uint64_t n_entries;     /* tar entries */
+    uint64_t tar_bytes;     /* length of the uncompressed tar stream */
+    uint64_t n_chunks, n_unique;
+} mkhost_layer_result;
+
+/* cacheID arithmetic of a COPY/ADD step from the build context.  prefix = seed+directive+args.
+ * from_paths are the directive's sources (globbed and joined like resolveFromPaths).  *crc_out is what
+ * checksum.Sum32() returns; format it with "%x" for the cacheID.  n_threads: file readers (0 = default). */
+int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, const char *context_dir,
+                         const char *const *from_paths, size_t n_paths, int n_threads, uint32_t *crc_out,
+                         uint64_t *stream_len_out, char *err, size_t errlen);
+
+/* Commit one layer from copy operations against an EMPTY MemFS rooted at root_dir (FROM scratch): packs
+ * the sorted entries as a tar stream into one arena, digests it (TarDigest) and chunks every regular
+ * file (chunk table).  now_unix = clk.Now() for synthesized ancestors (mem_fs.go:562). */
+int mkhost_commit_copy_ops(mksnap_t *eng, const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops,
+                           size_t n_ops, int n_threads, mkhost_layer_result *out, char *err, size_t errlen);
+
+/* No-GPU introspection for the CPU tests: one line per item, '\n' separated, NUL terminated.
+ *   stream : "P <relpath>" | "L <target>" | "F <size> <abs path>"   in CRC stream order
+ *   layer  : "<typeflag> <mode octal> <uid> <gid> <size> <mtime> <dst> <hdr.Name> <src>"  in tar order
+ * Return the number of bytes needed (including NUL); if > cap nothing is written. */
+size_t mkhost_describe_context_stream(const char *context_dir, const char *const *from_paths, size_t n_paths,
+                                      char *out, size_t cap, char *err, size_t errlen);
+size_t mkhost_describe_layer(const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops,
+                             char *out, size_t cap, char *err, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

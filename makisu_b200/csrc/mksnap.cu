@@ -90,7 +90,7 @@ struct mksnap {
 
     TileRec *d_tiles = nullptr;
     CUtensorMap tm_main[MAX_SLOTS][3], tm_halo[MAX_SLOTS]; // per slot: arena viewed as [rows][128 B]
-    int gear_cfg = 1;                                       // index into the k_gear_scan instantiations
+    int gear_cfg = 3;                                       // index into the k_gear_scan instantiations
     uint32_t *d_pool = nullptr;
     uint32_t pool_cap = 0;
     uint32_t *d_pool_count = nullptr;
@@ -304,7 +304,7 @@ int merkle_root(mksnap *h, cudaStream_t s)
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, s));
         k_sha256_ranges<<<sha_grid(h), SHA_THREADS, 0, s>>>(cur, nullptr, nullptr, nullptr, next_n, nullptr, 0,
                                                             8192, cur_n * 32, h->d_merkle[which], &h->d_sc->work,
-                                                            nullptr);
+                                                            nullptr, 1u);
         LAUNCH_OK(h);
         cur = h->d_merkle[which];
         cur_n = next_n;
@@ -454,8 +454,9 @@ static int create_impl(mksnap *h)
         CK(h, cudaFuncSetAttribute(k_gear_scan<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<8, 4>::SMEM));
         CK(h, cudaFuncSetAttribute(k_gear_scan<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<12, 3>::SMEM));
         CK(h, cudaFuncSetAttribute(k_gear_scan<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<16, 2>::SMEM));
-        const char *e = getenv("MKSNAP_GEAR_CFG"); // tuning knob: 0 = 8 warps x 4 stages, 1 = 12x3, 2 = 16x2
-        if (e && e[0] >= '0' && e[0] <= '2')
+        CK(h, cudaFuncSetAttribute(k_gear_scan<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<16, 3>::SMEM));
+        const char *e = getenv("MKSNAP_GEAR_CFG"); // tuning knob: 0 = 8 warps x 4 stages, 1 = 12x3, 2 = 16x2, 3 = 16x3
+        if (e && e[0] >= '0' && e[0] <= '3')
             h->gear_cfg = e[0] - '0';
     }
     uint64_t pc = std::max<uint64_t>(1u << 20, c.device_arena_bytes / 128);
@@ -724,7 +725,8 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         CK(h, cudaMemsetAsync(h->d_pool_count, 0, 4, sk));
         int rc = h->gear_cfg == 0   ? launch_gear<8, 4>(h, slot, 0, n_regions, sk)
                  : h->gear_cfg == 1 ? launch_gear<12, 3>(h, slot, 1, n_regions, sk)
-                                    : launch_gear<16, 2>(h, slot, 2, n_regions, sk);
+                 : h->gear_cfg == 2 ? launch_gear<16, 2>(h, slot, 2, n_regions, sk)
+                                    : launch_gear<16, 3>(h, slot, 2, n_regions, sk);
         if (rc)
             return rc;
     }
@@ -748,7 +750,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     if (n_files) {
         k_sha256_ranges<<<sha_grid(h), SHA_THREADS, 0, sk>>>(d_arena, h->d_chunk_start, h->d_chunk_len,
                                                             &h->d_sc->batch_chunks, 0, &h->d_sc->n_chunks, 0, 0, 0,
-                                                            h->d_digests, &h->d_sc->work, &h->d_sc->err);
+                                                            h->d_digests, &h->d_sc->work, &h->d_sc->err, 1u);
         LAUNCH_OK(h);
         k_batch_end<<<1, 32, 0, sk>>>(h->d_sc);
         LAUNCH_OK(h);
@@ -758,7 +760,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, sk));
         k_sha256_ranges<<<(uint32_t)std::min<uint64_t>(sha_grid(h), (n_rng + 3) / 4), SHA_THREADS, 0, sk>>>(
             d_arena, m.d_rstart, m.d_rlen, nullptr, n_rng, nullptr, 0, 0, 0, h->d_stream_digests + h->n_streams * 32,
-            &h->d_sc->work, nullptr);
+            &h->d_sc->work, nullptr, 1u);
         LAUNCH_OK(h);
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, sk));
     }

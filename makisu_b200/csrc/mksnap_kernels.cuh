@@ -62,6 +62,28 @@ template <int K> __device__ __forceinline__ uint32_t byte_of(uint32_t w)
 {
     return __byte_perm(w, 0, 0x4440 + K); // zero-extended byte K
 }
+// a*2^k + b and a + b on the FMA pipe (IMAD): the ALU pipe (LOP3/SHF/PRMT, half rate on B200) is the
+// bottleneck of every kernel here, so additions that the compiler would emit as IADD3 are steered to IMAD.
+__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// ptxas folds "a*1+b" back into IADD3; with the multiplier in a register it knows nothing about (the
+// host passes 1 as a kernel argument) the addition stays an IMAD on the FMA pipe.
+__device__ __forceinline__ uint32_t fma_add_rt(uint32_t a, uint32_t b, uint32_t one)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t fma_2a_plus_b(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
 __device__ __forceinline__ uint32_t tab_addr(uint32_t lane_base, uint32_t byte)
 {
     return byte * 128u + lane_base;
@@ -247,6 +269,7 @@ k_crc32_extents(const uint8_t *__restrict__ arena, const CrcExtent *__restrict__
 // pool entry = pos_in_region | strict<<31.
 // ------------------------------------------------------------------------
 constexpr uint32_t GEAR_TILE = 4096; // bytes per TileRec region (= one warp x 32 rows x 128 B)
+constexpr uint32_t GEAR_POOL_BLOCK = 512; // pool entries a warp reserves per global atomic
 
 struct TileRec {
     uint32_t base;  // first pool entry of this region
@@ -301,13 +324,13 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
         const uint32_t g1 = lds_u32(tab_addr(G, byte_of<1>(word))); \
         const uint32_t g2 = lds_u32(tab_addr(G, byte_of<2>(word))); \
         const uint32_t g3 = lds_u32(tab_addr(G, byte_of<3>(word))); \
-        h = h * 2u + g0;                                            \
+        h = fma_2a_plus_b(h, g0);                                   \
         hv[(k0)] = h;                                               \
-        h = h * 2u + g1;                                            \
+        h = fma_2a_plus_b(h, g1);                                   \
         hv[(k0) + 1] = h;                                           \
-        h = h * 2u + g2;                                            \
+        h = fma_2a_plus_b(h, g2);                                   \
         hv[(k0) + 2] = h;                                           \
-        h = h * 2u + g3;                                            \
+        h = fma_2a_plus_b(h, g3);                                   \
         hv[(k0) + 3] = h;                                           \
     }
 
@@ -319,9 +342,12 @@ template <int GEAR_WARPS, int GEAR_STAGES> struct GearCfg {
     // shared layout (offsets from a 1024-aligned base)
     static constexpr uint32_t OFF_TILES = 0;
     static constexpr uint32_t OFF_HALO = OFF_TILES + GEAR_STAGES * TILE_BYTES;
-    static constexpr uint32_t OFF_GEAR = OFF_HALO + GEAR_STAGES * 1024;
+    // halo rows: slot s at OFF_HALO + s*128 inside one 1 KiB block; a 128 B box landing at address bits
+    // [7:9] = s is stored with swizzle phase s (chunk c at c ^ s)
+    static constexpr uint32_t OFF_GEAR = OFF_HALO + 1024;
     static constexpr uint32_t OFF_BARS = OFF_GEAR + 256 * 32 * 4;
-    static constexpr uint32_t SMEM = OFF_BARS + 2 * GEAR_STAGES * 8 + 1024 /* alignment slack */;
+    static constexpr uint32_t SMEM = OFF_BARS + 2 * GEAR_STAGES * 8;
+    static_assert(GEAR_STAGES <= 8, "halo slots share one 1 KiB block");
 };
 
 template <int GEAR_WARPS, int GEAR_STAGES>
@@ -332,8 +358,8 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
             uint32_t *__restrict__ pool_count, uint32_t *__restrict__ err_flag)
 {
     using Cfg = GearCfg<GEAR_WARPS, GEAR_STAGES>;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t sbase = smem_u32(smem_raw);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t bar_full = sbase + Cfg::OFF_BARS, bar_empty = bar_full + GEAR_STAGES * 8;
 
@@ -363,7 +389,7 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
                 for (uint32_t b = 0; b < Cfg::ROWS / Cfg::BOX_ROWS; ++b)
                     tma_load_2d(sbase + Cfg::OFF_TILES + s * Cfg::TILE_BYTES + b * Cfg::BOX_ROWS * 128u, &tm_main, 0,
                                 row0 + (int32_t)(b * Cfg::BOX_ROWS), bar_full + s * 8);
-                tma_load_2d(sbase + Cfg::OFF_HALO + s * 1024u, &tm_halo, 0, row0 - 1, bar_full + s * 8);
+                tma_load_2d(sbase + Cfg::OFF_HALO + s * 128u, &tm_halo, 0, row0 - 1, bar_full + s * 8);
             }
         }
         return;
@@ -374,6 +400,7 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
     const uint32_t row = warp * 32u + lane;
     const uint32_t swz = (row & 7u) << 4;
     uint32_t it = 0;
+    uint32_t blk_next = 0, blk_end = 0; // this warp's private slice of the pool (warp-uniform)
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t s = it % GEAR_STAGES;
         const uint32_t sb = sbase + Cfg::OFF_TILES + s * Cfg::TILE_BYTES;
@@ -384,7 +411,7 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
         {
             uint32_t addr;
             if (warp == 0) {
-                addr = sbase + Cfg::OFF_HALO + s * 1024u + 96u + lane; // one-row box lands unswizzled
+                addr = sbase + Cfg::OFF_HALO + s * 128u + (((6u + (lane >> 4)) ^ s) << 4) + (lane & 15u);
             } else {
                 const uint32_t pr = warp * 32u - 1u; // previous row, chunks 6 and 7
                 addr = sb + pr * 128u + (((6u + (lane >> 4)) ^ (pr & 7u)) << 4) + (lane & 15u);
@@ -464,22 +491,30 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
                 incl += v;
         }
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        uint32_t base = 0;
-        if (lane == 0) {
-            if (total) {
-                base = atomicAdd(pool_count, total);
-                if (base + total > pool_cap || base + total < base) {
+        if (total > blk_end - blk_next) { // refill: rare (every ~GEAR_POOL_BLOCK candidates)
+            uint32_t nb = 0;
+            if (lane == 0) {
+                const uint32_t want = total > GEAR_POOL_BLOCK ? total : GEAR_POOL_BLOCK;
+                nb = atomicAdd(pool_count, want);
+                if (nb + want > pool_cap || nb + want < nb) {
                     atomicExch(err_flag, 1u);
-                    base = 0xFFFFFFFFu;
+                    nb = 0xFFFFFFFFu;
                 }
             }
+            nb = __shfl_sync(0xFFFFFFFFu, nb, 0);
+            blk_next = nb;
+            blk_end = nb == 0xFFFFFFFFu ? nb : nb + (total > GEAR_POOL_BLOCK ? total : GEAR_POOL_BLOCK);
+        }
+        const uint32_t base = blk_next;
+        if (base != 0xFFFFFFFFu)
+            blk_next += total;
+        if (lane == 0) {
             TileRec tr;
             tr.base = base;
-            tr.count = total;
+            tr.count = base == 0xFFFFFFFFu ? 0u : total;
             tiles[(size_t)tile * GEAR_WARPS + warp] = tr;
         }
         if (total) {
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
             if (base != 0xFFFFFFFFu && cnt) {
                 uint32_t o = base + incl - cnt;
                 const uint32_t p0 = lane * 128u;
@@ -623,7 +658,7 @@ __global__ void k_batch_end(SessionCounters *sc)
 // ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 
-__device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16])
+__device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], const uint32_t one)
 {
     constexpr uint32_t K[64] = {
         0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
@@ -644,16 +679,16 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16])
             const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
             const uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
             const uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
-            wi = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+            wi = fma_add_rt(fma_add_rt(w[i & 15], s0, one), fma_add_rt(w[(i + 9) & 15], s1, one), one);
             w[i & 15] = wi;
         }
         const uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
         const uint32_t ch = (e & f) ^ (~e & g);
-        const uint32_t t1 = h + S1 + ch + K[i] + wi;
+        const uint32_t t1 = fma_add_rt(fma_add_rt(h, S1, one), fma_add_rt(ch, wi + K[i], one), one);
         const uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
         const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-        h = g; g = f; f = e; e = d + t1;
-        d = c; c = b; b = a; a = t1 + S0 + mj;
+        h = g; g = f; f = e; e = fma_add_rt(d, t1, one);
+        d = c; c = b; b = a; a = fma_add_rt(fma_add_rt(t1, S0, one), mj, one);
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d;
     st[4] += e; st[5] += f; st[6] += g; st[7] += h;
@@ -668,7 +703,7 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
                 const uint64_t *__restrict__ len, const uint32_t *__restrict__ n_dev, uint64_t n_host,
                 const unsigned long long *__restrict__ first_dev, uint64_t first_host, /* index of range 0 in start/len/out */
                 uint64_t uni_len, uint64_t uni_total, uint8_t *__restrict__ out,
-                uint32_t *__restrict__ work_counter, const uint32_t *__restrict__ skip_if_err)
+                uint32_t *__restrict__ work_counter, const uint32_t *__restrict__ skip_if_err, const uint32_t one)
 {
     if (skip_if_err && *skip_if_err)
         return;
@@ -683,6 +718,11 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
     uint64_t my = 0;            // range index
     uint32_t phase = 0;         // 0 idle, 1 data blocks, 2 needs extra length block
     bool exhausted = false;
+    uint4 pf[5];                // next block's aligned 80-byte window, loaded while this block compresses
+    bool pf_ok = false;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        pf[k] = make_uint4(0, 0, 0, 0);
 
     for (;;) {
         // ---- refill idle lanes (warp-aggregated fetch) ----
@@ -707,6 +747,7 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
                     }
                     done = 0;
                     phase = 1;
+                    pf_ok = false;
                     st[0] = 0x6a09e667; st[1] = 0xbb67ae85; st[2] = 0x3c6ef372; st[3] = 0xa54ff53a;
                     st[4] = 0x510e527f; st[5] = 0x9b05688c; st[6] = 0x1f83d9ab; st[7] = 0x5be0cd19;
                 } else {
@@ -734,13 +775,28 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
             const uint32_t a = (uint32_t)((uintptr_t)p & 15u);
             const uint4 *q = reinterpret_cast<const uint4 *>(p - a);
             uint32_t x[20];
+            if (!pf_ok) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    // only touch 16-byte words that intersect [p, p+min(rem,64))
+                    pf[k] = make_uint4(0, 0, 0, 0);
+                    if ((uint64_t)(16 * k) < (uint64_t)a + (rem < 64 ? rem : 64))
+                        pf[k] = __ldg(q + k);
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                // only touch 16-byte words that intersect [p, p+min(rem,64))
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if ((uint64_t)(16 * k) < (uint64_t)a + (rem < 64 ? rem : 64))
-                    v = __ldg(q + k);
-                x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+                x[4 * k] = pf[k].x; x[4 * k + 1] = pf[k].y; x[4 * k + 2] = pf[k].z; x[4 * k + 3] = pf[k].w;
+            }
+            pf_ok = rem > 64; // another data-bearing iteration follows: fetch it now, use it after the compress
+            if (pf_ok) {
+                const uint64_t rem2 = rem - 64;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    pf[k] = make_uint4(0, 0, 0, 0);
+                    if ((uint64_t)(16 * k) < (uint64_t)a + (rem2 < 64 ? rem2 : 64))
+                        pf[k] = __ldg(q + 4 + k);
+                }
             }
             uint32_t y[18];
 #pragma unroll
@@ -775,7 +831,7 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
                 }
             }
         }
-        sha256_compress(st, w);
+        sha256_compress(st, w, one);
         if (last) {
             uint4 o0, o1;
             o0.x = __byte_perm(st[0], 0, 0x0123); o0.y = __byte_perm(st[1], 0, 0x0123);

@@ -1,0 +1,158 @@
+"""ctypes binding of libmkhost.so (include/mkhost.h): the C++ host side above the mksnap C-ABI.
+
+Mirrors the reference names: context_crc32 ~ addCopyStep.SetCacheID, commit_copy_ops ~ commitLayer over
+MemFS.AddLayerByCopyOps, encode_tar_header ~ tario.WriteHeader.  No hashing happens here or in libmkhost.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from pathlib import Path
+from typing import List, Sequence
+
+from . import abi
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmkhost.so"
+
+
+class TarHeader(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("linkname", C.c_char_p), ("mode", C.c_int64), ("uid", C.c_int64),
+                ("gid", C.c_int64), ("size", C.c_int64), ("mtime_ns", C.c_int64), ("typeflag", C.c_char)]
+
+
+class CopyOp(C.Structure):
+    _fields_ = [("src_root", C.c_char_p), ("srcs", C.POINTER(C.c_char_p)), ("n_srcs", C.c_size_t),
+                ("work_dir", C.c_char_p), ("dst", C.c_char_p), ("uid", C.c_int32), ("gid", C.c_int32)]
+
+
+class LayerResult(C.Structure):
+    _fields_ = [("tar_digest", C.c_uint8 * 32), ("root", C.c_uint8 * 32), ("n_entries", C.c_uint64),
+                ("tar_bytes", C.c_uint64), ("n_chunks", C.c_uint64), ("n_unique", C.c_uint64)]
+
+
+_P = C.c_void_p
+SYMBOLS = [
+    ("mkhost_encode_tar_header", C.c_size_t, [C.POINTER(TarHeader), _P, C.c_size_t]),
+    ("mkhost_context_crc32", C.c_int, [_P, _P, C.c_size_t, C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_int,
+                                       C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t]),
+    ("mkhost_commit_copy_ops", C.c_int, [_P, C.c_char_p, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_int,
+                                         C.POINTER(LayerResult), C.c_char_p, C.c_size_t]),
+    ("mkhost_describe_context_stream", C.c_size_t, [C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_char_p,
+                                                    C.c_size_t, C.c_char_p, C.c_size_t]),
+    ("mkhost_describe_layer", C.c_size_t, [C.c_char_p, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_char_p,
+                                           C.c_size_t, C.c_char_p, C.c_size_t]),
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        abi.load()  # libmksnap first (libmkhost links against it)
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(f"{LIB_PATH} not found: run __graft_entry__.build()")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, res, args in SYMBOLS:
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _strs(items: Sequence[str]):
+    arr = (C.c_char_p * max(1, len(items)))(*[os.fsencode(s) for s in items])
+    return arr
+
+
+@dataclass
+class CopyOperation:
+    """snapshot.NewCopyOperation(srcs, srcRoot, workDir, dst, chown...) (lib/snapshot/copy_op.go:45)."""
+    srcs: List[str]
+    src_root: str
+    work_dir: str
+    dst: str
+    uid: int = 0
+    gid: int = 0
+
+
+def _ops(ops: Sequence[CopyOperation]):
+    keep = []
+    arr = (CopyOp * max(1, len(ops)))()
+    for i, o in enumerate(ops):
+        s = _strs(o.srcs)
+        keep.append(s)
+        arr[i].src_root = os.fsencode(o.src_root)
+        arr[i].srcs = s
+        arr[i].n_srcs = len(o.srcs)
+        arr[i].work_dir = os.fsencode(o.work_dir)
+        arr[i].dst = os.fsencode(o.dst)
+        arr[i].uid, arr[i].gid = o.uid, o.gid
+    return arr, keep
+
+
+def encode_tar_header(name: str, mode: int, uid: int, gid: int, size: int, mtime_ns: int, typeflag: bytes,
+                      linkname: str = "") -> bytes:
+    h = TarHeader(os.fsencode(name), os.fsencode(linkname), mode, uid, gid, size, mtime_ns, typeflag)
+    buf = C.create_string_buffer(8192)
+    n = load().mkhost_encode_tar_header(C.byref(h), buf, len(buf))
+    if n == 0:
+        raise HostError("header not encodable")
+    return buf.raw[:n]
+
+
+def describe_context_stream(context_dir: str, from_paths: Sequence[str]) -> List[str]:
+    err = C.create_string_buffer(1024)
+    p = _strs(from_paths)
+    n = load().mkhost_describe_context_stream(os.fsencode(context_dir), p, len(from_paths), None, 0, err, len(err))
+    if n == 0:
+        raise HostError(err.value.decode())
+    buf = C.create_string_buffer(n)
+    load().mkhost_describe_context_stream(os.fsencode(context_dir), p, len(from_paths), buf, n, err, len(err))
+    return [l for l in os.fsdecode(buf.value).split("\n") if l]
+
+
+def describe_layer(root_dir: str, now_unix: int, ops: Sequence[CopyOperation]) -> List[str]:
+    err = C.create_string_buffer(1024)
+    arr, keep = _ops(ops)
+    n = load().mkhost_describe_layer(os.fsencode(root_dir), now_unix, arr, len(ops), None, 0, err, len(err))
+    if n == 0:
+        raise HostError(err.value.decode())
+    buf = C.create_string_buffer(n)
+    arr, keep = _ops(ops)
+    load().mkhost_describe_layer(os.fsencode(root_dir), now_unix, arr, len(ops), buf, n, err, len(err))
+    return [l for l in os.fsdecode(buf.value).split("\n") if l]
+
+
+def context_crc32(eng: abi.Engine, prefix: bytes, context_dir: str, from_paths: Sequence[str], n_threads: int = 0):
+    """-> (crc32 value as checksum.Sum32() would return it, stream length)."""
+    err = C.create_string_buffer(1024)
+    crc, slen = C.c_uint32(), C.c_uint64()
+    rc = load().mkhost_context_crc32(eng.h, prefix, len(prefix), os.fsencode(context_dir), _strs(from_paths),
+                                     len(from_paths), n_threads, C.byref(crc), C.byref(slen), err, len(err))
+    if rc:
+        raise HostError(err.value.decode())
+    return crc.value, slen.value
+
+
+def copy_step_cache_id(eng: abi.Engine, seed: str, directive: str, args: str, context_dir: str,
+                       from_paths: Sequence[str]) -> str:
+    crc, _ = context_crc32(eng, (seed + directive + args).encode(), context_dir, from_paths)
+    return "%x" % crc  # add_copy_step.go:119
+
+
+def commit_copy_ops(eng: abi.Engine, root_dir: str, now_unix: int, ops: Sequence[CopyOperation], n_threads: int = 0):
+    err = C.create_string_buffer(1024)
+    arr, keep = _ops(ops)
+    out = LayerResult()
+    rc = load().mkhost_commit_copy_ops(eng.h, os.fsencode(root_dir), now_unix, arr, len(ops), n_threads, C.byref(out),
+                                       err, len(err))
+    if rc:
+        raise HostError(err.value.decode())
+    return {"tar_digest": "sha256:" + bytes(out.tar_digest).hex(), "root": bytes(out.root), "n_entries": out.n_entries,
+            "tar_bytes": out.tar_bytes, "n_chunks": out.n_chunks, "n_unique": out.n_unique}

@@ -1,0 +1,1091 @@
+// mkhost.cpp — host side above the mksnap C-ABI (see include/mkhost.h).
+//
+// C++ stand-in for the Go code a cgo build of makisu would keep on this path: the filepath.Walk-ordered
+// context stream (cacheID), the MemFS copy-op layer (entry order + tar headers) and the arena packer.
+// It does no hashing; digests come from libmksnap (GPU).  Reference line numbers are cited per function.
+#include "../../include/mkhost.h"
+
+#include <dirent.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct HostError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+std::string errno_str(const std::string &what, const std::string &path)
+{
+    return what + " " + path + ": " + strerror(errno);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Go path helpers (path.Clean / filepath.Join / filepath.Rel, lexical)
+// ---------------------------------------------------------------------------------------------------
+std::string go_clean(const std::string &p)
+{
+    if (p.empty())
+        return ".";
+    const bool rooted = p[0] == '/';
+    std::vector<std::string> parts;
+    size_t i = 0;
+    while (i < p.size()) {
+        while (i < p.size() && p[i] == '/')
+            ++i;
+        size_t j = i;
+        while (j < p.size() && p[j] != '/')
+            ++j;
+        if (j > i) {
+            std::string e = p.substr(i, j - i);
+            if (e == ".") {
+            } else if (e == "..") {
+                if (!parts.empty() && parts.back() != "..")
+                    parts.pop_back();
+                else if (!rooted)
+                    parts.push_back("..");
+            } else {
+                parts.push_back(e);
+            }
+        }
+        i = j;
+    }
+    std::string out = rooted ? "/" : "";
+    for (size_t k = 0; k < parts.size(); ++k) {
+        if (k)
+            out += "/";
+        out += parts[k];
+    }
+    return out.empty() ? "." : out;
+}
+
+std::string go_join(const std::string &a, const std::string &b)
+{
+    if (a.empty())
+        return b.empty() ? "" : go_clean(b);
+    if (b.empty())
+        return go_clean(a);
+    return go_clean(a + "/" + b);
+}
+
+std::string go_rel(const std::string &basepath, const std::string &targpath)
+{
+    const std::string base = go_clean(basepath), targ = go_clean(targpath);
+    if (base == targ)
+        return ".";
+    auto split = [](const std::string &s) {
+        std::vector<std::string> v;
+        size_t i = 0;
+        while (i < s.size()) {
+            size_t j = s.find('/', i);
+            if (j == std::string::npos)
+                j = s.size();
+            if (j > i)
+                v.push_back(s.substr(i, j - i));
+            i = j + 1;
+        }
+        return v;
+    };
+    auto bv = split(base == "." ? "" : base), tv = split(targ == "." ? "" : targ);
+    size_t k = 0;
+    while (k < bv.size() && k < tv.size() && bv[k] == tv[k])
+        ++k;
+    std::string out;
+    for (size_t i = k; i < bv.size(); ++i)
+        out += out.empty() ? ".." : "/..";
+    for (size_t i = k; i < tv.size(); ++i)
+        out += (out.empty() ? "" : "/") + tv[i];
+    return out.empty() ? "." : out;
+}
+
+// lib/pathutils/path.go:41-68
+std::string abs_path(const std::string &p)
+{
+    std::string t = p;
+    while (!t.empty() && t.back() == '/')
+        t.pop_back();
+    return go_clean("/" + t);
+}
+std::string rel_path(const std::string &p)
+{
+    size_t i = 0;
+    while (i < p.size() && p[i] == '/')
+        ++i;
+    return p.substr(i);
+}
+std::vector<std::string> split_path(const std::string &p)
+{
+    std::vector<std::string> v;
+    size_t i = 0;
+    while (i < p.size()) {
+        while (i < p.size() && p[i] == '/')
+            ++i;
+        size_t j = i;
+        while (j < p.size() && p[j] != '/')
+            ++j;
+        if (j > i)
+            v.push_back(p.substr(i, j - i));
+        i = j;
+    }
+    return v;
+}
+std::string path_base(const std::string &p)
+{
+    std::string t = p;
+    while (t.size() > 1 && t.back() == '/')
+        t.pop_back();
+    size_t i = t.rfind('/');
+    return i == std::string::npos ? t : t.substr(i + 1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// filepath.Walk / Match / Glob (go1.14)
+// ---------------------------------------------------------------------------------------------------
+std::vector<std::string> sorted_names(const std::string &dir)
+{
+    std::vector<std::string> names;
+    DIR *d = opendir(dir.c_str());
+    if (!d)
+        throw HostError(errno_str("open", dir));
+    while (struct dirent *e = readdir(d)) {
+        if (!strcmp(e->d_name, ".") || !strcmp(e->d_name, ".."))
+            continue;
+        names.emplace_back(e->d_name);
+    }
+    closedir(d);
+    std::sort(names.begin(), names.end()); // sort.Strings: bytewise
+    return names;
+}
+
+enum WalkRet { W_CONT, W_SKIPDIR };
+using WalkFn = std::function<WalkRet(const std::string &, const struct stat &)>;
+
+WalkRet walk_rec(const std::string &path, const struct stat &st, const WalkFn &fn)
+{
+    if (!S_ISDIR(st.st_mode))
+        return fn(path, st);
+    std::vector<std::string> names = sorted_names(path);
+    WalkRet r = fn(path, st);
+    if (r != W_CONT)
+        return r;
+    for (const auto &n : names) {
+        const std::string fnm = path == "/" ? "/" + n : path + "/" + n;
+        struct stat cst;
+        if (lstat(fnm.c_str(), &cst) != 0)
+            throw HostError(errno_str("lstat", fnm));
+        r = walk_rec(fnm, cst, fn);
+        if (r != W_CONT) {
+            if (!S_ISDIR(cst.st_mode) || r != W_SKIPDIR)
+                return r;
+        }
+    }
+    return W_CONT;
+}
+
+void go_walk(const std::string &root, const WalkFn &fn)
+{
+    struct stat st;
+    if (lstat(root.c_str(), &st) != 0)
+        throw HostError(errno_str("lstat", root));
+    walk_rec(root, st, fn);
+}
+
+bool has_meta(const std::string &p) { return p.find_first_of("*?[\\") != std::string::npos; }
+
+bool go_match(const char *pat, const char *name)
+{
+    // filepath.Match: '*' any run of non-separators, '?' one non-separator, [class], '\\' escape
+    while (*pat) {
+        if (*pat == '*') {
+            while (*pat == '*')
+                ++pat;
+            for (const char *t = name;; ++t) {
+                if (go_match(pat, t))
+                    return true;
+                if (!*t || *t == '/')
+                    return false;
+            }
+        }
+        if (!*name)
+            return false;
+        if (*pat == '?') {
+            if (*name == '/')
+                return false;
+            ++pat, ++name;
+        } else if (*pat == '[') {
+            ++pat;
+            bool neg = *pat == '^';
+            if (neg)
+                ++pat;
+            bool ok = false;
+            while (*pat && *pat != ']') {
+                char lo = *pat;
+                if (lo == '\\' && pat[1])
+                    lo = *++pat;
+                char hi = lo;
+                if (pat[1] == '-' && pat[2] && pat[2] != ']') {
+                    pat += 2;
+                    hi = *pat;
+                    if (hi == '\\' && pat[1])
+                        hi = *++pat;
+                }
+                if (lo <= *name && *name <= hi)
+                    ok = true;
+                ++pat;
+            }
+            if (*pat == ']')
+                ++pat;
+            if (ok == neg)
+                return false;
+            ++name;
+        } else {
+            if (*pat == '\\' && pat[1])
+                ++pat;
+            if (*pat != *name)
+                return false;
+            ++pat, ++name;
+        }
+    }
+    return !*name;
+}
+
+std::vector<std::string> go_glob(const std::string &pattern)
+{
+    std::vector<std::string> out;
+    if (!has_meta(pattern)) {
+        struct stat st;
+        if (lstat(pattern.c_str(), &st) == 0)
+            out.push_back(pattern);
+        return out;
+    }
+    size_t slash = pattern.rfind('/');
+    std::string dir = slash == std::string::npos ? "." : (slash == 0 ? "/" : pattern.substr(0, slash));
+    const std::string file = slash == std::string::npos ? pattern : pattern.substr(slash + 1);
+    if (dir == pattern)
+        return out;
+    std::vector<std::string> dirs = has_meta(dir) ? go_glob(dir) : std::vector<std::string>{dir};
+    for (const auto &d : dirs) {
+        struct stat st;
+        if (stat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode))
+            continue;
+        for (const auto &n : sorted_names(d))
+            if (go_match(file.c_str(), n.c_str()))
+                out.push_back(d == "/" ? "/" + n : d + "/" + n);
+    }
+    return out;
+}
+
+// lib/utils/utils.go:161-163
+bool is_special(const struct stat &st)
+{
+    return S_ISCHR(st.st_mode) || S_ISBLK(st.st_mode) || S_ISFIFO(st.st_mode) || S_ISSOCK(st.st_mode);
+}
+
+std::string read_link(const std::string &p)
+{
+    std::string buf(4096, '\0');
+    ssize_t n = readlink(p.c_str(), &buf[0], buf.size());
+    if (n < 0)
+        throw HostError(errno_str("read link", p));
+    buf.resize((size_t)n);
+    return buf;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context stream (add_copy_step.go:153-184,194-238)
+// ---------------------------------------------------------------------------------------------------
+struct Seg {
+    char kind; // 'P' path bytes, 'L' link target bytes, 'F' file content
+    std::string bytes;
+    std::string path;
+    uint64_t size = 0;
+};
+
+std::vector<std::string> resolve_from_paths(const std::string &ctx_dir, const char *const *paths, size_t n)
+{
+    std::vector<std::string> sources;
+    for (size_t i = 0; i < n; ++i) {
+        const std::string src = go_join(ctx_dir, paths[i]);
+        std::vector<std::string> m = go_glob(src);
+        if (m.empty())
+            sources.push_back(src);
+        else
+            sources.insert(sources.end(), m.begin(), m.end());
+    }
+    return sources;
+}
+
+std::vector<Seg> context_segments(const std::string &ctx_dir, const char *const *paths, size_t n)
+{
+    std::vector<Seg> segs;
+    for (const auto &source : resolve_from_paths(ctx_dir, paths, n)) {
+        try {
+            go_walk(source, [&](const std::string &path, const struct stat &st) -> WalkRet {
+                if (is_special(st))
+                    return S_ISDIR(st.st_mode) ? W_SKIPDIR : W_CONT;
+                Seg p;
+                p.kind = 'P';
+                p.bytes = go_rel(ctx_dir, path);
+                segs.push_back(std::move(p));
+                if (S_ISDIR(st.st_mode))
+                    return W_CONT;
+                if (S_ISLNK(st.st_mode)) {
+                    Seg l;
+                    l.kind = 'L';
+                    l.bytes = read_link(path);
+                    segs.push_back(std::move(l));
+                    return W_CONT;
+                }
+                Seg f;
+                f.kind = 'F';
+                f.path = path;
+                f.size = (uint64_t)st.st_size;
+                segs.push_back(std::move(f));
+                return W_CONT;
+            });
+        } catch (const HostError &e) {
+            throw HostError("walk " + source + ": " + e.what());
+        }
+    }
+    return segs;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// parallel file reader: fills arena memory with pread()
+// ---------------------------------------------------------------------------------------------------
+struct ReadJob {
+    std::string path;
+    uint64_t file_off;
+    uint64_t len;
+    uint8_t *dst;
+};
+
+void run_reads(const std::vector<ReadJob> &jobs, int n_threads)
+{
+    if (jobs.empty())
+        return;
+    if (n_threads <= 0)
+        n_threads = (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
+    n_threads = (int)std::min<size_t>((size_t)n_threads, jobs.size());
+    std::atomic<size_t> next{0};
+    std::atomic<bool> failed{false};
+    std::string first_err;
+    std::mutex mu_obj, *mu = &mu_obj;
+    auto worker = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= jobs.size() || failed.load())
+                return;
+            const ReadJob &j = jobs[i];
+            int fd = open(j.path.c_str(), O_RDONLY | O_CLOEXEC);
+            std::string err;
+            if (fd < 0) {
+                err = errno_str("open", j.path);
+            } else {
+                uint64_t done = 0;
+                while (done < j.len) {
+                    ssize_t r = pread(fd, j.dst + done, j.len - done, (off_t)(j.file_off + done));
+                    if (r < 0) {
+                        err = errno_str("read", j.path);
+                        break;
+                    }
+                    if (r == 0) {
+                        err = "copy file " + j.path + " to tar writer: unexpected EOF"; // io.CopyN
+                        break;
+                    }
+                    done += (uint64_t)r;
+                }
+                close(fd); // the reference leaks this fd (add_copy_step.go:230-237)
+            }
+            if (!err.empty()) {
+                std::lock_guard<std::mutex> g(*mu);
+                if (!failed.exchange(true))
+                    first_err = err;
+                return;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t)
+        th.emplace_back(worker);
+    worker();
+    for (auto &t : th)
+        t.join();
+
+    if (failed.load())
+        throw HostError(first_err);
+}
+
+uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+void ck(mksnap_t *eng, int rc, const char *what)
+{
+    if (rc != 0)
+        throw HostError(std::string(what) + ": " + mksnap_last_error(eng));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tar header (go1.14 archive/tar Writer.WriteHeader via tario.WriteHeader)
+// ---------------------------------------------------------------------------------------------------
+struct Hdr {
+    std::string name, linkname;
+    int64_t mode = 0, uid = 0, gid = 0, size = 0, mtime_ns = 0;
+    char typeflag = '0';
+};
+
+bool is_ascii(const std::string &s)
+{
+    for (unsigned char c : s)
+        if (c >= 0x80)
+            return false;
+    return true;
+}
+std::string to_ascii(const std::string &s)
+{
+    std::string o;
+    for (unsigned char c : s)
+        if (c < 0x80)
+            o.push_back((char)c);
+    return o;
+}
+bool split_ustar(const std::string &name, std::string &prefix, std::string &suffix)
+{
+    size_t length = name.size();
+    if (length <= 100 || !is_ascii(name))
+        return false;
+    if (length > 156)
+        length = 156;
+    else if (name[length - 1] == '/')
+        --length;
+    size_t i = name.substr(0, length).rfind('/');
+    if (i == std::string::npos || i == 0)
+        return false;
+    size_t nlen = name.size() - i - 1, plen = i;
+    if (nlen > 100 || nlen == 0 || plen > 155)
+        return false;
+    prefix = name.substr(0, i);
+    suffix = name.substr(i + 1);
+    return true;
+}
+void fmt_string(uint8_t *b, size_t size, const std::string &s)
+{
+    size_t n = std::min(s.size(), size);
+    memcpy(b, s.data(), n);
+    if (s.size() < size)
+        b[s.size()] = 0;
+    if (s.size() > size && b[size - 1] == '/') {
+        size_t k = size;
+        while (k > 0 && s[k - 1] == '/')
+            --k;
+        b[k] = 0;
+    }
+}
+bool fits_octal(size_t n, int64_t x) { return x >= 0 && (uint64_t)x < (1ull << ((n - 1) * 3)); }
+void fmt_octal(uint8_t *b, size_t size, int64_t x)
+{
+    if (!fits_octal(size, x))
+        x = 0;
+    char tmp[32];
+    snprintf(tmp, sizeof tmp, "%llo", (unsigned long long)x);
+    std::string s = tmp;
+    if (size > s.size() + 1)
+        s = std::string(size - s.size() - 1, '0') + s;
+    fmt_string(b, size, s);
+}
+void finish_block(uint8_t *b)
+{
+    memcpy(b + 257, "ustar\0", 6);
+    memcpy(b + 263, "00", 2);
+    memset(b + 148, ' ', 8);
+    uint32_t chk = 0;
+    for (int i = 0; i < 512; ++i)
+        chk += b[i];
+    fmt_octal(b + 148, 7, chk);
+    b[155] = ' ';
+}
+void template_v7plus(uint8_t *b, const Hdr &h, const std::string &name, const std::string &link, bool ascii_only)
+{
+    memset(b, 0, 512);
+    b[156] = (uint8_t)h.typeflag;
+    fmt_string(b + 0, 100, ascii_only ? to_ascii(name) : name);
+    fmt_string(b + 157, 100, ascii_only ? to_ascii(link) : link);
+    fmt_octal(b + 100, 8, h.mode);
+    fmt_octal(b + 108, 8, h.uid);
+    fmt_octal(b + 116, 8, h.gid);
+    fmt_octal(b + 124, 12, h.size);
+    fmt_octal(b + 136, 12, h.mtime_ns / 1000000000ll);
+    fmt_string(b + 265, 32, "");
+    fmt_string(b + 297, 32, "");
+    fmt_octal(b + 329, 8, 0);
+    fmt_octal(b + 337, 8, 0);
+}
+std::string pax_record(const std::string &k, const std::string &v)
+{
+    size_t size = k.size() + v.size() + 3;
+    size += std::to_string(size).size();
+    std::string rec = std::to_string(size) + " " + k + "=" + v + "\n";
+    if (rec.size() != size) {
+        size = rec.size();
+        rec = std::to_string(size) + " " + k + "=" + v + "\n";
+    }
+    return rec;
+}
+
+// returns header bytes (512 or PAX 512 + data + 512)
+std::string encode_header(Hdr h)
+{
+    h.mtime_ns = (h.mtime_ns / 1000000000ll) * 1000000000ll; // write.go:61 Truncate(1s); Writer's Round is then a no-op
+    std::map<std::string, std::string> pax;
+    bool ustar_ok = true;
+    auto verify_string = [&](const std::string &s, size_t size, const char *key) {
+        bool too_long = s.size() > size;
+        if (!is_ascii(s) || too_long) {
+            std::string a, b;
+            if (!(key && !strcmp(key, "path") && split_ustar(s, a, b)))
+                ustar_ok = false;
+            if (!key)
+                throw HostError("archive/tar: header field cannot be encoded");
+            pax[key] = s;
+        }
+    };
+    auto verify_numeric = [&](int64_t n, size_t size, const char *key) {
+        if (!fits_octal(size, n)) {
+            ustar_ok = false;
+            if (!key)
+                throw HostError("archive/tar: header field too long");
+            pax[key] = std::to_string(n);
+        }
+    };
+    verify_string(h.name, 100, "path");
+    verify_string(h.linkname, 100, "linkpath");
+    verify_numeric(h.mode, 8, nullptr);
+    verify_numeric(h.uid, 8, "uid");
+    verify_numeric(h.gid, 8, "gid");
+    verify_numeric(h.size, 12, "size");
+    verify_numeric(h.mtime_ns / 1000000000ll, 12, "mtime");
+    if ((h.typeflag == '0' || h.typeflag == '3' || h.typeflag == '4' || h.typeflag == '6') && !h.name.empty() &&
+        h.name.back() == '/')
+        throw HostError("archive/tar: filename may not have trailing slash");
+    uint8_t blk[512];
+    if (ustar_ok) {
+        std::string prefix, name = h.name, sfx;
+        if (split_ustar(h.name, prefix, sfx))
+            name = sfx;
+        else
+            prefix.clear();
+        template_v7plus(blk, h, name, h.linkname, false);
+        fmt_string(blk + 345, 155, prefix);
+        finish_block(blk);
+        return std::string((const char *)blk, 512);
+    }
+    std::string out;
+    if (!pax.empty()) {
+        std::string data;
+        for (const auto &kv : pax) // std::map iterates in sorted key order
+            data += pax_record(kv.first, kv.second);
+        size_t sl = h.name.rfind('/');
+        std::string dir = sl == std::string::npos ? "" : h.name.substr(0, sl + 1);
+        std::string file = sl == std::string::npos ? h.name : h.name.substr(sl + 1);
+        std::string xname = to_ascii(go_join(go_join(dir, "PaxHeaders.0"), file));
+        if (xname.size() > 100)
+            xname.resize(100);
+        while (!xname.empty() && xname.back() == '/')
+            xname.pop_back();
+        memset(blk, 0, 512);
+        blk[156] = 'x';
+        fmt_string(blk, 100, xname);
+        fmt_octal(blk + 100, 8, 0);
+        fmt_octal(blk + 108, 8, 0);
+        fmt_octal(blk + 116, 8, 0);
+        fmt_octal(blk + 124, 12, (int64_t)data.size());
+        fmt_octal(blk + 136, 12, 0);
+        finish_block(blk);
+        out.assign((const char *)blk, 512);
+        out += data;
+        out.append((512 - data.size() % 512) % 512, '\0');
+    }
+    template_v7plus(blk, h, h.name, h.linkname, true);
+    finish_block(blk);
+    out.append((const char *)blk, 512);
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MemFS (copy-op path): lib/snapshot/mem_fs.go, mem_layer.go
+// ---------------------------------------------------------------------------------------------------
+struct MemFile {
+    std::string src, dst;
+    Hdr hdr;
+};
+struct Node {
+    MemFile mf;
+    std::map<std::string, std::unique_ptr<Node>> children;
+};
+
+class MemFS
+{
+  public:
+    MemFS(const std::string &root, int64_t now_unix) : root_(root), now_(now_unix)
+    {
+        struct stat st;
+        if (lstat(root.c_str(), &st) != 0)
+            throw HostError("unable to stat root dir: " + root);
+        tree_.mf.src = root;
+        tree_.mf.dst = "/";
+        tree_.mf.hdr = create_header(root, "/", &st, nullptr);
+    }
+
+    // mem_layer.go:152-190
+    Hdr create_header(const std::string &src, const std::string &dst, const struct stat *st, const Hdr *from)
+    {
+        Hdr h;
+        if (from) { // tar.FileInfoHeader(hdr.FileInfo())
+            h = *from;
+            h.mode &= 07777;
+            if (h.typeflag != '0')
+                h.size = 0;
+            h.linkname.clear();
+        } else {
+            const mode_t m = st->st_mode;
+            h.mode = m & 0777;
+            if (m & S_ISUID) h.mode |= 04000;
+            if (m & S_ISGID) h.mode |= 02000;
+            if (m & S_ISVTX) h.mode |= 01000;
+            h.mtime_ns = (int64_t)st->st_mtim.tv_sec * 1000000000ll + st->st_mtim.tv_nsec;
+            h.uid = st->st_uid;
+            h.gid = st->st_gid;
+            if (S_ISREG(m)) { h.typeflag = '0'; h.size = st->st_size; }
+            else if (S_ISDIR(m)) h.typeflag = '5';
+            else if (S_ISLNK(m)) h.typeflag = '2';
+            else if (S_ISCHR(m)) h.typeflag = '3';
+            else if (S_ISBLK(m)) h.typeflag = '4';
+            else if (S_ISFIFO(m)) h.typeflag = '6';
+            else throw HostError("archive/tar: sockets not supported");
+        }
+        h.name = rel_path(dst);
+        const std::string asrc = abs_path(src);
+        if (h.typeflag == '5') {
+            if (asrc.empty() || asrc.back() != '/')
+                h.name += "/";
+        } else if (h.typeflag == '2' && !from) {
+            std::string target = read_link(asrc);
+            if (!target.empty() && target[0] == '/') {
+                if (target.compare(0, root_.size(), root_) != 0)
+                    throw HostError("trim symlink root: failed to trim root prefix " + root_ + " from path " + target);
+                target = abs_path(target.substr(root_.size()));
+            }
+            h.linkname = target;
+        }
+        return h;
+    }
+
+    std::map<std::string, MemFile> add_layer_by_copy_ops(const mkhost_copy_op *ops, size_t n)
+    {
+        std::map<std::string, MemFile> layer; // std::map == sort.Strings order (mem_layer.go:232-244)
+        for (size_t i = 0; i < n; ++i)
+            add_to_layer(layer, ops[i]);
+        return layer;
+    }
+
+  private:
+    std::string root_;
+    int64_t now_;
+    Node tree_;
+
+    // utils.go:37-52 (no blacklist on the copy path; mountpoints are the caller's concern)
+    static bool should_skip(const std::string &p, const struct stat &st)
+    {
+        return path_base(p).compare(0, 8, ".wh..wh.") == 0 || is_special(st);
+    }
+
+    void tree_put(const MemFile &mf)
+    {
+        Node *node = &tree_;
+        auto parts = split_path(mf.dst);
+        for (size_t i = 0; i < parts.size(); ++i) {
+            const bool last = i + 1 == parts.size();
+            auto it = node->children.find(parts[i]);
+            if (it != node->children.end()) {
+                if (last) {
+                    auto nn = std::make_unique<Node>();
+                    nn->mf = mf;
+                    if (mf.hdr.typeflag == '5')
+                        nn->children = std::move(it->second->children);
+                    it->second = std::move(nn);
+                } else {
+                    node = it->second.get();
+                }
+            } else if (last) {
+                auto nn = std::make_unique<Node>();
+                nn->mf = mf;
+                node->children[parts[i]] = std::move(nn);
+            } else {
+                throw HostError("missing intermediate directory " + parts[i] + " in " + mf.dst);
+            }
+        }
+    }
+
+    void add_header(std::map<std::string, MemFile> &layer, const std::string &src, const std::string &dst, const Hdr &hdr)
+    {
+        MemFile mf{abs_path(src), abs_path(dst), hdr};
+        layer[mf.dst] = mf;
+        tree_put(mf);
+    }
+
+    // tario/compare.go:24-120
+    static bool is_similar(const Hdr &h, const Hdr &nh)
+    {
+        if (h.name.empty() && nh.name.empty())
+            return true;
+        const bool teq = h.mtime_ns / 1000000000ll == nh.mtime_ns / 1000000000ll;
+        const bool meq = (h.mode & 07777) == (nh.mode & 07777);
+        switch (h.typeflag) {
+        case '2': return nh.typeflag == '2' && h.linkname == nh.linkname;
+        case '1': return nh.typeflag == '1' && teq && h.linkname == nh.linkname && h.uid == nh.uid && h.gid == nh.gid && meq;
+        case '5': return nh.typeflag == '5' && teq && h.uid == nh.uid && h.gid == nh.gid && meq;
+        case '0': return nh.typeflag == '0' && teq && h.uid == nh.uid && h.gid == nh.gid && h.size == nh.size && meq;
+        default: throw HostError(std::string("unsupported type ") + h.typeflag);
+        }
+    }
+
+    bool is_updated(const std::string &p, const Hdr &hdr)
+    {
+        Node *cur = &tree_;
+        for (const auto &part : split_path(p)) {
+            auto it = cur->children.find(part);
+            if (it == cur->children.end())
+                return true;
+            cur = it->second.get();
+        }
+        return !is_similar(cur->mf.hdr, hdr);
+    }
+
+    // mem_fs.go:509-569
+    std::string add_ancestors(std::map<std::string, MemFile> &layer, const std::string &dst, bool inclusive, int depth,
+                              int64_t uid, int64_t gid)
+    {
+        if (depth >= 1024)
+            throw HostError("symlink loop at " + dst);
+        Node *last_ancestor = &tree_, *cur = &tree_;
+        auto parts = split_path(dst);
+        const size_t end = inclusive ? parts.size() : (parts.empty() ? 0 : parts.size() - 1);
+        size_t i = 0;
+        for (; i < end; ++i) {
+            auto it = cur->children.find(parts[i]);
+            if (it == cur->children.end())
+                break;
+            const MemFile mf = it->second->mf;
+            add_header(layer, mf.src, mf.dst, mf.hdr);
+            Node *n = cur->children[parts[i]].get();
+            if (n->mf.hdr.typeflag == '5') {
+                last_ancestor = n;
+                cur = n;
+            } else if (n->mf.hdr.typeflag == '2') {
+                std::string remaining;
+                for (size_t k = i + 1; k < parts.size(); ++k)
+                    remaining = go_join(remaining, parts[k]);
+                return add_ancestors(layer, go_join(n->mf.hdr.linkname, remaining), inclusive, depth + 1, uid, gid);
+            }
+        }
+        for (size_t j = i; j < end; ++j) {
+            std::string cp;
+            for (size_t k = 0; k <= j; ++k)
+                cp = go_join(cp, parts[k]);
+            cp = abs_path(cp);
+            Hdr hdr = create_header("", cp, nullptr, &last_ancestor->mf.hdr);
+            hdr.mtime_ns = now_ * 1000000000ll; // clk.Now()
+            hdr.uid = uid;
+            hdr.gid = gid;
+            add_header(layer, "", cp, hdr);
+        }
+        return dst;
+    }
+
+    void maybe_add(std::map<std::string, MemFile> &layer, const std::string &src, const std::string &dst, const Hdr &hdr)
+    {
+        if (is_updated(dst, hdr) && dst != "/") {
+            add_ancestors(layer, abs_path(dst), false, 0, 0, 0);
+            add_header(layer, src, dst, hdr);
+        }
+    }
+
+    // mem_fs.go:353-420
+    void add_to_layer(std::map<std::string, MemFile> &layer, const mkhost_copy_op &c)
+    {
+        if (c.n_srcs == 0)
+            throw HostError("check copy param: srcs cannot be empty");
+        std::string dst = c.dst;
+        const bool dir_fmt = (!dst.empty() && dst.back() == '/') || dst == "." || dst == "..";
+        if (c.n_srcs > 1 && !dir_fmt)
+            throw HostError("check copy param: tarring multiple sources, destination must end with \"/\"");
+        if (dst.empty() || dst[0] != '/') {
+            if (!c.work_dir || c.work_dir[0] != '/')
+                throw HostError("check copy param: dst is not absolute path, must specify absolute working directory");
+            std::string d = go_join(c.work_dir, dst);
+            dst = dir_fmt ? d + "/" : d;
+        }
+        bool create_dst = true;
+        const std::string src_root = c.src_root;
+        if (c.n_srcs == 1) {
+            const std::string s = go_join(src_root, rel_path(c.srcs[0]));
+            struct stat st;
+            if (stat(s.c_str(), &st) != 0)
+                throw HostError(errno_str("stat src", s));
+            if (!S_ISDIR(st.st_mode))
+                create_dst = false;
+        }
+        if (create_dst) {
+            std::string resolved = add_ancestors(layer, abs_path(dst), true, 0, c.uid, c.gid);
+            if (resolved.empty() || resolved.back() != '/')
+                resolved += "/";
+            dst = resolved;
+        }
+        for (size_t k = 0; k < c.n_srcs; ++k) {
+            // evalSymlinks (utils.go:249-324): sources inside a build context are not symlinked dirs here
+            const std::string src = go_join(src_root, rel_path(c.srcs[k]));
+            go_walk(src, [&](const std::string &cur, const struct stat &st) -> WalkRet {
+                if (should_skip(cur, st))
+                    return S_ISDIR(st.st_mode) ? W_SKIPDIR : W_CONT;
+                std::string cur_dst;
+                if (cur == src) {
+                    if (S_ISDIR(st.st_mode))
+                        return W_CONT;
+                    cur_dst = dst.back() != '/' ? dst : go_join(dst, path_base(src));
+                } else {
+                    cur_dst = go_join(dst, cur.substr(src.size()));
+                }
+                Hdr hdr = create_header(cur, cur_dst, &st, nullptr);
+                hdr.uid = c.uid;
+                hdr.gid = c.gid;
+                maybe_add(layer, cur, cur_dst, hdr);
+                return W_CONT;
+            });
+        }
+    }
+};
+
+void set_err(char *err, size_t n, const std::string &s)
+{
+    if (err && n) {
+        snprintf(err, n, "%s", s.c_str());
+    }
+}
+
+} // namespace
+
+// =====================================================================================================
+extern "C" {
+
+size_t mkhost_encode_tar_header(const mkhost_tar_header *h, uint8_t *out, size_t cap)
+{
+    try {
+        Hdr x;
+        x.name = h->name ? h->name : "";
+        while (!x.name.empty() && x.name[0] == '/') // write.go:57 strings.TrimLeft(h.Name, "/")
+            x.name.erase(0, 1);
+        x.linkname = h->linkname ? h->linkname : "";
+        x.mode = h->mode; x.uid = h->uid; x.gid = h->gid; x.size = h->size; x.mtime_ns = h->mtime_ns;
+        x.typeflag = h->typeflag;
+        std::string b = encode_header(x);
+        if (b.size() > cap)
+            return 0;
+        memcpy(out, b.data(), b.size());
+        return b.size();
+    } catch (const std::exception &) {
+        return 0;
+    }
+}
+
+size_t mkhost_describe_context_stream(const char *context_dir, const char *const *from_paths, size_t n_paths, char *out,
+                                      size_t cap, char *err, size_t errlen)
+{
+    try {
+        std::string s;
+        for (const auto &g : context_segments(go_clean(context_dir), from_paths, n_paths)) {
+            if (g.kind == 'F')
+                s += "F " + std::to_string(g.size) + " " + g.path + "\n";
+            else
+                s += std::string(1, g.kind) + " " + g.bytes + "\n";
+        }
+        if (s.size() + 1 <= cap)
+            memcpy(out, s.c_str(), s.size() + 1);
+        return s.size() + 1;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("hash context sources: ") + e.what());
+        return 0;
+    }
+}
+
+size_t mkhost_describe_layer(const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops, char *out,
+                             size_t cap, char *err, size_t errlen)
+{
+    try {
+        MemFS fs(root_dir, now_unix);
+        auto layer = fs.add_layer_by_copy_ops(ops, n_ops);
+        std::string s;
+        char tmp[128];
+        for (const auto &kv : layer) {
+            const Hdr &h = kv.second.hdr;
+            snprintf(tmp, sizeof tmp, "%c %llo %lld %lld %lld %lld ", h.typeflag, (unsigned long long)h.mode, (long long)h.uid,
+                     (long long)h.gid, (long long)h.size, (long long)(h.mtime_ns / 1000000000ll));
+            s += tmp + kv.second.dst + " " + h.name + " " + kv.second.src + "\n";
+        }
+        if (s.size() + 1 <= cap)
+            memcpy(out, s.c_str(), s.size() + 1);
+        return s.size() + 1;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("create layer by copy ops: ") + e.what());
+        return 0;
+    }
+}
+
+int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, const char *context_dir,
+                         const char *const *from_paths, size_t n_paths, int n_threads, uint32_t *crc_out,
+                         uint64_t *stream_len_out, char *err, size_t errlen)
+{
+    try {
+        std::vector<Seg> segs = context_segments(go_clean(context_dir), from_paths, n_paths);
+        uint64_t total = prefix_len;
+        for (const auto &g : segs)
+            total += g.kind == 'F' ? g.size : g.bytes.size();
+        ck(eng, mksnap_begin(eng), "begin");
+
+        void *hp = nullptr;
+        uint64_t cap = 0;
+        int32_t aid = -1;
+        uint64_t pos = 0;
+        std::vector<mksnap_extent> ext;
+        std::vector<ReadJob> jobs;
+        auto acquire = [&]() {
+            ck(eng, mksnap_arena_acquire(eng, &hp, &cap, &aid), "arena acquire");
+            pos = 0;
+            ext.clear();
+            jobs.clear();
+        };
+        auto flush = [&]() {
+            run_reads(jobs, n_threads);
+            ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), nullptr, 0), "arena submit");
+            aid = -1;
+        };
+        acquire();
+        uint64_t after = total; // stream bytes not yet placed
+        auto put_bytes = [&](const void *p, size_t n) {
+            if (n == 0)
+                return;
+            uint64_t o = align_up(pos, 16);
+            if (o + n > cap) {
+                flush();
+                acquire();
+                o = 0;
+            }
+            if (n > cap)
+                throw HostError("path string larger than the arena");
+            memcpy((uint8_t *)hp + o, p, n);
+            after -= n;
+            ext.push_back(mksnap_extent{o, n, after, MKSNAP_X_CRC, 0});
+            pos = o + n;
+        };
+        put_bytes(prefix, prefix_len);
+        for (const auto &g : segs) {
+            if (g.kind != 'F') {
+                put_bytes(g.bytes.data(), g.bytes.size());
+                continue;
+            }
+            uint64_t done = 0; // CRC is linear: a file may be split across arenas at any 16-byte boundary
+            while (done < g.size) {
+                uint64_t o = align_up(pos, 512);
+                if (o + 4096 > cap) {
+                    flush();
+                    acquire();
+                    o = 0;
+                }
+                uint64_t n = std::min<uint64_t>(g.size - done, (cap - o) / 16 * 16);
+                jobs.push_back(ReadJob{g.path, done, n, (uint8_t *)hp + o});
+                after -= n;
+                ext.push_back(mksnap_extent{o, n, after, MKSNAP_X_CRC, 0});
+                pos = o + n;
+                done += n;
+            }
+        }
+        flush();
+        mksnap_result res;
+        ck(eng, mksnap_finish(eng, &res), "finish");
+        if (res.crc_bytes != total)
+            throw HostError("internal: stream length mismatch");
+        *crc_out = mksnap_ctx_crc32(&res);
+        if (stream_len_out)
+            *stream_len_out = total;
+        return 0;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("hash context sources: ") + e.what());
+        return -1;
+    }
+}
+
+int mkhost_commit_copy_ops(mksnap_t *eng, const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops,
+                           int n_threads, mkhost_layer_result *out, char *err, size_t errlen)
+{
+    try {
+        MemFS fs(root_dir, now_unix);
+        auto layer = fs.add_layer_by_copy_ops(ops, n_ops);
+        ck(eng, mksnap_begin(eng), "begin");
+        void *hp = nullptr;
+        uint64_t cap = 0;
+        int32_t aid = -1;
+        ck(eng, mksnap_arena_acquire(eng, &hp, &cap, &aid), "arena acquire");
+        uint8_t *a = (uint8_t *)hp;
+        uint64_t pos = 0;
+        std::vector<mksnap_extent> ext;
+        std::vector<ReadJob> jobs;
+        for (const auto &kv : layer) { // commitLayer: alphabetical order of absolute dst (mem_fs.go:424-433)
+            const MemFile &mf = kv.second;
+            const std::string hb = encode_header(mf.hdr);
+            const uint64_t body = (mf.hdr.typeflag == '0') ? (uint64_t)mf.hdr.size : 0;
+            const uint64_t need = hb.size() + align_up(body, 512);
+            if (pos + need + 1024 > cap)
+                throw HostError("write diffs: layer tar exceeds the arena (" + std::to_string(cap) + " bytes)");
+            memcpy(a + pos, hb.data(), hb.size());
+            pos += hb.size();
+            if (body) {
+                jobs.push_back(ReadJob{mf.src, 0, body, a + pos});
+                ext.push_back(mksnap_extent{pos, body, 0, MKSNAP_X_CDC, 0});
+                const uint64_t padded = align_up(body, 512);
+                memset(a + pos + body, 0, padded - body);
+                pos += padded;
+            }
+        }
+        memset(a + pos, 0, 1024); // tar.Writer.Close: two zero blocks
+        pos += 1024;
+        run_reads(jobs, n_threads);
+        mksnap_range rng{0, pos};
+        ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), &rng, 1), "arena submit");
+        mksnap_result res;
+        ck(eng, mksnap_finish(eng, &res), "finish");
+        ck(eng, mksnap_get_stream_digests(eng, out->tar_digest, 1), "stream digests");
+        memcpy(out->root, res.root, 32);
+        out->n_entries = layer.size();
+        out->tar_bytes = pos;
+        out->n_chunks = res.n_chunks;
+        out->n_unique = res.n_unique;
+        return 0;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("failed to generate diff layer: ") + e.what());
+        return -1;
+    }
+}
+
+} // extern "C"

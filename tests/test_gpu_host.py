@@ -1,0 +1,87 @@
+"""-m gpu: the C++ host side driving the GPU through the C-ABI, against the oracle's reference restatement:
+cacheID of a COPY step (add_copy_step.go:102-122) and TarDigest of the committed layer (common.go:67-111)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+NOW = 1_600_000_000
+
+
+def _mk(root, rel, data=b"", mode=0o644, mtime=1_500_000_000):
+    p = os.path.join(root, rel)
+    os.makedirs(os.path.dirname(p), exist_ok=True)
+    with open(p, "wb") as f:
+        f.write(data)
+    os.chmod(p, mode)
+    os.utime(p, (mtime, mtime))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from makisu_b200.abi import Engine
+    e = Engine(device=0, device_arena_bytes=64 << 20, n_host_arenas=2, host_arena_bytes=8 << 20, max_extents=1 << 14)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def ctx(tmp_path_factory):
+    c = str(tmp_path_factory.mktemp("ctx"))
+    rng = np.random.default_rng(42)
+    _mk(c, "Dockerfile", b"FROM scratch\nCOPY . /app/\n")
+    for d in range(4):
+        for i in range(12):
+            n = int(rng.integers(0, 600_000))
+            _mk(c, f"d{d}/f{i:03d}.bin", rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+    _mk(c, "big.bin", rng.integers(0, 256, 11_000_000, dtype=np.uint8).tobytes())  # larger than one 8 MiB arena
+    _mk(c, "empty", b"")
+    _mk(c, "zeros", bytes(300_000))
+    os.symlink("big.bin", os.path.join(c, "link"))
+    for d, _, _ in os.walk(c):
+        os.utime(d, (1_500_000_000, 1_500_000_000))
+    return c
+
+
+def test_copy_step_cache_id_matches_reference_restatement(eng, ctx):
+    from makisu_b200 import host
+    from oracle import ctx_crc
+    seed = ctx_crc.from_step_cache_id(ctx_crc.plan_seed(True, False), "scratch")
+    for args, paths in [(". /app/", ["."]), ("d1 d2 big.bin /x/", ["d1", "d2", "big.bin"]), ("d*/f00?.bin /y/", ["d*/f00?.bin"])]:
+        want = ctx_crc.copy_step_cache_id(seed, "COPY", args, ctx, paths)
+        got = host.copy_step_cache_id(eng, seed, "COPY", args, ctx, paths)
+        assert got == want, (args, got, want)
+    # TestCopyStepSetCacheID relations (copy_step_test.go:51-169)
+    a = host.copy_step_cache_id(eng, seed, "COPY", ". /app/", ctx, ["."])
+    assert a == host.copy_step_cache_id(eng, seed, "COPY", ". /app/", ctx, ["."])
+    assert a != host.copy_step_cache_id(eng, seed + "x", "COPY", ". /app/", ctx, ["."])
+    assert a != host.copy_step_cache_id(eng, seed, "COPY", ". /app2/", ctx, ["."])
+
+
+def test_commit_layer_tar_digest_and_chunk_table(ctx, tmp_path):
+    from makisu_b200 import host
+    from makisu_b200.abi import Engine
+    from oracle import layer_tar as lt
+    from oracle import lib as olib
+    root = tmp_path / "root"
+    root.mkdir()
+    os.chmod(root, 0o755)
+    with Engine(device=0, device_arena_bytes=64 << 20, n_host_arenas=1, host_arena_bytes=64 << 20, max_extents=1 << 14) as eng:
+        got = host.commit_copy_ops(eng, str(root), NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 3, 4)])
+    fs = lt.MemFS(lambda: NOW, str(root))
+    entries = fs.add_layer_by_copy_ops([lt.CopyOperation.new(["/"], ctx, "/", "/app/", uid=3, gid=4)])
+    blob = b"".join(lt.layer_tar_chunks(entries))
+    assert got["n_entries"] == len(entries) and got["tar_bytes"] == len(blob)
+    assert got["tar_digest"] == lt.tar_digest(entries)
+    # chunk table over the regular files of the layer, in tar order
+    arena = np.frombuffer(blob, dtype=np.uint8)
+    offs, lens, pos = [], [], 0
+    for e in entries:
+        pos += len(lt.entry_header_bytes(e))
+        if e.hdr.typeflag == lt.TYPE_REG and e.hdr.size:
+            offs.append(pos)
+            lens.append(e.hdr.size)
+            pos += (e.hdr.size + 511) // 512 * 512
+    want = olib.chunk_table(arena, offs, lens)
+    assert got["n_chunks"] == want["n_chunks"] and got["n_unique"] == want["n_unique"] and got["root"] == want["root"]
