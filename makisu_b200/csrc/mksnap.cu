@@ -302,7 +302,7 @@ int merkle_root(mksnap *h, cudaStream_t s)
     for (;;) {
         const uint64_t next_n = cur_n == 0 ? 1 : (cur_n + 255) / 256;
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, s));
-        k_sha256_ranges<<<sha_grid(h), SHA_THREADS, 0, s>>>(cur, nullptr, nullptr, nullptr, next_n, nullptr, 0,
+        k_sha256_ranges<true><<<sha_grid(h), SHA_THREADS, 0, s>>>(cur, nullptr, nullptr, nullptr, next_n, nullptr, 0,
                                                             8192, cur_n * 32, h->d_merkle[which], &h->d_sc->work,
                                                             nullptr, 1u);
         LAUNCH_OK(h);
@@ -459,7 +459,8 @@ static int create_impl(mksnap *h)
         if (e && e[0] >= '0' && e[0] <= '3')
             h->gear_cfg = e[0] - '0';
     }
-    uint64_t pc = std::max<uint64_t>(1u << 20, c.device_arena_bytes / 128);
+    // expected candidates = bytes/4096; 32x headroom, plus one private block per resident gear warp (x2)
+    uint64_t pc = std::max<uint64_t>(1u << 20, c.device_arena_bytes / 128) + 2ull * h->sm_count * 32 * GEAR_POOL_BLOCK;
     if (pc > 0xFFFFFFF0ull)
         pc = 0xFFFFFFF0ull;
     h->pool_cap = (uint32_t)pc;
@@ -748,7 +749,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     }
     CK(h, cudaEventRecord(h->ev[3], sk));
     if (n_files) {
-        k_sha256_ranges<<<sha_grid(h), SHA_THREADS, 0, sk>>>(d_arena, h->d_chunk_start, h->d_chunk_len,
+        k_sha256_ranges<true><<<sha_grid(h), SHA_THREADS, 0, sk>>>(d_arena, h->d_chunk_start, h->d_chunk_len,
                                                             &h->d_sc->batch_chunks, 0, &h->d_sc->n_chunks, 0, 0, 0,
                                                             h->d_digests, &h->d_sc->work, &h->d_sc->err, 1u);
         LAUNCH_OK(h);
@@ -758,7 +759,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     CK(h, cudaEventRecord(h->ev[4], sk));
     if (n_rng) {
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, sk));
-        k_sha256_ranges<<<(uint32_t)std::min<uint64_t>(sha_grid(h), (n_rng + 3) / 4), SHA_THREADS, 0, sk>>>(
+        k_sha256_ranges<false><<<(uint32_t)std::min<uint64_t>(sha_grid(h), (n_rng + 3) / 4), SHA_THREADS, 0, sk>>>(
             d_arena, m.d_rstart, m.d_rlen, nullptr, n_rng, nullptr, 0, 0, 0, h->d_stream_digests + h->n_streams * 32,
             &h->d_sc->work, nullptr, 1u);
         LAUNCH_OK(h);

@@ -269,7 +269,7 @@ k_crc32_extents(const uint8_t *__restrict__ arena, const CrcExtent *__restrict__
 // pool entry = pos_in_region | strict<<31.
 // ------------------------------------------------------------------------
 constexpr uint32_t GEAR_TILE = 4096; // bytes per TileRec region (= one warp x 32 rows x 128 B)
-constexpr uint32_t GEAR_POOL_BLOCK = 512; // pool entries a warp reserves per global atomic
+constexpr uint32_t GEAR_POOL_BLOCK = 256; // pool entries a warp reserves per global atomic
 
 struct TileRec {
     uint32_t base;  // first pool entry of this region
@@ -442,12 +442,17 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
 #pragma unroll
                 for (int i = 1; i < 16; ++i)
                     m = min(m, hv[i]);
-                if (m < loose_lim) { // ~0.4 % of lane-chunks
+                if (m < loose_lim) { // ~0.4 % of lane-chunks; the warp pays for it ~12 % of the time
                     uint32_t bl = 0, bs = 0;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        bl |= (hv[i] < loose_lim ? 1u : 0u) << i;
-                        bs |= (hv[i] < strict_lim ? 1u : 0u) << i;
+                    for (int i = 0; i < 16; ++i)
+                        if (hv[i] < loose_lim)
+                            bl |= 1u << i;
+                    if (m < strict_lim) { // 1/16 of those
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (hv[i] < strict_lim)
+                                bs |= 1u << i;
                     }
                     const uint32_t sh = (c & 1) * 16;
                     if ((c >> 1) == 1) { mL1 |= bl << sh; mS1 |= bs << sh; }
@@ -474,9 +479,14 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
             }
             if (m < loose_lim) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    mL0 |= (L[i] < loose_lim ? 1u : 0u) << i;
-                    mS0 |= (L[i] < strict_lim ? 1u : 0u) << i;
+                for (int i = 0; i < 32; ++i)
+                    if (L[i] < loose_lim)
+                        mL0 |= 1u << i;
+                if (m < strict_lim) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (L[i] < strict_lim)
+                            mS0 |= 1u << i;
                 }
             }
         }
@@ -658,6 +668,14 @@ __global__ void k_batch_end(SessionCounters *sc)
 // ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 
+// FMA_ADDS = true: additions as IMAD (throughput: many chunks, ALU pipe saturated);
+// false: plain adds (IADD3, shorter dependent chain) for the latency-bound serial streams.
+template <bool FMA_ADDS> __device__ __forceinline__ uint32_t sha_add(uint32_t a, uint32_t b, uint32_t one)
+{
+    return FMA_ADDS ? fma_add_rt(a, b, one) : a + b;
+}
+
+template <bool FMA_ADDS>
 __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], const uint32_t one)
 {
     constexpr uint32_t K[64] = {
@@ -679,16 +697,16 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], 
             const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
             const uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
             const uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
-            wi = fma_add_rt(fma_add_rt(w[i & 15], s0, one), fma_add_rt(w[(i + 9) & 15], s1, one), one);
+            wi = sha_add<FMA_ADDS>(sha_add<FMA_ADDS>(w[i & 15], s0, one), sha_add<FMA_ADDS>(w[(i + 9) & 15], s1, one), one);
             w[i & 15] = wi;
         }
         const uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
         const uint32_t ch = (e & f) ^ (~e & g);
-        const uint32_t t1 = fma_add_rt(fma_add_rt(h, S1, one), fma_add_rt(ch, wi + K[i], one), one);
+        const uint32_t t1 = sha_add<FMA_ADDS>(sha_add<FMA_ADDS>(h, S1, one), sha_add<FMA_ADDS>(ch, wi + K[i], one), one);
         const uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
         const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-        h = g; g = f; f = e; e = fma_add_rt(d, t1, one);
-        d = c; c = b; b = a; a = fma_add_rt(fma_add_rt(t1, S0, one), mj, one);
+        h = g; g = f; f = e; e = sha_add<FMA_ADDS>(d, t1, one);
+        d = c; c = b; b = a; a = sha_add<FMA_ADDS>(sha_add<FMA_ADDS>(t1, S0, one), mj, one);
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d;
     st[4] += e; st[5] += f; st[6] += g; st[7] += h;
@@ -698,6 +716,7 @@ constexpr int SHA_THREADS = 128;
 
 // mode 0: ranges from (start[], len[]) arrays, count read from *n_dev (or n_host if n_dev==nullptr)
 // mode 1: uniform ranges of `uni_len` bytes over [0, uni_total) of `data` (Merkle levels)
+template <bool FMA_ADDS>
 __global__ void __launch_bounds__(SHA_THREADS)
 k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ start,
                 const uint64_t *__restrict__ len, const uint32_t *__restrict__ n_dev, uint64_t n_host,
@@ -831,7 +850,7 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
                 }
             }
         }
-        sha256_compress(st, w, one);
+        sha256_compress<FMA_ADDS>(st, w, one);
         if (last) {
             uint4 o0, o1;
             o0.x = __byte_perm(st[0], 0, 0x0123); o0.y = __byte_perm(st[1], 0, 0x0123);
