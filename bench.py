@@ -192,7 +192,7 @@ def cpu_reference_pass(sample_mib: int, file_bytes: int):
     return dict(bytes=nbytes, s_crc=t1 - t0, s_sha=t2 - t1, s_total=t2 - t0, crc="%x" % crc, n_files=n_files)
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -200,13 +200,12 @@ def run_reference_arm(args):
     sample_mib = min(args.cpu_sample_mib, 512)
     for _ in range(args.warmup):
         cpu_reference_pass(min(sample_mib, 64), file_bytes)
-    t0 = time.perf_counter()
-    tot = 0
+    tot, dt = 0, 0.0
     last = None
     for _ in range(args.steps):
-        last = cpu_reference_pass(sample_mib, file_bytes)
+        last = cpu_reference_pass(sample_mib, file_bytes)  # synthetic content is generated outside the timed part
         tot += last["bytes"]
-    dt = time.perf_counter() - t0
+        dt += last["s_total"]
     v = tot / GiB / dt
     line = {
         "impl": "reference", "metric": "snapshot_hash_throughput", "value": v, "unit": "GiB/s", "n_gpus": args.gpus,
@@ -220,14 +219,25 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries (NCCL prints its version there) get stderr until the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, emit)
         return
 
     import torch
@@ -473,7 +483,7 @@ def main():
             "gpu_launches_per_step": launches // max(1, args.steps), "tar_digest": tar,
             "clocks": summarize_clocks(rows),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
