@@ -90,7 +90,7 @@ struct mksnap {
 
     TileRec *d_tiles = nullptr;
     CUtensorMap tm_main[MAX_SLOTS][3], tm_halo[MAX_SLOTS]; // per slot: arena viewed as [rows][128 B]
-    int gear_cfg = 3;                                       // index into the k_gear_scan instantiations
+    int gear_cfg = 5;                                       // index into the k_gear_scan instantiations
     uint32_t *d_pool = nullptr;
     uint32_t pool_cap = 0;
     uint32_t *d_pool_count = nullptr;
@@ -434,7 +434,7 @@ static int create_impl(mksnap *h)
     CK(h, cudaMemset(h->d_sc, 0, sizeof(SessionCounters)));
     CK(h, cudaHostAlloc(&h->h_sc, sizeof(SessionCounters), cudaHostAllocDefault));
 
-    const uint64_t n_tiles = c.device_arena_bytes / GEAR_TILE + 64; // one TileRec per 4 KiB region (+ tile round-up)
+    const uint64_t n_tiles = c.device_arena_bytes / GEAR_TILE + 128; // one TileRec per 4 KiB region (+ tile round-up)
     CK(h, cudaMalloc(&h->d_tiles, n_tiles * sizeof(TileRec)));
     {
         EncodeTiledFn enc = nullptr;
@@ -455,8 +455,10 @@ static int create_impl(mksnap *h)
         CK(h, cudaFuncSetAttribute(k_gear_scan<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<12, 3>::SMEM));
         CK(h, cudaFuncSetAttribute(k_gear_scan<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<16, 2>::SMEM));
         CK(h, cudaFuncSetAttribute(k_gear_scan<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<16, 3>::SMEM));
+        CK(h, cudaFuncSetAttribute(k_gear_scan<20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<20, 2>::SMEM));
+        CK(h, cudaFuncSetAttribute(k_gear_scan<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<24, 2>::SMEM));
         const char *e = getenv("MKSNAP_GEAR_CFG"); // tuning knob: 0 = 8 warps x 4 stages, 1 = 12x3, 2 = 16x2, 3 = 16x3
-        if (e && e[0] >= '0' && e[0] <= '3')
+        if (e && e[0] >= '0' && e[0] <= '5') // 4 = 20x2, 5 = 24x2
             h->gear_cfg = e[0] - '0';
     }
     // expected candidates = bytes/4096; 32x headroom, plus one private block per resident gear warp (x2)
@@ -727,7 +729,9 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         int rc = h->gear_cfg == 0   ? launch_gear<8, 4>(h, slot, 0, n_regions, sk)
                  : h->gear_cfg == 1 ? launch_gear<12, 3>(h, slot, 1, n_regions, sk)
                  : h->gear_cfg == 2 ? launch_gear<16, 2>(h, slot, 2, n_regions, sk)
-                                    : launch_gear<16, 3>(h, slot, 2, n_regions, sk);
+                 : h->gear_cfg == 3 ? launch_gear<16, 3>(h, slot, 2, n_regions, sk)
+                 : h->gear_cfg == 4 ? launch_gear<20, 2>(h, slot, 2, n_regions, sk)
+                                    : launch_gear<24, 2>(h, slot, 2, n_regions, sk);
         if (rc)
             return rc;
     }

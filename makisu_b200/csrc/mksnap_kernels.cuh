@@ -493,14 +493,23 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
 
         // ordered compaction: lane l's candidates precede lane l+1's
         const uint32_t cnt = __popc(mL0) + __popc(mL1) + __popc(mL2) + __popc(mL3);
-        uint32_t incl = cnt;
+        // exclusive prefix over lanes.  Nearly always every lane holds 0 or 1 candidate: two ballots do it.
+        const uint32_t b1 = __ballot_sync(0xFFFFFFFFu, cnt != 0);
+        const uint32_t b2 = __ballot_sync(0xFFFFFFFFu, cnt > 1);
+        uint32_t incl, total;
+        if (b2 == 0) {
+            incl = __popc(b1 & (0xFFFFFFFFu >> (31 - lane)));
+            total = __popc(b1);
+        } else {
+            incl = cnt;
 #pragma unroll
-        for (int sft = 1; sft < 32; sft <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, sft);
-            if (lane >= sft)
-                incl += v;
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, sft);
+                if (lane >= sft)
+                    incl += v;
+            }
+            total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         if (total > blk_end - blk_next) { // refill: rare (every ~GEAR_POOL_BLOCK candidates)
             uint32_t nb = 0;
             if (lane == 0) {

@@ -1,0 +1,160 @@
+"""-m gpu: bigger cases -- offsets beyond 4 GiB, Zipf-sized files (BASELINE configs[3]), duplicate-heavy
+content (configs[4]), one long file, and size-independent properties at multi-GiB where the oracle is too slow."""
+import zlib
+
+import numpy as np
+import pytest
+
+from tests.util import cdc_extents, crc_extents
+
+pytestmark = pytest.mark.gpu
+GiB = 1 << 30
+
+
+def _ext(off, ln, suffix, flags):
+    from makisu_b200.abi import Extent
+    e = Extent()
+    e.arena_off, e.len, e.crc_suffix, e.flags = off, ln, suffix, flags
+    return e
+
+
+def test_offsets_beyond_4gib_match_low_offsets(oracle_lib):
+    """Same 48 MiB at offset 0 and at 5 GiB + 512: identical cuts/digests, CRC of the concatenation."""
+    from makisu_b200.abi import Engine, MKSNAP_X_CDC, MKSNAP_X_CRC
+    n = 48 << 20
+    hi = 5 * GiB + 512
+    with Engine(device=0, device_arena_bytes=6 * GiB, max_extents=64) as eng:
+        eng.begin()
+        eng.synth_fill(0, 0, n, 77)
+        data = eng.device_download(0, 0, n)
+        np.testing.assert_array_equal(data[:4096], oracle_lib.synth_fill(0, 4096, 77))
+        eng.device_upload(0, hi, data)
+        eng.device_submit(0, hi + n, [_ext(0, n, n, MKSNAP_X_CRC | MKSNAP_X_CDC), _ext(hi, n, 0, MKSNAP_X_CRC | MKSNAP_X_CDC)])
+        res = eng.finish()
+        assert eng.ctx_crc32(res) == zlib.crc32(data.tobytes(), zlib.crc32(data.tobytes()))
+        want = oracle_lib.chunk_table(data, [0], [n])
+        assert res.n_chunks == 2 * want["n_chunks"] and res.n_unique == want["n_unique"]
+        ends, digs = eng.get_chunks(res.n_chunks)
+        k = want["n_chunks"]
+        np.testing.assert_array_equal(ends[:k], want["ends"])
+        np.testing.assert_array_equal(ends[k:], want["ends"] + np.uint64(hi))
+        np.testing.assert_array_equal(digs[:k], want["digests"])
+        np.testing.assert_array_equal(digs[k:], want["digests"])
+        assert bytes(res.root) == want["root"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from makisu_b200.abi import Engine
+    e = Engine(device=0, device_arena_bytes=3 * GiB, n_host_arenas=0, max_extents=1 << 17)
+    yield e
+    e.close()
+
+
+def _pack_files(files):
+    offs, pos = [], 0
+    for f in files:
+        pos = (pos + 511) // 512 * 512
+        offs.append(pos)
+        pos += len(f)
+    arena = np.zeros((pos + 511) // 512 * 512 + 512, dtype=np.uint8)
+    for f, o in zip(files, offs):
+        arena[o:o + len(f)] = f
+    return arena, offs
+
+
+def _check_against_oracle(eng, oracle_lib, files):
+    arena, offs = _pack_files(files)
+    lens = [len(f) for f in files]
+    eng.begin()
+    eng.device_upload(0, 0, arena)
+    ext, total = crc_extents(offs, lens, list(range(len(files))), flags_extra=[2] * len(files))
+    eng.device_submit(0, arena.size, ext)
+    res = eng.finish()
+    want = oracle_lib.chunk_table(arena, offs, lens)
+    crc = 0
+    for f in files:
+        crc = zlib.crc32(f.tobytes(), crc)
+    assert eng.ctx_crc32(res) == crc
+    assert (res.n_chunks, res.n_unique) == (want["n_chunks"], want["n_unique"]) and bytes(res.root) == want["root"]
+    ends, digs = eng.get_chunks(res.n_chunks)
+    np.testing.assert_array_equal(ends, want["ends"])
+    np.testing.assert_array_equal(digs, want["digests"])
+    return res
+
+
+def test_zipf_sized_files(eng, oracle_lib):
+    """BASELINE configs[3] at reduced scale: sizes ~ Zipf(1.1) clipped to [10 B, 64 MiB], long tail included."""
+    rng = np.random.default_rng(0xC4)
+    sizes = np.clip((rng.zipf(1.1, 600).astype(np.float64) * 10), 10, 64 << 20).astype(np.int64)
+    sizes[0] = 64 << 20
+    sizes = sizes[np.cumsum(sizes) < 400 << 20]
+    files = [rng.integers(0, 256, int(s), dtype=np.uint8) for s in sizes]
+    res = _check_against_oracle(eng, oracle_lib, files)
+    assert res.n_files == len(files)
+
+
+def test_duplicate_heavy_context(eng, oracle_lib):
+    """BASELINE configs[4] at reduced scale: files assembled from a pool holding 20 % unique content, in
+    256 KiB pieces (>= max chunk, so CDC resynchronises inside every piece)."""
+    rng = np.random.default_rng(0xC5)
+    piece = 256 << 10
+    n_pieces = 800
+    pool = [rng.integers(0, 256, piece, dtype=np.uint8) for _ in range(n_pieces // 5)]
+    files = []
+    for _ in range(40):
+        k = int(rng.integers(5, 40))
+        files.append(np.concatenate([pool[int(rng.integers(0, len(pool)))] for _ in range(k)]))
+    res = _check_against_oracle(eng, oracle_lib, files)
+    ratio = res.n_unique / res.n_chunks
+    assert 0.1 < ratio < 0.5, ratio
+
+
+def test_one_long_file(eng, oracle_lib):
+    rng = np.random.default_rng(8)
+    _check_against_oracle(eng, oracle_lib, [rng.integers(0, 256, 200 << 20, dtype=np.uint8)])
+
+
+def test_properties_at_2gib(eng, oracle_lib):
+    """No oracle pass over the data: (i) one submit == two submits == three reordered submits (CRC linearity,
+    table order independence); (ii) idempotence; (iii) crc(A||B) == combine(crc(A), crc(B), |B|);
+    (iv) duplicating the context leaves the table and root unchanged and doubles n_chunks."""
+    from makisu_b200.abi import MKSNAP_X_CDC, MKSNAP_X_CRC
+    n_files, fb = 4096, 512 << 10
+    total = n_files * fb
+    eng.begin()
+    eng.synth_fill(0, 0, total, 0xABC)
+    eng.finish()
+    fl = MKSNAP_X_CRC | MKSNAP_X_CDC
+
+    def run(groups):
+        eng.begin()
+        for g in groups:
+            eng.device_submit(0, total, [_ext(i * fb, fb, total - (i + 1) * fb, fl) for i in g])
+        r = eng.finish()
+        return eng.ctx_crc32(r), r.n_chunks, r.n_unique, bytes(r.root)
+
+    allf = list(range(n_files))
+    one = run([allf])
+    assert one == run([allf])                                        # idempotent
+    assert one == run([allf[: n_files // 3], allf[n_files // 3:]])   # split submits
+    perm = list(np.random.default_rng(1).permutation(n_files))
+    assert one == run([perm[:1000], perm[1000:3000], perm[3000:]])   # any order: suffixes carry the position
+    # (iii) CRC of the two halves, combined on the host
+    half = n_files // 2
+    eng.begin()
+    eng.device_submit(0, total, [_ext(i * fb, fb, (half - 1 - i) * fb, MKSNAP_X_CRC) for i in range(half)])
+    ra = eng.finish()
+    eng.begin()
+    eng.device_submit(0, total, [_ext(i * fb, fb, (n_files - 1 - i) * fb, MKSNAP_X_CRC) for i in range(half, n_files)])
+    rb = eng.finish()
+    assert oracle_lib.L().mko_crc32_combine(eng.ctx_crc32(ra), eng.ctx_crc32(rb), (n_files - half) * fb) == one[0]
+    # (iv) the same files twice (CDC only)
+    eng.begin()
+    eng.device_submit(0, total, [_ext(i * fb, fb, 0, MKSNAP_X_CDC) for i in allf + allf])
+    rd = eng.finish()
+    assert rd.n_chunks == 2 * one[1] and rd.n_unique == one[2] and bytes(rd.root) == one[3]
+    # spot check: first and last file against the oracle
+    for i in (0, n_files - 1):
+        d = eng.device_download(0, i * fb, fb)
+        np.testing.assert_array_equal(d, oracle_lib.synth_fill(i * fb, fb, 0xABC))
