@@ -325,6 +325,23 @@ def main():
             assert hashlib.sha256(sample[prev:e_].tobytes()).digest() == d_.tobytes(), "chunk SHA-256 gate failed"
             prev = e_
         eng.device_upload(0, lay["meta_base"], np.frombuffer(lay["blob"], dtype=np.uint8))
+        # same gate at the far end of the arena (offsets ~48.8 GiB): the last file alone
+        last_off = (args.files - 1) * file_bytes
+        tail = eng.device_download(0, last_off, file_bytes)
+        one = np.zeros(1, dtype=EXT_DT)
+        one["arena_off"], one["len"], one["crc_suffix"], one["flags"] = last_off, file_bytes, 0, 3
+        eng.begin()
+        eng.lib.mksnap_device_submit(eng.h, 0, used, ext_ptr(one), 1, None, 0)
+        rt = eng.finish()
+        assert eng.ctx_crc32(rt) == zlib.crc32(tail.tobytes()), "CRC-32 gate failed at high offset"
+        ends, digs = eng.get_chunks(rt.n_chunks)
+        prev = last_off
+        for e_, d_ in zip(ends, digs):
+            e_ = int(e_)
+            assert hashlib.sha256(tail[prev - last_off:e_ - last_off].tobytes()).digest() == d_.tobytes(), \
+                "chunk SHA-256 gate failed at high offset"
+            prev = e_
+        assert prev == last_off + file_bytes
 
     # ---- device-resident timing ----
     for _ in range(args.warmup):

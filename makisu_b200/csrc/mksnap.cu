@@ -90,7 +90,8 @@ struct mksnap {
 
     TileRec *d_tiles = nullptr;
     CUtensorMap tm_main[MAX_SLOTS][3], tm_halo[MAX_SLOTS]; // per slot: arena viewed as [rows][128 B]
-    int gear_cfg = 5;                                       // index into the k_gear_scan instantiations
+    int gear_cfg = 5;
+    bool sha_fma = true;                                    // chunk SHA-256: additions on the FMA pipe                                       // index into the k_gear_scan instantiations
     uint32_t *d_pool = nullptr;
     uint32_t pool_cap = 0;
     uint32_t *d_pool_count = nullptr;
@@ -458,6 +459,9 @@ static int create_impl(mksnap *h)
         CK(h, cudaFuncSetAttribute(k_gear_scan<20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<20, 2>::SMEM));
         CK(h, cudaFuncSetAttribute(k_gear_scan<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<24, 2>::SMEM));
         const char *e = getenv("MKSNAP_GEAR_CFG"); // tuning knob: 0 = 8 warps x 4 stages, 1 = 12x3, 2 = 16x2, 3 = 16x3
+        const char *e2 = getenv("MKSNAP_SHA_FMA"); // tuning knob: 0 = plain adds in the chunk SHA-256 kernel
+        if (e2 && e2[0] == '0')
+            h->sha_fma = false;
         if (e && e[0] >= '0' && e[0] <= '5') // 4 = 20x2, 5 = 24x2
             h->gear_cfg = e[0] - '0';
     }
@@ -753,9 +757,14 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     }
     CK(h, cudaEventRecord(h->ev[3], sk));
     if (n_files) {
-        k_sha256_ranges<true><<<sha_grid(h), SHA_THREADS, 0, sk>>>(d_arena, h->d_chunk_start, h->d_chunk_len,
-                                                            &h->d_sc->batch_chunks, 0, &h->d_sc->n_chunks, 0, 0, 0,
-                                                            h->d_digests, &h->d_sc->work, &h->d_sc->err, 1u);
+        if (h->sha_fma)
+            k_sha256_ranges<true><<<sha_grid(h), SHA_THREADS, 0, sk>>>(d_arena, h->d_chunk_start, h->d_chunk_len,
+                                                                      &h->d_sc->batch_chunks, 0, &h->d_sc->n_chunks, 0, 0,
+                                                                      0, h->d_digests, &h->d_sc->work, &h->d_sc->err, 1u);
+        else
+            k_sha256_ranges<false><<<sha_grid(h), SHA_THREADS, 0, sk>>>(d_arena, h->d_chunk_start, h->d_chunk_len,
+                                                                       &h->d_sc->batch_chunks, 0, &h->d_sc->n_chunks, 0,
+                                                                       0, 0, h->d_digests, &h->d_sc->work, &h->d_sc->err, 1u);
         LAUNCH_OK(h);
         k_batch_end<<<1, 32, 0, sk>>>(h->d_sc);
         LAUNCH_OK(h);
