@@ -467,6 +467,7 @@ def main():
             for s_ in range(streams):
                 rng_[s_].arena_off = s_ * per * file_bytes
                 rng_[s_].len = per * file_bytes
+                rng_[s_].stream, rng_[s_].flags = s_, 0
             eng.begin()
             eng.lib.mksnap_device_submit(eng.h, 0, used, None, 0, rng_, streams)
             eng.finish()

@@ -88,11 +88,18 @@ typedef struct {
     uint32_t reserved;
 } mksnap_extent;
 
-/* A byte range digested as ONE serial SHA-256 stream (replaces the tarDigester
- * sha256.New() sink of lib/builder/step/common.go:44-55).  arena_off multiple of 16. */
+/* A piece of a serial SHA-256 stream (replaces the tarDigester sha256.New() sink of
+ * lib/builder/step/common.go:44-55: every tar.Writer write lands in one stream).  arena_off multiple of 16.
+ * `stream` is a caller-chosen slot in [0, max_extents): the digest of the stream lands in row `stream` of the
+ * stream-digest table.  A stream may span several submits (a layer tar larger than one arena): every piece but
+ * the last carries MKSNAP_R_MORE and a length that is a multiple of 64; the device keeps the SHA-256 midstate
+ * between submits.  At most one piece per stream per submit. */
+#define MKSNAP_R_MORE 1u
 typedef struct {
     uint64_t arena_off;
     uint64_t len;
+    uint32_t stream;
+    uint32_t flags;
 } mksnap_range;
 
 typedef struct {
@@ -104,7 +111,7 @@ typedef struct {
     uint64_t n_chunks;
     uint64_t n_unique;      /* rows of the sorted-unique table */
     uint8_t root[32];       /* fan-out-256 Merkle root of the table = layer content address */
-    uint64_t n_streams;     /* serial SHA-256 streams digested */
+    uint64_t n_streams;     /* rows of the stream-digest table (highest finished stream slot + 1) */
 } mksnap_result;
 
 typedef struct {
@@ -176,7 +183,7 @@ uint32_t mksnap_ctx_crc32(const mksnap_result *res);
 int mksnap_get_chunks(mksnap_t *h, uint64_t *ends, uint8_t *digests, uint64_t capacity);
 /* sorted-unique 32-byte digest table */
 int mksnap_get_table(mksnap_t *h, uint8_t *table, uint64_t capacity_rows);
-/* serial-stream digests in (submit, range) order: the TarDigest bytes of
+/* stream digests, row = stream slot: the TarDigest bytes of
  * lib/builder/step/common.go:86 (hex-encode and prefix "sha256:" on the host). */
 int mksnap_get_stream_digests(mksnap_t *h, uint8_t *digests, uint64_t capacity);
 

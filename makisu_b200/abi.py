@@ -43,7 +43,10 @@ class Extent(C.Structure):
 
 
 class Range(C.Structure):
-    _fields_ = [("arena_off", C.c_uint64), ("len", C.c_uint64)]
+    _fields_ = [("arena_off", C.c_uint64), ("len", C.c_uint64), ("stream", C.c_uint32), ("flags", C.c_uint32)]
+
+
+MKSNAP_R_MORE = 1
 
 
 class Result(C.Structure):

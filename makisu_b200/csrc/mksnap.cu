@@ -37,11 +37,13 @@ struct MetaSet {
     uint32_t *h_piece_base = nullptr;
     CdcFile *h_files = nullptr;
     uint64_t *h_rstart = nullptr, *h_rlen = nullptr;
+    uint32_t *h_rstream = nullptr, *h_rflags = nullptr;
     // device mirrors
     CrcExtent *d_crc = nullptr;
     uint32_t *d_piece_base = nullptr;
     CdcFile *d_files = nullptr;
     uint64_t *d_rstart = nullptr, *d_rlen = nullptr;
+    uint32_t *d_rstream = nullptr, *d_rflags = nullptr;
     cudaEvent_t ev_done = nullptr; // kernels that read this set have finished
     bool in_flight = false;
 };
@@ -90,7 +92,7 @@ struct mksnap {
 
     TileRec *d_tiles = nullptr;
     CUtensorMap tm_main[MAX_SLOTS][3], tm_halo[MAX_SLOTS]; // per slot: arena viewed as [rows][128 B]
-    int gear_cfg = 5;
+    int gear_cfg = 3;
     bool sha_fma = true;                                    // chunk SHA-256: additions on the FMA pipe                                       // index into the k_gear_scan instantiations
     uint32_t *d_pool = nullptr;
     uint32_t pool_cap = 0;
@@ -105,6 +107,8 @@ struct mksnap {
     uint8_t *d_digests = nullptr;
     uint64_t max_streams = 0;
     uint8_t *d_stream_digests = nullptr;
+    StreamState *d_stream_state = nullptr;
+    std::vector<uint8_t> stream_open; // host shadow: stream slot has a parked midstate
     uint64_t n_streams = 0;
     uint64_t stream_base = 0; // bytes of arenas submitted before the current one
     uint64_t crc_bytes = 0;
@@ -305,7 +309,7 @@ int merkle_root(mksnap *h, cudaStream_t s)
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, s));
         k_sha256_ranges<true><<<sha_grid(h), SHA_THREADS, 0, s>>>(cur, nullptr, nullptr, nullptr, next_n, nullptr, 0,
                                                             8192, cur_n * 32, h->d_merkle[which], &h->d_sc->work,
-                                                            nullptr, 1u);
+                                                            nullptr, 1u, nullptr, nullptr, nullptr);
         LAUNCH_OK(h);
         cur = h->d_merkle[which];
         cur_n = next_n;
@@ -359,14 +363,47 @@ static int make_row_map(mksnap *h, EncodeTiledFn enc, CUtensorMap *out, void *ba
     return 0;
 }
 
-template <int W, int S> static int launch_gear(mksnap *h, uint32_t slot, int cfg_idx, uint32_t n_regions, cudaStream_t sk)
+// (re)allocate everything whose size follows the number of table rows: radix keys/payload, sorted and unique
+// tables, flags/positions, histograms, Merkle levels, scan temporaries.  Called at create (rows = max_chunks)
+// and again by mksnap_comm_init (rows = max_chunks x ranks: every rank merges the union of all tables).
+static int alloc_table_buffers(mksnap *h, uint64_t rows)
 {
-    using Cfg = GearCfg<W, S>;
-    const uint32_t n_tiles = (n_regions + W - 1) / W;
+    for (int k = 0; k < 2; k++) {
+        cudaFree(h->d_keys[k]); cudaFree(h->d_idx[k]); cudaFree(h->d_merkle[k]);
+        h->d_keys[k] = nullptr; h->d_idx[k] = nullptr; h->d_merkle[k] = nullptr;
+    }
+    cudaFree(h->d_sorted); cudaFree(h->d_table); cudaFree(h->d_flags); cudaFree(h->d_pos); cudaFree(h->d_hist);
+    cudaFree(h->d_scan_tmp);
+    h->d_sorted = h->d_table = nullptr;
+    h->d_flags = h->d_pos = h->d_hist = h->d_scan_tmp = nullptr;
+    h->table_cap = 0;
+    for (int k = 0; k < 2; k++) {
+        CK(h, cudaMalloc(&h->d_keys[k], rows * 8));
+        CK(h, cudaMalloc(&h->d_idx[k], rows * 4));
+    }
+    CK(h, cudaMalloc(&h->d_sorted, rows * 32));
+    CK(h, cudaMalloc(&h->d_table, rows * 32));
+    CK(h, cudaMalloc(&h->d_flags, rows * 4));
+    CK(h, cudaMalloc(&h->d_pos, rows * 4));
+    const uint64_t hist_words = 256ull * ((rows + SORT_TILE - 1) / SORT_TILE + 1);
+    CK(h, cudaMalloc(&h->d_hist, hist_words * 4));
+    const uint64_t merkle_rows = rows / 256 + 2;
+    CK(h, cudaMalloc(&h->d_merkle[0], merkle_rows * 32));
+    CK(h, cudaMalloc(&h->d_merkle[1], (merkle_rows / 256 + 2) * 32));
+    h->scan_tmp_words = std::max(rows, std::max<uint64_t>(hist_words, h->cfg.max_extents)) / SCAN_ITEMS * 2 + 4096;
+    CK(h, cudaMalloc(&h->d_scan_tmp, h->scan_tmp_words * 4));
+    h->table_cap = rows;
+    return 0;
+}
+
+template <int GROUPS> static int launch_gear(mksnap *h, uint32_t slot, uint32_t n_regions, cudaStream_t sk)
+{
+    using Cfg = GearCfg<GROUPS>;
+    const uint32_t n_tiles = (n_regions + Cfg::TILE_WARPS - 1) / Cfg::TILE_WARPS;
     const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)h->sm_count);
-    k_gear_scan<W, S><<<grid, Cfg::THREADS, Cfg::SMEM, sk>>>(h->tm_main[slot][cfg_idx], h->tm_halo[slot], n_tiles, h->d_gear,
-                                                            h->prm.strict_lim, h->prm.loose_lim, h->d_tiles, h->d_pool,
-                                                            h->pool_cap, h->d_pool_count, &h->d_sc->err);
+    k_gear_scan<GROUPS><<<grid, Cfg::THREADS, Cfg::SMEM, sk>>>(h->tm_main[slot][0], h->tm_halo[slot], n_tiles, h->d_gear,
+                                                              h->prm.strict_lim, h->prm.loose_lim, h->d_tiles, h->d_pool,
+                                                              h->pool_cap, h->d_pool_count, &h->d_sc->err);
     LAUNCH_OK(h);
     return 0;
 }
@@ -414,11 +451,15 @@ static int create_impl(mksnap *h)
         CK(h, cudaHostAlloc(&m.h_files, mx * sizeof(CdcFile), cudaHostAllocDefault));
         CK(h, cudaHostAlloc(&m.h_rstart, mx * 8, cudaHostAllocDefault));
         CK(h, cudaHostAlloc(&m.h_rlen, mx * 8, cudaHostAllocDefault));
+        CK(h, cudaHostAlloc(&m.h_rstream, mx * 4, cudaHostAllocDefault));
+        CK(h, cudaHostAlloc(&m.h_rflags, mx * 4, cudaHostAllocDefault));
         CK(h, cudaMalloc(&m.d_crc, mx * sizeof(CrcExtent)));
         CK(h, cudaMalloc(&m.d_piece_base, (mx + 1) * 4));
         CK(h, cudaMalloc(&m.d_files, mx * sizeof(CdcFile)));
         CK(h, cudaMalloc(&m.d_rstart, mx * 8));
         CK(h, cudaMalloc(&m.d_rlen, mx * 8));
+        CK(h, cudaMalloc(&m.d_rstream, mx * 4));
+        CK(h, cudaMalloc(&m.d_rflags, mx * 4));
         CK(h, cudaEventCreateWithFlags(&m.ev_done, cudaEventDisableTiming));
     }
 
@@ -446,23 +487,17 @@ static int create_impl(mksnap *h)
         const uint64_t n_rows = (c.device_arena_bytes + SLOT_SLACK) / 128;
         for (uint32_t s = 0; s < h->n_slots; s++) {
             int rc;
-            if ((rc = make_row_map(h, enc, &h->tm_main[s][0], h->d_slot[s], n_rows, GearCfg<8, 4>::BOX_ROWS)) ||
-                (rc = make_row_map(h, enc, &h->tm_main[s][1], h->d_slot[s], n_rows, GearCfg<12, 3>::BOX_ROWS)) ||
-                (rc = make_row_map(h, enc, &h->tm_main[s][2], h->d_slot[s], n_rows, GearCfg<16, 2>::BOX_ROWS)) ||
+            if ((rc = make_row_map(h, enc, &h->tm_main[s][0], h->d_slot[s], n_rows, GearCfg<3>::BOX_ROWS)) ||
                 (rc = make_row_map(h, enc, &h->tm_halo[s], h->d_slot[s], n_rows, 1)))
                 return rc;
         }
-        CK(h, cudaFuncSetAttribute(k_gear_scan<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<8, 4>::SMEM));
-        CK(h, cudaFuncSetAttribute(k_gear_scan<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<12, 3>::SMEM));
-        CK(h, cudaFuncSetAttribute(k_gear_scan<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<16, 2>::SMEM));
-        CK(h, cudaFuncSetAttribute(k_gear_scan<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<16, 3>::SMEM));
-        CK(h, cudaFuncSetAttribute(k_gear_scan<20, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<20, 2>::SMEM));
-        CK(h, cudaFuncSetAttribute(k_gear_scan<24, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<24, 2>::SMEM));
-        const char *e = getenv("MKSNAP_GEAR_CFG"); // tuning knob: 0 = 8 warps x 4 stages, 1 = 12x3, 2 = 16x2, 3 = 16x3
+        CK(h, cudaFuncSetAttribute(k_gear_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<2>::SMEM));
+        CK(h, cudaFuncSetAttribute(k_gear_scan<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<3>::SMEM));
         const char *e2 = getenv("MKSNAP_SHA_FMA"); // tuning knob: 0 = plain adds in the chunk SHA-256 kernel
         if (e2 && e2[0] == '0')
             h->sha_fma = false;
-        if (e && e[0] >= '0' && e[0] <= '5') // 4 = 20x2, 5 = 24x2
+        const char *e = getenv("MKSNAP_GEAR_CFG"); // tuning knob: consumer warp groups per CTA (2 or 3, x8 warps)
+        if (e && (e[0] == '2' || e[0] == '3'))
             h->gear_cfg = e[0] - '0';
     }
     // expected candidates = bytes/4096; 32x headroom, plus one private block per resident gear warp (x2)
@@ -483,23 +518,15 @@ static int create_impl(mksnap *h)
     CK(h, cudaMalloc(&h->d_digests, mc * 32));
     h->max_streams = mx;
     CK(h, cudaMalloc(&h->d_stream_digests, h->max_streams * 32));
+    CK(h, cudaMalloc(&h->d_stream_state, h->max_streams * sizeof(StreamState)));
+    CK(h, cudaMemset(h->d_stream_state, 0, h->max_streams * sizeof(StreamState)));
+    h->stream_open.assign(h->max_streams, 0);
 
-    h->table_cap = mc;
-    for (int k = 0; k < 2; k++) {
-        CK(h, cudaMalloc(&h->d_keys[k], mc * 8));
-        CK(h, cudaMalloc(&h->d_idx[k], mc * 4));
+    {
+        int rc = alloc_table_buffers(h, mc);
+        if (rc)
+            return rc;
     }
-    CK(h, cudaMalloc(&h->d_sorted, mc * 32));
-    CK(h, cudaMalloc(&h->d_table, mc * 32));
-    CK(h, cudaMalloc(&h->d_flags, mc * 4));
-    CK(h, cudaMalloc(&h->d_pos, mc * 4));
-    const uint64_t hist_words = 256ull * ((mc + SORT_TILE - 1) / SORT_TILE + 1);
-    CK(h, cudaMalloc(&h->d_hist, hist_words * 4));
-    const uint64_t merkle_rows = mc / 256 + 2;
-    CK(h, cudaMalloc(&h->d_merkle[0], merkle_rows * 32));
-    CK(h, cudaMalloc(&h->d_merkle[1], (merkle_rows / 256 + 2) * 32));
-    h->scan_tmp_words = std::max(mc, std::max(hist_words, mx)) / SCAN_ITEMS * 2 + 4096;
-    CK(h, cudaMalloc(&h->d_scan_tmp, h->scan_tmp_words * 4));
 
     for (int i = 0; i < N_EV; i++)
         CK(h, cudaEventCreate(&h->ev[i]));
@@ -572,7 +599,8 @@ void mksnap_destroy(mksnap_t *h)
     }
     for (auto &m : h->meta) {
         cudaFreeHost(m.h_crc); cudaFreeHost(m.h_piece_base); cudaFreeHost(m.h_files);
-        cudaFreeHost(m.h_rstart); cudaFreeHost(m.h_rlen);
+        cudaFreeHost(m.h_rstart); cudaFreeHost(m.h_rlen); cudaFreeHost(m.h_rstream); cudaFreeHost(m.h_rflags);
+        cudaFree(m.d_rstream); cudaFree(m.d_rflags);
         cudaFree(m.d_crc); cudaFree(m.d_piece_base); cudaFree(m.d_files); cudaFree(m.d_rstart); cudaFree(m.d_rlen);
         if (m.ev_done)
             cudaEventDestroy(m.ev_done);
@@ -581,7 +609,7 @@ void mksnap_destroy(mksnap_t *h)
     cudaFree(h->d_tiles); cudaFree(h->d_pool); cudaFree(h->d_pool_count); cudaFree(h->d_counts); cudaFree(h->d_bases);
     cudaFree(h->d_scan_tmp);
     cudaFree(h->d_chunk_start); cudaFree(h->d_chunk_len); cudaFree(h->d_chunk_end); cudaFree(h->d_digests);
-    cudaFree(h->d_stream_digests);
+    cudaFree(h->d_stream_digests); cudaFree(h->d_stream_state);
     for (int k = 0; k < 2; k++) {
         cudaFree(h->d_keys[k]); cudaFree(h->d_idx[k]); cudaFree(h->d_merkle[k]);
     }
@@ -599,6 +627,8 @@ int mksnap_begin(mksnap_t *h)
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaStreamSynchronize(h->s_comp));
     CK(h, cudaMemsetAsync(h->d_sc, 0, sizeof(SessionCounters), h->s_comp));
+    CK(h, cudaMemsetAsync(h->d_stream_state, 0, h->max_streams * sizeof(StreamState), h->s_comp));
+    std::fill(h->stream_open.begin(), h->stream_open.end(), 0);
     h->n_streams = 0;
     h->stream_base = 0;
     h->crc_bytes = 0;
@@ -646,8 +676,6 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     if (n_ext > h->cfg.max_extents || n_rng > h->cfg.max_extents)
         return fail(h, MKSNAP_E_CAPACITY, "too many extents/ranges (%llu/%llu > %llu)", (unsigned long long)n_ext,
                     (unsigned long long)n_rng, (unsigned long long)h->cfg.max_extents);
-    if (h->n_streams + n_rng > h->max_streams)
-        return fail(h, MKSNAP_E_CAPACITY, "too many streams in session");
 
     MetaSet &m = h->meta[h->submit_idx % h->meta.size()];
     if (m.in_flight) {
@@ -681,8 +709,20 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     for (uint64_t i = 0; i < n_rng; i++) {
         if ((rng[i].arena_off & 15) || rng[i].arena_off > used || rng[i].len > used - rng[i].arena_off)
             return fail(h, MKSNAP_E_INVAL, "range %llu out of bounds or not 16-byte aligned", (unsigned long long)i);
+        if (rng[i].stream >= h->max_streams)
+            return fail(h, MKSNAP_E_CAPACITY, "range %llu: stream slot %u >= %llu", (unsigned long long)i, rng[i].stream,
+                        (unsigned long long)h->max_streams);
+        if ((rng[i].flags & MKSNAP_R_MORE) && (rng[i].len == 0 || rng[i].len % 64))
+            return fail(h, MKSNAP_E_INVAL, "range %llu: a piece with MKSNAP_R_MORE must be a non-empty multiple of 64 bytes",
+                        (unsigned long long)i);
+        for (uint64_t j = 0; j < i; j++)
+            if (rng[j].stream == rng[i].stream)
+                return fail(h, MKSNAP_E_INVAL, "ranges %llu and %llu: one piece per stream per submit", (unsigned long long)j,
+                            (unsigned long long)i);
         m.h_rstart[i] = rng[i].arena_off;
         m.h_rlen[i] = rng[i].len;
+        m.h_rstream[i] = rng[i].stream;
+        m.h_rflags[i] = rng[i].flags;
     }
 
     uint8_t *d_arena = h->d_slot[slot];
@@ -713,6 +753,8 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     if (n_rng) {
         CK(h, cudaMemcpyAsync(m.d_rstart, m.h_rstart, n_rng * 8, cudaMemcpyHostToDevice, sc));
         CK(h, cudaMemcpyAsync(m.d_rlen, m.h_rlen, n_rng * 8, cudaMemcpyHostToDevice, sc));
+        CK(h, cudaMemcpyAsync(m.d_rstream, m.h_rstream, n_rng * 4, cudaMemcpyHostToDevice, sc));
+        CK(h, cudaMemcpyAsync(m.d_rflags, m.h_rflags, n_rng * 4, cudaMemcpyHostToDevice, sc));
     }
     h->stats.h2d_bytes += n_crc * sizeof(CrcExtent) + (n_crc ? (n_crc + 1) * 4 : 0) + n_files * sizeof(CdcFile) + n_rng * 16;
     CK(h, cudaEventRecord(h->ev_copy_done, sc));
@@ -730,12 +772,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     if (n_files) {
         const uint32_t n_regions = (uint32_t)((used + GEAR_TILE - 1) / GEAR_TILE);
         CK(h, cudaMemsetAsync(h->d_pool_count, 0, 4, sk));
-        int rc = h->gear_cfg == 0   ? launch_gear<8, 4>(h, slot, 0, n_regions, sk)
-                 : h->gear_cfg == 1 ? launch_gear<12, 3>(h, slot, 1, n_regions, sk)
-                 : h->gear_cfg == 2 ? launch_gear<16, 2>(h, slot, 2, n_regions, sk)
-                 : h->gear_cfg == 3 ? launch_gear<16, 3>(h, slot, 2, n_regions, sk)
-                 : h->gear_cfg == 4 ? launch_gear<20, 2>(h, slot, 2, n_regions, sk)
-                                    : launch_gear<24, 2>(h, slot, 2, n_regions, sk);
+        int rc = h->gear_cfg == 2 ? launch_gear<2>(h, slot, n_regions, sk) : launch_gear<3>(h, slot, n_regions, sk);
         if (rc)
             return rc;
     }
@@ -760,11 +797,13 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         if (h->sha_fma)
             k_sha256_ranges<true><<<sha_grid(h), SHA_THREADS, 0, sk>>>(d_arena, h->d_chunk_start, h->d_chunk_len,
                                                                       &h->d_sc->batch_chunks, 0, &h->d_sc->n_chunks, 0, 0,
-                                                                      0, h->d_digests, &h->d_sc->work, &h->d_sc->err, 1u);
+                                                                      0, h->d_digests, &h->d_sc->work, &h->d_sc->err, 1u, nullptr, nullptr,
+                                                                      nullptr);
         else
             k_sha256_ranges<false><<<sha_grid(h), SHA_THREADS, 0, sk>>>(d_arena, h->d_chunk_start, h->d_chunk_len,
                                                                        &h->d_sc->batch_chunks, 0, &h->d_sc->n_chunks, 0,
-                                                                       0, 0, h->d_digests, &h->d_sc->work, &h->d_sc->err, 1u);
+                                                                       0, 0, h->d_digests, &h->d_sc->work, &h->d_sc->err, 1u, nullptr, nullptr,
+                                                                      nullptr);
         LAUNCH_OK(h);
         k_batch_end<<<1, 32, 0, sk>>>(h->d_sc);
         LAUNCH_OK(h);
@@ -773,8 +812,8 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     if (n_rng) {
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, sk));
         k_sha256_ranges<false><<<(uint32_t)std::min<uint64_t>(sha_grid(h), (n_rng + 3) / 4), SHA_THREADS, 0, sk>>>(
-            d_arena, m.d_rstart, m.d_rlen, nullptr, n_rng, nullptr, 0, 0, 0, h->d_stream_digests + h->n_streams * 32,
-            &h->d_sc->work, nullptr, 1u);
+            d_arena, m.d_rstart, m.d_rlen, nullptr, n_rng, nullptr, 0, 0, 0, h->d_stream_digests, &h->d_sc->work, nullptr,
+            1u, m.d_rstream, m.d_rflags, h->d_stream_state);
         LAUNCH_OK(h);
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, sk));
     }
@@ -784,7 +823,9 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     m.in_flight = true;
     h->slot_used[slot] = true;
     h->have_submit_times = true;
-    h->n_streams += n_rng;
+    for (uint64_t i = 0; i < n_rng; i++)
+        if (!(rng[i].flags & MKSNAP_R_MORE))
+            h->n_streams = std::max<uint64_t>(h->n_streams, (uint64_t)rng[i].stream + 1);
     h->stream_base += used;
     h->crc_bytes += crc_bytes;
     h->submit_idx++;
@@ -892,6 +933,8 @@ int mksnap_finish(mksnap_t *h, mksnap_result *out)
     h->stats.d2h_bytes += sizeof(SessionCounters);
     if (h->h_sc->err & 1u)
         return fail(h, MKSNAP_E_CAPACITY, "gear candidate pool overflow (capacity %u entries): pathologically dense candidates", h->pool_cap);
+    if (h->h_sc->err & 4u)
+        return fail(h, MKSNAP_E_CUDA, "k_gear_scan: dynamic shared memory does not start where the layout plan assumes");
     if (h->h_sc->err & 2u)
         return fail(h, MKSNAP_E_CAPACITY, "chunk table overflow (max_chunks = %llu)", (unsigned long long)h->max_chunks);
     const uint64_t n = h->h_sc->n_chunks;
@@ -1065,6 +1108,12 @@ int mksnap_comm_init(mksnap_t *h, const uint8_t id[128], int32_t n_ranks, int32_
         return fail(h, MKSNAP_E_NCCL, "ncclCommInitRank: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(r) : "?");
     h->n_ranks = n_ranks;
     h->rank = rank;
+    if (n_ranks > 1) { // the merged table can hold every rank's rows
+        CK(h, cudaStreamSynchronize(h->s_comp));
+        int rc2 = alloc_table_buffers(h, h->max_chunks * (uint64_t)n_ranks);
+        if (rc2)
+            return rc2;
+    }
     CK(h, cudaMalloc(&h->d_gcount, (size_t)n_ranks * GH_WORDS * sizeof(unsigned long long)));
     return 0;
 }

@@ -318,12 +318,18 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
 }
 
 // roll 4 bytes of `word` into h, keeping every intermediate state in hv[k0..k0+3]
+// address of G[byte K of word] for this lane: one PRMT -> {G.b3, G.b2, word.bK, G.b0}
+template <int K> __device__ __forceinline__ uint32_t gear_addr(uint32_t word, uint32_t G)
+{
+    return __byte_perm(word, G, 0x7604 + (K << 4));
+}
+
 #define MK_GEAR_BYTES(word, k0)                                     \
     {                                                               \
-        const uint32_t g0 = lds_u32(tab_addr(G, byte_of<0>(word))); \
-        const uint32_t g1 = lds_u32(tab_addr(G, byte_of<1>(word))); \
-        const uint32_t g2 = lds_u32(tab_addr(G, byte_of<2>(word))); \
-        const uint32_t g3 = lds_u32(tab_addr(G, byte_of<3>(word))); \
+        const uint32_t g0 = lds_u32(gear_addr<0>(word, G));         \
+        const uint32_t g1 = lds_u32(gear_addr<1>(word, G));         \
+        const uint32_t g2 = lds_u32(gear_addr<2>(word, G));         \
+        const uint32_t g3 = lds_u32(gear_addr<3>(word, G));         \
         h = fma_2a_plus_b(h, g0);                                   \
         hv[(k0)] = h;                                               \
         h = fma_2a_plus_b(h, g1);                                   \
@@ -334,48 +340,67 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
         hv[(k0) + 3] = h;                                           \
     }
 
-template <int GEAR_WARPS, int GEAR_STAGES> struct GearCfg {
-    static constexpr uint32_t ROWS = GEAR_WARPS * 32;
+// Tiles are 8 warps x 32 rows x 128 B = 32 KiB (one TMA op); GEAR_GROUPS groups of 8 consumer warps take the
+// CTA's tiles round-robin, so the pipeline depth (stages) is independent of how many warps hide latency.
+// Shared-memory plan (ABSOLUTE shared-window addresses; the kernel has no static shared memory, so the dynamic
+// region starts at the architecture's reserved 1 KiB, s0 = 0x400):
+//   [s0, s0 + 3*32 KiB)    stages 0..2
+//   [0x20000, 0x30000)     gear table, 256-byte stride: value v of lane l at 0x20000 + v*256 + l*4.  With the
+//                          table on a 64 KiB boundary ONE PRMT builds a lookup address
+//                          (bytes {lane*4, data byte, 0x02, 0x00}): no multiply/add per lookup.
+//   [0x30000, 0x38000)     stage 3
+//   0x38000 / 0x38400      halo rows (one 128 B row per stage) / mbarriers
+template <int GEAR_GROUPS> struct GearCfg {
+    static constexpr uint32_t STAGES = 4;
+    static constexpr uint32_t TILE_WARPS = 8;
+    static constexpr uint32_t ROWS = TILE_WARPS * 32;
     static constexpr uint32_t TILE_BYTES = ROWS * 128;
-    static constexpr uint32_t BOX_ROWS = ROWS > 256 ? 128 : ROWS; // rows per TMA op (tensor-map box)
-    static constexpr uint32_t THREADS = (GEAR_WARPS + 1) * 32;
-    // shared layout (offsets from a 1024-aligned base)
-    static constexpr uint32_t OFF_TILES = 0;
-    static constexpr uint32_t OFF_HALO = OFF_TILES + GEAR_STAGES * TILE_BYTES;
-    // halo rows: slot s at OFF_HALO + s*128 inside one 1 KiB block; a 128 B box landing at address bits
-    // [7:9] = s is stored with swizzle phase s (chunk c at c ^ s)
-    static constexpr uint32_t OFF_GEAR = OFF_HALO + 1024;
-    static constexpr uint32_t OFF_BARS = OFF_GEAR + 256 * 32 * 4;
-    static constexpr uint32_t SMEM = OFF_BARS + 2 * GEAR_STAGES * 8;
-    static_assert(GEAR_STAGES <= 8, "halo slots share one 1 KiB block");
+    static constexpr uint32_t BOX_ROWS = ROWS;
+    static constexpr uint32_t CONSUMER_WARPS = GEAR_GROUPS * TILE_WARPS;
+    static constexpr uint32_t THREADS = (CONSUMER_WARPS + 1) * 32;
+    static constexpr uint32_t GEAR_ABS = 0x20000;
+    static constexpr uint32_t STAGE3_ABS = 0x30000;
+    static constexpr uint32_t HALO_ABS = 0x38000;
+    static constexpr uint32_t BARS_ABS = 0x38400;
+    static constexpr uint32_t END_ABS = BARS_ABS + 2 * STAGES * 8;
+    static constexpr uint32_t SMEM = END_ABS - 1024; // dynamic bytes to request when the region starts at 0x400
+    static_assert(END_ABS <= 227 * 1024 + 1024, "exceeds the 227 KiB per-CTA limit");
+    __device__ static uint32_t stage_addr(uint32_t s0, uint32_t s) { return s < 3 ? s0 + s * TILE_BYTES : STAGE3_ABS; }
 };
 
-template <int GEAR_WARPS, int GEAR_STAGES>
-__global__ void __launch_bounds__((GEAR_WARPS + 1) * 32, 1)
+template <int GEAR_GROUPS>
+__global__ void __launch_bounds__((GEAR_GROUPS * 8 + 1) * 32, 1)
 k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
             uint32_t n_tiles, const uint32_t *__restrict__ gear, uint32_t strict_lim, uint32_t loose_lim,
             TileRec *__restrict__ tiles, uint32_t *__restrict__ pool, uint32_t pool_cap,
             uint32_t *__restrict__ pool_count, uint32_t *__restrict__ err_flag)
 {
-    using Cfg = GearCfg<GEAR_WARPS, GEAR_STAGES>;
+    using Cfg = GearCfg<GEAR_GROUPS>;
+    constexpr uint32_t GEAR_STAGES = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t s0 = smem_u32(smem_raw); // stages 0..2 live at the start of the dynamic region
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t bar_full = sbase + Cfg::OFF_BARS, bar_empty = bar_full + GEAR_STAGES * 8;
+    const uint32_t bar_full = Cfg::BARS_ABS, bar_empty = bar_full + GEAR_STAGES * 8;
+    const uint32_t halo_abs = Cfg::HALO_ABS;
+    if (s0 + 3 * Cfg::TILE_BYTES > Cfg::GEAR_ABS || (s0 & 1023u)) { // layout assumption violated: fail loudly
+        if (threadIdx.x == 0)
+            atomicExch(err_flag, 4u);
+        return;
+    }
 
-    // lane-replicated gear table: value v of lane l at OFF_GEAR + v*128 + l*4
+    // lane-replicated gear table, 256-byte stride: value v of lane l at GEAR_ABS + v*256 + l*4
     for (uint32_t i = threadIdx.x; i < 256u * 32u; i += blockDim.x)
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(sbase + Cfg::OFF_GEAR + i * 4u), "r"(__ldg(gear + (i >> 5))));
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(Cfg::GEAR_ABS + (i >> 5) * 256u + (i & 31u) * 4u), "r"(__ldg(gear + (i >> 5))));
     if (threadIdx.x == 0) {
         for (int s = 0; s < GEAR_STAGES; ++s) {
             mbar_init(bar_full + s * 8, 1);
-            mbar_init(bar_empty + s * 8, GEAR_WARPS);
+            mbar_init(bar_empty + s * 8, Cfg::TILE_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == GEAR_WARPS) {
+    if (warp == Cfg::CONSUMER_WARPS) {
         // ------------------------- TMA producer -------------------------
         if (lane == 0) {
             uint32_t it = 0;
@@ -387,36 +412,41 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
                 const int32_t row0 = (int32_t)(tile * Cfg::ROWS);
 #pragma unroll
                 for (uint32_t b = 0; b < Cfg::ROWS / Cfg::BOX_ROWS; ++b)
-                    tma_load_2d(sbase + Cfg::OFF_TILES + s * Cfg::TILE_BYTES + b * Cfg::BOX_ROWS * 128u, &tm_main, 0,
+                    tma_load_2d(Cfg::stage_addr(s0, s) + b * Cfg::BOX_ROWS * 128u, &tm_main, 0,
                                 row0 + (int32_t)(b * Cfg::BOX_ROWS), bar_full + s * 8);
-                tma_load_2d(sbase + Cfg::OFF_HALO + s * 128u, &tm_halo, 0, row0 - 1, bar_full + s * 8);
+                tma_load_2d(halo_abs + s * 128u, &tm_halo, 0, row0 - 1, bar_full + s * 8);
             }
         }
         return;
     }
 
     // ----------------------------- consumers -----------------------------
-    const uint32_t G = sbase + Cfg::OFF_GEAR + lane * 4u;
-    const uint32_t row = warp * 32u + lane;
+    const uint32_t G = Cfg::GEAR_ABS + lane * 4u; // bytes {lane*4, 0x00, 0x02, 0x00}
+    const uint32_t group = warp / Cfg::TILE_WARPS, wt = warp % Cfg::TILE_WARPS; // wt = warp within the tile
+    const uint32_t row = wt * 32u + lane;
     const uint32_t swz = (row & 7u) << 4;
-    uint32_t it = 0;
     uint32_t blk_next = 0, blk_end = 0; // this warp's private slice of the pool (warp-uniform)
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    // CTA-local tile sequence it = 0,1,2,... (global tile = blockIdx.x + it*gridDim.x); group g takes it = g (mod GROUPS)
+    for (uint32_t it = group;; it += GEAR_GROUPS) {
+        const uint64_t tile64 = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
+        if (tile64 >= n_tiles)
+            break;
+        const uint32_t tile = (uint32_t)tile64;
         const uint32_t s = it % GEAR_STAGES;
-        const uint32_t sb = sbase + Cfg::OFF_TILES + s * Cfg::TILE_BYTES;
+        const uint32_t sb = Cfg::stage_addr(s0, s);
         mbar_wait(bar_full + s * 8, (it / GEAR_STAGES) & 1u);
 
         // carry into lane 0: hash of the 32 bytes before the warp's first row, one byte per lane
         uint32_t a_warp;
         {
             uint32_t addr;
-            if (warp == 0) {
-                addr = sbase + Cfg::OFF_HALO + s * 128u + (((6u + (lane >> 4)) ^ s) << 4) + (lane & 15u);
+            if (wt == 0) {
+                addr = halo_abs + s * 128u + (((6u + (lane >> 4)) ^ s) << 4) + (lane & 15u);
             } else {
-                const uint32_t pr = warp * 32u - 1u; // previous row, chunks 6 and 7
+                const uint32_t pr = wt * 32u - 1u; // previous row, chunks 6 and 7
                 addr = sb + pr * 128u + (((6u + (lane >> 4)) ^ (pr & 7u)) << 4) + (lane & 15u);
             }
-            uint32_t v = lds_u32(tab_addr(G, lds_u8(addr))) << (31u - lane);
+            uint32_t v = lds_u32(gear_addr<0>(lds_u8(addr), G)) << (31u - lane);
 #pragma unroll
             for (int sft = 16; sft; sft >>= 1)
                 v += __shfl_xor_sync(0xFFFFFFFFu, v, sft);
@@ -531,7 +561,7 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
             TileRec tr;
             tr.base = base;
             tr.count = base == 0xFFFFFFFFu ? 0u : total;
-            tiles[(size_t)tile * GEAR_WARPS + warp] = tr;
+            tiles[(size_t)tile * Cfg::TILE_WARPS + wt] = tr;
         }
         if (total) {
             if (base != 0xFFFFFFFFu && cnt) {
@@ -684,6 +714,17 @@ template <bool FMA_ADDS> __device__ __forceinline__ uint32_t sha_add(uint32_t a,
     return FMA_ADDS ? fma_add_rt(a, b, one) : a + b;
 }
 
+// x + K (round constant): IMAD(one, K, x) keeps this add off the ALU pipe as well; after unrolling K is an
+// immediate operand of the IMAD.
+template <bool FMA_ADDS> __device__ __forceinline__ uint32_t sha_addk(uint32_t x, uint32_t k, uint32_t one)
+{
+    if (!FMA_ADDS)
+        return x + k;
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(one), "r"(k), "r"(x));
+    return d;
+}
+
 template <bool FMA_ADDS>
 __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], const uint32_t one)
 {
@@ -723,6 +764,14 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], 
 
 constexpr int SHA_THREADS = 128;
 
+// midstate of a serial stream that continues in a later submit
+struct StreamState {
+    uint32_t st[8];
+    unsigned long long bytes; // bytes compressed so far (multiple of 64)
+    uint32_t open;            // 1 = a piece with MKSNAP_R_MORE was seen and the stream is not finished
+    uint32_t pad;
+};
+
 // mode 0: ranges from (start[], len[]) arrays, count read from *n_dev (or n_host if n_dev==nullptr)
 // mode 1: uniform ranges of `uni_len` bytes over [0, uni_total) of `data` (Merkle levels)
 template <bool FMA_ADDS>
@@ -731,7 +780,9 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
                 const uint64_t *__restrict__ len, const uint32_t *__restrict__ n_dev, uint64_t n_host,
                 const unsigned long long *__restrict__ first_dev, uint64_t first_host, /* index of range 0 in start/len/out */
                 uint64_t uni_len, uint64_t uni_total, uint8_t *__restrict__ out,
-                uint32_t *__restrict__ work_counter, const uint32_t *__restrict__ skip_if_err, const uint32_t one)
+                uint32_t *__restrict__ work_counter, const uint32_t *__restrict__ skip_if_err, const uint32_t one,
+                const uint32_t *__restrict__ rng_stream, const uint32_t *__restrict__ rng_flags,
+                StreamState *__restrict__ sstate)
 {
     if (skip_if_err && *skip_if_err)
         return;
@@ -743,7 +794,9 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
     const uint8_t *p = nullptr; // next block to read
     uint64_t total = 0;         // range length
     uint64_t done = 0;          // bytes already compressed
-    uint64_t my = 0;            // range index
+    uint64_t my = 0;            // range index (row of `out`; the stream slot in stream mode)
+    uint64_t prior = 0;         // bytes of this stream compressed in earlier pieces
+    bool more = false;          // this piece is not the last of its stream
     uint32_t phase = 0;         // 0 idle, 1 data blocks, 2 needs extra length block
     bool exhausted = false;
     uint4 pf[5];                // next block's aligned 80-byte window, loaded while this block compresses
@@ -776,8 +829,21 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
                     done = 0;
                     phase = 1;
                     pf_ok = false;
+                    prior = 0;
+                    more = false;
                     st[0] = 0x6a09e667; st[1] = 0xbb67ae85; st[2] = 0x3c6ef372; st[3] = 0xa54ff53a;
                     st[4] = 0x510e527f; st[5] = 0x9b05688c; st[6] = 0x1f83d9ab; st[7] = 0x5be0cd19;
+                    if (rng_stream) { // serial stream piece: resume the saved midstate, digest row = stream slot
+                        const uint32_t sid = rng_stream[my];
+                        more = (rng_flags[my] & 1u) != 0;
+                        my = sid;
+                        if (sstate[sid].open) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                st[k] = sstate[sid].st[k];
+                            prior = sstate[sid].bytes;
+                        }
+                    }
                 } else {
                     exhausted = true;
                 }
@@ -795,8 +861,8 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
 #pragma unroll
             for (int i = 0; i < 14; ++i)
                 w[i] = 0;
-            w[14] = (uint32_t)((total * 8) >> 32);
-            w[15] = (uint32_t)(total * 8);
+            w[14] = (uint32_t)(((prior + total) * 8) >> 32);
+            w[15] = (uint32_t)((prior + total) * 8);
             last = true;
         } else {
             // aligned 80-byte window covering [p, p+64)
@@ -851,8 +917,8 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
                     w[i] = v;
                 }
                 if (rb < 56) {
-                    w[14] = (uint32_t)((total * 8) >> 32);
-                    w[15] = (uint32_t)(total * 8);
+                    w[14] = (uint32_t)(((prior + total) * 8) >> 32);
+                    w[15] = (uint32_t)((prior + total) * 8);
                     last = true;
                 } else {
                     phase = 2;
@@ -869,10 +935,20 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
             uint4 *dst = reinterpret_cast<uint4 *>(out + my * 32);
             dst[0] = o0;
             dst[1] = o1;
+            if (rng_stream)
+                sstate[my].open = 0;
             phase = 0;
         } else if (phase == 1) {
             p += 64;
             done += 64;
+            if (more && done == total) { // piece boundary (length is a multiple of 64): park the midstate
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    sstate[my].st[k] = st[k];
+                sstate[my].bytes = prior + total;
+                sstate[my].open = 1;
+                phase = 0;
+            }
         }
     }
 }

@@ -1046,18 +1046,38 @@ int mkhost_commit_copy_ops(mksnap_t *eng, const char *root_dir, int64_t now_unix
         void *hp = nullptr;
         uint64_t cap = 0;
         int32_t aid = -1;
-        ck(eng, mksnap_arena_acquire(eng, &hp, &cap, &aid), "arena acquire");
-        uint8_t *a = (uint8_t *)hp;
-        uint64_t pos = 0;
+        uint8_t *a = nullptr;
+        uint64_t pos = 0, tar_bytes = 0;
         std::vector<mksnap_extent> ext;
         std::vector<ReadJob> jobs;
+        auto acquire = [&]() {
+            ck(eng, mksnap_arena_acquire(eng, &hp, &cap, &aid), "arena acquire");
+            a = (uint8_t *)hp;
+            pos = 0;
+            ext.clear();
+            jobs.clear();
+        };
+        // The arena is the tar stream.  A layer larger than one arena goes out in pieces (multiples of 512
+        // bytes, so of 64): stream 0 continues across submits, the device keeps the SHA-256 midstate.
+        auto flush = [&](bool last) {
+            run_reads(jobs, n_threads);
+            mksnap_range rng{0, pos, 0, last ? 0u : MKSNAP_R_MORE};
+            ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), &rng, 1), "arena submit");
+            tar_bytes += pos;
+            if (!last)
+                acquire();
+        };
+        acquire();
         for (const auto &kv : layer) { // commitLayer: alphabetical order of absolute dst (mem_fs.go:424-433)
             const MemFile &mf = kv.second;
             const std::string hb = encode_header(mf.hdr);
             const uint64_t body = (mf.hdr.typeflag == '0') ? (uint64_t)mf.hdr.size : 0;
             const uint64_t need = hb.size() + align_up(body, 512);
-            if (pos + need + 1024 > cap)
-                throw HostError("write diffs: layer tar exceeds the arena (" + std::to_string(cap) + " bytes)");
+            if (need > cap)
+                throw HostError("write diffs: entry " + mf.dst + " (" + std::to_string(need) +
+                                " bytes) exceeds the arena; a file is chunked within one arena");
+            if (pos + need > cap)
+                flush(false);
             memcpy(a + pos, hb.data(), hb.size());
             pos += hb.size();
             if (body) {
@@ -1068,11 +1088,12 @@ int mkhost_commit_copy_ops(mksnap_t *eng, const char *root_dir, int64_t now_unix
                 pos += padded;
             }
         }
+        if (pos + 1024 > cap)
+            flush(false);
         memset(a + pos, 0, 1024); // tar.Writer.Close: two zero blocks
         pos += 1024;
-        run_reads(jobs, n_threads);
-        mksnap_range rng{0, pos};
-        ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), &rng, 1), "arena submit");
+        flush(true);
+        pos = tar_bytes;
         mksnap_result res;
         ck(eng, mksnap_finish(eng, &res), "finish");
         ck(eng, mksnap_get_stream_digests(eng, out->tar_digest, 1), "stream digests");

@@ -69,6 +69,10 @@ def test_commit_layer_tar_digest_and_chunk_table(ctx, tmp_path):
     os.chmod(root, 0o755)
     with Engine(device=0, device_arena_bytes=64 << 20, n_host_arenas=1, host_arena_bytes=64 << 20, max_extents=1 << 14) as eng:
         got = host.commit_copy_ops(eng, str(root), NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 3, 4)])
+    # same layer through 12 MiB arenas: the tar stream continues across submits (SHA-256 midstate on the device)
+    with Engine(device=0, device_arena_bytes=12 << 20, n_host_arenas=2, host_arena_bytes=12 << 20, max_extents=1 << 14) as eng:
+        got2 = host.commit_copy_ops(eng, str(root), NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 3, 4)])
+    assert got2 == got
     fs = lt.MemFS(lambda: NOW, str(root))
     entries = fs.add_layer_by_copy_ops([lt.CopyOperation.new(["/"], ctx, "/", "/app/", uid=3, gid=4)])
     blob = b"".join(lt.layer_tar_chunks(entries))

@@ -165,3 +165,39 @@ def test_synth_fill_matches_oracle(eng, oracle_lib):
     got = eng.device_download(0, 4096, 1 << 20)
     np.testing.assert_array_equal(got, oracle_lib.synth_fill(4096, 1 << 20, 0xC2))
     eng.finish()
+
+
+def test_sha256_stream_continues_across_submits(eng):
+    """One serial stream fed in three pieces over three submits (MKSNAP_R_MORE), next to an unrelated one-shot
+    stream: the midstate survives between submits (a layer tar larger than one arena)."""
+    from makisu_b200.abi import Range, MKSNAP_R_MORE
+    rng = np.random.default_rng(31)
+    data = _rand(rng, 3 * 65536 + 4096 + 77)
+    other = _rand(rng, 1000)
+    cuts = [0, 65536, 65536 + 128 * 1024, data.size]
+    eng.begin()
+    for i in range(3):
+        piece = data[cuts[i]:cuts[i + 1]]
+        arena, offs = pack([piece, other])
+        eng.device_upload(0, 0, arena)
+        r = Range()
+        r.arena_off, r.len, r.stream, r.flags = offs[0], piece.size, 5, (MKSNAP_R_MORE if i < 2 else 0)
+        rs = [r]
+        if i == 1:
+            r2 = Range()
+            r2.arena_off, r2.len, r2.stream, r2.flags = offs[1], other.size, 2, 0
+            rs.append(r2)
+        eng.device_submit(0, arena.size, [], rs)
+    res = eng.finish()
+    assert res.n_streams == 6
+    got = eng.get_stream_digests(6)
+    assert got[5].tobytes() == hashlib.sha256(data.tobytes()).digest()
+    assert got[2].tobytes() == hashlib.sha256(other.tobytes()).digest()
+    # misuse is rejected loudly
+    from makisu_b200.abi import MksnapError
+    eng.begin()
+    bad = Range()
+    bad.arena_off, bad.len, bad.stream, bad.flags = 0, 100, 0, MKSNAP_R_MORE
+    with pytest.raises(MksnapError):
+        eng.device_submit(0, 4096, [], [bad])
+    eng.finish()

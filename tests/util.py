@@ -49,8 +49,8 @@ def cdc_extents(offs, lens):
 
 def ranges(offs, lens):
     out = []
-    for o, l in zip(offs, lens):
+    for i, (o, l) in enumerate(zip(offs, lens)):
         r = Range()
-        r.arena_off, r.len = o, l
+        r.arena_off, r.len, r.stream, r.flags = o, l, i, 0
         out.append(r)
     return out
