@@ -399,3 +399,99 @@ void mko_synth_fill(uint8_t *dst, uint64_t byte_off, uint64_t n, uint64_t seed)
         memcpy(dst + 8 * i, &v, 8);
     }
 }
+
+/* ======================================================================= */
+/* SHA-256 with the x86 SHA extensions (baseline timing only)              */
+/* ======================================================================= */
+/* The reference's Go 1.14 crypto/sha256 uses hand-written AVX2 assembly on amd64; a scalar C loop would
+ * understate the CPU baseline.  This path (SHA-NI, the fastest single-thread SHA-256 this host offers) is used
+ * by bench.py's cpu_baseline / --impl reference when the CPU has it; tests check it against the scalar code. */
+#if defined(__x86_64__)
+#include <cpuid.h>
+#include <immintrin.h>
+
+int mko_have_sha_ni(void)
+{
+    unsigned a, b, c, d;
+    if (!__get_cpuid_count(7, 0, &a, &b, &c, &d))
+        return 0;
+    return (b >> 29) & 1; /* CPUID.7.0:EBX.SHA */
+}
+
+__attribute__((target("sha,sse4.1,ssse3"))) static void sha256_blocks_ni(uint32_t st[8], const uint8_t *p, size_t nblk)
+{
+    const __m128i MASK = _mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL);
+    __m128i TMP = _mm_loadu_si128((const __m128i *)&st[0]);
+    __m128i STATE1 = _mm_loadu_si128((const __m128i *)&st[4]);
+    TMP = _mm_shuffle_epi32(TMP, 0xB1);          /* CDAB */
+    STATE1 = _mm_shuffle_epi32(STATE1, 0x1B);    /* EFGH */
+    __m128i STATE0 = _mm_alignr_epi8(TMP, STATE1, 8); /* ABEF */
+    STATE1 = _mm_blend_epi16(STATE1, TMP, 0xF0);      /* CDGH */
+    while (nblk--) {
+        const __m128i S0 = STATE0, S1 = STATE1;
+        __m128i M[4], MSG;
+        for (int i = 0; i < 4; i++)
+            M[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(p + 16 * i)), MASK);
+        for (int r = 0; r < 16; r++) {
+            MSG = _mm_add_epi32(M[r & 3], _mm_loadu_si128((const __m128i *)&SHA_K[4 * r]));
+            STATE1 = _mm_sha256rnds2_epu32(STATE1, STATE0, MSG);
+            if (r >= 3 && r < 15) { /* schedule words 16+4(r-3) .. : W[t] for the group used at round r+1 */
+                __m128i t = _mm_alignr_epi8(M[r & 3], M[(r + 3) & 3], 4);
+                M[(r + 1) & 3] = _mm_sha256msg2_epu32(_mm_add_epi32(M[(r + 1) & 3], t), M[r & 3]);
+            }
+            MSG = _mm_shuffle_epi32(MSG, 0x0E);
+            STATE0 = _mm_sha256rnds2_epu32(STATE0, STATE1, MSG);
+            if (r >= 1 && r < 13)
+                M[(r + 3) & 3] = _mm_sha256msg1_epu32(M[(r + 3) & 3], M[r & 3]);
+        }
+        STATE0 = _mm_add_epi32(STATE0, S0);
+        STATE1 = _mm_add_epi32(STATE1, S1);
+        p += 64;
+    }
+    TMP = _mm_shuffle_epi32(STATE0, 0x1B);       /* FEBA */
+    STATE1 = _mm_shuffle_epi32(STATE1, 0xB1);    /* DCHG */
+    STATE0 = _mm_blend_epi16(TMP, STATE1, 0xF0); /* DCBA */
+    STATE1 = _mm_alignr_epi8(STATE1, TMP, 8);    /* ABEF -> HGFE */
+    _mm_storeu_si128((__m128i *)&st[0], STATE0);
+    _mm_storeu_si128((__m128i *)&st[4], STATE1);
+}
+#else
+int mko_have_sha_ni(void) { return 0; }
+#endif
+
+/* streaming update that uses SHA-NI for whole blocks when available (same context layout) */
+void mko_sha256_update_fast(mko_sha256_ctx *c, const uint8_t *p, size_t n)
+{
+#if defined(__x86_64__)
+    static int have = -1;
+    if (have < 0)
+        have = mko_have_sha_ni();
+    if (have) {
+        c->nbytes += n;
+        if (c->fill) {
+            size_t take = 64 - c->fill;
+            if (take > n)
+                take = n;
+            memcpy(c->buf + c->fill, p, take);
+            c->fill += (uint32_t)take;
+            p += take;
+            n -= take;
+            if (c->fill < 64)
+                return;
+            sha256_blocks_ni(c->h, c->buf, 1);
+            c->fill = 0;
+        }
+        if (n >= 64) {
+            sha256_blocks_ni(c->h, p, n / 64);
+            p += n / 64 * 64;
+            n %= 64;
+        }
+        if (n) {
+            memcpy(c->buf, p, n);
+            c->fill = (uint32_t)n;
+        }
+        return;
+    }
+#endif
+    mko_sha256_update(c, p, n);
+}

@@ -55,6 +55,9 @@ void mko_sha256_init(mko_sha256_ctx *c);
 void mko_sha256_update(mko_sha256_ctx *c, const uint8_t *p, size_t n);
 void mko_sha256_final(mko_sha256_ctx *c, uint8_t out[32]);
 void mko_sha256(const uint8_t *p, size_t n, uint8_t out[32]);
+/* baseline timing: SHA-NI for whole blocks when the CPU has it (else identical to mko_sha256_update) */
+int mko_have_sha_ni(void);
+void mko_sha256_update_fast(mko_sha256_ctx *c, const uint8_t *p, size_t n);
 
 /* ---- Gear-32 content-defined chunking ------------------ */
 typedef struct {

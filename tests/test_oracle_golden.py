@@ -212,3 +212,25 @@ def test_cdc_cut_rule_bruteforce():
         prev = cut
     assert [int(x) for x in olib.cdc_cuts(d)] == ends
     assert olib.L().mko_gear_at(d.ctypes.data, 1000) == int(h[1000])
+
+
+def test_sha_ni_baseline_path_matches_scalar():
+    import ctypes
+    L = olib.L()
+    L.mko_sha256_init.argtypes = [ctypes.c_void_p]
+    L.mko_sha256_update_fast.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    L.mko_sha256_final.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(2)
+    for n in [0, 1, 63, 64, 65, 127, 128, 1000, 100003]:
+        d = rng.integers(0, 256, n, dtype=np.uint8)
+        ctx = (ctypes.c_uint8 * 128)()
+        L.mko_sha256_init(ctx)
+        pos = 0
+        for step in [7, 64, 1, 500, 10**6]:
+            k = min(step, n - pos)
+            if k > 0:
+                L.mko_sha256_update_fast(ctx, d.ctypes.data + pos, k)
+                pos += k
+        out = (ctypes.c_uint8 * 32)()
+        L.mko_sha256_final(ctx, out)
+        assert bytes(out) == hashlib.sha256(d.tobytes()).digest() == olib.sha256(d)
