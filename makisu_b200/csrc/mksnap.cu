@@ -500,8 +500,10 @@ static int create_impl(mksnap *h)
         if (e && (e[0] == '2' || e[0] == '3'))
             h->gear_cfg = e[0] - '0';
     }
-    // expected candidates = bytes/4096; 32x headroom, plus one private block per resident gear warp (x2)
-    uint64_t pc = std::max<uint64_t>(1u << 20, c.device_arena_bytes / 128) + 2ull * h->sm_count * 32 * GEAR_POOL_BLOCK;
+    // expected candidates = bytes >> loose_bits; 8x headroom (32x at the default 12 bits would be wasteful for
+    // dense parameter sets), plus one private block per resident gear warp (x2)
+    uint64_t pc = std::max<uint64_t>(1u << 20, (c.device_arena_bytes >> h->cfg.cdc.loose_bits) * 8) +
+                  2ull * h->sm_count * 32 * GEAR_POOL_BLOCK;
     if (pc > 0xFFFFFFF0ull)
         pc = 0xFFFFFFF0ull;
     h->pool_cap = (uint32_t)pc;

@@ -158,3 +158,42 @@ def test_properties_at_2gib(eng, oracle_lib):
     for i in (0, n_files - 1):
         d = eng.device_download(0, i * fb, fb)
         np.testing.assert_array_equal(d, oracle_lib.synth_fill(i * fb, fb, 0xABC))
+
+
+def test_25m_row_table_sort_unique():
+    """Scale test of K3 (radix sort + unique) and the Merkle root: tiny CDC parameters turn 4 GiB of random
+    bytes into > 20 M distinct chunks.  The table must equal numpy's
+    sorted-unique of the chunk digests (bytewise order == big-endian u64 column order)."""
+    from makisu_b200.abi import CdcParams, Engine, MKSNAP_X_CDC
+    p = CdcParams(64, 128, 256, 8, 6)
+    n_files, fb = 4096, 1 << 20
+    with Engine(device=0, device_arena_bytes=4 * GiB, max_extents=8192, max_chunks=40_000_000, cdc=p) as e:
+        e.begin()
+        e.synth_fill(0, 0, n_files * fb, 0x5157)
+        e.device_submit(0, n_files * fb, [_ext(i * fb, fb, 0, MKSNAP_X_CDC) for i in range(n_files)])
+        r = e.finish()
+        assert r.n_chunks > 24_000_000
+        _, d = e.get_chunks(r.n_chunks)
+        k = d.view(">u8").reshape(-1, 4)
+        order = np.lexsort((k[:, 3], k[:, 2], k[:, 1], k[:, 0]))
+        ks = k[order]
+        distinct = 1 + int((ks[1:] != ks[:-1]).any(axis=1).sum())
+        # (a handful of 1-byte file tails share a byte value, so distinct is a few less than n_chunks)
+        assert r.n_chunks - 50 < distinct <= r.n_chunks
+        assert r.n_unique == distinct
+        t = e.get_table(r.n_unique).view(">u8").reshape(-1, 4)
+        np.testing.assert_array_equal(t, ks[np.concatenate([[True], (ks[1:] != ks[:-1]).any(axis=1)])])
+
+
+def test_nccl_gather_world_of_one():
+    """The all-gather/merge path with a 1-rank communicator (runs on a single-GPU box): result == finish()."""
+    from makisu_b200.abi import Engine, MKSNAP_X_CDC, MKSNAP_X_CRC
+    fb = 1 << 20
+    with Engine(device=0, device_arena_bytes=256 << 20, max_extents=4096) as e:
+        e.comm_init(Engine.comm_unique_id(), 1, 0)
+        e.begin()
+        e.synth_fill(0, 0, 200 * fb, 99)
+        e.device_submit(0, 200 * fb, [_ext(i * fb, fb, (199 - i) * fb, MKSNAP_X_CDC | MKSNAP_X_CRC) for i in range(200)])
+        r = e.finish()
+        g = e.allgather_tables()
+        assert (g.n_chunks, g.n_unique, bytes(g.root), e.ctx_crc32(g)) == (r.n_chunks, r.n_unique, bytes(r.root), e.ctx_crc32(r))
