@@ -72,6 +72,12 @@ int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, c
  * file (chunk table).  now_unix = clk.Now() for synthesized ancestors (mem_fs.go:562). */
 int mkhost_commit_copy_ops(mksnap_t *eng, const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops,
                            size_t n_ops, int n_threads, mkhost_layer_result *out, char *err, size_t errlen);
+/* Same, and additionally writes the uncompressed layer tar (the packed arenas, byte for byte what
+ * tar.Writer would have produced) to tar_fd -- the stream the Go side feeds to pgzip (common.go:47-55,
+ * SURVEY section 8f-1).  SHA-256 of those bytes == out->tar_digest. */
+int mkhost_commit_copy_ops_to_fd(mksnap_t *eng, const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops,
+                                 size_t n_ops, int n_threads, int tar_fd, mkhost_layer_result *out, char *err,
+                                 size_t errlen);
 
 /* No-GPU introspection for the CPU tests: one line per item, '\n' separated, NUL terminated.
  *   stream : "P <relpath>" | "L <target>" | "F <size> <abs path>"   in CRC stream order

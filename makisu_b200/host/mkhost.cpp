@@ -1039,6 +1039,13 @@ int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, c
 int mkhost_commit_copy_ops(mksnap_t *eng, const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops,
                            int n_threads, mkhost_layer_result *out, char *err, size_t errlen)
 {
+    return mkhost_commit_copy_ops_to_fd(eng, root_dir, now_unix, ops, n_ops, n_threads, -1, out, err, errlen);
+}
+
+int mkhost_commit_copy_ops_to_fd(mksnap_t *eng, const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops,
+                                 size_t n_ops, int n_threads, int tar_fd, mkhost_layer_result *out, char *err,
+                                 size_t errlen)
+{
     try {
         MemFS fs(root_dir, now_unix);
         auto layer = fs.add_layer_by_copy_ops(ops, n_ops);
@@ -1061,6 +1068,18 @@ int mkhost_commit_copy_ops(mksnap_t *eng, const char *root_dir, int64_t now_unix
         // bytes, so of 64): stream 0 continues across submits, the device keeps the SHA-256 midstate.
         auto flush = [&](bool last) {
             run_reads(jobs, n_threads);
+            if (tar_fd >= 0) { // the arena is the tar stream: hand it on before the arena is recycled
+                uint64_t w = 0;
+                while (w < pos) {
+                    ssize_t r = write(tar_fd, a + w, pos - w);
+                    if (r < 0) {
+                        if (errno == EINTR)
+                            continue;
+                        throw HostError(std::string("write layer tar: ") + strerror(errno));
+                    }
+                    w += (uint64_t)r;
+                }
+            }
             mksnap_range rng{0, pos, 0, last ? 0u : MKSNAP_R_MORE};
             ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), &rng, 1), "arena submit");
             tar_bytes += pos;

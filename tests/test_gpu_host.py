@@ -73,6 +73,19 @@ def test_commit_layer_tar_digest_and_chunk_table(ctx, tmp_path):
     with Engine(device=0, device_arena_bytes=12 << 20, n_host_arenas=2, host_arena_bytes=12 << 20, max_extents=1 << 14) as eng:
         got2 = host.commit_copy_ops(eng, str(root), NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 3, 4)])
     assert got2 == got
+    # and the emitted tar: byte-identical to the reference-order stream, digest == TarDigest, readable by tar
+    import hashlib
+    import tarfile
+    tar_path = tmp_path / "layer.tar"
+    with Engine(device=0, device_arena_bytes=12 << 20, n_host_arenas=2, host_arena_bytes=12 << 20, max_extents=1 << 14) as eng:
+        with open(tar_path, "wb") as f:
+            got3 = host.commit_copy_ops(eng, str(root), NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 3, 4)],
+                                        tar_fd=f.fileno())
+    assert got3 == got
+    data = open(tar_path, "rb").read()
+    assert "sha256:" + hashlib.sha256(data).hexdigest() == got["tar_digest"] and len(data) == got["tar_bytes"]
+    names = [m.name for m in tarfile.open(tar_path).getmembers()]
+    assert names[0] == "app" and "app/big.bin" in names and "app/link" in names
     fs = lt.MemFS(lambda: NOW, str(root))
     entries = fs.add_layer_by_copy_ops([lt.CopyOperation.new(["/"], ctx, "/", "/app/", uid=3, gid=4)])
     blob = b"".join(lt.layer_tar_chunks(entries))

@@ -1,0 +1,95 @@
+"""CPU: randomised agreement between the C++ host side and the oracle (both restate the same reference code
+independently: one in C++, one in Python) -- tar header bytes over fuzzed fields, and stream / layer order over
+random directory trees."""
+import os
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from makisu_b200 import host
+from oracle import ctx_crc, layer_tar as lt
+
+name_chars = st.sampled_from(list("abcXYZ019._-+ ~") + ["é", "ß", "日"])
+segment = st.text(name_chars, min_size=1, max_size=60).filter(lambda s: s not in (".", ".."))
+path = st.lists(segment, min_size=1, max_size=6).map("/".join)
+
+
+@settings(max_examples=300, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(name=path, link=st.one_of(st.just(""), path), mode=st.integers(0, 0o7777), uid=st.integers(0, 1 << 34),
+       gid=st.integers(0, 1 << 22), size=st.integers(0, 1 << 36), mtime=st.integers(0, (1 << 33) - 1),
+       frac=st.integers(0, 999_999_999), kind=st.sampled_from([b"0", b"5", b"2", b"1"]), lead=st.booleans())
+def test_tar_header_fuzz(name, link, mode, uid, gid, size, mtime, frac, kind, lead):
+    if kind == b"5":
+        name += "/"
+    if kind != b"2" and kind != b"1":
+        link = ""
+    if kind != b"0":
+        size = 0
+    h = lt.Header(name=name, mode=mode, uid=uid, gid=gid, size=size, mtime_ns=mtime * 10**9 + frac, typeflag=kind,
+                  linkname=link)
+    want = lt.encode_header(lt.replace(h, mtime_ns=mtime * 10**9))  # write.go:61 truncation, then the writer
+    got = host.encode_tar_header(("/" if lead else "") + name, mode, uid, gid, size, h.mtime_ns, kind, link)
+    assert got == want
+
+
+def _random_tree(root, rng, depth=0):
+    n = int(rng.integers(1, 7))
+    for _ in range(n):
+        nm = "".join(rng.choice(list("abAB01._-"), size=int(rng.integers(1, 9))))
+        if nm in (".", "..") or os.path.lexists(os.path.join(root, nm)):
+            continue
+        p = os.path.join(root, nm)
+        r = rng.random()
+        if r < 0.3 and depth < 3:
+            os.mkdir(p)
+            _random_tree(p, rng, depth + 1)
+        elif r < 0.4:
+            os.symlink("some/target" if rng.random() < 0.5 else "../up/target", p)
+        else:
+            with open(p, "wb") as f:
+                f.write(os.urandom(int(rng.integers(0, 3000))))
+            os.chmod(p, int(rng.choice([0o644, 0o600, 0o755, 0o4755, 0o1777])))
+        os.utime(p, (1_400_000_000 + int(rng.integers(0, 10**8)),) * 2, follow_symlinks=False)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_trees_stream_and_layer_order(tmp_path, seed):
+    rng = np.random.default_rng(seed)
+    ctx = tmp_path / "ctx"
+    ctx.mkdir()
+    _random_tree(str(ctx), rng)
+    for d, _, _ in os.walk(ctx):
+        os.utime(d, (1_450_000_000, 1_450_000_000))
+    want = []
+    for s in ctx_crc.context_segments(str(ctx), ["."]):
+        want.append(("P " + os.fsdecode(s.data)) if s.kind == "bytes" else f"F {s.size} {s.path}")
+    got = [("P " + g[2:]) if g.startswith("L ") else g for g in host.describe_context_stream(str(ctx), ["."])]
+    assert got == want
+    root = tmp_path / "root"
+    root.mkdir()
+    fs = lt.MemFS(lambda: 1_600_000_000, str(root))
+    entries = fs.add_layer_by_copy_ops([lt.CopyOperation.new(["/"], str(ctx), "/", "/opt/app/", uid=5, gid=6)])
+    o = ["%s %o %d %d %d %d %s %s %s" % (e.hdr.typeflag.decode(), e.hdr.mode, e.hdr.uid, e.hdr.gid, e.hdr.size,
+                                         e.hdr.mtime_ns // 10**9, e.dst, e.hdr.name, e.src) for e in entries]
+    assert host.describe_layer(str(root), 1_600_000_000, [host.CopyOperation(["/"], str(ctx), "/", "/opt/app/", 5, 6)]) == o
+    # and the header bytes of every entry
+    for e in entries:
+        hb = lt.entry_header_bytes(e)
+        assert host.encode_tar_header(e.hdr.name, e.hdr.mode, e.hdr.uid, e.hdr.gid, e.hdr.size, e.hdr.mtime_ns,
+                                      e.hdr.typeflag, e.hdr.linkname) == hb
+
+
+def test_absolute_symlink_outside_root_is_an_error_in_both(tmp_path):
+    """mem_layer.go:176-181: an absolute link target must lie under the MemFS root (TrimRoot fails otherwise)."""
+    ctx = tmp_path / "ctx"
+    ctx.mkdir()
+    os.symlink("/abs/elsewhere", ctx / "l")
+    root = tmp_path / "root"
+    root.mkdir()
+    with pytest.raises(ValueError):
+        lt.MemFS(lambda: 0, str(root)).add_layer_by_copy_ops([lt.CopyOperation.new(["/"], str(ctx), "/", "/x/")])
+    with pytest.raises(host.HostError) as ei:
+        host.describe_layer(str(root), 0, [host.CopyOperation(["/"], str(ctx), "/", "/x/")])
+    assert "trim" in str(ei.value)
