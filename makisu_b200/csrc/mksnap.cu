@@ -265,8 +265,8 @@ int sort_unique_root(mksnap *h, const uint8_t *src, uint64_t n, cudaStream_t s)
         LAUNCH_OK(h);
         const uint32_t nblocks = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
         int cur = 0;
-        for (int pass = 0; pass < 8; pass++) {
-            const int shift = pass * 8;
+        for (int pass = 0; pass < SORT_KEY_BITS / 8; pass++) {
+            const int shift = 64 - SORT_KEY_BITS + pass * 8;
             k_radix_hist<<<nblocks, SORT_THREADS, 0, s>>>(h->d_keys[cur], n, shift, h->d_hist, nblocks);
             LAUNCH_OK(h);
             int rc = scan_u32(h, h->d_hist, h->d_hist, (uint64_t)256 * nblocks, s);
@@ -279,7 +279,7 @@ int sort_unique_root(mksnap *h, const uint8_t *src, uint64_t n, cudaStream_t s)
         }
         k_gather_digests<<<(uint32_t)((2 * n + tb - 1) / tb), tb, 0, s>>>(src, h->d_idx[cur], n, h->d_sorted);
         LAUNCH_OK(h);
-        k_fix_ties<<<(uint32_t)((n + tb - 1) / tb), tb, 0, s>>>(h->d_keys[cur], n, h->d_sorted);
+        k_fix_ties<<<(uint32_t)((n + tb - 1) / tb), tb, 0, s>>>(h->d_keys[cur], n, h->d_sorted, 64 - SORT_KEY_BITS);
         LAUNCH_OK(h);
         k_unique_flags<<<(uint32_t)((n + tb - 1) / tb), tb, 0, s>>>(h->d_sorted, n, h->d_flags);
         LAUNCH_OK(h);

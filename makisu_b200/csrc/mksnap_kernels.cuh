@@ -1021,8 +1021,10 @@ __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t *in, uint64_t
 
 // ------------------------------------------------------------------------
 // K3: LSD radix sort of (u64 key, u32 payload), 8 bits per pass, then unique.
-// key = first 8 digest bytes big-endian; ties beyond 64 bits are fixed up by
-// k_fix_ties so the final order is the full bytewise order.
+// key = first 8 digest bytes big-endian.  Only the top SORT_KEY_BITS are radix-sorted (SHA-256 output is
+// uniform: at 10^7..10^8 rows a 32-bit prefix leaves runs of a few rows); k_fix_ties then orders every run of
+// equal prefix on the full 256 bits, so the final order is the full bytewise order.
+constexpr int SORT_KEY_BITS = 32;
 // ------------------------------------------------------------------------
 constexpr uint32_t SORT_THREADS = 256;
 constexpr uint32_t SORT_ITEMS = 16;
@@ -1131,15 +1133,16 @@ __device__ __forceinline__ int digest_cmp(const uint8_t *a, const uint8_t *b)
 }
 
 // runs of equal 64-bit prefix: insertion sort on the full digest (linear when the run is all duplicates)
-__global__ void k_fix_ties(const uint64_t *__restrict__ keys, uint64_t n, uint8_t *__restrict__ d)
+__global__ void k_fix_ties(const uint64_t *__restrict__ keys, uint64_t n, uint8_t *__restrict__ d, int shift)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
-    if (i > 0 && keys[i - 1] == keys[i])
+    const uint64_t ki = keys[i] >> shift; // only the bits the radix passes sorted on
+    if (i > 0 && (keys[i - 1] >> shift) == ki)
         return; // not a run start
     uint64_t e = i + 1;
-    while (e < n && keys[e] == keys[i])
+    while (e < n && (keys[e] >> shift) == ki)
         ++e;
     for (uint64_t j = i + 1; j < e; ++j) {
         uint64_t k = j;
