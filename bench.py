@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--cpu-sample-mib", type=int, default=1536)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--tar-files", type=int, default=2048, help="files in the TarDigest side measurement")
+    ap.add_argument("--tar-files", type=int, default=256, help="files in the TarDigest side measurement")
     return ap.parse_args()
 
 
@@ -405,9 +405,16 @@ def main():
         if k.get("algorithmic_GBps"):
             k["frac_of_hbm_peak"] = k["algorithmic_GBps"] / peak
         k["share_of_step"] = k["ms"] / ms_step if ms_step else None
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch from the committed ncu capture, scaled to this launch's algorithmic bytes
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_gear_scan"]
+        traffic, traffic_src = tj["ratio"] * ctx_bytes, tj["source"]
+    except Exception:
+        pass
     roofline = {"kernel": "k_gear_scan (north_star's rolling-hash kernel)", "bound": "hbm",
                 "achieved": gbs(kern["ms_gear"]), "peak": peak, "unit": "GB/s",
-                "frac": (gbs(kern["ms_gear"]) or 0) / peak, "traffic": None, "peak_source": peak_src,
+                "frac": (gbs(kern["ms_gear"]) or 0) / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ctx_bytes,
                 "note": "dominant kernel BY TIME is K2 (SHA-256, integer-ALU bound, not HBM): see kernels[]"}
 
