@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--cpu-sample-mib", type=int, default=1536)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="uniform", choices=["uniform", "dup", "zipf"],
+                    help="uniform = BASELINE configs[2] (the bench line); dup = configs[4] (80 %% repeated content); "
+                         "zipf = configs[3] (Zipf-sized files 10 B..1 GiB, LPT-sharded by rank)")
     ap.add_argument("--tar-files", type=int, default=256, help="files in the TarDigest side measurement")
     return ap.parse_args()
 
@@ -110,6 +113,63 @@ def context_layout(n_files: int, file_bytes: int, n_dirs: int, rank: int):
     used = meta_base + len(blob)
     return dict(file_off=file_off, blob=bytes(blob), meta_base=meta_base, ext=ext, used=used, stream_len=total,
                 data_bytes=data_end)
+
+
+def layout_from_files(names, file_off, file_len, data_end):
+    """CRC stream = name_i || content_i in list order; every file is also a CDC extent.  Paths go to a meta
+    region after the data.  file_off may repeat (dup workload: several files share one pool region)."""
+    n = len(names)
+    lens = np.array([len(x) for x in names], dtype=np.uint64)
+    moff = np.concatenate([[0], np.cumsum((lens + 15) // 16 * 16)[:-1]]).astype(np.uint64)
+    blob = bytearray(int(((lens + 15) // 16 * 16).sum()))
+    for i, x in enumerate(names):
+        blob[int(moff[i]):int(moff[i]) + len(x)] = x
+    blob += b"\0" * (-len(blob) % 512)
+    meta_base = (int(data_end) + 511) // 512 * 512
+    ext = np.zeros(2 * n, dtype=EXT_DT)
+    ext["arena_off"][0::2] = moff + np.uint64(meta_base)
+    ext["len"][0::2] = lens
+    ext["flags"][0::2] = 1
+    ext["arena_off"][1::2] = file_off
+    ext["len"][1::2] = file_len
+    ext["flags"][1::2] = 3
+    total = int(ext["len"].sum())
+    ext["crc_suffix"] = np.uint64(total) - np.cumsum(ext["len"]).astype(np.uint64)
+    return dict(blob=bytes(blob), meta_base=meta_base, ext=ext, used=meta_base + len(blob), stream_len=total,
+                data_bytes=int(np.asarray(file_len, dtype=np.uint64).sum()), fill_bytes=int(data_end))
+
+
+def special_layout(args, rank, world):
+    """dup: n files of file_kib drawn (with repetition) from a pool holding 20 % as many distinct regions.
+    zipf: sizes ~ Zipf(1.1)*10 B clipped to [10 B, 1 GiB] until ~files*file_kib bytes in total, whole list LPT-sharded."""
+    from makisu_b200 import shard
+    fb = args.file_kib << 10
+    rng = np.random.default_rng(0xC5 if args.workload == "dup" else 0xC4)
+    if args.workload == "dup":
+        pool = max(1, args.files // 5)
+        pick = rng.integers(0, pool, args.files)
+        pick[:pool] = np.arange(pool)  # every pool region appears at least once
+        names = [b"d%03d/f%06d_r%d.bin" % (i % args.dirs, i, rank) for i in range(args.files)]
+        return layout_from_files(names, pick.astype(np.uint64) * np.uint64(fb), np.full(args.files, fb, dtype=np.uint64), pool * fb), None
+    target = args.files * fb
+    sizes = []
+    tot = 0
+    while tot < target:
+        z = np.clip(rng.zipf(1.1, 4096).astype(np.float64) * 10, 10, 1 << 30).astype(np.int64)
+        for v in z:
+            if tot >= target:
+                break
+            sizes.append(int(v))
+            tot += int(v)
+    sizes = np.array(sizes, dtype=np.int64)
+    shards = shard.lpt_shard(sizes, world)
+    mine = shards[rank]
+    ml = sizes[mine]
+    off = np.concatenate([[0], np.cumsum((ml + 511) // 512 * 512)[:-1]]).astype(np.uint64)
+    data_end = int(off[-1] + (ml[-1] + 511) // 512 * 512) if len(ml) else 0
+    names = [b"z/f%07d.bin" % i for i in mine]
+    info = {"n_files_total": int(len(sizes)), "imbalance": shard.imbalance(sizes, shards), "largest_file": int(sizes.max())}
+    return layout_from_files(names, off, ml.astype(np.uint64), data_end), info
 
 
 def ext_ptr(a: np.ndarray):
@@ -286,7 +346,13 @@ def main():
         return float(t.item())
 
     file_bytes = args.file_kib << 10
-    lay = context_layout(args.files, file_bytes, args.dirs, rank)
+    wl_info = None
+    if args.workload == "uniform":
+        lay = context_layout(args.files, file_bytes, args.dirs, rank)
+        lay["fill_bytes"] = lay["data_bytes"]
+    else:
+        lay, wl_info = special_layout(args, rank, world)
+        args.no_e2e = True  # the e2e leg is defined on the uniform workload
     used = lay["used"]
     arena_bytes = (used + (1 << 20)) // 512 * 512
     n_ext = len(lay["ext"])
@@ -298,7 +364,7 @@ def main():
         eng.comm_init(uid[0], world, rank)
 
     # ---- synthetic context, generated on the device (seed differs per rank: shards are distinct) ----
-    eng.synth_fill(0, 0, lay["data_bytes"], 0xC3 + 1000 * rank)
+    eng.synth_fill(0, 0, (lay["fill_bytes"] + 15) // 16 * 16, 0xC3 + 1000 * rank)
     eng.device_upload(0, lay["meta_base"], np.frombuffer(lay["blob"], dtype=np.uint8))
     eng.sync()
     ext = lay["ext"]
@@ -317,7 +383,7 @@ def main():
     res0 = one_step()
     res1 = one_step()
     assert bytes(res0.root) == bytes(res1.root) and res0.crc_pure == res1.crc_pure, "non-deterministic digests"
-    if world == 1:
+    if world == 1 and args.workload == "uniform":
         eng.begin()
         sub = context_layout(gate_files, file_bytes, 1, rank)
         # same bytes, sub-context of the first files: needs its own meta strings
@@ -524,6 +590,8 @@ def main():
                        "l2": "inputs (48.8 GiB) >> L2 (126 MB): no flush needed", "sharding": f"files by rank, dp{world}",
                        "host_affinity": affinity_note,
                        "n_chunks": int(res.n_chunks), "n_unique": int(res.n_unique), "cache_id": "%x" % eng.ctx_crc32(res),
+                       "dedup_ratio_unique_over_total": (int(res.n_unique) / int(res.n_chunks)) if res.n_chunks else None,
+                       "workload_kind": args.workload, "workload_info": wl_info,
                        "root": bytes(res.root).hex()},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "gpu_launches_per_step": launches // max(1, args.steps), "tar_digest": tar,

@@ -784,6 +784,15 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         k_select_cuts<0><<<nb, 128, 0, sk>>>(m.d_files, (uint32_t)n_files, h->prm, h->d_tiles, h->d_pool, h->d_counts,
                                              nullptr, h->d_sc, h->max_chunks, 0, nullptr, nullptr, nullptr);
         LAUNCH_OK(h);
+        uint64_t big_files = 0;
+        for (uint64_t i = 0; i < n_files; i++)
+            big_files += m.h_files[i].len >= SELECT_BIG_FILE;
+        if (big_files) {
+            k_select_cuts_big<0><<<(uint32_t)n_files, SELB_THREADS, 0, sk>>>(m.d_files, (uint32_t)n_files, h->prm, h->d_tiles,
+                                                                          h->d_pool, h->d_counts, nullptr, h->d_sc,
+                                                                          h->max_chunks, 0, nullptr, nullptr, nullptr);
+            LAUNCH_OK(h);
+        }
         int rc = scan_u32(h, h->d_counts, h->d_bases, n_files, sk);
         if (rc)
             return rc;
@@ -793,6 +802,13 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
                                              h->d_bases, h->d_sc, h->max_chunks, h->stream_base, h->d_chunk_start,
                                              h->d_chunk_len, h->d_chunk_end);
         LAUNCH_OK(h);
+        if (big_files) {
+            k_select_cuts_big<1><<<(uint32_t)n_files, SELB_THREADS, 0, sk>>>(m.d_files, (uint32_t)n_files, h->prm, h->d_tiles,
+                                                                          h->d_pool, h->d_counts, h->d_bases, h->d_sc,
+                                                                          h->max_chunks, h->stream_base, h->d_chunk_start,
+                                                                          h->d_chunk_len, h->d_chunk_end);
+            LAUNCH_OK(h);
+        }
     }
     CK(h, cudaEventRecord(h->ev[3], sk));
     if (n_files) {

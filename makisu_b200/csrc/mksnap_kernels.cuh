@@ -607,6 +607,36 @@ struct SessionCounters {
     uint32_t work;                 // work-stealing counter of K2
 };
 
+// One application of the cut rule from `prev`, reading tile records and candidates from
+// global memory.
+__device__ __forceinline__ uint64_t select_one_cut(uint64_t prev, uint64_t end, const CdcParamsDev &prm,
+                                                   const TileRec *__restrict__ tiles, const uint32_t *__restrict__ pool)
+{
+    const uint64_t rem = end - prev;
+    if (rem <= prm.min_size)
+        return end;
+    const uint64_t limit_end = prev + (rem < prm.max_size ? rem : prm.max_size);
+    const uint64_t lo = prev + prm.min_size - 1;
+    const uint64_t normal_pos = prev + prm.normal_size - 1; // pos >= this: loose accepted
+    for (uint64_t t = lo / GEAR_TILE; t * GEAR_TILE < limit_end; ++t) {
+        const TileRec tr = tiles[t];
+        const uint64_t tb = t * GEAR_TILE;
+        for (uint32_t j = 0; j < tr.count; ++j) {
+            const uint32_t ent = __ldg(pool + tr.base + j);
+            const uint64_t pos = tb + (ent & 0x7FFFFFFFu);
+            if (pos < lo)
+                continue;
+            if (pos >= limit_end)
+                return limit_end;
+            if (pos >= normal_pos || (ent >> 31))
+                return pos + 1;
+        }
+    }
+    return limit_end;
+}
+
+constexpr uint64_t SELECT_BIG_FILE = 4ull << 20; // files at least this long get a CTA and shared-memory staging
+
 template <int PASS>
 __global__ void __launch_bounds__(128)
 k_select_cuts(const CdcFile *__restrict__ files, uint32_t n_files, CdcParamsDev prm,
@@ -622,6 +652,8 @@ k_select_cuts(const CdcFile *__restrict__ files, uint32_t n_files, CdcParamsDev 
     if (PASS == 1 && sc->err)
         return;
     const CdcFile fl = files[f];
+    if (fl.len >= SELECT_BIG_FILE)
+        return; // k_select_cuts_big owns this file
     uint64_t prev = fl.off;
     const uint64_t end = fl.off + fl.len;
     uint64_t out = 0;
@@ -629,34 +661,7 @@ k_select_cuts(const CdcFile *__restrict__ files, uint32_t n_files, CdcParamsDev 
         out = sc->n_chunks + bases[f];
     uint32_t n = 0;
     while (prev < end) {
-        const uint64_t rem = end - prev;
-        uint64_t cut;
-        if (rem <= prm.min_size) {
-            cut = end;
-        } else {
-            const uint64_t limit_end = prev + (rem < prm.max_size ? rem : prm.max_size);
-            const uint64_t lo = prev + prm.min_size - 1;
-            const uint64_t normal_pos = prev + prm.normal_size - 1; // pos >= this: loose accepted
-            cut = 0;
-            for (uint64_t t = lo / GEAR_TILE; t * GEAR_TILE < limit_end && !cut; ++t) {
-                const TileRec tr = tiles[t];
-                const uint64_t tb = t * GEAR_TILE;
-                for (uint32_t j = 0; j < tr.count; ++j) {
-                    const uint32_t ent = __ldg(pool + tr.base + j);
-                    const uint64_t pos = tb + (ent & 0x7FFFFFFFu);
-                    if (pos < lo)
-                        continue;
-                    if (pos >= limit_end)
-                        break;
-                    if (pos >= normal_pos || (ent >> 31)) {
-                        cut = pos + 1;
-                        break;
-                    }
-                }
-            }
-            if (!cut)
-                cut = limit_end;
-        }
+        const uint64_t cut = select_one_cut(prev, end, prm, tiles, pool);
         if (PASS == 1) {
             if (out + n < max_chunks) {
                 chunk_start[out + n] = prev;
@@ -669,6 +674,172 @@ k_select_cuts(const CdcFile *__restrict__ files, uint32_t n_files, CdcParamsDev 
     }
     if (PASS == 0)
         counts[f] = n;
+}
+
+// Long files: a single thread chasing TileRecs and pool entries through L2 costs ~3 us per chunk (a 1 GiB file
+// would take ~200 ms).  Here a CTA owns the file: it stages the tile records and the (position-ordered)
+// candidates of an 8 MiB window in shared memory, then thread 0 runs the same sequential rule over shared
+// memory with a monotone cursor -- O(candidates + chunks) shared-memory steps, ~7 ms per GiB.
+constexpr uint32_t SELB_THREADS = 128;
+constexpr uint32_t SELB_REGIONS = 2048;  // window = 8 MiB of file
+constexpr uint32_t SELB_CANDS = 8192;    // candidate capacity of a window (expected 2048 at the default mask)
+
+template <int PASS>
+__global__ void __launch_bounds__(SELB_THREADS)
+k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParamsDev prm,
+                  const TileRec *__restrict__ tiles, const uint32_t *__restrict__ pool,
+                  uint32_t *__restrict__ counts, const uint32_t *__restrict__ bases,
+                  SessionCounters *__restrict__ sc, uint64_t max_chunks, uint64_t stream_base,
+                  uint64_t *__restrict__ chunk_start, uint64_t *__restrict__ chunk_len,
+                  uint64_t *__restrict__ chunk_end_out)
+{
+    const uint32_t f = blockIdx.x;
+    if (f >= n_files)
+        return;
+    const CdcFile fl = files[f];
+    if (fl.len < SELECT_BIG_FILE)
+        return;
+    if (PASS == 1 && sc->err)
+        return;
+    __shared__ uint32_t s_off[SELB_REGIONS + 1]; // exclusive prefix of candidate counts per region
+    __shared__ uint32_t s_cand[SELB_CANDS];      // offset within the window | strict << 31
+    __shared__ uint32_t s_w[SELB_THREADS / 32];
+    __shared__ uint32_t s_nreg;                  // regions of the window that were staged
+    __shared__ unsigned long long s_prev;
+    __shared__ uint32_t s_n;
+
+    const uint64_t end = fl.off + fl.len;
+    uint64_t out = 0;
+    if (PASS == 1)
+        out = sc->n_chunks + bases[f];
+    if (threadIdx.x == 0) {
+        s_prev = fl.off;
+        s_n = 0;
+    }
+    __syncthreads();
+    for (;;) {
+        const uint64_t prev0 = s_prev;
+        if (prev0 >= end)
+            break;
+        // ---- stage the window starting at the region of the first eligible position ----
+        const uint64_t lo0 = prev0 + prm.min_size - 1;
+        const uint64_t t0 = lo0 / GEAR_TILE;
+        const uint64_t t_last = (end - 1) / GEAR_TILE;
+        const uint32_t want = (uint32_t)((t_last - t0 + 1 < SELB_REGIONS) ? (t_last - t0 + 1) : SELB_REGIONS);
+        // counts -> exclusive prefix (each thread owns a contiguous run of regions)
+        constexpr uint32_t PER = SELB_REGIONS / SELB_THREADS;
+        uint32_t cnt[PER], bs[PER], mine = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < PER; ++k) {
+            const uint32_t r = threadIdx.x * PER + k;
+            cnt[k] = 0;
+            bs[k] = 0;
+            if (r < want) {
+                const TileRec tr = tiles[t0 + r];
+                cnt[k] = tr.count;
+                bs[k] = tr.base;
+            }
+            mine += cnt[k];
+        }
+        // block exclusive scan of `mine`
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, sft);
+            if (lane >= sft)
+                incl += v;
+        }
+        if (lane == 31)
+            s_w[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (uint32_t k = 0; k < warp; ++k)
+            woff += s_w[k];
+        uint32_t o = woff + incl - mine;
+#pragma unroll
+        for (uint32_t k = 0; k < PER; ++k) {
+            const uint32_t r = threadIdx.x * PER + k;
+            s_off[r] = o;
+            if (o + cnt[k] <= SELB_CANDS) {
+                for (uint32_t j = 0; j < cnt[k]; ++j) {
+                    const uint32_t ent = __ldg(pool + bs[k] + j);
+                    s_cand[o + j] = (r * GEAR_TILE + (ent & 0x7FFFFFFFu)) | (ent & 0x80000000u);
+                }
+            }
+            o += cnt[k];
+        }
+        if (threadIdx.x == SELB_THREADS - 1)
+            s_off[SELB_REGIONS] = o;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // regions usable = those whose candidates all fit in s_cand
+            uint32_t nreg = want;
+            while (nreg > 0 && s_off[nreg] > SELB_CANDS)
+                --nreg;
+            s_nreg = nreg;
+            // ---- sequential rule over the staged window ----
+            const uint64_t wbase = t0 * GEAR_TILE;                 // arena offset of window position 0
+            const uint64_t wend = wbase + (uint64_t)nreg * GEAR_TILE; // staged candidates cover [wbase, wend)
+            const uint32_t ncand = s_off[nreg];
+            uint64_t prev = prev0;
+            uint32_t j = 0, n = s_n;
+            for (;;) {
+                if (prev >= end)
+                    break;
+                const uint64_t rem = end - prev;
+                uint64_t cut;
+                if (rem <= prm.min_size) {
+                    cut = end;
+                } else {
+                    const uint64_t limit_end = prev + (rem < prm.max_size ? rem : prm.max_size);
+                    if (limit_end > wend && wend < end)
+                        break; // search range leaves the staged window: restage from here
+                    const uint64_t lo = prev + prm.min_size - 1;
+                    const uint64_t normal_pos = prev + prm.normal_size - 1;
+                    while (j < ncand && wbase + (s_cand[j] & 0x7FFFFFFFu) < lo)
+                        ++j;
+                    cut = 0;
+                    for (uint32_t q = j; q < ncand; ++q) {
+                        const uint32_t ent = s_cand[q];
+                        const uint64_t pos = wbase + (ent & 0x7FFFFFFFu);
+                        if (pos >= limit_end)
+                            break;
+                        if (pos >= normal_pos || (ent >> 31)) {
+                            cut = pos + 1;
+                            break;
+                        }
+                    }
+                    if (!cut)
+                        cut = limit_end;
+                }
+                if (PASS == 1 && out + n < max_chunks) {
+                    chunk_start[out + n] = prev;
+                    chunk_len[out + n] = cut - prev;
+                    chunk_end_out[out + n] = stream_base + cut;
+                }
+                ++n;
+                prev = cut;
+            }
+            if (prev == prev0 && prev < end) {
+                // pathologically dense candidates: the staged window is too short for one search range.
+                // Make progress with one cut straight from global memory.
+                const uint64_t cut = select_one_cut(prev, end, prm, tiles, pool);
+                if (PASS == 1 && out + n < max_chunks) {
+                    chunk_start[out + n] = prev;
+                    chunk_len[out + n] = cut - prev;
+                    chunk_end_out[out + n] = stream_base + cut;
+                }
+                ++n;
+                prev = cut;
+            }
+            s_prev = prev;
+            s_n = n;
+        }
+        __syncthreads();
+    }
+    if (PASS == 0 && threadIdx.x == 0)
+        counts[f] = s_n;
 }
 
 // after the scan of counts: publish the batch chunk count / overflow

@@ -197,3 +197,28 @@ def test_nccl_gather_world_of_one():
         r = e.finish()
         g = e.allgather_tables()
         assert (g.n_chunks, g.n_unique, bytes(g.root), e.ctx_crc32(g)) == (r.n_chunks, r.n_unique, bytes(r.root), e.ctx_crc32(r))
+
+
+@pytest.mark.parametrize("params", [(64, 128, 256, 8, 6), (64, 256, 1024, 4, 3), (4096, 16384, 131072, 16, 12)])
+def test_big_file_selection_paths(oracle_lib, params):
+    """Files >= 4 MiB take the CTA-per-file selection kernel (shared-memory window); very dense masks force its
+    global-memory fallback.  Mixed with small files; everything must equal the oracle."""
+    from makisu_b200.abi import CdcParams, Engine
+    import oracle.lib as olib
+    p = CdcParams(*params)
+    op = olib.CdcParams(*params)
+    rng = np.random.default_rng(17)
+    files = [rng.integers(0, 256, n, dtype=np.uint8) for n in (9 << 20, 1000, (4 << 20), (4 << 20) - 1, 5 << 20, 0, 70000)]
+    files.append(np.zeros(6 << 20, dtype=np.uint8))
+    arena, offs = _pack_files(files)
+    lens = [len(f) for f in files]
+    with Engine(device=0, device_arena_bytes=64 << 20, max_extents=64, max_chunks=2_000_000, cdc=p) as e:
+        e.begin()
+        e.device_upload(0, 0, arena)
+        e.device_submit(0, arena.size, cdc_extents(offs, lens))
+        res = e.finish()
+        want = oracle_lib.chunk_table(arena, offs, lens, op)
+        assert (res.n_chunks, res.n_unique) == (want["n_chunks"], want["n_unique"]) and bytes(res.root) == want["root"]
+        ends, digs = e.get_chunks(res.n_chunks)
+        np.testing.assert_array_equal(ends, want["ends"])
+        np.testing.assert_array_equal(digs, want["digests"])
