@@ -357,7 +357,8 @@ def main():
     arena_bytes = (used + (1 << 20)) // 512 * 512
     n_ext = len(lay["ext"])
 
-    eng = Engine(device=local, device_arena_bytes=arena_bytes, n_host_arenas=0, max_extents=n_ext + 16)
+    eng = Engine(device=local, device_arena_bytes=arena_bytes, n_host_arenas=0, max_extents=n_ext + 16,
+                 max_chunks=max(arena_bytes, lay["data_bytes"]) // 4096 + n_ext + 1024)
     if world > 1:
         uid = [Engine.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)

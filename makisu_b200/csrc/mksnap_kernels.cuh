@@ -704,7 +704,6 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
     __shared__ uint32_t s_off[SELB_REGIONS + 1]; // exclusive prefix of candidate counts per region
     __shared__ uint32_t s_cand[SELB_CANDS];      // offset within the window | strict << 31
     __shared__ uint32_t s_w[SELB_THREADS / 32];
-    __shared__ uint32_t s_nreg;                  // regions of the window that were staged
     __shared__ unsigned long long s_prev;
     __shared__ uint32_t s_n;
 
@@ -721,9 +720,8 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
         const uint64_t prev0 = s_prev;
         if (prev0 >= end)
             break;
-        // ---- stage the window starting at the region of the first eligible position ----
-        const uint64_t lo0 = prev0 + prm.min_size - 1;
-        const uint64_t t0 = lo0 / GEAR_TILE;
+        // ---- stage the window starting at the region that holds `prev` ----
+        const uint64_t t0 = prev0 / GEAR_TILE;
         const uint64_t t_last = (end - 1) / GEAR_TILE;
         const uint32_t want = (uint32_t)((t_last - t0 + 1 < SELB_REGIONS) ? (t_last - t0 + 1) : SELB_REGIONS);
         // counts -> exclusive prefix (each thread owns a contiguous run of regions)
@@ -741,7 +739,6 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
             }
             mine += cnt[k];
         }
-        // block exclusive scan of `mine`
         const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         uint32_t incl = mine;
 #pragma unroll
@@ -772,69 +769,90 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
         if (threadIdx.x == SELB_THREADS - 1)
             s_off[SELB_REGIONS] = o;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            // regions usable = those whose candidates all fit in s_cand
+        if (warp == 0) {
+            // regions usable = those whose candidates all fit in s_cand (warp-uniform)
             uint32_t nreg = want;
             while (nreg > 0 && s_off[nreg] > SELB_CANDS)
                 --nreg;
-            s_nreg = nreg;
-            // ---- sequential rule over the staged window ----
-            const uint64_t wbase = t0 * GEAR_TILE;                 // arena offset of window position 0
-            const uint64_t wend = wbase + (uint64_t)nreg * GEAR_TILE; // staged candidates cover [wbase, wend)
+            // ---- the sequential rule, 32 candidates per step; positions are 32-bit offsets from wbase ----
+            const uint64_t wbase = t0 * GEAR_TILE;
+            const uint32_t wend = nreg * GEAR_TILE;                        // staged candidates cover [0, wend)
+            const bool file_ends_here = wbase + wend >= end;
+            const uint32_t fend = file_ends_here ? (uint32_t)(end - wbase) : 0xFFFFFFFFu; // file end, if inside
             const uint32_t ncand = s_off[nreg];
-            uint64_t prev = prev0;
+            uint32_t prev = (uint32_t)(prev0 - wbase);
             uint32_t j = 0, n = s_n;
+            bool progressed = false;
             for (;;) {
-                if (prev >= end)
+                if (file_ends_here && prev >= fend)
                     break;
-                const uint64_t rem = end - prev;
-                uint64_t cut;
+                const uint32_t rem = file_ends_here ? fend - prev : 0xFFFFFFFFu; // >= max when the end is far away
+                uint32_t cut;
                 if (rem <= prm.min_size) {
-                    cut = end;
+                    cut = fend;
                 } else {
-                    const uint64_t limit_end = prev + (rem < prm.max_size ? rem : prm.max_size);
-                    if (limit_end > wend && wend < end)
-                        break; // search range leaves the staged window: restage from here
-                    const uint64_t lo = prev + prm.min_size - 1;
-                    const uint64_t normal_pos = prev + prm.normal_size - 1;
-                    while (j < ncand && wbase + (s_cand[j] & 0x7FFFFFFFu) < lo)
-                        ++j;
-                    cut = 0;
-                    for (uint32_t q = j; q < ncand; ++q) {
-                        const uint32_t ent = s_cand[q];
-                        const uint64_t pos = wbase + (ent & 0x7FFFFFFFu);
-                        if (pos >= limit_end)
-                            break;
-                        if (pos >= normal_pos || (ent >> 31)) {
-                            cut = pos + 1;
+                    const uint32_t limit = prev + (rem < prm.max_size ? rem : prm.max_size);
+                    if (limit > wend && !file_ends_here)
+                        break; // the search range leaves the staged window: restage from `prev`
+                    const uint32_t lo = prev + prm.min_size - 1;
+                    const uint32_t normal_pos = prev + prm.normal_size - 1;
+                    // cursor to the first candidate at or after lo
+                    for (;;) {
+                        const uint32_t q = j + lane;
+                        const uint32_t pos = q < ncand ? (s_cand[q] & 0x7FFFFFFFu) : 0x7FFFFFFFu;
+                        const uint32_t ge = __ballot_sync(0xFFFFFFFFu, pos >= lo);
+                        if (ge) {
+                            j += __ffs(ge) - 1;
                             break;
                         }
+                        j += 32;
                     }
-                    if (!cut)
-                        cut = limit_end;
+                    // first qualifying candidate before limit
+                    cut = limit;
+                    for (uint32_t q0 = j;; q0 += 32) {
+                        const uint32_t q = q0 + lane;
+                        const uint32_t ent = q < ncand ? s_cand[q] : 0x7FFFFFFFu;
+                        const uint32_t pos = ent & 0x7FFFFFFFu;
+                        const bool stop = pos >= limit;
+                        const bool qual = !stop && (pos >= normal_pos || (ent >> 31));
+                        const uint32_t bq = __ballot_sync(0xFFFFFFFFu, qual);
+                        const uint32_t bstop = __ballot_sync(0xFFFFFFFFu, stop);
+                        const uint32_t fq = bq ? (uint32_t)__ffs(bq) - 1 : 32u;
+                        const uint32_t fs = bstop ? (uint32_t)__ffs(bstop) - 1 : 32u;
+                        if (fq < fs) {
+                            cut = __shfl_sync(0xFFFFFFFFu, pos, fq) + 1;
+                            break;
+                        }
+                        if (fs < 32)
+                            break; // reached limit without a qualifying candidate
+                    }
                 }
-                if (PASS == 1 && out + n < max_chunks) {
-                    chunk_start[out + n] = prev;
+                if (PASS == 1 && lane == 0 && out + n < max_chunks) {
+                    chunk_start[out + n] = wbase + prev;
                     chunk_len[out + n] = cut - prev;
-                    chunk_end_out[out + n] = stream_base + cut;
+                    chunk_end_out[out + n] = stream_base + wbase + cut;
                 }
                 ++n;
                 prev = cut;
+                progressed = true;
             }
-            if (prev == prev0 && prev < end) {
+            uint64_t prev64 = wbase + prev;
+            if (!progressed && prev64 < end) {
                 // pathologically dense candidates: the staged window is too short for one search range.
                 // Make progress with one cut straight from global memory.
-                const uint64_t cut = select_one_cut(prev, end, prm, tiles, pool);
-                if (PASS == 1 && out + n < max_chunks) {
-                    chunk_start[out + n] = prev;
-                    chunk_len[out + n] = cut - prev;
+                const uint64_t cut = select_one_cut(prev64, end, prm, tiles, pool);
+                if (PASS == 1 && lane == 0 && out + n < max_chunks) {
+                    chunk_start[out + n] = prev64;
+                    chunk_len[out + n] = cut - prev64;
                     chunk_end_out[out + n] = stream_base + cut;
                 }
                 ++n;
-                prev = cut;
+                prev64 = cut;
             }
-            s_prev = prev;
-            s_n = n;
+            if (lane == 0) {
+                s_prev = prev64;
+                s_n = n;
+            }
         }
         __syncthreads();
     }
