@@ -677,12 +677,69 @@ k_select_cuts(const CdcFile *__restrict__ files, uint32_t n_files, CdcParamsDev 
 }
 
 // Long files: a single thread chasing TileRecs and pool entries through L2 costs ~3 us per chunk (a 1 GiB file
-// would take ~200 ms).  Here a CTA owns the file: it stages the tile records and the (position-ordered)
-// candidates of an 8 MiB window in shared memory, then thread 0 runs the same sequential rule over shared
-// memory with a monotone cursor -- O(candidates + chunks) shared-memory steps, ~7 ms per GiB.
+// would take ~200 ms).  Here a CTA owns the file and works window by window (4 MiB of file):
+//   1. stage: tile records -> block scan -> the window's candidates, position ordered, in shared memory;
+//   2. next[]: for EVERY candidate q, in parallel, apply the cut rule with prev = pos(q)+1 and record where
+//      the chain goes (another candidate, a forced/end position, or "beyond this window");
+//   3. chase: one thread follows next[] from the current cut -- one shared-memory load per chunk.
+// The rule itself is sel_rule(): identical to select_one_cut() but over the staged list.
 constexpr uint32_t SELB_THREADS = 128;
-constexpr uint32_t SELB_REGIONS = 2048;  // window = 8 MiB of file
-constexpr uint32_t SELB_CANDS = 8192;    // candidate capacity of a window (expected 2048 at the default mask)
+constexpr uint32_t SELB_REGIONS = 1024; // window = 4 MiB of file
+constexpr uint32_t SELB_CANDS = 4096;   // candidate capacity of a window (expected 1024 at the default mask)
+constexpr uint32_t NX_CAND = 0u << 30;  // value = candidate index: cut = pos(value) + 1
+constexpr uint32_t NX_POS = 1u << 30;   // value = window-relative cut position that is not after a candidate
+constexpr uint32_t NX_OUT = 2u << 30;   // the search range leaves the staged window: restage
+constexpr uint32_t NX_VAL = (1u << 30) - 1;
+
+struct SelWin {
+    const uint32_t *cand; // offset | strict << 31, ascending
+    uint32_t ncand;
+    uint32_t wend;        // staged candidates cover window offsets [0, wend)
+    uint32_t fend;        // file end as a window offset, or 0xFFFFFFFF if beyond the window
+};
+
+// first index >= from whose position is >= lo (cand is sorted)
+__device__ __forceinline__ uint32_t sel_lower_bound(const SelWin &w, uint32_t from, uint32_t lo)
+{
+    uint32_t a = from, b = w.ncand;
+    while (a < b) {
+        const uint32_t m = (a + b) >> 1;
+        if ((w.cand[m] & 0x7FFFFFFFu) < lo)
+            a = m + 1;
+        else
+            b = m;
+    }
+    return a;
+}
+
+// cut rule from window offset `prev`; `from` = an index at or before the first candidate that can matter
+__device__ __forceinline__ uint32_t sel_rule(const SelWin &w, const CdcParamsDev &prm, uint32_t prev, uint32_t from)
+{
+    const bool ends = w.fend != 0xFFFFFFFFu;
+    const uint32_t rem = ends ? w.fend - prev : 0xFFFFFFFFu;
+    if (rem <= prm.min_size)
+        return NX_POS | w.fend;
+    const uint32_t limit = prev + (rem < prm.max_size ? rem : prm.max_size);
+    if (limit > w.wend && !ends)
+        return NX_OUT;
+    const uint32_t lo = prev + prm.min_size - 1;
+    const uint32_t normal_pos = prev + prm.normal_size - 1;
+    // candidates are ~4 KiB apart and min is 4 KiB: a short linear probe usually beats the binary search
+    uint32_t q = from;
+    for (int k = 0; k < 4 && q < w.ncand && (w.cand[q] & 0x7FFFFFFFu) < lo; ++k)
+        ++q;
+    if (q < w.ncand && (w.cand[q] & 0x7FFFFFFFu) < lo)
+        q = sel_lower_bound(w, q, lo);
+    for (; q < w.ncand; ++q) {
+        const uint32_t ent = w.cand[q];
+        const uint32_t pos = ent & 0x7FFFFFFFu;
+        if (pos >= limit)
+            break;
+        if (pos >= normal_pos || (ent >> 31))
+            return NX_CAND | q;
+    }
+    return NX_POS | limit;
+}
 
 template <int PASS>
 __global__ void __launch_bounds__(SELB_THREADS)
@@ -703,6 +760,7 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
         return;
     __shared__ uint32_t s_off[SELB_REGIONS + 1]; // exclusive prefix of candidate counts per region
     __shared__ uint32_t s_cand[SELB_CANDS];      // offset within the window | strict << 31
+    __shared__ uint32_t s_next[SELB_CANDS];      // where the chain goes from each candidate
     __shared__ uint32_t s_w[SELB_THREADS / 32];
     __shared__ unsigned long long s_prev;
     __shared__ uint32_t s_n;
@@ -720,11 +778,10 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
         const uint64_t prev0 = s_prev;
         if (prev0 >= end)
             break;
-        // ---- stage the window starting at the region that holds `prev` ----
+        // ---- 1. stage the window that starts at the region holding `prev` ----
         const uint64_t t0 = prev0 / GEAR_TILE;
         const uint64_t t_last = (end - 1) / GEAR_TILE;
         const uint32_t want = (uint32_t)((t_last - t0 + 1 < SELB_REGIONS) ? (t_last - t0 + 1) : SELB_REGIONS);
-        // counts -> exclusive prefix (each thread owns a contiguous run of regions)
         constexpr uint32_t PER = SELB_REGIONS / SELB_THREADS;
         uint32_t cnt[PER], bs[PER], mine = 0;
 #pragma unroll
@@ -769,65 +826,49 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
         if (threadIdx.x == SELB_THREADS - 1)
             s_off[SELB_REGIONS] = o;
         __syncthreads();
-        if (warp == 0) {
-            // regions usable = those whose candidates all fit in s_cand (warp-uniform)
-            uint32_t nreg = want;
-            while (nreg > 0 && s_off[nreg] > SELB_CANDS)
-                --nreg;
-            // ---- the sequential rule, 32 candidates per step; positions are 32-bit offsets from wbase ----
-            const uint64_t wbase = t0 * GEAR_TILE;
-            const uint32_t wend = nreg * GEAR_TILE;                        // staged candidates cover [0, wend)
-            const bool file_ends_here = wbase + wend >= end;
-            const uint32_t fend = file_ends_here ? (uint32_t)(end - wbase) : 0xFFFFFFFFu; // file end, if inside
-            const uint32_t ncand = s_off[nreg];
+        uint32_t nreg = want; // regions whose candidates all fit in s_cand (same value in every thread)
+        while (nreg > 0 && s_off[nreg] > SELB_CANDS)
+            --nreg;
+        const uint64_t wbase = t0 * GEAR_TILE;
+        SelWin w;
+        w.cand = s_cand;
+        w.ncand = s_off[nreg];
+        w.wend = nreg * GEAR_TILE;
+        w.fend = (wbase + w.wend >= end) ? (uint32_t)(end - wbase) : 0xFFFFFFFFu;
+        // ---- 2. next[] for every candidate, in parallel ----
+        for (uint32_t q = threadIdx.x; q < w.ncand; q += SELB_THREADS) {
+            const uint32_t prev = (s_cand[q] & 0x7FFFFFFFu) + 1;
+            s_next[q] = (w.fend != 0xFFFFFFFFu && prev >= w.fend) ? (NX_POS | w.fend) : sel_rule(w, prm, prev, q + 1);
+        }
+        __syncthreads();
+        // ---- 3. chase the chain ----
+        if (threadIdx.x == 0) {
             uint32_t prev = (uint32_t)(prev0 - wbase);
-            uint32_t j = 0, n = s_n;
+            uint32_t n = s_n;
             bool progressed = false;
+            // is `prev` the position right after a staged candidate?
+            uint32_t cur = 0xFFFFFFFFu;
+            if (prev > 0) {
+                const uint32_t q = sel_lower_bound(w, 0, prev - 1);
+                if (q < w.ncand && (s_cand[q] & 0x7FFFFFFFu) == prev - 1)
+                    cur = q;
+            }
             for (;;) {
-                if (file_ends_here && prev >= fend)
+                if (w.fend != 0xFFFFFFFFu && prev >= w.fend)
                     break;
-                const uint32_t rem = file_ends_here ? fend - prev : 0xFFFFFFFFu; // >= max when the end is far away
+                const uint32_t nx = cur != 0xFFFFFFFFu ? s_next[cur] : sel_rule(w, prm, prev, 0);
+                const uint32_t kind = nx & ~NX_VAL, val = nx & NX_VAL;
+                if (kind == NX_OUT)
+                    break;
                 uint32_t cut;
-                if (rem <= prm.min_size) {
-                    cut = fend;
+                if (kind == NX_CAND) {
+                    cut = (s_cand[val] & 0x7FFFFFFFu) + 1;
+                    cur = val;
                 } else {
-                    const uint32_t limit = prev + (rem < prm.max_size ? rem : prm.max_size);
-                    if (limit > wend && !file_ends_here)
-                        break; // the search range leaves the staged window: restage from `prev`
-                    const uint32_t lo = prev + prm.min_size - 1;
-                    const uint32_t normal_pos = prev + prm.normal_size - 1;
-                    // cursor to the first candidate at or after lo
-                    for (;;) {
-                        const uint32_t q = j + lane;
-                        const uint32_t pos = q < ncand ? (s_cand[q] & 0x7FFFFFFFu) : 0x7FFFFFFFu;
-                        const uint32_t ge = __ballot_sync(0xFFFFFFFFu, pos >= lo);
-                        if (ge) {
-                            j += __ffs(ge) - 1;
-                            break;
-                        }
-                        j += 32;
-                    }
-                    // first qualifying candidate before limit
-                    cut = limit;
-                    for (uint32_t q0 = j;; q0 += 32) {
-                        const uint32_t q = q0 + lane;
-                        const uint32_t ent = q < ncand ? s_cand[q] : 0x7FFFFFFFu;
-                        const uint32_t pos = ent & 0x7FFFFFFFu;
-                        const bool stop = pos >= limit;
-                        const bool qual = !stop && (pos >= normal_pos || (ent >> 31));
-                        const uint32_t bq = __ballot_sync(0xFFFFFFFFu, qual);
-                        const uint32_t bstop = __ballot_sync(0xFFFFFFFFu, stop);
-                        const uint32_t fq = bq ? (uint32_t)__ffs(bq) - 1 : 32u;
-                        const uint32_t fs = bstop ? (uint32_t)__ffs(bstop) - 1 : 32u;
-                        if (fq < fs) {
-                            cut = __shfl_sync(0xFFFFFFFFu, pos, fq) + 1;
-                            break;
-                        }
-                        if (fs < 32)
-                            break; // reached limit without a qualifying candidate
-                    }
+                    cut = val;
+                    cur = 0xFFFFFFFFu;
                 }
-                if (PASS == 1 && lane == 0 && out + n < max_chunks) {
+                if (PASS == 1 && out + n < max_chunks) {
                     chunk_start[out + n] = wbase + prev;
                     chunk_len[out + n] = cut - prev;
                     chunk_end_out[out + n] = stream_base + wbase + cut;
@@ -841,7 +882,7 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
                 // pathologically dense candidates: the staged window is too short for one search range.
                 // Make progress with one cut straight from global memory.
                 const uint64_t cut = select_one_cut(prev64, end, prm, tiles, pool);
-                if (PASS == 1 && lane == 0 && out + n < max_chunks) {
+                if (PASS == 1 && out + n < max_chunks) {
                     chunk_start[out + n] = prev64;
                     chunk_len[out + n] = cut - prev64;
                     chunk_end_out[out + n] = stream_base + cut;
@@ -849,10 +890,8 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
                 ++n;
                 prev64 = cut;
             }
-            if (lane == 0) {
-                s_prev = prev64;
-                s_n = n;
-            }
+            s_prev = prev64;
+            s_n = n;
         }
         __syncthreads();
     }
