@@ -684,7 +684,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         CK(h, cudaEventSynchronize(m.ev_done));
         m.in_flight = false;
     }
-    uint64_t n_crc = 0, n_files = 0, pieces = 0, cdc_bytes = 0, crc_bytes = 0;
+    uint64_t n_crc = 0, n_files = 0, pieces = 0, cdc_bytes = 0, crc_bytes = 0, big_slots = 0;
     for (uint64_t i = 0; i < n_ext; i++) {
         const mksnap_extent &x = ext[i];
         if ((x.arena_off & 15) || x.arena_off > used || x.len > used - x.arena_off)
@@ -703,11 +703,17 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         if (x.flags & MKSNAP_X_CDC) {
             m.h_files[n_files].off = x.arena_off;
             m.h_files[n_files].len = x.len;
+            m.h_files[n_files].scratch = big_slots;
+            if (x.len >= SELECT_BIG_FILE)
+                big_slots += x.len / h->prm.min_size + 2;
             cdc_bytes += x.len;
             n_files++;
         }
     }
     m.h_piece_base[n_crc] = (uint32_t)pieces;
+    if (big_slots > h->table_cap) // the cut lists of the big files live in the (idle) radix key buffer
+        return fail(h, MKSNAP_E_CAPACITY, "big-file cut lists need %llu slots, max_chunks allows %llu",
+                    (unsigned long long)big_slots, (unsigned long long)h->table_cap);
     for (uint64_t i = 0; i < n_rng; i++) {
         if ((rng[i].arena_off & 15) || rng[i].arena_off > used || rng[i].len > used - rng[i].arena_off)
             return fail(h, MKSNAP_E_INVAL, "range %llu out of bounds or not 16-byte aligned", (unsigned long long)i);
@@ -784,13 +790,10 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         k_select_cuts<0><<<nb, 128, 0, sk>>>(m.d_files, (uint32_t)n_files, h->prm, h->d_tiles, h->d_pool, h->d_counts,
                                              nullptr, h->d_sc, h->max_chunks, 0, nullptr, nullptr, nullptr);
         LAUNCH_OK(h);
-        uint64_t big_files = 0;
-        for (uint64_t i = 0; i < n_files; i++)
-            big_files += m.h_files[i].len >= SELECT_BIG_FILE;
+        const bool big_files = big_slots != 0;
         if (big_files) {
-            k_select_cuts_big<0><<<(uint32_t)n_files, SELB_THREADS, 0, sk>>>(m.d_files, (uint32_t)n_files, h->prm, h->d_tiles,
-                                                                          h->d_pool, h->d_counts, nullptr, h->d_sc,
-                                                                          h->max_chunks, 0, nullptr, nullptr, nullptr);
+            k_select_cuts_big<<<(uint32_t)n_files, SELB_THREADS, 0, sk>>>(m.d_files, (uint32_t)n_files, h->prm, h->d_tiles,
+                                                                       h->d_pool, h->d_counts, h->d_keys[0]);
             LAUNCH_OK(h);
         }
         int rc = scan_u32(h, h->d_counts, h->d_bases, n_files, sk);
@@ -803,10 +806,9 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
                                              h->d_chunk_len, h->d_chunk_end);
         LAUNCH_OK(h);
         if (big_files) {
-            k_select_cuts_big<1><<<(uint32_t)n_files, SELB_THREADS, 0, sk>>>(m.d_files, (uint32_t)n_files, h->prm, h->d_tiles,
-                                                                          h->d_pool, h->d_counts, h->d_bases, h->d_sc,
-                                                                          h->max_chunks, h->stream_base, h->d_chunk_start,
-                                                                          h->d_chunk_len, h->d_chunk_end);
+            k_expand_big_cuts<<<(uint32_t)n_files, 256, 0, sk>>>(m.d_files, (uint32_t)n_files, h->d_counts, h->d_bases,
+                                                              h->d_keys[0], h->d_sc, h->max_chunks, h->stream_base,
+                                                              h->d_chunk_start, h->d_chunk_len, h->d_chunk_end);
             LAUNCH_OK(h);
         }
     }

@@ -590,6 +590,7 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
 struct CdcFile {
     uint64_t off;
     uint64_t len;
+    uint64_t scratch; // big files: first slot of this file's cut list in the scratch buffer (len/min + 2 slots)
 };
 
 struct CdcParamsDev {
@@ -741,23 +742,21 @@ __device__ __forceinline__ uint32_t sel_rule(const SelWin &w, const CdcParamsDev
     return NX_POS | limit;
 }
 
-template <int PASS>
+// Single pass: the cut END offsets (relative to the file start, fit 40 bits -> stored as u64) go to `cuts`
+// at files[f].scratch; k_expand_big_cuts turns them into chunk records once the bases are known.
 __global__ void __launch_bounds__(SELB_THREADS)
 k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParamsDev prm,
                   const TileRec *__restrict__ tiles, const uint32_t *__restrict__ pool,
-                  uint32_t *__restrict__ counts, const uint32_t *__restrict__ bases,
-                  SessionCounters *__restrict__ sc, uint64_t max_chunks, uint64_t stream_base,
-                  uint64_t *__restrict__ chunk_start, uint64_t *__restrict__ chunk_len,
-                  uint64_t *__restrict__ chunk_end_out)
+                  uint32_t *__restrict__ counts, uint64_t *__restrict__ cuts)
 {
+    constexpr int PASS = 0;
     const uint32_t f = blockIdx.x;
     if (f >= n_files)
         return;
     const CdcFile fl = files[f];
     if (fl.len < SELECT_BIG_FILE)
         return;
-    if (PASS == 1 && sc->err)
-        return;
+    uint64_t *const my_cuts = cuts + fl.scratch;
     __shared__ uint32_t s_off[SELB_REGIONS + 1]; // exclusive prefix of candidate counts per region
     __shared__ uint32_t s_cand[SELB_CANDS];      // offset within the window | strict << 31
     __shared__ uint32_t s_next[SELB_CANDS];      // where the chain goes from each candidate
@@ -766,9 +765,6 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
     __shared__ uint32_t s_n;
 
     const uint64_t end = fl.off + fl.len;
-    uint64_t out = 0;
-    if (PASS == 1)
-        out = sc->n_chunks + bases[f];
     if (threadIdx.x == 0) {
         s_prev = fl.off;
         s_n = 0;
@@ -868,11 +864,7 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
                     cut = val;
                     cur = 0xFFFFFFFFu;
                 }
-                if (PASS == 1 && out + n < max_chunks) {
-                    chunk_start[out + n] = wbase + prev;
-                    chunk_len[out + n] = cut - prev;
-                    chunk_end_out[out + n] = stream_base + wbase + cut;
-                }
+                my_cuts[n] = wbase + cut - fl.off;
                 ++n;
                 prev = cut;
                 progressed = true;
@@ -882,11 +874,7 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
                 // pathologically dense candidates: the staged window is too short for one search range.
                 // Make progress with one cut straight from global memory.
                 const uint64_t cut = select_one_cut(prev64, end, prm, tiles, pool);
-                if (PASS == 1 && out + n < max_chunks) {
-                    chunk_start[out + n] = prev64;
-                    chunk_len[out + n] = cut - prev64;
-                    chunk_end_out[out + n] = stream_base + cut;
-                }
+                my_cuts[n] = cut - fl.off;
                 ++n;
                 prev64 = cut;
             }
@@ -895,8 +883,35 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
         }
         __syncthreads();
     }
-    if (PASS == 0 && threadIdx.x == 0)
+    if (threadIdx.x == 0)
         counts[f] = s_n;
+    (void)PASS;
+}
+
+// chunk records of the big files from their cut lists (one CTA per file, coalesced)
+__global__ void __launch_bounds__(256)
+k_expand_big_cuts(const CdcFile *__restrict__ files, uint32_t n_files, const uint32_t *__restrict__ counts,
+                  const uint32_t *__restrict__ bases, const uint64_t *__restrict__ cuts,
+                  const SessionCounters *__restrict__ sc, uint64_t max_chunks, uint64_t stream_base,
+                  uint64_t *__restrict__ chunk_start, uint64_t *__restrict__ chunk_len,
+                  uint64_t *__restrict__ chunk_end_out)
+{
+    const uint32_t f = blockIdx.x;
+    if (f >= n_files || sc->err)
+        return;
+    const CdcFile fl = files[f];
+    if (fl.len < SELECT_BIG_FILE)
+        return;
+    const uint64_t out = sc->n_chunks + bases[f];
+    const uint64_t *c = cuts + fl.scratch;
+    for (uint32_t j = threadIdx.x; j < counts[f]; j += blockDim.x) {
+        const uint64_t s0 = j ? c[j - 1] : 0, e0 = c[j];
+        if (out + j < max_chunks) {
+            chunk_start[out + j] = fl.off + s0;
+            chunk_len[out + j] = e0 - s0;
+            chunk_end_out[out + j] = stream_base + fl.off + e0;
+        }
+    }
 }
 
 // after the scan of counts: publish the batch chunk count / overflow
