@@ -78,6 +78,12 @@ int mkhost_commit_copy_ops(mksnap_t *eng, const char *root_dir, int64_t now_unix
 int mkhost_commit_copy_ops_to_fd(mksnap_t *eng, const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops,
                                  size_t n_ops, int n_threads, int tar_fd, mkhost_layer_result *out, char *err,
                                  size_t errlen);
+/* flags for mkhost_commit_copy_ops_ex */
+#define MKHOST_NO_TAR_DIGEST 1u /* leave TarDigest to the caller (Go's sha256.New() fed from the same bytes, see
+                                   INTEGRATION.md section 3): out->tar_digest is zeroed, no serial stream is submitted */
+int mkhost_commit_copy_ops_ex(mksnap_t *eng, const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops,
+                              size_t n_ops, int n_threads, int tar_fd, uint32_t flags, mkhost_layer_result *out,
+                              char *err, size_t errlen);
 
 /* No-GPU introspection for the CPU tests: one line per item, '\n' separated, NUL terminated.
  *   stream : "P <relpath>" | "L <target>" | "F <size> <abs path>"   in CRC stream order

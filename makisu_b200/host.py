@@ -40,6 +40,8 @@ SYMBOLS = [
                                          C.POINTER(LayerResult), C.c_char_p, C.c_size_t]),
     ("mkhost_commit_copy_ops_to_fd", C.c_int, [_P, C.c_char_p, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_int, C.c_int,
                                                C.POINTER(LayerResult), C.c_char_p, C.c_size_t]),
+    ("mkhost_commit_copy_ops_ex", C.c_int, [_P, C.c_char_p, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_int, C.c_int,
+                                            C.c_uint32, C.POINTER(LayerResult), C.c_char_p, C.c_size_t]),
     ("mkhost_describe_context_stream", C.c_size_t, [C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_char_p,
                                                     C.c_size_t, C.c_char_p, C.c_size_t]),
     ("mkhost_describe_layer", C.c_size_t, [C.c_char_p, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_char_p,
@@ -148,14 +150,17 @@ def copy_step_cache_id(eng: abi.Engine, seed: str, directive: str, args: str, co
     return "%x" % crc  # add_copy_step.go:119
 
 
+MKHOST_NO_TAR_DIGEST = 1
+
+
 def commit_copy_ops(eng: abi.Engine, root_dir: str, now_unix: int, ops: Sequence[CopyOperation], n_threads: int = 0,
-                    tar_fd: int = -1):
+                    tar_fd: int = -1, flags: int = 0):
     """commitLayer over AddLayerByCopyOps; tar_fd >= 0 also receives the uncompressed layer tar."""
     err = C.create_string_buffer(1024)
     arr, keep = _ops(ops)
     out = LayerResult()
-    rc = load().mkhost_commit_copy_ops_to_fd(eng.h, os.fsencode(root_dir), now_unix, arr, len(ops), n_threads, tar_fd,
-                                             C.byref(out), err, len(err))
+    rc = load().mkhost_commit_copy_ops_ex(eng.h, os.fsencode(root_dir), now_unix, arr, len(ops), n_threads, tar_fd, flags,
+                                          C.byref(out), err, len(err))
     if rc:
         raise HostError(err.value.decode())
     return {"tar_digest": "sha256:" + bytes(out.tar_digest).hex(), "root": bytes(out.root), "n_entries": out.n_entries,

@@ -1046,6 +1046,14 @@ int mkhost_commit_copy_ops_to_fd(mksnap_t *eng, const char *root_dir, int64_t no
                                  size_t n_ops, int n_threads, int tar_fd, mkhost_layer_result *out, char *err,
                                  size_t errlen)
 {
+    return mkhost_commit_copy_ops_ex(eng, root_dir, now_unix, ops, n_ops, n_threads, tar_fd, 0, out, err, errlen);
+}
+
+int mkhost_commit_copy_ops_ex(mksnap_t *eng, const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops,
+                              size_t n_ops, int n_threads, int tar_fd, uint32_t flags, mkhost_layer_result *out,
+                              char *err, size_t errlen)
+{
+    const bool want_tar_digest = !(flags & MKHOST_NO_TAR_DIGEST);
     try {
         MemFS fs(root_dir, now_unix);
         auto layer = fs.add_layer_by_copy_ops(ops, n_ops);
@@ -1081,7 +1089,7 @@ int mkhost_commit_copy_ops_to_fd(mksnap_t *eng, const char *root_dir, int64_t no
                 }
             }
             mksnap_range rng{0, pos, 0, last ? 0u : MKSNAP_R_MORE};
-            ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), &rng, 1), "arena submit");
+            ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), &rng, want_tar_digest ? 1 : 0), "arena submit");
             tar_bytes += pos;
             if (!last)
                 acquire();
@@ -1115,7 +1123,9 @@ int mkhost_commit_copy_ops_to_fd(mksnap_t *eng, const char *root_dir, int64_t no
         pos = tar_bytes;
         mksnap_result res;
         ck(eng, mksnap_finish(eng, &res), "finish");
-        ck(eng, mksnap_get_stream_digests(eng, out->tar_digest, 1), "stream digests");
+        memset(out->tar_digest, 0, 32);
+        if (want_tar_digest)
+            ck(eng, mksnap_get_stream_digests(eng, out->tar_digest, 1), "stream digests");
         memcpy(out->root, res.root, 32);
         out->n_entries = layer.size();
         out->tar_bytes = pos;
