@@ -85,6 +85,24 @@ int mkhost_commit_copy_ops_ex(mksnap_t *eng, const char *root_dir, int64_t now_u
                               size_t n_ops, int n_threads, int tar_fd, uint32_t flags, mkhost_layer_result *out,
                               char *err, size_t errlen);
 
+/* Persistent mirror of snapshot.MemFS (lib/snapshot/mem_fs.go:60-83): layers accumulate in the merged tree, later
+ * layers contain only entries whose header is not "similar" (lib/tario/compare.go) to what the tree holds, scans
+ * emit whiteouts for children that vanished (mem_fs.go:459-480), `blacklist` as in NewMemFS(clk, root, blacklist). */
+typedef struct mkhost_memfs mkhost_memfs;
+mkhost_memfs *mkhost_memfs_new(const char *root_dir, const char *const *blacklist, size_t n_blacklist, char *err,
+                               size_t errlen);
+void mkhost_memfs_free(mkhost_memfs *m);
+/* AddLayerByCopyOps / AddLayerByScan followed by commitLayer on the GPU (flags: MKHOST_NO_TAR_DIGEST). */
+int mkhost_memfs_commit_copy_ops(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops,
+                                 int n_threads, int tar_fd, uint32_t flags, mkhost_layer_result *out, char *err,
+                                 size_t errlen);
+int mkhost_memfs_commit_scan(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, int n_threads, int tar_fd, uint32_t flags,
+                             mkhost_layer_result *out, char *err, size_t errlen);
+/* the same two without a GPU: entry list as text (format below); they DO merge the layer into the tree */
+size_t mkhost_memfs_describe_copy_ops(mkhost_memfs *m, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops, char *out,
+                                      size_t cap, char *err, size_t errlen);
+size_t mkhost_memfs_describe_scan(mkhost_memfs *m, int64_t now_unix, char *out, size_t cap, char *err, size_t errlen);
+
 /* No-GPU introspection for the CPU tests: one line per item, '\n' separated, NUL terminated.
  *   stream : "P <relpath>" | "L <target>" | "F <size> <abs path>"   in CRC stream order
  *   layer  : "<typeflag> <mode octal> <uid> <gid> <size> <mtime> <dst> <hdr.Name> <src>"  in tar order

@@ -42,6 +42,15 @@ SYMBOLS = [
                                                C.POINTER(LayerResult), C.c_char_p, C.c_size_t]),
     ("mkhost_commit_copy_ops_ex", C.c_int, [_P, C.c_char_p, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_int, C.c_int,
                                             C.c_uint32, C.POINTER(LayerResult), C.c_char_p, C.c_size_t]),
+    ("mkhost_memfs_new", _P, [C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_char_p, C.c_size_t]),
+    ("mkhost_memfs_free", None, [_P]),
+    ("mkhost_memfs_commit_copy_ops", C.c_int, [_P, _P, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_int, C.c_int, C.c_uint32,
+                                               C.POINTER(LayerResult), C.c_char_p, C.c_size_t]),
+    ("mkhost_memfs_commit_scan", C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.POINTER(LayerResult),
+                                           C.c_char_p, C.c_size_t]),
+    ("mkhost_memfs_describe_copy_ops", C.c_size_t, [_P, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_char_p, C.c_size_t,
+                                                    C.c_char_p, C.c_size_t]),
+    ("mkhost_memfs_describe_scan", C.c_size_t, [_P, C.c_int64, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     ("mkhost_describe_context_stream", C.c_size_t, [C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_char_p,
                                                     C.c_size_t, C.c_char_p, C.c_size_t]),
     ("mkhost_describe_layer", C.c_size_t, [C.c_char_p, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_char_p,
@@ -165,3 +174,58 @@ def commit_copy_ops(eng: abi.Engine, root_dir: str, now_unix: int, ops: Sequence
         raise HostError(err.value.decode())
     return {"tar_digest": "sha256:" + bytes(out.tar_digest).hex(), "root": bytes(out.root), "n_entries": out.n_entries,
             "tar_bytes": out.tar_bytes, "n_chunks": out.n_chunks, "n_unique": out.n_unique}
+
+
+def _layer_dict(out: LayerResult):
+    return {"tar_digest": "sha256:" + bytes(out.tar_digest).hex(), "root": bytes(out.root), "n_entries": out.n_entries,
+            "tar_bytes": out.tar_bytes, "n_chunks": out.n_chunks, "n_unique": out.n_unique}
+
+
+class MemFS:
+    """snapshot.NewMemFS(clk, root, blacklist): layers accumulate; AddLayerByCopyOps / AddLayerByScan either
+    described as text (no GPU) or committed through an Engine."""
+    _BUF = 16 << 20
+
+    def __init__(self, root: str, blacklist: Sequence[str] = ()):
+        err = C.create_string_buffer(1024)
+        self._bl = _strs(list(blacklist))
+        self.h = load().mkhost_memfs_new(os.fsencode(root), self._bl, len(blacklist), err, len(err))
+        if not self.h:
+            raise HostError(err.value.decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            load().mkhost_memfs_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def describe_copy_ops(self, now_unix: int, ops: Sequence[CopyOperation]) -> List[str]:
+        err, buf = C.create_string_buffer(1024), C.create_string_buffer(self._BUF)
+        arr, keep = _ops(ops)
+        n = load().mkhost_memfs_describe_copy_ops(self.h, now_unix, arr, len(ops), buf, len(buf), err, len(err))
+        if n == 0 or n > len(buf):
+            raise HostError(err.value.decode() or "describe buffer too small")
+        return [l for l in os.fsdecode(buf.value).split("\n") if l]
+
+    def describe_scan(self, now_unix: int) -> List[str]:
+        err, buf = C.create_string_buffer(1024), C.create_string_buffer(self._BUF)
+        n = load().mkhost_memfs_describe_scan(self.h, now_unix, buf, len(buf), err, len(err))
+        if n == 0 or n > len(buf):
+            raise HostError(err.value.decode() or "describe buffer too small")
+        return [l for l in os.fsdecode(buf.value).split("\n") if l]
+
+    def commit_copy_ops(self, eng: abi.Engine, now_unix: int, ops: Sequence[CopyOperation], n_threads: int = 0,
+                        tar_fd: int = -1, flags: int = 0):
+        err, out = C.create_string_buffer(1024), LayerResult()
+        arr, keep = _ops(ops)
+        if load().mkhost_memfs_commit_copy_ops(self.h, eng.h, now_unix, arr, len(ops), n_threads, tar_fd, flags,
+                                               C.byref(out), err, len(err)):
+            raise HostError(err.value.decode())
+        return _layer_dict(out)
+
+    def commit_scan(self, eng: abi.Engine, now_unix: int, n_threads: int = 0, tar_fd: int = -1, flags: int = 0):
+        err, out = C.create_string_buffer(1024), LayerResult()
+        if load().mkhost_memfs_commit_scan(self.h, eng.h, now_unix, n_threads, tar_fd, flags, C.byref(out), err, len(err)):
+            raise HostError(err.value.decode())
+        return _layer_dict(out)

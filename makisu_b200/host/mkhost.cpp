@@ -630,6 +630,8 @@ std::string encode_header(Hdr h)
 struct MemFile {
     std::string src, dst;
     Hdr hdr;
+    bool whiteout = false;  // whiteoutMemFile (mem_layer.go:91-132): header-only entry ".wh.<base>"
+    std::string deleted;    // path it deletes (the layer key)
 };
 struct Node {
     MemFile mf;
@@ -639,7 +641,8 @@ struct Node {
 class MemFS
 {
   public:
-    MemFS(const std::string &root, int64_t now_unix) : root_(root), now_(now_unix)
+    MemFS(const std::string &root, int64_t now_unix, std::vector<std::string> blacklist = {})
+        : root_(root), now_(now_unix), blacklist_(std::move(blacklist))
     {
         struct stat st;
         if (lstat(root.c_str(), &st) != 0)
@@ -693,6 +696,8 @@ class MemFS
         return h;
     }
 
+    void set_now(int64_t now_unix) { now_ = now_unix; }
+
     std::map<std::string, MemFile> add_layer_by_copy_ops(const mkhost_copy_op *ops, size_t n)
     {
         std::map<std::string, MemFile> layer; // std::map == sort.Strings order (mem_layer.go:232-244)
@@ -701,10 +706,72 @@ class MemFS
         return layer;
     }
 
+    // AddLayerByScan / createLayerByScan (mem_fs.go:260-270,315-341): metadata diff of the root against the
+    // merged tree, whiteouts for children that vanished.  (Mountpoint filtering, utils.go:46-50, is the caller's
+    // job here: synthetic roots have none.)
+    std::map<std::string, MemFile> add_layer_by_scan()
+    {
+        std::map<std::string, MemFile> layer;
+        go_walk(root_, [&](const std::string &src, const struct stat &st) -> WalkRet {
+            if (should_skip(src, st) || is_descendant_of_any(src, blacklist_))
+                return S_ISDIR(st.st_mode) ? W_SKIPDIR : W_CONT;
+            if (src.compare(0, root_.size(), root_) != 0)
+                throw HostError("failed to trim root prefix " + root_ + " from path " + src);
+            const std::string dst = abs_path(src.substr(root_.size()));
+            Hdr hdr = create_header(src, dst, &st, nullptr);
+            maybe_add(layer, src, dst, hdr, true);
+            return W_CONT;
+        });
+        return layer;
+    }
+
   private:
     std::string root_;
     int64_t now_;
+    std::vector<std::string> blacklist_;
     Node tree_;
+
+    // pathutils.IsDescendantOfAny (lib/pathutils/path.go:24-36)
+    static bool is_descendant_of_any(const std::string &path, const std::vector<std::string> &ancestors)
+    {
+        const std::string p = abs_path(path);
+        size_t sl = p.rfind('/');
+        const std::string dir = (sl == 0 ? std::string("/") : p.substr(0, sl)) + "/";
+        for (const auto &anc : ancestors) {
+            const std::string a = abs_path(anc);
+            if (p == a || a == "/" || dir.compare(0, a.size() + 1, a + "/") == 0)
+                return true;
+        }
+        return false;
+    }
+
+    void tree_delete(const std::string &path)
+    {
+        Node *node = &tree_;
+        auto parts = split_path(path);
+        for (size_t i = 0; i < parts.size(); ++i) {
+            auto it = node->children.find(parts[i]);
+            if (it != node->children.end()) {
+                if (i + 1 == parts.size())
+                    node->children.erase(it);
+                else
+                    node = it->second.get();
+            } else if (i + 1 != parts.size()) {
+                throw HostError("missing intermediate dir " + parts[i] + " in " + path);
+            }
+        }
+    }
+
+    static MemFile make_whiteout(const std::string &deleted, const std::string &wpath)
+    {
+        MemFile mf;
+        mf.dst = wpath;
+        mf.whiteout = true;
+        mf.deleted = deleted;
+        mf.hdr.name = rel_path(wpath); // &tar.Header{Name: RelPath(whiteoutPath)}: everything else zero
+        mf.hdr.typeflag = '0';         // TypeRegA is promoted to TypeReg by tar.Writer
+        return mf;
+    }
 
     // utils.go:37-52 (no blacklist on the copy path; mountpoints are the caller's concern)
     static bool should_skip(const std::string &p, const struct stat &st)
@@ -741,7 +808,19 @@ class MemFS
 
     void add_header(std::map<std::string, MemFile> &layer, const std::string &src, const std::string &dst, const Hdr &hdr)
     {
-        MemFile mf{abs_path(src), abs_path(dst), hdr};
+        const std::string adst = abs_path(dst);
+        const std::string base = path_base(adst);
+        if (base.compare(0, 4, ".wh.") == 0) { // mem_layer.go:198-206: a whiteout file found on disk / in a layer
+            size_t sl = adst.rfind('/');
+            const std::string deleted = abs_path(adst.substr(0, sl + 1) + base.substr(4));
+            layer[deleted] = make_whiteout(deleted, adst);
+            tree_delete(deleted);
+            return;
+        }
+        MemFile mf;
+        mf.src = abs_path(src);
+        mf.dst = adst;
+        mf.hdr = hdr;
         layer[mf.dst] = mf;
         tree_put(mf);
     }
@@ -762,8 +841,9 @@ class MemFS
         }
     }
 
-    bool is_updated(const std::string &p, const Hdr &hdr)
+    bool is_updated(const std::string &p, const Hdr &hdr, Node **found)
     {
+        *found = nullptr;
         Node *cur = &tree_;
         for (const auto &part : split_path(p)) {
             auto it = cur->children.find(part);
@@ -771,6 +851,7 @@ class MemFS
                 return true;
             cur = it->second.get();
         }
+        *found = cur;
         return !is_similar(cur->mf.hdr, hdr);
     }
 
@@ -815,11 +896,36 @@ class MemFS
         return dst;
     }
 
-    void maybe_add(std::map<std::string, MemFile> &layer, const std::string &src, const std::string &dst, const Hdr &hdr)
+    // mem_fs.go:440-482
+    void maybe_add(std::map<std::string, MemFile> &layer, const std::string &src, const std::string &dst, const Hdr &hdr,
+                   bool create_whiteout)
     {
-        if (is_updated(dst, hdr) && dst != "/") {
+        Node *n = nullptr;
+        const bool updated = is_updated(dst, hdr, &n);
+        // the reference ranges over the children of the node found BEFORE the update replaces it
+        std::vector<std::pair<std::string, std::string>> kids; // (dst, src)
+        if (create_whiteout && hdr.typeflag == '5' && n)
+            for (const auto &kv : n->children)
+                kids.emplace_back(kv.second->mf.dst, kv.second->mf.src);
+        if (updated && dst != "/") {
             add_ancestors(layer, abs_path(dst), false, 0, 0, 0);
             add_header(layer, src, dst, hdr);
+        }
+        for (const auto &k : kids) {
+            struct stat st;
+            if (lstat(k.second.c_str(), &st) == 0)
+                continue; // still on disk
+            if (errno != ENOENT)
+                throw HostError(errno_str("check on disk", k.first));
+            const std::string ap = abs_path(k.first);
+            const std::string base = path_base(ap);
+            if (base.compare(0, 4, ".wh.") == 0)
+                throw HostError("base name contains whiteout prefix: " + k.first);
+            size_t sl = ap.rfind('/');
+            const std::string wpath = go_join(ap.substr(0, sl + 1), ".wh." + base);
+            layer[k.first] = make_whiteout(k.first, wpath);
+            tree_delete(k.first);
+            add_ancestors(layer, k.first, false, 0, 0, 0);
         }
     }
 
@@ -871,7 +977,7 @@ class MemFS
                 Hdr hdr = create_header(cur, cur_dst, &st, nullptr);
                 hdr.uid = c.uid;
                 hdr.gid = c.gid;
-                maybe_add(layer, cur, cur_dst, hdr);
+                maybe_add(layer, cur, cur_dst, hdr, false);
                 return W_CONT;
             });
         }
@@ -885,7 +991,113 @@ void set_err(char *err, size_t n, const std::string &s)
     }
 }
 
+std::string describe_layer_text(const std::map<std::string, MemFile> &layer)
+{
+    std::string s;
+    char tmp[128];
+    for (const auto &kv : layer) {
+        const Hdr &h = kv.second.hdr;
+        snprintf(tmp, sizeof tmp, "%c %llo %lld %lld %lld %lld ", h.typeflag, (unsigned long long)h.mode, (long long)h.uid,
+                 (long long)h.gid, (long long)h.size, (long long)(h.mtime_ns / 1000000000ll));
+        s += tmp + kv.second.dst + " " + h.name + " " + kv.second.src + "\n";
+    }
+    return s;
+}
+
+// MemFS.commitLayer (mem_fs.go:424-433) + tario.WriteEntry, with the arena as the tar.Writer sink
+void commit_layer(mksnap_t *eng, const std::map<std::string, MemFile> &layer, int n_threads, int tar_fd, uint32_t flags,
+                  mkhost_layer_result *out)
+{
+    const bool want_tar_digest = !(flags & MKHOST_NO_TAR_DIGEST);
+    ck(eng, mksnap_begin(eng), "begin");
+    void *hp = nullptr;
+    uint64_t cap = 0;
+    int32_t aid = -1;
+    uint8_t *a = nullptr;
+    uint64_t pos = 0, tar_bytes = 0;
+    std::vector<mksnap_extent> ext;
+    std::vector<ReadJob> jobs;
+    auto acquire = [&]() {
+        ck(eng, mksnap_arena_acquire(eng, &hp, &cap, &aid), "arena acquire");
+        a = (uint8_t *)hp;
+        pos = 0;
+        ext.clear();
+        jobs.clear();
+    };
+    // The arena is the tar stream.  A layer larger than one arena goes out in pieces (multiples of 512
+    // bytes, so of 64): stream 0 continues across submits, the device keeps the SHA-256 midstate.
+    auto flush = [&](bool last) {
+        run_reads(jobs, n_threads);
+        if (tar_fd >= 0) { // hand the tar bytes on before the arena is recycled
+            uint64_t w = 0;
+            while (w < pos) {
+                ssize_t r = write(tar_fd, a + w, pos - w);
+                if (r < 0) {
+                    if (errno == EINTR)
+                        continue;
+                    throw HostError(std::string("write layer tar: ") + strerror(errno));
+                }
+                w += (uint64_t)r;
+            }
+        }
+        mksnap_range rng{0, pos, 0, last ? 0u : MKSNAP_R_MORE};
+        ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), &rng, want_tar_digest ? 1 : 0), "arena submit");
+        tar_bytes += pos;
+        if (!last)
+            acquire();
+    };
+    acquire();
+    for (const auto &kv : layer) { // alphabetical order of the layer keys (mem_layer.go:232-244)
+        const MemFile &mf = kv.second;
+        const std::string hb = encode_header(mf.hdr);
+        const uint64_t body = (!mf.whiteout && mf.hdr.typeflag == '0') ? (uint64_t)mf.hdr.size : 0;
+        const uint64_t need = hb.size() + align_up(body, 512);
+        if (need > cap)
+            throw HostError("write diffs: entry " + mf.dst + " (" + std::to_string(need) +
+                            " bytes) exceeds the arena; a file is chunked within one arena");
+        if (pos + need > cap)
+            flush(false);
+        memcpy(a + pos, hb.data(), hb.size());
+        pos += hb.size();
+        if (body) {
+            jobs.push_back(ReadJob{mf.src, 0, body, a + pos});
+            ext.push_back(mksnap_extent{pos, body, 0, MKSNAP_X_CDC, 0});
+            const uint64_t padded = align_up(body, 512);
+            memset(a + pos + body, 0, padded - body);
+            pos += padded;
+        }
+    }
+    if (pos + 1024 > cap)
+        flush(false);
+    memset(a + pos, 0, 1024); // tar.Writer.Close: two zero blocks
+    pos += 1024;
+    flush(true);
+    mksnap_result res;
+    ck(eng, mksnap_finish(eng, &res), "finish");
+    memset(out->tar_digest, 0, 32);
+    if (want_tar_digest)
+        ck(eng, mksnap_get_stream_digests(eng, out->tar_digest, 1), "stream digests");
+    memcpy(out->root, res.root, 32);
+    out->n_entries = layer.size();
+    out->tar_bytes = tar_bytes;
+    out->n_chunks = res.n_chunks;
+    out->n_unique = res.n_unique;
+}
+
+size_t emit_text(const std::string &s, char *out, size_t cap)
+{
+    if (s.size() + 1 <= cap)
+        memcpy(out, s.c_str(), s.size() + 1);
+    return s.size() + 1;
+}
+
 } // namespace
+
+// persistent snapshot.MemFS mirror (layers accumulate in the merged tree, like context.BuildContext.MemFS)
+struct mkhost_memfs {
+    MemFS fs;
+    mkhost_memfs(const std::string &root, std::vector<std::string> bl) : fs(root, 0, std::move(bl)) {}
+};
 
 // =====================================================================================================
 extern "C" {
@@ -935,21 +1147,76 @@ size_t mkhost_describe_layer(const char *root_dir, int64_t now_unix, const mkhos
 {
     try {
         MemFS fs(root_dir, now_unix);
-        auto layer = fs.add_layer_by_copy_ops(ops, n_ops);
-        std::string s;
-        char tmp[128];
-        for (const auto &kv : layer) {
-            const Hdr &h = kv.second.hdr;
-            snprintf(tmp, sizeof tmp, "%c %llo %lld %lld %lld %lld ", h.typeflag, (unsigned long long)h.mode, (long long)h.uid,
-                     (long long)h.gid, (long long)h.size, (long long)(h.mtime_ns / 1000000000ll));
-            s += tmp + kv.second.dst + " " + h.name + " " + kv.second.src + "\n";
-        }
-        if (s.size() + 1 <= cap)
-            memcpy(out, s.c_str(), s.size() + 1);
-        return s.size() + 1;
+        return emit_text(describe_layer_text(fs.add_layer_by_copy_ops(ops, n_ops)), out, cap);
     } catch (const std::exception &e) {
         set_err(err, errlen, std::string("create layer by copy ops: ") + e.what());
         return 0;
+    }
+}
+
+mkhost_memfs *mkhost_memfs_new(const char *root_dir, const char *const *blacklist, size_t n_blacklist, char *err,
+                               size_t errlen)
+{
+    try {
+        std::vector<std::string> bl;
+        for (size_t i = 0; i < n_blacklist; ++i)
+            bl.emplace_back(blacklist[i]);
+        return new mkhost_memfs(root_dir, std::move(bl));
+    } catch (const std::exception &e) {
+        set_err(err, errlen, e.what());
+        return nullptr;
+    }
+}
+
+void mkhost_memfs_free(mkhost_memfs *m) { delete m; }
+
+size_t mkhost_memfs_describe_copy_ops(mkhost_memfs *m, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops, char *out,
+                                      size_t cap, char *err, size_t errlen)
+{
+    try {
+        m->fs.set_now(now_unix);
+        return emit_text(describe_layer_text(m->fs.add_layer_by_copy_ops(ops, n_ops)), out, cap);
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("create layer by copy ops: ") + e.what());
+        return 0;
+    }
+}
+
+size_t mkhost_memfs_describe_scan(mkhost_memfs *m, int64_t now_unix, char *out, size_t cap, char *err, size_t errlen)
+{
+    try {
+        m->fs.set_now(now_unix);
+        return emit_text(describe_layer_text(m->fs.add_layer_by_scan()), out, cap);
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("create layer by scan: ") + e.what());
+        return 0;
+    }
+}
+
+int mkhost_memfs_commit_copy_ops(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops,
+                                 int n_threads, int tar_fd, uint32_t flags, mkhost_layer_result *out, char *err,
+                                 size_t errlen)
+{
+    try {
+        m->fs.set_now(now_unix);
+        commit_layer(eng, m->fs.add_layer_by_copy_ops(ops, n_ops), n_threads, tar_fd, flags, out);
+        return 0;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("failed to generate diff layer: ") + e.what());
+        return -1;
+    }
+}
+
+int mkhost_memfs_commit_scan(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, int n_threads, int tar_fd, uint32_t flags,
+                             mkhost_layer_result *out, char *err, size_t errlen)
+{
+    try {
+        m->fs.set_now(now_unix);
+        commit_layer(eng, m->fs.add_layer_by_scan(), n_threads, tar_fd, flags, out);
+        return 0;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("failed to generate diff layer: ") + e.what());
+        return -1;
     }
 }
 
@@ -1053,84 +1320,9 @@ int mkhost_commit_copy_ops_ex(mksnap_t *eng, const char *root_dir, int64_t now_u
                               size_t n_ops, int n_threads, int tar_fd, uint32_t flags, mkhost_layer_result *out,
                               char *err, size_t errlen)
 {
-    const bool want_tar_digest = !(flags & MKHOST_NO_TAR_DIGEST);
     try {
         MemFS fs(root_dir, now_unix);
-        auto layer = fs.add_layer_by_copy_ops(ops, n_ops);
-        ck(eng, mksnap_begin(eng), "begin");
-        void *hp = nullptr;
-        uint64_t cap = 0;
-        int32_t aid = -1;
-        uint8_t *a = nullptr;
-        uint64_t pos = 0, tar_bytes = 0;
-        std::vector<mksnap_extent> ext;
-        std::vector<ReadJob> jobs;
-        auto acquire = [&]() {
-            ck(eng, mksnap_arena_acquire(eng, &hp, &cap, &aid), "arena acquire");
-            a = (uint8_t *)hp;
-            pos = 0;
-            ext.clear();
-            jobs.clear();
-        };
-        // The arena is the tar stream.  A layer larger than one arena goes out in pieces (multiples of 512
-        // bytes, so of 64): stream 0 continues across submits, the device keeps the SHA-256 midstate.
-        auto flush = [&](bool last) {
-            run_reads(jobs, n_threads);
-            if (tar_fd >= 0) { // the arena is the tar stream: hand it on before the arena is recycled
-                uint64_t w = 0;
-                while (w < pos) {
-                    ssize_t r = write(tar_fd, a + w, pos - w);
-                    if (r < 0) {
-                        if (errno == EINTR)
-                            continue;
-                        throw HostError(std::string("write layer tar: ") + strerror(errno));
-                    }
-                    w += (uint64_t)r;
-                }
-            }
-            mksnap_range rng{0, pos, 0, last ? 0u : MKSNAP_R_MORE};
-            ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), &rng, want_tar_digest ? 1 : 0), "arena submit");
-            tar_bytes += pos;
-            if (!last)
-                acquire();
-        };
-        acquire();
-        for (const auto &kv : layer) { // commitLayer: alphabetical order of absolute dst (mem_fs.go:424-433)
-            const MemFile &mf = kv.second;
-            const std::string hb = encode_header(mf.hdr);
-            const uint64_t body = (mf.hdr.typeflag == '0') ? (uint64_t)mf.hdr.size : 0;
-            const uint64_t need = hb.size() + align_up(body, 512);
-            if (need > cap)
-                throw HostError("write diffs: entry " + mf.dst + " (" + std::to_string(need) +
-                                " bytes) exceeds the arena; a file is chunked within one arena");
-            if (pos + need > cap)
-                flush(false);
-            memcpy(a + pos, hb.data(), hb.size());
-            pos += hb.size();
-            if (body) {
-                jobs.push_back(ReadJob{mf.src, 0, body, a + pos});
-                ext.push_back(mksnap_extent{pos, body, 0, MKSNAP_X_CDC, 0});
-                const uint64_t padded = align_up(body, 512);
-                memset(a + pos + body, 0, padded - body);
-                pos += padded;
-            }
-        }
-        if (pos + 1024 > cap)
-            flush(false);
-        memset(a + pos, 0, 1024); // tar.Writer.Close: two zero blocks
-        pos += 1024;
-        flush(true);
-        pos = tar_bytes;
-        mksnap_result res;
-        ck(eng, mksnap_finish(eng, &res), "finish");
-        memset(out->tar_digest, 0, 32);
-        if (want_tar_digest)
-            ck(eng, mksnap_get_stream_digests(eng, out->tar_digest, 1), "stream digests");
-        memcpy(out->root, res.root, 32);
-        out->n_entries = layer.size();
-        out->tar_bytes = pos;
-        out->n_chunks = res.n_chunks;
-        out->n_unique = res.n_unique;
+        commit_layer(eng, fs.add_layer_by_copy_ops(ops, n_ops), n_threads, tar_fd, flags, out);
         return 0;
     } catch (const std::exception &e) {
         set_err(err, errlen, std::string("failed to generate diff layer: ") + e.what());

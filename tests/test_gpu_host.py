@@ -102,3 +102,56 @@ def test_commit_layer_tar_digest_and_chunk_table(ctx, tmp_path):
             pos += (e.hdr.size + 511) // 512 * 512
     want = olib.chunk_table(arena, offs, lens)
     assert got["n_chunks"] == want["n_chunks"] and got["n_unique"] == want["n_unique"] and got["root"] == want["root"]
+
+
+def test_memfs_scan_layers_with_whiteouts(eng, tmp_path):
+    """AddLayerByScan committed on the GPU: first layer, an empty second layer (Go's 1024-zero-byte tar), then a
+    layer of whiteouts -- TarDigest equals the oracle's stream each time (mem_fs_test.go:1038)."""
+    import shutil
+    from makisu_b200 import host
+    from oracle import layer_tar as lt
+    root = tmp_path / "r"
+    rng = np.random.default_rng(3)
+    _mk(str(root), "d/keep.bin", rng.integers(0, 256, 300_000, dtype=np.uint8).tobytes())
+    _mk(str(root), "d/gone.bin", rng.integers(0, 256, 70_000, dtype=np.uint8).tobytes())
+    _mk(str(root), "d/sub/x.bin", b"x" * 5000)
+    for d, _, _ in os.walk(root):
+        os.utime(d, (1_500_000_000, 1_500_000_000))
+    o = lt.MemFS(lambda: NOW, str(root))
+    h = host.MemFS(str(root))
+    a = h.commit_scan(eng, NOW)
+    assert a["tar_digest"] == lt.tar_digest(o.add_layer_by_scan()) and a["n_entries"] == 5
+    b = h.commit_scan(eng, NOW)
+    assert b["n_entries"] == 0 and b["tar_bytes"] == 1024
+    assert b["tar_digest"] == lt.tar_digest(o.add_layer_by_scan()) == "sha256:5f70bf18a086007016e948b04aed3b82103a36bea41755b6cddfaf10ace3c6ef"
+    os.remove(root / "d" / "gone.bin")
+    shutil.rmtree(root / "d" / "sub")
+    os.utime(root / "d", (NOW, NOW))
+    c = h.commit_scan(eng, NOW)
+    assert c["tar_digest"] == lt.tar_digest(o.add_layer_by_scan()) and c["n_entries"] == 3 and c["n_chunks"] == 0
+    h.close()
+
+
+def test_add_layers_equal_copy_vs_scan_on_gpu(eng, tmp_path):
+    """TestAddLayersEqual (mem_fs_test.go:1118): the same tree committed via copy ops and via scan gives the same
+    tar bytes after the first header (the synthesized ancestor differs: clk.Now(), no trailing slash)."""
+    import hashlib
+    from makisu_b200 import host
+    src = tmp_path / "src"
+    _mk(str(src), "test1/test2/f.bin", bytes(range(256)) * 2000, mtime=NOW - 50)
+    os.symlink("f.bin", src / "test1" / "test2" / "lnk")
+    for d in ("test1/test2", "test1", "."):
+        os.utime(src / d, (NOW - 40, NOW - 40))
+    root1 = tmp_path / "root1"
+    root1.mkdir()
+    t1, t2 = tmp_path / "a.tar", tmp_path / "b.tar"
+    with open(t1, "wb") as f:
+        r1 = host.MemFS(str(root1)).commit_copy_ops(eng, NOW, [host.CopyOperation(["/test1"], str(src), "/", "/test1/",
+                                                                                  os.getuid(), os.getgid())], tar_fd=f.fileno())
+    with open(t2, "wb") as f:
+        r2 = host.MemFS(str(src)).commit_scan(eng, NOW, tar_fd=f.fileno())
+    b1, b2 = open(t1, "rb").read(), open(t2, "rb").read()
+    assert b1[512:] == b2[512:] and b1[:5] == b"test1" and b2[:6] == b"test1/"
+    assert r1["root"] == r2["root"] and r1["n_chunks"] == r2["n_chunks"] > 0
+    assert r1["tar_digest"] == "sha256:" + hashlib.sha256(b1).hexdigest()
+    assert r2["tar_digest"] == "sha256:" + hashlib.sha256(b2).hexdigest()

@@ -142,3 +142,55 @@ def test_copy_multiple_sources_needs_dir_dst(ctx, tmp_path):
     with pytest.raises(host.HostError) as ei:
         host.describe_layer(str(tmp_path), NOW, [host.CopyOperation(["/a", "/c.txt"], ctx, "/", "/x")])
     assert "destination must end with" in str(ei.value)
+
+
+def _desc(entries):
+    return _desc_from_oracle(entries)
+
+
+def test_memfs_sequence_scan_whiteout_copy_matches_oracle(tmp_path):
+    """mem_fs_test.go: TestCreateLayerByScan (:572), TestAddLayerByScanWhiteout (:1038), metadata-only diff
+    (compare_test.go:577) -- the same sequence of layers on the C++ MemFS and on the oracle's."""
+    root = tmp_path / "r"
+    _mk(root, "d/keep.txt", b"k")
+    _mk(root, "d/gone.txt", b"g")
+    _mk(root, "d/sub/x.bin", b"x" * 5000)
+    _mk(root, "skip/me.txt", b"no")
+    _mk(root, ".wh..wh.aufs", b"meta")
+    os.symlink("keep.txt", root / "d" / "lnk")
+    os.mkfifo(root / "d" / "fifo")
+    for d, _, _ in os.walk(root):
+        os.utime(d, (1_500_000_000, 1_500_000_000))
+    bl = [str(root / "skip")]
+    o = lt.MemFS(lambda: NOW, str(root), blacklist=bl)
+    h = host.MemFS(str(root), bl)
+    first = h.describe_scan(NOW)
+    assert first == _desc(o.add_layer_by_scan())
+    assert [l.split(" ")[6] for l in first] == ["/d", "/d/gone.txt", "/d/keep.txt", "/d/lnk", "/d/sub", "/d/sub/x.bin"]
+    assert h.describe_scan(NOW) == _desc(o.add_layer_by_scan()) == []          # nothing changed
+    with open(root / "d" / "keep.txt", "wb") as f:                             # same size, same mtime => similar
+        f.write(b"K")
+    os.utime(root / "d" / "keep.txt", (1_500_000_000, 1_500_000_000))
+    assert h.describe_scan(NOW) == _desc(o.add_layer_by_scan()) == []
+    os.remove(root / "d" / "gone.txt")                                         # => whiteout + touched parent
+    import shutil
+    shutil.rmtree(root / "d" / "sub")
+    os.utime(root / "d", (NOW, NOW))
+    third = h.describe_scan(NOW)
+    assert third == _desc(o.add_layer_by_scan())
+    assert [l.split(" ")[7] for l in third] == ["d/", "d/.wh.gone.txt", "d/.wh.sub"]
+    # a copy op on top of the scanned tree: ancestors that exist are re-added, new ones synthesized
+    ctx = tmp_path / "ctx"
+    _mk(ctx, "n/new.txt", b"new")
+    for d, _, _ in os.walk(ctx):
+        os.utime(d, (1_500_000_000, 1_500_000_000))
+    got = h.describe_copy_ops(NOW + 5, [host.CopyOperation(["/n"], str(ctx), "/", "/d/deep/er/", 1, 2)])
+    want = _desc(lt.MemFS.add_layer_by_copy_ops(o, [lt.CopyOperation.new(["/n"], str(ctx), "/", "/d/deep/er/", uid=1, gid=2)]))
+    # oracle clock is fixed at NOW; only the synthesized ancestors' mtime differs
+    assert [l.split(" ")[6:] for l in got] == [l.split(" ")[6:] for l in want]
+    assert [l.split(" ")[6] for l in got] == ["/d", "/d/deep", "/d/deep/er", "/d/deep/er/new.txt"]
+    # same copy again: nothing new except the re-added ancestors (reference behaviour of addAncestors)
+    again = h.describe_copy_ops(NOW + 5, [host.CopyOperation(["/n"], str(ctx), "/", "/d/deep/er/", 1, 2)])
+    want2 = _desc(lt.MemFS.add_layer_by_copy_ops(o, [lt.CopyOperation.new(["/n"], str(ctx), "/", "/d/deep/er/", uid=1, gid=2)]))
+    assert [l.split(" ")[6] for l in again] == [l.split(" ")[6] for l in want2]
+    h.close()
