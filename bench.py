@@ -357,8 +357,12 @@ def main():
     arena_bytes = (used + (1 << 20)) // 512 * 512
     n_ext = len(lay["ext"])
 
+    cdc = None
+    if os.environ.get("MKSNAP_BENCH_CDC"):  # experiment knob: "min,normal,max,strict_bits,loose_bits" (not the bench line)
+        from makisu_b200.abi import CdcParams
+        cdc = CdcParams(*[int(v) for v in os.environ["MKSNAP_BENCH_CDC"].split(",")])
     eng = Engine(device=local, device_arena_bytes=arena_bytes, n_host_arenas=0, max_extents=n_ext + 16,
-                 max_chunks=max(arena_bytes, lay["data_bytes"]) // 4096 + n_ext + 1024)
+                 max_chunks=max(arena_bytes, lay["data_bytes"]) // 4096 + n_ext + 1024, cdc=cdc)
     if world > 1:
         uid = [Engine.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)

@@ -104,6 +104,8 @@ struct mksnap {
     // session tables
     uint64_t max_chunks = 0;
     uint64_t *d_chunk_start = nullptr, *d_chunk_len = nullptr, *d_chunk_end = nullptr;
+    uint32_t *d_order = nullptr; // K2 work order of the current batch (batch-relative chunk indices)
+    bool sha_order = true;
     uint8_t *d_digests = nullptr;
     uint64_t max_streams = 0;
     uint8_t *d_stream_digests = nullptr;
@@ -309,7 +311,7 @@ int merkle_root(mksnap *h, cudaStream_t s)
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, s));
         k_sha256_ranges<true><<<sha_grid(h), SHA_THREADS, 0, s>>>(cur, nullptr, nullptr, nullptr, next_n, nullptr, 0,
                                                             8192, cur_n * 32, h->d_merkle[which], &h->d_sc->work,
-                                                            nullptr, 1u, nullptr, nullptr, nullptr);
+                                                            nullptr, 1u, nullptr, nullptr, nullptr, nullptr);
         LAUNCH_OK(h);
         cur = h->d_merkle[which];
         cur_n = next_n;
@@ -496,6 +498,9 @@ static int create_impl(mksnap *h)
         const char *e2 = getenv("MKSNAP_SHA_FMA"); // tuning knob: 0 = plain adds in the chunk SHA-256 kernel
         if (e2 && e2[0] == '0')
             h->sha_fma = false;
+        const char *e3 = getenv("MKSNAP_SHA_ORDER"); // tuning knob: 0 = hash chunks in file order instead of longest first
+        if (e3 && e3[0] == '0')
+            h->sha_order = false;
         const char *e = getenv("MKSNAP_GEAR_CFG"); // tuning knob: consumer warp groups per CTA (2 or 3, x8 warps)
         if (e && (e[0] == '2' || e[0] == '3'))
             h->gear_cfg = e[0] - '0';
@@ -516,6 +521,7 @@ static int create_impl(mksnap *h)
     const uint64_t mc = h->max_chunks;
     CK(h, cudaMalloc(&h->d_chunk_start, mc * 8));
     CK(h, cudaMalloc(&h->d_chunk_len, mc * 8));
+    CK(h, cudaMalloc(&h->d_order, mc * 4));
     CK(h, cudaMalloc(&h->d_chunk_end, mc * 8));
     CK(h, cudaMalloc(&h->d_digests, mc * 32));
     h->max_streams = mx;
@@ -610,7 +616,7 @@ void mksnap_destroy(mksnap_t *h)
     cudaFree(h->d_consts); cudaFree(h->d_gear); cudaFree(h->d_sc); cudaFreeHost(h->h_sc);
     cudaFree(h->d_tiles); cudaFree(h->d_pool); cudaFree(h->d_pool_count); cudaFree(h->d_counts); cudaFree(h->d_bases);
     cudaFree(h->d_scan_tmp);
-    cudaFree(h->d_chunk_start); cudaFree(h->d_chunk_len); cudaFree(h->d_chunk_end); cudaFree(h->d_digests);
+    cudaFree(h->d_order); cudaFree(h->d_chunk_start); cudaFree(h->d_chunk_len); cudaFree(h->d_chunk_end); cudaFree(h->d_digests);
     cudaFree(h->d_stream_digests); cudaFree(h->d_stream_state);
     for (int k = 0; k < 2; k++) {
         cudaFree(h->d_keys[k]); cudaFree(h->d_idx[k]); cudaFree(h->d_merkle[k]);
@@ -799,7 +805,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         int rc = scan_u32(h, h->d_counts, h->d_bases, n_files, sk);
         if (rc)
             return rc;
-        k_batch_begin<<<1, 32, 0, sk>>>(h->d_sc, h->d_counts, h->d_bases, (uint32_t)n_files, h->max_chunks, cdc_bytes);
+        k_batch_begin<<<1, 64, 0, sk>>>(h->d_sc, h->d_counts, h->d_bases, (uint32_t)n_files, h->max_chunks, cdc_bytes);
         LAUNCH_OK(h);
         k_select_cuts<1><<<nb, 128, 0, sk>>>(m.d_files, (uint32_t)n_files, h->prm, h->d_tiles, h->d_pool, h->d_counts,
                                              h->d_bases, h->d_sc, h->max_chunks, h->stream_base, h->d_chunk_start,
@@ -814,16 +820,24 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     }
     CK(h, cudaEventRecord(h->ev[3], sk));
     if (n_files) {
+        const uint32_t *order = nullptr;
+        if (h->sha_order) { // longest chunks first (see k_len_order)
+            k_len_hist<<<h->sm_count * 2, LEN_THREADS, 0, sk>>>(h->d_chunk_len, h->d_sc);
+            LAUNCH_OK(h);
+            k_len_order<<<h->sm_count * 2, LEN_THREADS, 0, sk>>>(h->d_chunk_len, h->d_sc, h->d_order);
+            LAUNCH_OK(h);
+            order = h->d_order;
+        }
         if (h->sha_fma)
             k_sha256_ranges<true><<<sha_grid(h), SHA_THREADS, 0, sk>>>(d_arena, h->d_chunk_start, h->d_chunk_len,
                                                                       &h->d_sc->batch_chunks, 0, &h->d_sc->n_chunks, 0, 0,
                                                                       0, h->d_digests, &h->d_sc->work, &h->d_sc->err, 1u, nullptr, nullptr,
-                                                                      nullptr);
+                                                                      nullptr, order);
         else
             k_sha256_ranges<false><<<sha_grid(h), SHA_THREADS, 0, sk>>>(d_arena, h->d_chunk_start, h->d_chunk_len,
                                                                        &h->d_sc->batch_chunks, 0, &h->d_sc->n_chunks, 0,
                                                                        0, 0, h->d_digests, &h->d_sc->work, &h->d_sc->err, 1u, nullptr, nullptr,
-                                                                      nullptr);
+                                                                      nullptr, order);
         LAUNCH_OK(h);
         k_batch_end<<<1, 32, 0, sk>>>(h->d_sc);
         LAUNCH_OK(h);
@@ -833,7 +847,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, sk));
         k_sha256_ranges<false><<<(uint32_t)std::min<uint64_t>(sha_grid(h), (n_rng + 3) / 4), SHA_THREADS, 0, sk>>>(
             d_arena, m.d_rstart, m.d_rlen, nullptr, n_rng, nullptr, 0, 0, 0, h->d_stream_digests, &h->d_sc->work, nullptr,
-            1u, m.d_rstream, m.d_rflags, h->d_stream_state);
+            1u, m.d_rstream, m.d_rflags, h->d_stream_state, nullptr);
         LAUNCH_OK(h);
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, sk));
     }

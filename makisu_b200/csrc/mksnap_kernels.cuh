@@ -606,7 +606,11 @@ struct SessionCounters {
     uint32_t err;                  // 1 = candidate pool overflow, 2 = chunk table overflow
     uint32_t crc_acc;              // XOR accumulator of K0
     uint32_t work;                 // work-stealing counter of K2
+    uint32_t len_bins[64];         // K2 work order: chunks of the batch per length class (2 KiB classes)
+    uint32_t len_cursor[64];       //   slots handed out per class while the order is written
 };
+constexpr uint32_t LEN_CLASSES = 64;
+constexpr uint32_t LEN_CLASS_SHIFT = 11;
 
 // One application of the cut rule from `prev`, reading tile records and candidates from
 // global memory.
@@ -918,6 +922,10 @@ k_expand_big_cuts(const CdcFile *__restrict__ files, uint32_t n_files, const uin
 __global__ void k_batch_begin(SessionCounters *sc, const uint32_t *counts, const uint32_t *bases, uint32_t n_files,
                               uint64_t max_chunks, uint64_t cdc_bytes)
 {
+    if (blockIdx.x == 0 && threadIdx.x < LEN_CLASSES) {
+        sc->len_bins[threadIdx.x] = 0;
+        sc->len_cursor[threadIdx.x] = 0;
+    }
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         uint32_t total = n_files ? bases[n_files - 1] + counts[n_files - 1] : 0;
         sc->batch_chunks = total;
@@ -936,6 +944,80 @@ __global__ void k_batch_end(SessionCounters *sc)
             sc->n_chunks += sc->batch_chunks;
         sc->batch_chunks = 0;
         sc->work = 0;
+    }
+}
+
+// ------------------------------------------------------------------------
+// K2 work order.  A lane hashes one chunk serially (8 MB/s per lane with the SM full), so when the work list runs
+// dry every warp keeps issuing for as long as its LONGEST unfinished chunk lasts: with content-defined lengths
+// (4 KiB .. 128 KiB) that drain costs ~3.4 ms of 56 (measured against equal-length chunks).  Handing chunks out
+// longest class first leaves only the shortest ones for the end.  Counting sort by 2 KiB length class:
+// k_len_hist counts, k_len_order writes batch-relative chunk indices, largest class first (order inside a class
+// is arbitrary: digests are stored by chunk index, so the result does not depend on it).
+// ------------------------------------------------------------------------
+constexpr int LEN_THREADS = 256;
+constexpr int LEN_ITEMS = 8;
+
+__device__ __forceinline__ uint32_t len_class(uint64_t len)
+{
+    const uint64_t c = len >> LEN_CLASS_SHIFT;
+    return c < LEN_CLASSES - 1 ? (uint32_t)c : LEN_CLASSES - 1;
+}
+
+__global__ void __launch_bounds__(LEN_THREADS) k_len_hist(const uint64_t *__restrict__ len, SessionCounters *sc)
+{
+    if (sc->err)
+        return;
+    __shared__ uint32_t s_cnt[LEN_CLASSES];
+    if (threadIdx.x < LEN_CLASSES)
+        s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t n = sc->batch_chunks, first = sc->n_chunks;
+    for (uint64_t i = (uint64_t)blockIdx.x * LEN_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * LEN_THREADS)
+        atomicAdd(&s_cnt[len_class(len[first + i])], 1u);
+    __syncthreads();
+    if (threadIdx.x < LEN_CLASSES && s_cnt[threadIdx.x])
+        atomicAdd(&sc->len_bins[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(LEN_THREADS) k_len_order(const uint64_t *__restrict__ len, SessionCounters *sc,
+                                                           uint32_t *__restrict__ order)
+{
+    if (sc->err)
+        return;
+    __shared__ uint32_t s_cnt[LEN_CLASSES], s_base[LEN_CLASSES], s_got[LEN_CLASSES];
+    const uint32_t t = threadIdx.x;
+    if (t < LEN_CLASSES) { // first slot of class t = number of chunks in longer classes
+        uint32_t b = 0;
+        for (uint32_t c = t + 1; c < LEN_CLASSES; ++c)
+            b += sc->len_bins[c];
+        s_base[t] = b;
+    }
+    const uint64_t n = sc->batch_chunks, first = sc->n_chunks;
+    constexpr uint64_t TILE = (uint64_t)LEN_THREADS * LEN_ITEMS;
+    for (uint64_t t0 = (uint64_t)blockIdx.x * TILE; t0 < n; t0 += (uint64_t)gridDim.x * TILE) {
+        if (t < LEN_CLASSES)
+            s_cnt[t] = 0;
+        __syncthreads();
+        uint32_t cls[LEN_ITEMS], rank[LEN_ITEMS];
+#pragma unroll
+        for (int j = 0; j < LEN_ITEMS; ++j) {
+            const uint64_t i = t0 + (uint64_t)j * LEN_THREADS + t;
+            cls[j] = LEN_CLASSES;
+            if (i < n) {
+                cls[j] = len_class(len[first + i]);
+                rank[j] = atomicAdd(&s_cnt[cls[j]], 1u);
+            }
+        }
+        __syncthreads();
+        if (t < LEN_CLASSES && s_cnt[t])
+            s_got[t] = atomicAdd(&sc->len_cursor[t], s_cnt[t]);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < LEN_ITEMS; ++j)
+            if (cls[j] < LEN_CLASSES)
+                order[s_base[cls[j]] + s_got[cls[j]] + rank[j]] = (uint32_t)(t0 + (uint64_t)j * LEN_THREADS + t);
+        __syncthreads();
     }
 }
 
@@ -968,9 +1050,30 @@ template <bool FMA_ADDS> __device__ __forceinline__ uint32_t sha_addk(uint32_t x
     return d;
 }
 
+#ifndef SHA_SHR_MULHI
+#define SHA_SHR_MULHI 0
+#endif
+// Register budget: measured on B200 (ms per 52.43 GB): 8 CTAs/SM (64 regs) 59.3, 7 (72) 57.1, 6 (78) 55.8,
+// 5 (90) 54.9, 4 (93) 54.9 -- the kernel is ALU-pipe bound, 20 warps are enough to keep the pipe fed and the
+// extra registers remove moves.
+#ifndef SHA_MINBLOCKS
+#define SHA_MINBLOCKS 5
+#endif
+#define SHA_LAUNCH_BOUNDS __launch_bounds__(SHA_THREADS, SHA_MINBLOCKS)
+// x >> n as the high half of x * 2^(32-n): one IMAD.HI on the FMA pipe instead of one SHF on the ALU pipe.  The
+// multiplier is a runtime value (derived from the `one` kernel argument) so ptxas cannot turn it back into a shift.
+__device__ __forceinline__ uint32_t shr_mulhi(uint32_t x, uint32_t pow2)
+{
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(pow2));
+    return d;
+}
+
 template <bool FMA_ADDS>
 __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], const uint32_t one)
 {
+    const uint32_t p29 = one << 29, p22 = one << 22;
+    (void)p29; (void)p22;
     constexpr uint32_t K[64] = {
         0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
         0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
@@ -988,8 +1091,10 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], 
             wi = w[i];
         } else {
             const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
-            const uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
-            const uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
+            const uint32_t sh3 = (FMA_ADDS && SHA_SHR_MULHI >= 1) ? shr_mulhi(w15, p29) : (w15 >> 3);
+            const uint32_t sh10 = (FMA_ADDS && SHA_SHR_MULHI >= 2) ? shr_mulhi(w2, p22) : (w2 >> 10);
+            const uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ sh3;
+            const uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ sh10;
             wi = sha_add<FMA_ADDS>(sha_add<FMA_ADDS>(w[i & 15], s0, one), sha_add<FMA_ADDS>(w[(i + 9) & 15], s1, one), one);
             w[i & 15] = wi;
         }
@@ -1018,14 +1123,14 @@ struct StreamState {
 // mode 0: ranges from (start[], len[]) arrays, count read from *n_dev (or n_host if n_dev==nullptr)
 // mode 1: uniform ranges of `uni_len` bytes over [0, uni_total) of `data` (Merkle levels)
 template <bool FMA_ADDS>
-__global__ void __launch_bounds__(SHA_THREADS)
+__global__ void SHA_LAUNCH_BOUNDS
 k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ start,
                 const uint64_t *__restrict__ len, const uint32_t *__restrict__ n_dev, uint64_t n_host,
                 const unsigned long long *__restrict__ first_dev, uint64_t first_host, /* index of range 0 in start/len/out */
                 uint64_t uni_len, uint64_t uni_total, uint8_t *__restrict__ out,
                 uint32_t *__restrict__ work_counter, const uint32_t *__restrict__ skip_if_err, const uint32_t one,
                 const uint32_t *__restrict__ rng_stream, const uint32_t *__restrict__ rng_flags,
-                StreamState *__restrict__ sstate)
+                StreamState *__restrict__ sstate, const uint32_t *__restrict__ order /* work order or nullptr */)
 {
     if (skip_if_err && *skip_if_err)
         return;
@@ -1042,11 +1147,6 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
     bool more = false;          // this piece is not the last of its stream
     uint32_t phase = 0;         // 0 idle, 1 data blocks, 2 needs extra length block
     bool exhausted = false;
-    uint4 pf[5];                // next block's aligned 80-byte window, loaded while this block compresses
-    bool pf_ok = false;
-#pragma unroll
-    for (int k = 0; k < 5; ++k)
-        pf[k] = make_uint4(0, 0, 0, 0);
 
     for (;;) {
         // ---- refill idle lanes (warp-aggregated fetch) ----
@@ -1060,7 +1160,7 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
             if (phase == 0 && !exhausted) {
                 const uint64_t idx = (uint64_t)basei + __popc(need & ((1u << lane) - 1u));
                 if (idx < n) {
-                    my = first + idx;
+                    my = first + (order ? (uint64_t)order[idx] : idx);
                     if (start) {
                         p = data + start[my];
                         total = len[my];
@@ -1071,7 +1171,6 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
                     }
                     done = 0;
                     phase = 1;
-                    pf_ok = false;
                     prior = 0;
                     more = false;
                     st[0] = 0x6a09e667; st[1] = 0xbb67ae85; st[2] = 0x3c6ef372; st[3] = 0xa54ff53a;
@@ -1108,32 +1207,18 @@ k_sha256_ranges(const uint8_t *__restrict__ data, const uint64_t *__restrict__ s
             w[15] = (uint32_t)((prior + total) * 8);
             last = true;
         } else {
-            // aligned 80-byte window covering [p, p+64)
+            // aligned 80-byte window covering [p, p+64); only 16-byte words that intersect [p, p+min(rem,64)) are
+            // touched.  (Fetching the next block's window ahead of the compress was measured slower: 59.6 vs 56.2 ms.)
             const uint32_t a = (uint32_t)((uintptr_t)p & 15u);
             const uint4 *q = reinterpret_cast<const uint4 *>(p - a);
+            const uint32_t lim = a + (rem < 64 ? (uint32_t)rem : 64u);
             uint32_t x[20];
-            if (!pf_ok) {
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    // only touch 16-byte words that intersect [p, p+min(rem,64))
-                    pf[k] = make_uint4(0, 0, 0, 0);
-                    if ((uint64_t)(16 * k) < (uint64_t)a + (rem < 64 ? rem : 64))
-                        pf[k] = __ldg(q + k);
-                }
-            }
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                x[4 * k] = pf[k].x; x[4 * k + 1] = pf[k].y; x[4 * k + 2] = pf[k].z; x[4 * k + 3] = pf[k].w;
-            }
-            pf_ok = rem > 64; // another data-bearing iteration follows: fetch it now, use it after the compress
-            if (pf_ok) {
-                const uint64_t rem2 = rem - 64;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    pf[k] = make_uint4(0, 0, 0, 0);
-                    if ((uint64_t)(16 * k) < (uint64_t)a + (rem2 < 64 ? rem2 : 64))
-                        pf[k] = __ldg(q + 4 + k);
-                }
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if ((uint32_t)(16 * k) < lim)
+                    v = __ldg(q + k);
+                x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
             }
             uint32_t y[18];
 #pragma unroll
