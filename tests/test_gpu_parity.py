@@ -201,3 +201,32 @@ def test_sha256_stream_continues_across_submits(eng):
     with pytest.raises(MksnapError):
         eng.device_submit(0, 4096, [], [bad])
     eng.finish()
+
+
+def test_chunk_order_knob_is_result_neutral(oracle_lib, monkeypatch):
+    """K2 hands chunks out longest length class first (k_len_order); the digests are stored by chunk index, so the
+    chunk list, table and root must not depend on it -- also when a session spans several submits (order indices
+    are batch relative)."""
+    from makisu_b200.abi import Engine
+    rng = np.random.default_rng(33)
+    lens = [int(x) for x in rng.integers(0, 400000, 60)] + [0, 1, 4096, 131072, 131073]
+    segs = [_rand(rng, n) for n in lens]
+    arena, offs = pack(segs)
+    want = oracle_lib.chunk_table(arena, offs, lens)
+    got = []
+    for knob in ("1", "0"):
+        monkeypatch.setenv("MKSNAP_SHA_ORDER", knob)
+        with Engine(device=0, device_arena_bytes=64 << 20, max_extents=1 << 12) as e:
+            ext = cdc_extents(offs, lens)
+            e.begin()
+            e.device_upload(0, 0, arena)
+            half = len(ext) // 2
+            e.device_submit(0, arena.size, ext[:half])
+            e.device_submit(0, arena.size, ext[half:])
+            res = e.finish()
+            ends, dig = e.get_chunks(res.n_chunks)
+            got.append((bytes(res.root), res.n_chunks, res.n_unique, ends.copy(), dig.copy()))
+    for root, n, u, ends, dig in got:
+        assert root == want["root"] and n == want["n_chunks"] and u == want["n_unique"]
+        np.testing.assert_array_equal(ends, want["ends"])
+        np.testing.assert_array_equal(dig, want["digests"])
