@@ -11,6 +11,9 @@
  *   mkhost_commit_copy_ops    = MemFS.AddLayerByCopyOps + commitLayer + tario.WriteEntry, digested on the GPU
  *                               reference lib/snapshot/mem_fs.go:276-289,353-433,509-569, mem_layer.go:152-244,
  *                               lib/tario/write.go:28-68, lib/builder/step/common.go:35-111
+ *   mkhost_memfs_update_from_tar = MemFS.UpdateFromTarReader (untar=false) + go1.14 archive/tar Reader, with blob
+ *                               verification (DiffID) and the chunk table on the GPU
+ *                               reference lib/snapshot/mem_fs.go:165-255
  *   mkhost_encode_tar_header  = tario.WriteHeader + go1.14 archive/tar Writer.WriteHeader (USTAR / PAX)
  *   mkhost_describe_*         = the same host logic without a GPU (entry order / stream order as text), so the
  *                               CPU test-suite can diff it against the oracle.
@@ -102,6 +105,19 @@ int mkhost_memfs_commit_scan(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, i
 size_t mkhost_memfs_describe_copy_ops(mkhost_memfs *m, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops, char *out,
                                       size_t cap, char *err, size_t errlen);
 size_t mkhost_memfs_describe_scan(mkhost_memfs *m, int64_t now_unix, char *out, size_t cap, char *err, size_t errlen);
+
+/* UpdateFromTarReader(r, untar=false) (lib/snapshot/mem_fs.go:165-255; FROM / cache-hit path, from_step.go:118-134):
+ * merge an UNCOMPRESSED layer tar read from tar_fd (file or pipe; gunzip stays in Go, lib/tario/gzip.go) into the tree,
+ * hard links in a second pass, nothing written to disk.  The stream goes through the pinned arenas once:
+ * out->tar_digest = SHA-256 of every byte read up to EOF (the layer's DiffID: compare with the image config to
+ * verify the pulled blob, lib/docker/image/digest.go:42-50), out->root / n_chunks / n_unique = chunk table of the
+ * regular-file members (so base layers join the chunk-granular dedup), out->n_entries = headers merged (the
+ * count the reference logs).  flags: MKHOST_NO_TAR_DIGEST.  A member (header + padded body) must fit one arena. */
+int mkhost_memfs_update_from_tar(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, int tar_fd, uint32_t flags,
+                                 mkhost_layer_result *out, char *err, size_t errlen);
+/* the same merge without a GPU: merged layer as text (format below) */
+size_t mkhost_memfs_describe_update_from_tar(mkhost_memfs *m, int64_t now_unix, int tar_fd, char *out, size_t cap,
+                                             char *err, size_t errlen);
 
 /* No-GPU introspection for the CPU tests: one line per item, '\n' separated, NUL terminated.
  *   stream : "P <relpath>" | "L <target>" | "F <size> <abs path>"   in CRC stream order

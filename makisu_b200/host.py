@@ -51,6 +51,10 @@ SYMBOLS = [
     ("mkhost_memfs_describe_copy_ops", C.c_size_t, [_P, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_char_p, C.c_size_t,
                                                     C.c_char_p, C.c_size_t]),
     ("mkhost_memfs_describe_scan", C.c_size_t, [_P, C.c_int64, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
+    ("mkhost_memfs_update_from_tar", C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_uint32, C.POINTER(LayerResult), C.c_char_p,
+                                               C.c_size_t]),
+    ("mkhost_memfs_describe_update_from_tar", C.c_size_t, [_P, C.c_int64, C.c_int, C.c_char_p, C.c_size_t, C.c_char_p,
+                                                           C.c_size_t]),
     ("mkhost_describe_context_stream", C.c_size_t, [C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_char_p,
                                                     C.c_size_t, C.c_char_p, C.c_size_t]),
     ("mkhost_describe_layer", C.c_size_t, [C.c_char_p, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_char_p,
@@ -221,6 +225,21 @@ class MemFS:
         arr, keep = _ops(ops)
         if load().mkhost_memfs_commit_copy_ops(self.h, eng.h, now_unix, arr, len(ops), n_threads, tar_fd, flags,
                                                C.byref(out), err, len(err)):
+            raise HostError(err.value.decode())
+        return _layer_dict(out)
+
+    def describe_update_from_tar(self, now_unix: int, tar_fd: int) -> List[str]:
+        """UpdateFromTarReader(untar=false) without a GPU: the merged layer as text."""
+        err, buf = C.create_string_buffer(1024), C.create_string_buffer(self._BUF)
+        n = load().mkhost_memfs_describe_update_from_tar(self.h, now_unix, tar_fd, buf, len(buf), err, len(err))
+        if n == 0 or n > len(buf):
+            raise HostError(err.value.decode() or "describe buffer too small")
+        return [l for l in os.fsdecode(buf.value).split("\n") if l]
+
+    def update_from_tar(self, eng: abi.Engine, now_unix: int, tar_fd: int, flags: int = 0):
+        """UpdateFromTarReader(untar=false) through the GPU: DiffID of the blob + chunk table of its files."""
+        err, out = C.create_string_buffer(1024), LayerResult()
+        if load().mkhost_memfs_update_from_tar(self.h, eng.h, now_unix, tar_fd, flags, C.byref(out), err, len(err)):
             raise HostError(err.value.decode())
         return _layer_dict(out)
 

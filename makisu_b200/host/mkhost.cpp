@@ -625,6 +625,334 @@ std::string encode_header(Hdr h)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// go1.14 archive/tar: Header.FileInfo().Mode() and the Reader (reader.go Next/readHeader/parsePAX/mergePAX,
+// strconv.go parseNumeric/parseOctal/parsePAXTime, format.go getFormat).  Used by UpdateFromTarReader.
+// Sparse members (GNU 'S', PAX GNU.sparse.*) are rejected: docker layers do not carry them.
+// ---------------------------------------------------------------------------------------------------
+int64_t floor_sec(int64_t ns) // Time.Truncate(1s) compares equal iff the floored seconds are equal
+{
+    int64_t s = ns / 1000000000ll;
+    if (ns % 1000000000ll < 0)
+        --s;
+    return s;
+}
+
+constexpr uint32_t GO_MODE_DIR = 1u << 31, GO_MODE_SYMLINK = 1u << 27, GO_MODE_DEVICE = 1u << 26,
+                   GO_MODE_NAMED_PIPE = 1u << 25, GO_MODE_SOCKET = 1u << 24, GO_MODE_SETUID = 1u << 23,
+                   GO_MODE_SETGID = 1u << 22, GO_MODE_CHAR_DEVICE = 1u << 21, GO_MODE_STICKY = 1u << 20;
+
+uint32_t go_file_mode(const Hdr &h)
+{
+    const uint32_t m = (uint32_t)h.mode; // os.FileMode(h.Mode)
+    uint32_t mode = m & 0777;
+    if (m & 04000) mode |= GO_MODE_SETUID;
+    if (m & 02000) mode |= GO_MODE_SETGID;
+    if (m & 01000) mode |= GO_MODE_STICKY;
+    switch (m & ~07777u) {
+    case 040000: mode |= GO_MODE_DIR; break;
+    case 010000: mode |= GO_MODE_NAMED_PIPE; break;
+    case 0120000: mode |= GO_MODE_SYMLINK; break;
+    case 060000: mode |= GO_MODE_DEVICE; break;
+    case 020000: mode |= GO_MODE_DEVICE | GO_MODE_CHAR_DEVICE; break;
+    case 0140000: mode |= GO_MODE_SOCKET; break;
+    default: break;
+    }
+    switch (h.typeflag) {
+    case '2': mode |= GO_MODE_SYMLINK; break;
+    case '3': mode |= GO_MODE_DEVICE | GO_MODE_CHAR_DEVICE; break;
+    case '4': mode |= GO_MODE_DEVICE; break;
+    case '5': mode |= GO_MODE_DIR; break;
+    case '6': mode |= GO_MODE_NAMED_PIPE; break;
+    default: break;
+    }
+    return mode;
+}
+
+bool hdr_is_special(const Hdr &h) // utils.IsSpecialFile(hdr.FileInfo())
+{
+    return (go_file_mode(h) & (GO_MODE_CHAR_DEVICE | GO_MODE_DEVICE | GO_MODE_NAMED_PIPE | GO_MODE_SOCKET)) != 0;
+}
+
+struct TarErr : HostError {
+    using HostError::HostError;
+};
+[[noreturn]] void err_header() { throw TarErr("archive/tar: invalid tar header"); }
+
+std::string c_string(const uint8_t *b, size_t n)
+{
+    size_t k = 0;
+    while (k < n && b[k])
+        ++k;
+    return std::string((const char *)b, k);
+}
+
+int64_t parse_octal(const uint8_t *b, size_t n)
+{
+    while (n && (b[0] == ' ' || b[0] == 0)) { ++b; --n; }
+    while (n && (b[n - 1] == ' ' || b[n - 1] == 0)) --n;
+    if (!n)
+        return 0;
+    size_t k = 0;
+    while (k < n && b[k])
+        ++k;
+    if (!k)
+        err_header();
+    uint64_t x = 0;
+    for (size_t i = 0; i < k; ++i) {
+        if (b[i] < '0' || b[i] > '7' || (x >> 61))
+            err_header();
+        x = x * 8 + (b[i] - '0');
+    }
+    return (int64_t)x;
+}
+
+int64_t parse_numeric(const uint8_t *b, size_t n)
+{
+    if (n && (b[0] & 0x80)) { // base-256, two's complement when 0x40 is set
+        const uint8_t inv = (b[0] & 0x40) ? 0xFF : 0x00;
+        uint64_t x = 0;
+        for (size_t i = 0; i < n; ++i) {
+            uint8_t c = b[i] ^ inv;
+            if (i == 0)
+                c &= 0x7F;
+            if (x >> 56)
+                err_header();
+            x = (x << 8) | c;
+        }
+        if (x >> 63)
+            err_header();
+        return inv ? ~(int64_t)x : (int64_t)x;
+    }
+    return parse_octal(b, n);
+}
+
+int64_t parse_int10(const std::string &v)
+{
+    if (v.empty())
+        err_header();
+    size_t i = 0;
+    bool neg = false;
+    if (v[0] == '-' || v[0] == '+') { neg = v[0] == '-'; i = 1; }
+    if (i == v.size())
+        err_header();
+    int64_t x = 0;
+    for (; i < v.size(); ++i) {
+        if (v[i] < '0' || v[i] > '9' || x > (INT64_MAX - 9) / 10)
+            err_header();
+        x = x * 10 + (v[i] - '0');
+    }
+    return neg ? -x : x;
+}
+
+int64_t parse_pax_time(const std::string &s) // seconds[.fraction] -> ns, fraction truncated to 9 digits
+{
+    const size_t dot = s.find('.');
+    const std::string ss = s.substr(0, dot), sn = dot == std::string::npos ? "" : s.substr(dot + 1);
+    const int64_t secs = parse_int10(ss);
+    if (sn.empty())
+        return secs * 1000000000ll;
+    int64_t ns = 0;
+    for (size_t i = 0; i < 9; ++i) {
+        char c = i < sn.size() ? sn[i] : '0';
+        if (c < '0' || c > '9')
+            err_header();
+        ns = ns * 10 + (c - '0');
+    }
+    for (size_t i = 9; i < sn.size(); ++i)
+        if (sn[i] < '0' || sn[i] > '9')
+            err_header();
+    return (!ss.empty() && ss[0] == '-') ? secs * 1000000000ll - ns : secs * 1000000000ll + ns;
+}
+
+std::map<std::string, std::string> parse_pax_records(const uint8_t *b, size_t n)
+{
+    std::map<std::string, std::string> out;
+    size_t pos = 0;
+    while (pos < n) {
+        size_t sp = pos;
+        uint64_t len = 0;
+        while (sp < n && b[sp] != ' ') {
+            if (b[sp] < '0' || b[sp] > '9' || len > (1ull << 40))
+                err_header();
+            len = len * 10 + (b[sp] - '0');
+            ++sp;
+        }
+        if (sp == n || sp == pos || len < 5 || len > n - pos)
+            err_header();
+        const uint8_t *rec = b + sp + 1;
+        const size_t rlen = pos + len - (sp + 1);
+        if (rlen == 0 || rec[rlen - 1] != '\n')
+            err_header();
+        const uint8_t *eq = (const uint8_t *)memchr(rec, '=', rlen - 1);
+        if (!eq)
+            err_header();
+        std::string key((const char *)rec, eq - rec), val((const char *)eq + 1, rec + rlen - 1 - (eq + 1));
+        if (key.compare(0, 11, "GNU.sparse.") == 0)
+            throw TarErr("archive/tar: sparse entries are not supported");
+        if (!val.empty())
+            out[key] = val;
+        else
+            out.erase(key);
+        pos += len;
+    }
+    return out;
+}
+
+struct TarMember {
+    Hdr hdr;
+    uint64_t data_off = 0; // offset of the data in the tar stream
+    uint64_t data_len = 0; // bytes the Reader exposes (0 for header-only types)
+    uint64_t arena_off = 0; // where the data sits in the arena it was placed in (ingest only)
+};
+
+// where the stream comes from / goes to: memory (describe) or fd -> pinned arenas (ingest)
+struct TarSource {
+    virtual ~TarSource() = default;
+    virtual bool read_header(uint8_t out[512]) = 0;                                 // false: clean EOF at a block boundary
+    virtual const uint8_t *place(const uint8_t hdr[512], uint64_t nb, bool file_content, uint64_t *arena_off) = 0; // header + padded body, contiguous
+    virtual void end_marker(const uint8_t zero[512]) = 0;                          // first zero block seen
+    virtual uint64_t stream_pos() const = 0;                                        // bytes consumed so far
+};
+
+bool is_header_only(char t) { return t == '1' || t == '2' || t == '3' || t == '4' || t == '5' || t == '6'; }
+
+std::vector<TarMember> read_tar(TarSource &src)
+{
+    std::vector<TarMember> members;
+    std::map<std::string, std::string> pax;
+    std::string gnu_name, gnu_link;
+    uint8_t blk[512];
+    static const uint8_t zero[512] = {0};
+    for (;;) {
+        if (!src.read_header(blk))
+            return members;
+        if (memcmp(blk, zero, 512) == 0) {
+            src.end_marker(blk);
+            return members;
+        }
+        const int64_t want = parse_octal(blk + 148, 8);
+        int64_t us = 0, sg = 0;
+        for (int i = 0; i < 512; ++i) {
+            const uint8_t c = (i >= 148 && i < 156) ? (uint8_t)' ' : blk[i];
+            us += c;
+            sg += (int8_t)c;
+        }
+        if (want != us && want != sg)
+            err_header();
+        enum { V7, USTAR, STAR, GNU } fmt = V7;
+        if (memcmp(blk + 257, "ustar\0", 6) == 0 && memcmp(blk + 508, "tar\0", 4) == 0)
+            fmt = STAR;
+        else if (memcmp(blk + 257, "ustar\0", 6) == 0)
+            fmt = USTAR;
+        else if (memcmp(blk + 257, "ustar ", 6) == 0 && memcmp(blk + 263, " \0", 2) == 0)
+            fmt = GNU;
+        Hdr h;
+        h.name = c_string(blk, 100);
+        h.mode = parse_numeric(blk + 100, 8);
+        h.uid = parse_numeric(blk + 108, 8);
+        h.gid = parse_numeric(blk + 116, 8);
+        h.size = parse_numeric(blk + 124, 12);
+        h.mtime_ns = parse_numeric(blk + 136, 12) * 1000000000ll;
+        h.typeflag = (char)blk[156];
+        h.linkname = c_string(blk + 157, 100);
+        if (fmt != V7) {
+            (void)parse_numeric(blk + 329, 8); // devmajor / devminor must parse
+            (void)parse_numeric(blk + 337, 8);
+            std::string prefix;
+            if (fmt == USTAR)
+                prefix = c_string(blk + 345, 155);
+            else if (fmt == STAR)
+                prefix = c_string(blk + 345, 131);
+            if (!prefix.empty())
+                h.name = prefix + "/" + h.name;
+        }
+        const bool meta = h.typeflag == 'x' || h.typeflag == 'g' || h.typeflag == 'L' || h.typeflag == 'K';
+        if (!meta) { // mergePAX, GNU long names, TypeRegA -- before the final size is known
+            if (h.typeflag == 'S')
+                throw TarErr("archive/tar: sparse entries are not supported");
+            for (const auto &kv : pax) {
+                if (kv.first == "path") h.name = kv.second;
+                else if (kv.first == "linkpath") h.linkname = kv.second;
+                else if (kv.first == "uid") h.uid = parse_int10(kv.second);
+                else if (kv.first == "gid") h.gid = parse_int10(kv.second);
+                else if (kv.first == "mtime") h.mtime_ns = parse_pax_time(kv.second);
+                else if (kv.first == "size") h.size = parse_int10(kv.second);
+            }
+            if (!gnu_name.empty()) h.name = gnu_name;
+            if (!gnu_link.empty()) h.linkname = gnu_link;
+            if (h.typeflag == '\0')
+                h.typeflag = (!h.name.empty() && h.name.back() == '/') ? '5' : '0';
+        }
+        const int64_t nb = is_header_only(h.typeflag) ? 0 : h.size;
+        if (nb < 0)
+            err_header();
+        const uint64_t data_off = src.stream_pos();
+        uint64_t arena_off = 0;
+        const uint8_t *body = src.place(blk, (uint64_t)nb, !meta && h.typeflag == '0' && nb > 0, &arena_off);
+        if (meta) {
+            if (h.typeflag == 'x') {
+                pax = parse_pax_records(body, (size_t)nb);
+            } else if (h.typeflag == 'g') {
+                (void)parse_pax_records(body, (size_t)nb);
+                throw TarErr("unsupported type 1100111"); // Next() returns the global header; IsSimilarHeader rejects it
+            } else if (h.typeflag == 'L') {
+                gnu_name = c_string(body, (size_t)nb);
+            } else {
+                gnu_link = c_string(body, (size_t)nb);
+            }
+            continue;
+        }
+        TarMember m;
+        m.hdr = h;
+        m.data_off = data_off;
+        m.data_len = (uint64_t)nb;
+        m.arena_off = arena_off;
+        members.push_back(std::move(m));
+        pax.clear();
+        gnu_name.clear();
+        gnu_link.clear();
+    }
+}
+
+struct MemTarSource : TarSource {
+    const uint8_t *p;
+    uint64_t n, pos = 0;
+    MemTarSource(const uint8_t *p_, uint64_t n_) : p(p_), n(n_) {}
+    bool read_header(uint8_t out[512]) override
+    {
+        if (pos == n)
+            return false;
+        if (n - pos < 512)
+            throw TarErr("unexpected EOF");
+        memcpy(out, p + pos, 512);
+        pos += 512;
+        return true;
+    }
+    const uint8_t *place(const uint8_t *, uint64_t nb, bool, uint64_t *arena_off) override
+    {
+        const uint64_t padded = align_up(nb, 512);
+        if (n - pos < padded)
+            throw TarErr("unexpected EOF");
+        const uint8_t *b = p + pos;
+        *arena_off = pos;
+        pos += padded;
+        return b;
+    }
+    void end_marker(const uint8_t *) override
+    {
+        static const uint8_t zero[512] = {0};
+        if (pos == n)
+            return;
+        if (n - pos < 512)
+            throw TarErr("unexpected EOF");
+        if (memcmp(p + pos, zero, 512) != 0)
+            err_header();
+        pos = n;
+    }
+    uint64_t stream_pos() const override { return pos; }
+};
+
+// ---------------------------------------------------------------------------------------------------
 // MemFS (copy-op path): lib/snapshot/mem_fs.go, mem_layer.go
 // ---------------------------------------------------------------------------------------------------
 struct MemFile {
@@ -722,6 +1050,32 @@ class MemFS
             maybe_add(layer, src, dst, hdr, true);
             return W_CONT;
         });
+        return layer;
+    }
+
+    // UpdateFromTarReader(r, untar=false) (mem_fs.go:165-255): merge the members of a base-layer tar into the tree,
+    // hard links in a second pass.  Nothing is written to disk.
+    std::map<std::string, MemFile> update_from_tar(const std::vector<TarMember> &members)
+    {
+        std::map<std::string, MemFile> layer;
+        std::map<std::string, Hdr> hardlinks; // the reference ranges over a Go map: order unspecified, result unaffected
+        for (const auto &m : members) {
+            Hdr hdr = m.hdr;
+            const std::string path = go_join(root_, hdr.name);
+            if (path_base(path).compare(0, 8, ".wh..wh.") == 0)
+                continue;
+            if (is_descendant_of_any(path, blacklist_) || hdr_is_special(hdr))
+                continue;
+            hdr.name = rel_path(hdr.name);
+            if (hdr.typeflag == '1') {
+                hdr.linkname = abs_path(hdr.linkname);
+                hardlinks[path] = hdr;
+            } else {
+                maybe_add(layer, abs_path(hdr.name), abs_path(hdr.name), hdr, false);
+            }
+        }
+        for (const auto &kv : hardlinks)
+            maybe_add(layer, abs_path(kv.second.name), abs_path(kv.second.name), kv.second, false);
         return layer;
     }
 
@@ -830,8 +1184,8 @@ class MemFS
     {
         if (h.name.empty() && nh.name.empty())
             return true;
-        const bool teq = h.mtime_ns / 1000000000ll == nh.mtime_ns / 1000000000ll;
-        const bool meq = (h.mode & 07777) == (nh.mode & 07777);
+        const bool teq = floor_sec(h.mtime_ns) == floor_sec(nh.mtime_ns);
+        const bool meq = go_file_mode(h) == go_file_mode(nh);
         switch (h.typeflag) {
         case '2': return nh.typeflag == '2' && h.linkname == nh.linkname;
         case '1': return nh.typeflag == '1' && teq && h.linkname == nh.linkname && h.uid == nh.uid && h.gid == nh.gid && meq;
@@ -1084,6 +1438,112 @@ void commit_layer(mksnap_t *eng, const std::map<std::string, MemFile> &layer, in
     out->n_unique = res.n_unique;
 }
 
+// UpdateFromTarReader with the GPU in the loop: the tar stream is read from `fd` straight into pinned arenas (the
+// arena IS the stream, so SHA-256 over the pieces is the layer's DiffID), members stay contiguous inside one arena so
+// every regular file body is one CDC extent.
+struct ArenaTarSource : TarSource {
+    mksnap_t *eng;
+    int fd;
+    bool want_digest;
+    uint8_t *a = nullptr;
+    uint64_t cap = 0, pos = 0, consumed = 0, tar_bytes = 0;
+    int32_t aid = -1;
+    std::vector<mksnap_extent> ext;
+
+    ArenaTarSource(mksnap_t *e, int f, bool d) : eng(e), fd(f), want_digest(d) { acquire(); }
+
+    void acquire()
+    {
+        void *hp = nullptr;
+        ck(eng, mksnap_arena_acquire(eng, &hp, &cap, &aid), "arena acquire");
+        a = (uint8_t *)hp;
+        cap = cap / 512 * 512;
+        pos = 0;
+        ext.clear();
+    }
+    void flush(bool last)
+    {
+        mksnap_range rng{0, pos, 0, last ? 0u : MKSNAP_R_MORE};
+        ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), &rng, want_digest ? 1 : 0), "arena submit");
+        tar_bytes += pos;
+        if (!last)
+            acquire();
+    }
+    uint64_t read_full(uint8_t *dst, uint64_t n)
+    {
+        uint64_t done = 0;
+        while (done < n) {
+            ssize_t r = read(fd, dst + done, n - done);
+            if (r < 0) {
+                if (errno == EINTR)
+                    continue;
+                throw HostError(std::string("read header: ") + strerror(errno));
+            }
+            if (r == 0)
+                break;
+            done += (uint64_t)r;
+        }
+        consumed += done;
+        return done;
+    }
+    bool read_header(uint8_t out[512]) override
+    {
+        const uint64_t r = read_full(out, 512);
+        if (r == 0)
+            return false;
+        if (r < 512)
+            throw TarErr("unexpected EOF");
+        return true;
+    }
+    const uint8_t *place(const uint8_t hdr[512], uint64_t nb, bool file_content, uint64_t *arena_off) override
+    {
+        const uint64_t padded = align_up(nb, 512), need = 512 + padded;
+        if (need > cap)
+            throw HostError("tar member of " + std::to_string(need) + " bytes exceeds the arena; a file is chunked within one arena");
+        if (pos + need > cap)
+            flush(false);
+        memcpy(a + pos, hdr, 512);
+        pos += 512;
+        if (read_full(a + pos, padded) < padded)
+            throw TarErr("unexpected EOF");
+        *arena_off = pos;
+        if (file_content)
+            ext.push_back(mksnap_extent{pos, nb, 0, MKSNAP_X_CDC, 0});
+        const uint8_t *body = a + pos;
+        pos += padded;
+        return body;
+    }
+    void raw(const uint8_t *p, uint64_t n)
+    {
+        if (pos + n > cap)
+            flush(false);
+        memcpy(a + pos, p, n);
+        pos += n;
+    }
+    void end_marker(const uint8_t zero[512]) override
+    {
+        raw(zero, 512);
+        uint8_t nxt[512];
+        const uint64_t r = read_full(nxt, 512);
+        if (r == 0)
+            return;
+        if (r < 512)
+            throw TarErr("unexpected EOF");
+        if (memcmp(nxt, zero, 512) != 0)
+            err_header();
+        raw(nxt, 512);
+        for (;;) { // whatever follows the end marker (record padding) still belongs to the blob that is digested
+            if (pos == cap)
+                flush(false);
+            const uint64_t got = read_full(a + pos, cap - pos);
+            pos += got;
+            if (got == 0)
+                return;
+        }
+    }
+    uint64_t stream_pos() const override { return consumed; }
+};
+
 size_t emit_text(const std::string &s, char *out, size_t cap)
 {
     if (s.size() + 1 <= cap)
@@ -1216,6 +1676,59 @@ int mkhost_memfs_commit_scan(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, i
         return 0;
     } catch (const std::exception &e) {
         set_err(err, errlen, std::string("failed to generate diff layer: ") + e.what());
+        return -1;
+    }
+}
+
+size_t mkhost_memfs_describe_update_from_tar(mkhost_memfs *m, int64_t now_unix, int tar_fd, char *out, size_t cap, char *err,
+                                             size_t errlen)
+{
+    try {
+        m->fs.set_now(now_unix);
+        std::vector<uint8_t> buf;
+        uint8_t tmp[65536];
+        for (;;) {
+            ssize_t r = read(tar_fd, tmp, sizeof tmp);
+            if (r < 0) {
+                if (errno == EINTR)
+                    continue;
+                throw HostError(std::string("read header: ") + strerror(errno));
+            }
+            if (r == 0)
+                break;
+            buf.insert(buf.end(), tmp, tmp + r);
+        }
+        MemTarSource src(buf.data(), buf.size());
+        return emit_text(describe_layer_text(m->fs.update_from_tar(read_tar(src))), out, cap);
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("update memfs from tar: ") + e.what());
+        return 0;
+    }
+}
+
+int mkhost_memfs_update_from_tar(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, int tar_fd, uint32_t flags,
+                                 mkhost_layer_result *out, char *err, size_t errlen)
+{
+    try {
+        m->fs.set_now(now_unix);
+        const bool want_digest = !(flags & MKHOST_NO_TAR_DIGEST);
+        ck(eng, mksnap_begin(eng), "begin");
+        ArenaTarSource src(eng, tar_fd, want_digest);
+        const std::vector<TarMember> members = read_tar(src);
+        src.flush(true);
+        mksnap_result res;
+        ck(eng, mksnap_finish(eng, &res), "finish");
+        memset(out->tar_digest, 0, 32);
+        if (want_digest)
+            ck(eng, mksnap_get_stream_digests(eng, out->tar_digest, 1), "stream digests");
+        memcpy(out->root, res.root, 32);
+        out->n_entries = m->fs.update_from_tar(members).size();
+        out->tar_bytes = src.tar_bytes;
+        out->n_chunks = res.n_chunks;
+        out->n_unique = res.n_unique;
+        return 0;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("update memfs from tar: ") + e.what());
         return -1;
     }
 }

@@ -4,6 +4,7 @@ SHA-256 is DigestPair.TarDigest.
 Restates
   reference lib/snapshot/mem_fs.go:69-83,276-289,353-433,440-569  (MemFS, AddLayerByCopyOps, addToLayer,
             commitLayer, maybeAddToLayer, isUpdated, addAncestors)
+  reference lib/snapshot/mem_fs.go:165-255                        (UpdateFromTarReader, untar=false)
   reference lib/snapshot/mem_layer.go:83-88,127-132,152-244       (commit, whiteout, createHeader, addHeader, rangeFiles)
   reference lib/snapshot/copy_op.go:45-80,149-174                 (NewCopyOperation, resolveDestination)
   reference lib/snapshot/utils.go:37-75                           (shouldSkip, walk)
@@ -36,11 +37,35 @@ WHITEOUT_PREFIX = ".wh."
 WHITEOUT_META_PREFIX = ".wh..wh."
 
 C_ISUID, C_ISGID, C_ISVTX = 0o4000, 0o2000, 0o1000
+# os.FileMode bits (go1.14 os/types.go)
+GO_MODE_DIR, GO_MODE_SYMLINK, GO_MODE_DEVICE, GO_MODE_NAMED_PIPE, GO_MODE_SOCKET = 1 << 31, 1 << 27, 1 << 26, 1 << 25, 1 << 24
+GO_MODE_SETUID, GO_MODE_SETGID, GO_MODE_CHAR_DEVICE, GO_MODE_STICKY = 1 << 23, 1 << 22, 1 << 21, 1 << 20
 
 
 # ---- pathutils (lib/pathutils/path.go) ----------------------------------------------
+def go_clean(p: str) -> str:
+    """path.Clean (go1.14 path/path.go) for the inputs this module sees."""
+    if p == "":
+        return "."
+    rooted = p.startswith("/")
+    out: List[str] = []
+    for e in p.split("/"):
+        if e in ("", "."):
+            continue
+        if e == "..":
+            if out and out[-1] != "..":
+                out.pop()
+            elif not rooted:
+                out.append("..")
+            continue
+        out.append(e)
+    s = "/".join(out)
+    return "/" + s if rooted else (s or ".")
+
+
 def abs_path(p: str) -> str:
-    return posixpath.join("/", p.rstrip("/")) if p.rstrip("/") else "/"
+    """pathutils.AbsPath: path.Join("/", strings.TrimRight(p, "/")) -- Join cleans the result."""
+    return go_clean("/" + p.rstrip("/"))
 
 
 def rel_path(p: str) -> str:
@@ -84,8 +109,26 @@ class Header:
     devminor: int = 0
 
     def file_mode_bits(self) -> int:
-        """Header.FileInfo().Mode() as comparable bits (perm + suid/sgid/sticky + type)."""
-        return (self.mode & 0o7777, self.typeflag)
+        """Header.FileInfo().Mode() (go1.14 archive/tar common.go headerFileInfo.Mode) as an os.FileMode integer:
+        permission bits, setuid/setgid/sticky, and the type bits implied by BOTH the c_IS* bits a foreign writer
+        left in Mode and the typeflag."""
+        m = self.mode & 0xFFFFFFFF          # os.FileMode(h.Mode): uint32
+        mode = m & 0o777
+        if m & C_ISUID:
+            mode |= GO_MODE_SETUID
+        if m & C_ISGID:
+            mode |= GO_MODE_SETGID
+        if m & C_ISVTX:
+            mode |= GO_MODE_STICKY
+        mode |= {0o40000: GO_MODE_DIR, 0o10000: GO_MODE_NAMED_PIPE, 0o120000: GO_MODE_SYMLINK, 0o60000: GO_MODE_DEVICE,
+                 0o20000: GO_MODE_DEVICE | GO_MODE_CHAR_DEVICE, 0o140000: GO_MODE_SOCKET}.get(m & ~0o7777 & 0xFFFFFFFF, 0)
+        mode |= {TYPE_SYMLINK: GO_MODE_SYMLINK, TYPE_CHAR: GO_MODE_DEVICE | GO_MODE_CHAR_DEVICE, TYPE_BLOCK: GO_MODE_DEVICE,
+                 TYPE_DIR: GO_MODE_DIR, TYPE_FIFO: GO_MODE_NAMED_PIPE}.get(self.typeflag, 0)
+        return mode
+
+    def is_special(self) -> bool:
+        """utils.IsSpecialFile(hdr.FileInfo()) (lib/utils/utils.go:161-163)."""
+        return bool(self.file_mode_bits() & (GO_MODE_CHAR_DEVICE | GO_MODE_DEVICE | GO_MODE_NAMED_PIPE | GO_MODE_SOCKET))
 
 
 def file_info_header(st: os.stat_result, link: str = "") -> Header:
@@ -278,6 +321,202 @@ def is_header_only(typeflag: bytes) -> bool:
 
 TRAILER = b"\0" * 1024  # tar.Writer.Close(): exactly two zero blocks
 
+
+
+# ---- go1.14 archive/tar Reader (stdlib, not vendored), restated ----------------------
+# reader.go: Reader.next / readHeader / parsePAX / mergePAX, strconv.go: parseNumeric / parseOctal / parsePAXTime,
+# format.go: getFormat.  Sparse files (GNU 'S', PAX GNU.sparse.*) are rejected: docker layers do not carry them.
+class TarHeaderError(ValueError):
+    """tar.ErrHeader"""
+
+
+def _c_string(b: bytes) -> bytes:
+    i = b.find(b"\0")
+    return b if i < 0 else b[:i]
+
+
+def _parse_octal(b: bytes) -> int:
+    b = b.strip(b" \0")
+    if not b:
+        return 0
+    b = _c_string(b)
+    if not b or any(c not in b"01234567" for c in b):
+        raise TarHeaderError("archive/tar: invalid tar header")
+    return int(b, 8)
+
+
+def _parse_numeric(b: bytes) -> int:
+    if b and b[0] & 0x80:  # base-256 (binary), two's complement when 0x40 is set
+        inv = 0xFF if b[0] & 0x40 else 0x00
+        x = 0
+        for i, c in enumerate(b):
+            c ^= inv
+            if i == 0:
+                c &= 0x7F
+            if x >> 56:
+                raise TarHeaderError("archive/tar: invalid tar header")
+            x = (x << 8) | c
+        if x >> 63:
+            raise TarHeaderError("archive/tar: invalid tar header")
+        return ~x if inv else x
+    return _parse_octal(b)
+
+
+def _parse_pax_time(s: str) -> int:
+    """seconds[.fraction] -> integer nanoseconds (strconv.go parsePAXTime: fraction truncated to 9 digits)."""
+    ss, _, sn = s.partition(".")
+    try:
+        secs = int(ss, 10)
+    except ValueError:
+        raise TarHeaderError("archive/tar: invalid tar header")
+    if not sn:
+        return secs * 10**9
+    if not sn.isdigit():
+        raise TarHeaderError("archive/tar: invalid tar header")
+    nsecs = int((sn + "0" * 9)[:9])
+    return secs * 10**9 - nsecs if ss.startswith("-") else secs * 10**9 + nsecs
+
+
+def _parse_pax_records(body: bytes) -> Dict[str, str]:
+    out: Dict[str, str] = {}
+    while body:
+        sp = body.find(b" ")
+        if sp < 0 or not body[:sp].isdigit():
+            raise TarHeaderError("archive/tar: invalid tar header")
+        n = int(body[:sp])
+        if n < 5 or n > len(body):
+            raise TarHeaderError("archive/tar: invalid tar header")
+        rec, body = body[sp + 1:n], body[n:]
+        if not rec.endswith(b"\n") or b"=" not in rec:
+            raise TarHeaderError("archive/tar: invalid tar header")
+        k, _, v = rec[:-1].partition(b"=")
+        key, val = k.decode("utf-8", "surrogateescape"), v.decode("utf-8", "surrogateescape")
+        if key.startswith("GNU.sparse."):
+            raise TarHeaderError("archive/tar: sparse entries are not supported by this restatement")
+        if val:
+            out[key] = val
+        else:
+            out.pop(key, None)
+    return out
+
+
+@dataclass
+class TarMember:
+    hdr: Header
+    data_off: int   # offset of the member's data in the stream
+    data_len: int   # bytes of data the Reader exposes (0 for header-only types)
+
+
+def read_tar(data: bytes) -> List[TarMember]:
+    """tar.Reader.Next() until io.EOF over an in-memory stream."""
+    members: List[TarMember] = []
+    pos = 0
+    pax: Dict[str, str] = {}
+    gnu_name = gnu_link = ""
+    while True:
+        blk = data[pos:pos + 512]
+        if len(blk) == 0:
+            return members                      # io.EOF at a block boundary
+        if len(blk) < 512:
+            raise TarHeaderError("unexpected EOF")
+        if blk == b"\0" * 512:
+            nxt = data[pos + 512:pos + 1024]
+            if len(nxt) == 0 or nxt == b"\0" * 512:
+                return members                  # one zero block at EOF, or two: end of archive
+            if len(nxt) < 512:
+                raise TarHeaderError("unexpected EOF")
+            raise TarHeaderError("archive/tar: invalid tar header")
+        pos += 512
+        # checksum: unsigned or signed sum with the field read as spaces
+        want = _parse_octal(blk[148:156])
+        b2 = blk[:148] + b" " * 8 + blk[156:]
+        unsigned = sum(b2)
+        signed = sum(c - 256 if c > 127 else c for c in b2)
+        if want != unsigned and want != signed:
+            raise TarHeaderError("archive/tar: invalid tar header")
+        magic, version = blk[257:263], blk[263:265]
+        if magic == b"ustar\0" and blk[508:512] == b"tar\0":
+            fmt = "star"
+        elif magic == b"ustar\0":
+            fmt = "ustar"
+        elif magic == b"ustar " and version == b" \0":
+            fmt = "gnu"
+        else:
+            fmt = "v7"
+        h = Header(name=_c_string(blk[0:100]).decode("utf-8", "surrogateescape"), mode=_parse_numeric(blk[100:108]),
+                   uid=_parse_numeric(blk[108:116]), gid=_parse_numeric(blk[116:124]), size=_parse_numeric(blk[124:136]),
+                   mtime_ns=_parse_numeric(blk[136:148]) * 10**9, typeflag=blk[156:157],
+                   linkname=_c_string(blk[157:257]).decode("utf-8", "surrogateescape"))
+        if fmt != "v7":
+            h.uname = _c_string(blk[265:297]).decode("utf-8", "surrogateescape")
+            h.gname = _c_string(blk[297:329]).decode("utf-8", "surrogateescape")
+            h.devmajor, h.devminor = _parse_numeric(blk[329:337]), _parse_numeric(blk[337:345])
+            prefix = b""
+            if fmt == "ustar":
+                prefix = _c_string(blk[345:500])
+            elif fmt == "star":
+                prefix = _c_string(blk[345:476])
+            if prefix:
+                h.name = prefix.decode("utf-8", "surrogateescape") + "/" + h.name
+        nb = 0 if is_header_only(h.typeflag) else h.size
+        if nb < 0:
+            raise TarHeaderError("archive/tar: invalid tar header")
+        if h.typeflag in (b"x", b"g"):
+            body = data[pos:pos + nb]
+            if len(body) < nb:
+                raise TarHeaderError("unexpected EOF")
+            pos += (nb + 511) // 512 * 512
+            recs = _parse_pax_records(body)
+            if h.typeflag == b"g":
+                raise TarHeaderError("unsupported type 1100111")  # Next() returns it; IsSimilarHeader then rejects 'g'
+            pax = recs
+            continue
+        if h.typeflag in (b"L", b"K"):
+            body = data[pos:pos + nb]
+            if len(body) < nb:
+                raise TarHeaderError("unexpected EOF")
+            pos += (nb + 511) // 512 * 512
+            if h.typeflag == b"L":
+                gnu_name = _c_string(body).decode("utf-8", "surrogateescape")
+            else:
+                gnu_link = _c_string(body).decode("utf-8", "surrogateescape")
+            continue
+        if h.typeflag == b"S":
+            raise TarHeaderError("archive/tar: sparse entries are not supported by this restatement")
+        for k, v in pax.items():  # mergePAX
+            try:
+                if k == "path":
+                    h.name = v
+                elif k == "linkpath":
+                    h.linkname = v
+                elif k == "uname":
+                    h.uname = v
+                elif k == "gname":
+                    h.gname = v
+                elif k == "uid":
+                    h.uid = int(v, 10)
+                elif k == "gid":
+                    h.gid = int(v, 10)
+                elif k == "mtime":
+                    h.mtime_ns = _parse_pax_time(v)
+                elif k == "size":
+                    h.size = int(v, 10)
+            except ValueError:
+                raise TarHeaderError("archive/tar: invalid tar header")
+        if gnu_name:
+            h.name = gnu_name
+        if gnu_link:
+            h.linkname = gnu_link
+        if h.typeflag == b"\0":  # TypeRegA
+            h.typeflag = TYPE_DIR if h.name.endswith("/") else TYPE_REG
+        nb = 0 if is_header_only(h.typeflag) else h.size
+        if nb < 0:
+            raise TarHeaderError("archive/tar: invalid tar header")
+        if pos + nb > len(data):
+            raise TarHeaderError("unexpected EOF")
+        members.append(TarMember(h, pos, nb))
+        pos += (nb + 511) // 512 * 512
+        pax, gnu_name, gnu_link = {}, "", ""
 
 # ---- tario.IsSimilarHeader (lib/tario/compare.go) -----------------------------------
 def is_similar_header(h: Header, nh: Header, ignore_time: bool = False) -> bool:
@@ -547,6 +786,32 @@ class MemFS:
             self._maybe_add(layer, src, dst, hdr, True)
 
         self._walk(root, self.blacklist, visit)
+        self.layers.append(layer)
+        return [layer[k] for k in sorted(layer, key=os.fsencode)]
+
+
+    def update_from_tar(self, data: bytes) -> List[MemFile]:
+        """UpdateFromTarReader(r, untar=false) (mem_fs.go:165-255): merge the headers of an (uncompressed) layer tar
+        into the tree; hard links in a second pass; nothing is written to disk.  Returns the merged layer in key
+        order (the reference only logs its count)."""
+        layer: Dict[str, MemFile] = {}
+        hardlinks: Dict[str, Header] = {}
+        for m in read_tar(data):
+            hdr = m.hdr
+            path = go_clean(self.root + "/" + hdr.name)  # filepath.Join(fs.tree.src, hdr.Name)
+            if posixpath.basename(path).startswith(WHITEOUT_META_PREFIX):
+                continue
+            if is_descendant_of_any(path, self.blacklist) or hdr.is_special() or self.is_mountpoint(path):
+                continue
+            hdr = replace(hdr, name=rel_path(hdr.name))
+            if hdr.typeflag == TYPE_LINK:
+                hdr.linkname = abs_path(hdr.linkname)
+                hardlinks[path] = hdr
+            else:
+                self._maybe_add(layer, abs_path(hdr.name), abs_path(hdr.name), hdr, False)
+        for path in sorted(hardlinks, key=os.fsencode):  # Go ranges over a map: order is unspecified, result is not affected
+            hdr = hardlinks[path]
+            self._maybe_add(layer, abs_path(hdr.name), abs_path(hdr.name), hdr, False)
         self.layers.append(layer)
         return [layer[k] for k in sorted(layer, key=os.fsencode)]
 

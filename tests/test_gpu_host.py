@@ -155,3 +155,88 @@ def test_add_layers_equal_copy_vs_scan_on_gpu(eng, tmp_path):
     assert r1["root"] == r2["root"] and r1["n_chunks"] == r2["n_chunks"] > 0
     assert r1["tar_digest"] == "sha256:" + hashlib.sha256(b1).hexdigest()
     assert r2["tar_digest"] == "sha256:" + hashlib.sha256(b2).hexdigest()
+
+
+@pytest.mark.parametrize("arena_mib", [64, 3])
+def test_update_from_tar_verifies_blob_and_chunks_files(ctx, tmp_path, arena_mib):
+    """UpdateFromTarReader(untar=false) (mem_fs.go:165-255) with the GPU in the loop: the stream read from an fd is
+    digested (DiffID of the pulled blob, digest.go:42-50) and its regular files are chunked; the MemFS merge equals
+    the oracle's.  3 MiB arenas: the stream spans many submits (SHA-256 midstate parked on the device), members never
+    straddle an arena, and tarfile's 10 KiB record padding after the end marker still belongs to the blob."""
+    import hashlib
+    import io
+    import tarfile
+    from makisu_b200 import host
+    from makisu_b200.abi import Engine
+    from oracle import layer_tar as lt
+    from oracle import lib as olib
+    rng = np.random.default_rng(5)
+    buf = io.BytesIO()
+    with tarfile.open(fileobj=buf, mode="w", format=tarfile.PAX_FORMAT) as tf:
+        def add(name, type_=tarfile.REGTYPE, data=b"", link="", mode=0o644):
+            ti = tarfile.TarInfo(name)
+            ti.type, ti.mode, ti.mtime, ti.linkname, ti.uid, ti.gid = type_, mode, 1_500_000_000, link, 7, 8
+            ti.size = len(data) if type_ == tarfile.REGTYPE else 0
+            tf.addfile(ti, io.BytesIO(data) if ti.size else None)
+        add("usr/", tarfile.DIRTYPE, mode=0o755)
+        add("usr/lib/", tarfile.DIRTYPE, mode=0o755)
+        shared = rng.integers(0, 256, 900_000, dtype=np.uint8).tobytes()
+        for i in range(14):
+            n = int(rng.integers(1, 700_000))
+            add(f"usr/lib/lib{i:02d}.so", data=rng.integers(0, 256, n, dtype=np.uint8).tobytes(), mode=0o755)
+        add("usr/lib/copy_a.bin", data=shared)
+        add("usr/lib/" + "d" * 150 + "/copy_b.bin", data=shared)            # PAX path record + duplicate content
+        add("usr/lib/alias.so", tarfile.LNKTYPE, link="usr/lib/lib00.so")
+        add("lib", tarfile.SYMTYPE, link="usr/lib", mode=0o777)
+        add("etc/empty", data=b"")
+        add("etc/.wh.removed", data=b"")
+        add("dev/null", tarfile.CHRTYPE)
+        add("zeros", data=bytes(400_000))
+    data = buf.getvalue()
+    assert len(data) % 10240 == 0
+    root = tmp_path / "root"
+    root.mkdir()
+    o = lt.MemFS(lambda: NOW, str(root))
+    want_layer = o.update_from_tar(data)
+    members = [m for m in lt.read_tar(data) if m.hdr.typeflag == lt.TYPE_REG and m.data_len]
+    want = olib.chunk_table(np.frombuffer(data, dtype=np.uint8), [m.data_off for m in members], [m.data_len for m in members])
+    tar_path = tmp_path / "base.tar"
+    tar_path.write_bytes(data)
+    h = host.MemFS(str(root))
+    with Engine(device=0, device_arena_bytes=arena_mib << 20, n_host_arenas=2, host_arena_bytes=arena_mib << 20,
+                max_extents=1 << 12) as eng:
+        with open(tar_path, "rb") as f:
+            got = h.update_from_tar(eng, NOW, f.fileno())
+        assert got["tar_digest"] == "sha256:" + hashlib.sha256(data).hexdigest()
+        assert got["tar_bytes"] == len(data) and got["n_entries"] == len(want_layer)
+        assert got["n_chunks"] == want["n_chunks"] and got["n_unique"] == want["n_unique"] and got["root"] == want["root"]
+        assert got["n_unique"] < got["n_chunks"]                                   # copy_a / copy_b dedup
+        # the tree now holds the base layer: the same blob again merges only what the reference would (the whiteout
+        # and its re-added parent), and still verifies
+        with open(tar_path, "rb") as f:
+            again = h.update_from_tar(eng, NOW, f.fileno())
+        want_again = o.update_from_tar(data)
+        assert [e.dst for e in want_again] == ["/etc", "/etc/.wh.removed"]
+        assert again["n_entries"] == len(want_again) and again["tar_digest"] == got["tar_digest"] and again["root"] == got["root"]
+        # through a pipe (gunzip | ingest), digest left to the caller
+        r, w = os.pipe()
+        import threading
+        t = threading.Thread(target=lambda: (os.write(w, data), os.close(w)))
+        t.start()
+        piped = host.MemFS(str(root)).update_from_tar(eng, NOW, r, flags=host.MKHOST_NO_TAR_DIGEST)
+        t.join()
+        os.close(r)
+        assert piped["root"] == got["root"] and piped["n_entries"] == got["n_entries"]
+        assert piped["tar_digest"] == "sha256:" + "00" * 32
+        # a member larger than the arena is refused loudly (a file is chunked within one arena)
+        if arena_mib == 3:
+            big = io.BytesIO()
+            with tarfile.open(fileobj=big, mode="w") as tf:
+                ti = tarfile.TarInfo("huge")
+                ti.size = 4 << 20
+                tf.addfile(ti, io.BytesIO(bytes(4 << 20)))
+            (tmp_path / "big.tar").write_bytes(big.getvalue())
+            with open(tmp_path / "big.tar", "rb") as f, pytest.raises(host.HostError) as ei:
+                h.update_from_tar(eng, NOW, f.fileno())
+            assert "exceeds the arena" in str(ei.value)
+    h.close()
