@@ -119,6 +119,20 @@ int mkhost_memfs_update_from_tar(mkhost_memfs *m, mksnap_t *eng, int64_t now_uni
 size_t mkhost_memfs_describe_update_from_tar(mkhost_memfs *m, int64_t now_unix, int tar_fd, char *out, size_t cap,
                                              char *err, size_t errlen);
 
+/* cache.Manager wire format (lib/cache/cache_manager.go:34-35,239-252).  key = "makisu_builder_cache_" + cacheID;
+ * entry = "<tarHex>,<gzipHex>" (createEntry), or "MAKISU_CACHE_EMPTY" for a nil pair (tar_hex == NULL).
+ * parse = parseEntry: error when there is no ',', otherwise SplitN(entry, ",", 2) -- no hex validation, like
+ * the reference.  Because old readers keep everything after the first ',' as the gzip digest, the chunk-table
+ * root cannot ride in the same value: it is stored under its own key "<key>_chunks" = "<rootHex>,<n_unique>",
+ * which readers that do not know it never fetch ("old readers must still parse").
+ * All return the number of bytes needed including NUL (nothing written if > cap), 0 on error. */
+size_t mkhost_cache_key(const char *cache_id, int chunk_table, char *out, size_t cap);
+size_t mkhost_cache_entry_create(const char *tar_hex, const char *gzip_hex, char *out, size_t cap);
+int mkhost_cache_entry_parse(const char *entry, char *tar_digest, size_t tar_cap, char *gzip_digest, size_t gzip_cap,
+                             char *err, size_t errlen);
+size_t mkhost_cache_chunk_entry_create(const uint8_t root[32], uint64_t n_unique, char *out, size_t cap);
+int mkhost_cache_chunk_entry_parse(const char *entry, uint8_t root[32], uint64_t *n_unique, char *err, size_t errlen);
+
 /* No-GPU introspection for the CPU tests: one line per item, '\n' separated, NUL terminated.
  *   stream : "P <relpath>" | "L <target>" | "F <size> <abs path>"   in CRC stream order
  *   layer  : "<typeflag> <mode octal> <uid> <gid> <size> <mtime> <dst> <hdr.Name> <src>"  in tar order

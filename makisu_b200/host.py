@@ -9,7 +9,7 @@ import ctypes as C
 import os
 from dataclasses import dataclass
 from pathlib import Path
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 from . import abi
 
@@ -55,6 +55,12 @@ SYMBOLS = [
                                                C.c_size_t]),
     ("mkhost_memfs_describe_update_from_tar", C.c_size_t, [_P, C.c_int64, C.c_int, C.c_char_p, C.c_size_t, C.c_char_p,
                                                            C.c_size_t]),
+    ("mkhost_cache_key", C.c_size_t, [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]),
+    ("mkhost_cache_entry_create", C.c_size_t, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
+    ("mkhost_cache_entry_parse", C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
+    ("mkhost_cache_chunk_entry_create", C.c_size_t, [C.POINTER(C.c_uint8), C.c_uint64, C.c_char_p, C.c_size_t]),
+    ("mkhost_cache_chunk_entry_parse", C.c_int, [C.c_char_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.c_char_p,
+                                                 C.c_size_t]),
     ("mkhost_describe_context_stream", C.c_size_t, [C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_char_p,
                                                     C.c_size_t, C.c_char_p, C.c_size_t]),
     ("mkhost_describe_layer", C.c_size_t, [C.c_char_p, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_char_p,
@@ -248,3 +254,36 @@ class MemFS:
         if load().mkhost_memfs_commit_scan(self.h, eng.h, now_unix, n_threads, tar_fd, flags, C.byref(out), err, len(err)):
             raise HostError(err.value.decode())
         return _layer_dict(out)
+
+
+# ---- cache.Manager wire format (lib/cache/cache_manager.go:34-35,239-252) --------------------------
+def cache_key(cache_id: str, chunk_table: bool = False) -> str:
+    buf = C.create_string_buffer(len(cache_id) + 64)
+    load().mkhost_cache_key(cache_id.encode(), int(chunk_table), buf, len(buf))
+    return buf.value.decode()
+
+
+def cache_entry_create(tar_hex: Optional[str], gzip_hex: str = "") -> str:
+    buf = C.create_string_buffer(len(tar_hex or "") + len(gzip_hex) + 32)
+    load().mkhost_cache_entry_create(None if tar_hex is None else tar_hex.encode(), gzip_hex.encode(), buf, len(buf))
+    return buf.value.decode()
+
+
+def cache_entry_parse(entry: str):
+    t, g, err = C.create_string_buffer(len(entry) + 16), C.create_string_buffer(len(entry) + 16), C.create_string_buffer(512)
+    if load().mkhost_cache_entry_parse(entry.encode(), t, len(t), g, len(g), err, len(err)):
+        raise HostError(err.value.decode())
+    return t.value.decode(), g.value.decode()
+
+
+def cache_chunk_entry_create(root: bytes, n_unique: int) -> str:
+    buf = C.create_string_buffer(128)
+    load().mkhost_cache_chunk_entry_create((C.c_uint8 * 32).from_buffer_copy(root), n_unique, buf, len(buf))
+    return buf.value.decode()
+
+
+def cache_chunk_entry_parse(entry: str):
+    root, n, err = (C.c_uint8 * 32)(), C.c_uint64(), C.create_string_buffer(512)
+    if load().mkhost_cache_chunk_entry_parse(entry.encode(), root, C.byref(n), err, len(err)):
+        raise HostError(err.value.decode())
+    return bytes(root), n.value

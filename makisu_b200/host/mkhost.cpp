@@ -1733,6 +1733,71 @@ int mkhost_memfs_update_from_tar(mkhost_memfs *m, mksnap_t *eng, int64_t now_uni
     }
 }
 
+// ---- cache.Manager wire format (lib/cache/cache_manager.go:34-35,239-252) ----
+size_t mkhost_cache_key(const char *cache_id, int chunk_table, char *out, size_t cap)
+{
+    return emit_text(std::string("makisu_builder_cache_") + (cache_id ? cache_id : "") + (chunk_table ? "_chunks" : ""), out, cap);
+}
+
+size_t mkhost_cache_entry_create(const char *tar_hex, const char *gzip_hex, char *out, size_t cap)
+{
+    if (!tar_hex) // createEntry(nil)
+        return emit_text("MAKISU_CACHE_EMPTY", out, cap);
+    return emit_text(std::string(tar_hex) + "," + (gzip_hex ? gzip_hex : ""), out, cap);
+}
+
+int mkhost_cache_entry_parse(const char *entry, char *tar_digest, size_t tar_cap, char *gzip_digest, size_t gzip_cap,
+                             char *err, size_t errlen)
+{
+    const std::string e = entry ? entry : "";
+    const size_t c = e.find(',');
+    if (c == std::string::npos) {
+        set_err(err, errlen, "parse redis entry: " + e);
+        return -1;
+    }
+    const std::string t = "sha256:" + e.substr(0, c), g = "sha256:" + e.substr(c + 1); // SplitN(entry, ",", 2)
+    if (t.size() + 1 > tar_cap || g.size() + 1 > gzip_cap) {
+        set_err(err, errlen, "parse redis entry: output buffer too small");
+        return -1;
+    }
+    memcpy(tar_digest, t.c_str(), t.size() + 1);
+    memcpy(gzip_digest, g.c_str(), g.size() + 1);
+    return 0;
+}
+
+size_t mkhost_cache_chunk_entry_create(const uint8_t root[32], uint64_t n_unique, char *out, size_t cap)
+{
+    static const char *hx = "0123456789abcdef";
+    std::string s;
+    for (int i = 0; i < 32; ++i) {
+        s += hx[root[i] >> 4];
+        s += hx[root[i] & 15];
+    }
+    return emit_text(s + "," + std::to_string(n_unique), out, cap);
+}
+
+int mkhost_cache_chunk_entry_parse(const char *entry, uint8_t root[32], uint64_t *n_unique, char *err, size_t errlen)
+{
+    const std::string e = entry ? entry : "";
+    auto nib = [](char c) { return c >= '0' && c <= '9' ? c - '0' : (c >= 'a' && c <= 'f' ? c - 'a' + 10 : -1); };
+    bool ok = e.size() > 65 && e[64] == ',';
+    for (int i = 0; ok && i < 64; ++i)
+        ok = nib(e[i]) >= 0;
+    uint64_t n = 0;
+    for (size_t i = 65; ok && i < e.size(); ++i) {
+        ok = e[i] >= '0' && e[i] <= '9' && n <= (UINT64_MAX - 9) / 10;
+        n = n * 10 + (uint64_t)(e[i] - '0');
+    }
+    if (!ok) {
+        set_err(err, errlen, "parse chunk table entry: " + e);
+        return -1;
+    }
+    for (int i = 0; i < 32; ++i)
+        root[i] = (uint8_t)(nib(e[2 * i]) * 16 + nib(e[2 * i + 1]));
+    *n_unique = n;
+    return 0;
+}
+
 int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, const char *context_dir,
                          const char *const *from_paths, size_t n_paths, int n_threads, uint32_t *crc_out,
                          uint64_t *stream_len_out, char *err, size_t errlen)

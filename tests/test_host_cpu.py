@@ -194,3 +194,31 @@ def test_memfs_sequence_scan_whiteout_copy_matches_oracle(tmp_path):
     want2 = _desc(lt.MemFS.add_layer_by_copy_ops(o, [lt.CopyOperation.new(["/n"], str(ctx), "/", "/d/deep/er/", uid=1, gid=2)]))
     assert [l.split(" ")[6] for l in again] == [l.split(" ")[6] for l in want2]
     h.close()
+
+
+def test_cache_entry_wire_format_matches_reference_and_old_readers():
+    """lib/cache/cache_manager.go:34-35,239-252: key prefix, "<tarHex>,<gzipHex>", MAKISU_CACHE_EMPTY, SplitN(…, 2).
+    The chunk-table root lives under its own key so an unmodified reader parses the layer entry exactly as before."""
+    from oracle import cache_entry as ce
+    t, g = "ab" * 32, "cd" * 32
+    assert host.cache_key("7d618f69") == ce.cache_key("7d618f69") == "makisu_builder_cache_7d618f69"
+    assert host.cache_key("7d618f69", True) == ce.cache_key("7d618f69", True) == "makisu_builder_cache_7d618f69_chunks"
+    assert host.cache_entry_create(t, g) == ce.create_entry(t, g) == t + "," + g
+    assert host.cache_entry_create(None) == ce.create_entry(None) == "MAKISU_CACHE_EMPTY"
+    assert host.cache_entry_parse(t + "," + g) == ce.parse_entry(t + "," + g) == ("sha256:" + t, "sha256:" + g)
+    # an old reader keeps everything after the first comma (SplitN 2): this is why the root is NOT a third field
+    assert host.cache_entry_parse("a,b,c") == ce.parse_entry("a,b,c") == ("sha256:a", "sha256:b,c")
+    for bad in ["", "MAKISU_CACHE_EMPTY", "nocomma"]:
+        with pytest.raises(host.HostError) as ei:
+            host.cache_entry_parse(bad)
+        with pytest.raises(ValueError) as eo:
+            ce.parse_entry(bad)
+        assert str(ei.value) == str(eo.value) == "parse redis entry: " + bad
+    root = bytes(range(32))
+    e = host.cache_chunk_entry_create(root, 572245)
+    assert e == ce.create_chunk_entry(root, 572245) and host.cache_chunk_entry_parse(e) == ce.parse_chunk_entry(e) == (root, 572245)
+    for bad in ["", "zz" * 32 + ",1", "ab" * 32, "ab" * 32 + ",", "ab" * 32 + ",x", "AB" * 32 + ",1"]:
+        with pytest.raises(host.HostError):
+            host.cache_chunk_entry_parse(bad)
+        with pytest.raises(ValueError):
+            ce.parse_chunk_entry(bad)
