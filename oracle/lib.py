@@ -51,6 +51,8 @@ def L():
         l.mko_chunk_table.restype = C.c_int
         l.mko_chunk_table.argtypes = [vp, vp, vp, sz, C.POINTER(CdcParams), vp, vp, vp, sz, C.POINTER(TableSummary)]
         l.mko_synth_fill.restype = None; l.mko_synth_fill.argtypes = [vp, u64, u64, u64]
+        l.mko_step_same_work.restype = sz
+        l.mko_step_same_work.argtypes = [vp, vp, vp, sz, C.POINTER(CdcParams), vp, vp, sz, vp]
         _L = l
     return _L
 

@@ -387,6 +387,45 @@ int mko_chunk_table(const uint8_t *arena, const uint64_t *offs, const uint64_t *
     return 0;
 }
 
+/* Baseline timing only (bench.py cpu_best_effort): the work of one GPU step over a slice of files -- CRC-32 of every
+ * file, Gear CDC, SHA-256 of every chunk through the SHA-NI path when the CPU has it.  Thread safe (no shared
+ * state): bench.py runs one call per host thread on disjoint slices.  Returns the number of chunks; digests may be
+ * NULL (then the last digest is folded into *sink so the work cannot be optimised away). */
+size_t mko_step_same_work(const uint8_t *arena, const uint64_t *offs, const uint64_t *lens, size_t n_files,
+                          const mko_cdc_params *p, uint32_t *crcs, uint8_t *digests, size_t cap, uint32_t *sink)
+{
+    size_t k = 0;
+    uint64_t max_len = 0;
+    for (size_t f = 0; f < n_files; f++)
+        if (lens[f] > max_len)
+            max_len = lens[f];
+    const size_t ends_cap = (size_t)(max_len / (p->min_size ? p->min_size : 1)) + 2;
+    uint64_t *ends = (uint64_t *)malloc(ends_cap * 8);
+    uint8_t dg[32] = {0};
+    uint32_t acc = 0;
+    for (size_t f = 0; f < n_files; f++) {
+        const uint8_t *base = arena + offs[f];
+        uint32_t c = mko_crc32_update(0, base, lens[f]);
+        if (crcs)
+            crcs[f] = c;
+        acc ^= c;
+        size_t n = mko_cdc_cuts(base, lens[f], p, ends, ends_cap);
+        uint64_t prev = 0;
+        for (size_t j = 0; j < n; j++) {
+            mko_sha256_ctx ctx;
+            mko_sha256_init(&ctx);
+            mko_sha256_update_fast(&ctx, base + prev, ends[j] - prev);
+            mko_sha256_final(&ctx, (digests && k < cap) ? digests + 32 * k : dg);
+            prev = ends[j];
+            k++;
+        }
+    }
+    free(ends);
+    if (sink)
+        *sink = acc ^ dg[0];
+    return k;
+}
+
 /* ======================================================================= */
 /* synthetic content                                                       */
 /* ======================================================================= */

@@ -102,6 +102,10 @@ int mko_chunk_table(const uint8_t *arena, const uint64_t *offs,
                     uint8_t *digests, uint8_t *table, size_t cap,
                     mko_table_summary *summary);
 
+/* baseline timing (bench.py): CRC-32 + Gear CDC + per-chunk SHA-256 (fast path) of a slice of files; thread safe */
+size_t mko_step_same_work(const uint8_t *arena, const uint64_t *offs, const uint64_t *lens, size_t n_files,
+                          const mko_cdc_params *p, uint32_t *crcs, uint8_t *digests, size_t cap, uint32_t *sink);
+
 /* ---- synthetic content generator shared with the device -
  * byte stream = little-endian u64 words, word i = mix64(seed + i), where i is
  * the absolute 8-byte word index in the arena.  dst covers arena bytes
