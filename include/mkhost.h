@@ -84,6 +84,16 @@ int mkhost_commit_copy_ops_to_fd(mksnap_t *eng, const char *root_dir, int64_t no
 /* flags for mkhost_commit_copy_ops_ex */
 #define MKHOST_NO_TAR_DIGEST 1u /* leave TarDigest to the caller (Go's sha256.New() fed from the same bytes, see
                                    INTEGRATION.md section 3): out->tar_digest is zeroed, no serial stream is submitted */
+/* MemFS entry points only (they need a tree to remember into):
+ * MKHOST_FILE_DIGESTS  also hash every regular file of the layer (one serial SHA-256 stream per file, stream slots
+ *                      1..n; the engine needs max_extents > n) and remember the digest in the tree.
+ * MKHOST_SCAN_CONTENT  mkhost_memfs_commit_scan: content-aware change detection.  Files the
+ *                      reference's IsSimilarHeader calls unchanged (same mtime second, size, mode, owner) are
+ *                      re-hashed on the GPU and compared with the remembered digest; a difference puts the file into
+ *                      the layer.  Removes the need for the sync() + 1 s sleep of mem_fs.go:291-311.  Implies
+ *                      MKHOST_FILE_DIGESTS.  No reference counterpart: with the flag clear the scan is the reference's. */
+#define MKHOST_FILE_DIGESTS 2u
+#define MKHOST_SCAN_CONTENT 4u
 int mkhost_commit_copy_ops_ex(mksnap_t *eng, const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops,
                               size_t n_ops, int n_threads, int tar_fd, uint32_t flags, mkhost_layer_result *out,
                               char *err, size_t errlen);
@@ -95,6 +105,9 @@ typedef struct mkhost_memfs mkhost_memfs;
 mkhost_memfs *mkhost_memfs_new(const char *root_dir, const char *const *blacklist, size_t n_blacklist, char *err,
                                size_t errlen);
 void mkhost_memfs_free(mkhost_memfs *m);
+/* SHA-256 of the content the tree remembers for the regular file at dst (MKHOST_FILE_DIGESTS / MKHOST_SCAN_CONTENT
+ * commits and ingests); returns 0 and fills out, or 1 when nothing is remembered for that path. */
+int mkhost_memfs_file_digest(mkhost_memfs *m, const char *dst, uint8_t out[32]);
 /* AddLayerByCopyOps / AddLayerByScan followed by commitLayer on the GPU (flags: MKHOST_NO_TAR_DIGEST). */
 int mkhost_memfs_commit_copy_ops(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops,
                                  int n_threads, int tar_fd, uint32_t flags, mkhost_layer_result *out, char *err,

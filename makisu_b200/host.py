@@ -44,6 +44,7 @@ SYMBOLS = [
                                             C.c_uint32, C.POINTER(LayerResult), C.c_char_p, C.c_size_t]),
     ("mkhost_memfs_new", _P, [C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_char_p, C.c_size_t]),
     ("mkhost_memfs_free", None, [_P]),
+    ("mkhost_memfs_file_digest", C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint8)]),
     ("mkhost_memfs_commit_copy_ops", C.c_int, [_P, _P, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_int, C.c_int, C.c_uint32,
                                                C.POINTER(LayerResult), C.c_char_p, C.c_size_t]),
     ("mkhost_memfs_commit_scan", C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.POINTER(LayerResult),
@@ -170,6 +171,8 @@ def copy_step_cache_id(eng: abi.Engine, seed: str, directive: str, args: str, co
 
 
 MKHOST_NO_TAR_DIGEST = 1
+MKHOST_FILE_DIGESTS = 2   # remember per-file SHA-256 in the MemFS tree
+MKHOST_SCAN_CONTENT = 4   # content-aware AddLayerByScan (implies FILE_DIGESTS)
 
 
 def commit_copy_ops(eng: abi.Engine, root_dir: str, now_unix: int, ops: Sequence[CopyOperation], n_threads: int = 0,
@@ -233,6 +236,11 @@ class MemFS:
                                                C.byref(out), err, len(err)):
             raise HostError(err.value.decode())
         return _layer_dict(out)
+
+    def file_digest(self, dst: str) -> Optional[bytes]:
+        """SHA-256 the tree remembers for the regular file at dst, or None."""
+        out = (C.c_uint8 * 32)()
+        return bytes(out) if load().mkhost_memfs_file_digest(self.h, os.fsencode(dst), out) == 0 else None
 
     def describe_update_from_tar(self, now_unix: int, tar_fd: int) -> List[str]:
         """UpdateFromTarReader(untar=false) without a GPU: the merged layer as text."""

@@ -13,6 +13,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <functional>
 #include <map>
@@ -960,6 +961,13 @@ struct MemFile {
     Hdr hdr;
     bool whiteout = false;  // whiteoutMemFile (mem_layer.go:91-132): header-only entry ".wh.<base>"
     std::string deleted;    // path it deletes (the layer key)
+    bool has_digest = false; // SHA-256 of the content the tree believes the file has (MKHOST_FILE_DIGESTS; ours)
+    std::array<uint8_t, 32> digest{};
+};
+struct Suspect { // regular file whose header is "similar" but whose remembered content digest can be checked
+    std::string src, dst;
+    Hdr hdr;
+    std::array<uint8_t, 32> known;
 };
 struct Node {
     MemFile mf;
@@ -1037,7 +1045,7 @@ class MemFS
     // AddLayerByScan / createLayerByScan (mem_fs.go:260-270,315-341): metadata diff of the root against the
     // merged tree, whiteouts for children that vanished.  (Mountpoint filtering, utils.go:46-50, is the caller's
     // job here: synthetic roots have none.)
-    std::map<std::string, MemFile> add_layer_by_scan()
+    std::map<std::string, MemFile> add_layer_by_scan(std::vector<Suspect> *suspects = nullptr)
     {
         std::map<std::string, MemFile> layer;
         go_walk(root_, [&](const std::string &src, const struct stat &st) -> WalkRet {
@@ -1047,10 +1055,51 @@ class MemFS
                 throw HostError("failed to trim root prefix " + root_ + " from path " + src);
             const std::string dst = abs_path(src.substr(root_.size()));
             Hdr hdr = create_header(src, dst, &st, nullptr);
+            if (suspects && hdr.typeflag == '0') { // content-aware scan: metadata says "unchanged" -- remember to check
+                Node *n = nullptr;
+                if (!is_updated(dst, hdr, &n) && n && n->mf.has_digest)
+                    suspects->push_back(Suspect{src, dst, hdr, n->mf.digest});
+            }
             maybe_add(layer, src, dst, hdr, true);
             return W_CONT;
         });
         return layer;
+    }
+
+    // a suspect whose content digest differs from the remembered one joins the layer exactly as if isUpdated had
+    // said so (mem_fs.go:440-457)
+    void add_changed(std::map<std::string, MemFile> &layer, const Suspect &sp)
+    {
+        add_ancestors(layer, abs_path(sp.dst), false, 0, 0, 0);
+        add_header(layer, sp.src, sp.dst, sp.hdr);
+    }
+
+    bool get_digest(const std::string &dst, uint8_t d[32])
+    {
+        Node *cur = &tree_;
+        for (const auto &part : split_path(dst)) {
+            auto it = cur->children.find(part);
+            if (it == cur->children.end())
+                return false;
+            cur = it->second.get();
+        }
+        if (!cur->mf.has_digest)
+            return false;
+        memcpy(d, cur->mf.digest.data(), 32);
+        return true;
+    }
+
+    void set_digest(const std::string &dst, const uint8_t d[32])
+    {
+        Node *cur = &tree_;
+        for (const auto &part : split_path(dst)) {
+            auto it = cur->children.find(part);
+            if (it == cur->children.end())
+                return;
+            cur = it->second.get();
+        }
+        cur->mf.has_digest = true;
+        memcpy(cur->mf.digest.data(), d, 32);
     }
 
     // UpdateFromTarReader(r, untar=false) (mem_fs.go:165-255): merge the members of a base-layer tar into the tree,
@@ -1360,9 +1409,12 @@ std::string describe_layer_text(const std::map<std::string, MemFile> &layer)
 
 // MemFS.commitLayer (mem_fs.go:424-433) + tario.WriteEntry, with the arena as the tar.Writer sink
 void commit_layer(mksnap_t *eng, const std::map<std::string, MemFile> &layer, int n_threads, int tar_fd, uint32_t flags,
-                  mkhost_layer_result *out)
+                  mkhost_layer_result *out, MemFS *remember = nullptr)
 {
     const bool want_tar_digest = !(flags & MKHOST_NO_TAR_DIGEST);
+    const bool file_digests = remember && (flags & (MKHOST_FILE_DIGESTS | MKHOST_SCAN_CONTENT));
+    std::vector<std::string> digest_dst; // stream slot 1+k <-> dst
+    std::vector<mksnap_range> rngs;
     ck(eng, mksnap_begin(eng), "begin");
     void *hp = nullptr;
     uint64_t cap = 0;
@@ -1394,8 +1446,10 @@ void commit_layer(mksnap_t *eng, const std::map<std::string, MemFile> &layer, in
                 w += (uint64_t)r;
             }
         }
-        mksnap_range rng{0, pos, 0, last ? 0u : MKSNAP_R_MORE};
-        ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), &rng, want_tar_digest ? 1 : 0), "arena submit");
+        if (want_tar_digest)
+            rngs.push_back(mksnap_range{0, pos, 0, last ? 0u : MKSNAP_R_MORE});
+        ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), rngs.data(), rngs.size()), "arena submit");
+        rngs.clear();
         tar_bytes += pos;
         if (!last)
             acquire();
@@ -1416,6 +1470,10 @@ void commit_layer(mksnap_t *eng, const std::map<std::string, MemFile> &layer, in
         if (body) {
             jobs.push_back(ReadJob{mf.src, 0, body, a + pos});
             ext.push_back(mksnap_extent{pos, body, 0, MKSNAP_X_CDC, 0});
+            if (file_digests) { // one serial stream per file: slot 1+k (slot 0 is the tar stream)
+                digest_dst.push_back(mf.dst);
+                rngs.push_back(mksnap_range{pos, body, (uint32_t)digest_dst.size(), 0});
+            }
             const uint64_t padded = align_up(body, 512);
             memset(a + pos + body, 0, padded - body);
             pos += padded;
@@ -1429,13 +1487,77 @@ void commit_layer(mksnap_t *eng, const std::map<std::string, MemFile> &layer, in
     mksnap_result res;
     ck(eng, mksnap_finish(eng, &res), "finish");
     memset(out->tar_digest, 0, 32);
-    if (want_tar_digest)
+    if (file_digests && !digest_dst.empty()) {
+        std::vector<uint8_t> d((digest_dst.size() + 1) * 32);
+        ck(eng, mksnap_get_stream_digests(eng, d.data(), digest_dst.size() + 1), "stream digests");
+        if (want_tar_digest)
+            memcpy(out->tar_digest, d.data(), 32);
+        for (size_t k = 0; k < digest_dst.size(); ++k)
+            remember->set_digest(digest_dst[k], d.data() + 32 * (k + 1));
+    } else if (want_tar_digest) {
         ck(eng, mksnap_get_stream_digests(eng, out->tar_digest, 1), "stream digests");
+    }
     memcpy(out->root, res.root, 32);
     out->n_entries = layer.size();
     out->tar_bytes = tar_bytes;
     out->n_chunks = res.n_chunks;
     out->n_unique = res.n_unique;
+}
+
+// SHA-256 of the current content of every suspect (one serial stream per file, thousands in flight; a file larger
+// than an arena continues across submits).
+std::vector<std::array<uint8_t, 32>> digest_files(mksnap_t *eng, const std::vector<Suspect> &files, int n_threads)
+{
+    std::vector<std::array<uint8_t, 32>> out(files.size());
+    if (files.empty())
+        return out;
+    ck(eng, mksnap_begin(eng), "begin");
+    void *hp = nullptr;
+    uint64_t cap = 0, pos = 0;
+    int32_t aid = -1;
+    std::vector<mksnap_range> rngs;
+    std::vector<ReadJob> jobs;
+    auto acquire = [&]() {
+        ck(eng, mksnap_arena_acquire(eng, &hp, &cap, &aid), "arena acquire");
+        cap = cap / 512 * 512;
+        pos = 0;
+        rngs.clear();
+        jobs.clear();
+    };
+    auto flush = [&]() {
+        run_reads(jobs, n_threads);
+        ck(eng, mksnap_arena_submit(eng, aid, pos, nullptr, 0, rngs.data(), rngs.size()), "arena submit");
+    };
+    acquire();
+    for (size_t k = 0; k < files.size(); ++k) {
+        const uint64_t size = (uint64_t)files[k].hdr.size;
+        uint64_t done = 0;
+        do {
+            if (cap - pos < 512) {
+                flush();
+                acquire();
+            }
+            const uint64_t n = std::min<uint64_t>(size - done, cap - pos); // cap - pos is a multiple of 512 (so of 64)
+            const bool more = done + n < size;
+            if (n)
+                jobs.push_back(ReadJob{files[k].src, done, n, (uint8_t *)hp + pos});
+            rngs.push_back(mksnap_range{pos, n, (uint32_t)k, more ? MKSNAP_R_MORE : 0u});
+            pos = align_up(pos + n, 512);
+            done += n;
+            if (more) { // at most one piece per stream per submit
+                flush();
+                acquire();
+            }
+        } while (done < size);
+    }
+    flush();
+    mksnap_result res;
+    ck(eng, mksnap_finish(eng, &res), "finish");
+    std::vector<uint8_t> d(files.size() * 32);
+    ck(eng, mksnap_get_stream_digests(eng, d.data(), files.size()), "stream digests");
+    for (size_t k = 0; k < files.size(); ++k)
+        memcpy(out[k].data(), d.data() + 32 * k, 32);
+    return out;
 }
 
 // UpdateFromTarReader with the GPU in the loop: the tar stream is read from `fd` straight into pinned arenas (the
@@ -1444,13 +1566,15 @@ void commit_layer(mksnap_t *eng, const std::map<std::string, MemFile> &layer, in
 struct ArenaTarSource : TarSource {
     mksnap_t *eng;
     int fd;
-    bool want_digest;
+    bool want_digest, file_digests;
     uint8_t *a = nullptr;
     uint64_t cap = 0, pos = 0, consumed = 0, tar_bytes = 0;
     int32_t aid = -1;
     std::vector<mksnap_extent> ext;
+    std::vector<mksnap_range> rngs;
+    uint32_t n_file_streams = 0; // regular-file members seen so far: member k hashes into stream slot 1+k
 
-    ArenaTarSource(mksnap_t *e, int f, bool d) : eng(e), fd(f), want_digest(d) { acquire(); }
+    ArenaTarSource(mksnap_t *e, int f, bool d, bool fd_) : eng(e), fd(f), want_digest(d), file_digests(fd_) { acquire(); }
 
     void acquire()
     {
@@ -1460,11 +1584,13 @@ struct ArenaTarSource : TarSource {
         cap = cap / 512 * 512;
         pos = 0;
         ext.clear();
+        rngs.clear();
     }
     void flush(bool last)
     {
-        mksnap_range rng{0, pos, 0, last ? 0u : MKSNAP_R_MORE};
-        ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), &rng, want_digest ? 1 : 0), "arena submit");
+        if (want_digest)
+            rngs.push_back(mksnap_range{0, pos, 0, last ? 0u : MKSNAP_R_MORE});
+        ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), rngs.data(), rngs.size()), "arena submit");
         tar_bytes += pos;
         if (!last)
             acquire();
@@ -1507,8 +1633,11 @@ struct ArenaTarSource : TarSource {
         if (read_full(a + pos, padded) < padded)
             throw TarErr("unexpected EOF");
         *arena_off = pos;
-        if (file_content)
+        if (file_content) {
             ext.push_back(mksnap_extent{pos, nb, 0, MKSNAP_X_CDC, 0});
+            if (file_digests)
+                rngs.push_back(mksnap_range{pos, nb, ++n_file_streams, 0});
+        }
         const uint8_t *body = a + pos;
         pos += padded;
         return body;
@@ -1630,6 +1759,11 @@ mkhost_memfs *mkhost_memfs_new(const char *root_dir, const char *const *blacklis
 
 void mkhost_memfs_free(mkhost_memfs *m) { delete m; }
 
+int mkhost_memfs_file_digest(mkhost_memfs *m, const char *dst, uint8_t out[32])
+{
+    return m && dst && m->fs.get_digest(abs_path(dst), out) ? 0 : 1;
+}
+
 size_t mkhost_memfs_describe_copy_ops(mkhost_memfs *m, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops, char *out,
                                       size_t cap, char *err, size_t errlen)
 {
@@ -1659,7 +1793,7 @@ int mkhost_memfs_commit_copy_ops(mkhost_memfs *m, mksnap_t *eng, int64_t now_uni
 {
     try {
         m->fs.set_now(now_unix);
-        commit_layer(eng, m->fs.add_layer_by_copy_ops(ops, n_ops), n_threads, tar_fd, flags, out);
+        commit_layer(eng, m->fs.add_layer_by_copy_ops(ops, n_ops), n_threads, tar_fd, flags, out, &m->fs);
         return 0;
     } catch (const std::exception &e) {
         set_err(err, errlen, std::string("failed to generate diff layer: ") + e.what());
@@ -1672,7 +1806,20 @@ int mkhost_memfs_commit_scan(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, i
 {
     try {
         m->fs.set_now(now_unix);
-        commit_layer(eng, m->fs.add_layer_by_scan(), n_threads, tar_fd, flags, out);
+        if (!(flags & MKHOST_SCAN_CONTENT)) {
+            commit_layer(eng, m->fs.add_layer_by_scan(), n_threads, tar_fd, flags, out, &m->fs);
+            return 0;
+        }
+        // content-aware scan: the reference trusts mtime+size and therefore sync()s and sleeps
+        // a second before every scan (mem_fs.go:291-311); here files the metadata calls unchanged are re-hashed on
+        // the GPU and compared with the digest remembered when they were committed.
+        std::vector<Suspect> suspects;
+        std::map<std::string, MemFile> layer = m->fs.add_layer_by_scan(&suspects);
+        const std::vector<std::array<uint8_t, 32>> now = digest_files(eng, suspects, n_threads);
+        for (size_t k = 0; k < suspects.size(); ++k)
+            if (now[k] != suspects[k].known)
+                m->fs.add_changed(layer, suspects[k]);
+        commit_layer(eng, layer, n_threads, tar_fd, flags, out, &m->fs);
         return 0;
     } catch (const std::exception &e) {
         set_err(err, errlen, std::string("failed to generate diff layer: ") + e.what());
@@ -1713,16 +1860,33 @@ int mkhost_memfs_update_from_tar(mkhost_memfs *m, mksnap_t *eng, int64_t now_uni
         m->fs.set_now(now_unix);
         const bool want_digest = !(flags & MKHOST_NO_TAR_DIGEST);
         ck(eng, mksnap_begin(eng), "begin");
-        ArenaTarSource src(eng, tar_fd, want_digest);
+        const bool file_digests = (flags & MKHOST_FILE_DIGESTS) != 0;
+        ArenaTarSource src(eng, tar_fd, want_digest, file_digests);
         const std::vector<TarMember> members = read_tar(src);
         src.flush(true);
         mksnap_result res;
         ck(eng, mksnap_finish(eng, &res), "finish");
         memset(out->tar_digest, 0, 32);
+        std::vector<uint8_t> d((size_t)(src.n_file_streams + 1) * 32);
+        if (want_digest || src.n_file_streams)
+            ck(eng, mksnap_get_stream_digests(eng, d.data(), src.n_file_streams + 1), "stream digests");
         if (want_digest)
-            ck(eng, mksnap_get_stream_digests(eng, out->tar_digest, 1), "stream digests");
+            memcpy(out->tar_digest, d.data(), 32);
         memcpy(out->root, res.root, 32);
-        out->n_entries = m->fs.update_from_tar(members).size();
+        const std::map<std::string, MemFile> layer = m->fs.update_from_tar(members);
+        out->n_entries = layer.size();
+        if (file_digests) { // remember the content digest of every regular member that made it into the tree
+            uint32_t k = 0;
+            for (const auto &mem : members) {
+                if (mem.hdr.typeflag != '0' || mem.data_len == 0)
+                    continue;
+                ++k;
+                const std::string dst = abs_path(mem.hdr.name);
+                auto it = layer.find(dst);
+                if (it != layer.end() && !it->second.whiteout && it->second.hdr.typeflag == '0')
+                    m->fs.set_digest(dst, d.data() + 32 * k);
+            }
+        }
         out->tar_bytes = src.tar_bytes;
         out->n_chunks = res.n_chunks;
         out->n_unique = res.n_unique;

@@ -545,6 +545,7 @@ class MemFile:
     hdr: Header
     whiteout: bool = False
     deleted: str = ""
+    digest: Optional[bytes] = None  # SHA-256 of the content the tree believes the file has (content-aware scan; ours)
 
 
 @dataclass
@@ -775,28 +776,57 @@ class MemFS:
         self.layers.append(layer)
         return [layer[k] for k in sorted(layer, key=os.fsencode)]  # mem_layer.go:232-244 sort.Strings
 
-    def add_layer_by_scan(self) -> List[MemFile]:
-        """AddLayerByScan (mem_fs.go:260-270,315-341)."""
+    def add_layer_by_scan(self, content_aware: bool = False) -> List[MemFile]:
+        """AddLayerByScan (mem_fs.go:260-270,315-341).  content_aware (ours): regular files whose
+        header is "similar" but whose remembered content digest differs from the file's current SHA-256 join the
+        layer as if isUpdated had said so."""
         layer: Dict[str, MemFile] = {}
         root = self.root
+        suspects: List[Tuple[str, str, Header, bytes]] = []
 
         def visit(src: str, st: os.stat_result):
             dst = trim_root(src, root)
             hdr = self.create_header(src, dst, st)
+            if content_aware and hdr.typeflag == TYPE_REG:
+                updated, node = self._is_updated(dst, hdr)
+                if not updated and node is not None and node.mf.digest is not None:
+                    suspects.append((src, dst, hdr, node.mf.digest))
             self._maybe_add(layer, src, dst, hdr, True)
 
         self._walk(root, self.blacklist, visit)
+        for src, dst, hdr, known in suspects:
+            with open(src, "rb") as f:
+                now = hashlib.sha256(f.read()).digest()
+            if now != known:
+                self._add_ancestors(layer, abs_path(dst), False, 0, 0, 0)
+                self._add_header(layer, src, dst, hdr)
         self.layers.append(layer)
         return [layer[k] for k in sorted(layer, key=os.fsencode)]
 
+    def _set_digest(self, dst: str, digest: bytes) -> None:
+        cur = self.tree
+        for part in split_path(dst):
+            if part not in cur.children:
+                return
+            cur = cur.children[part]
+        cur.mf.digest = digest
 
-    def update_from_tar(self, data: bytes) -> List[MemFile]:
+    def remember_content(self, entries: List[MemFile]) -> None:
+        """MKHOST_FILE_DIGESTS: after a layer is committed, remember the SHA-256 of every regular file in it."""
+        for e in entries:
+            if not e.whiteout and e.hdr.typeflag == TYPE_REG and e.hdr.size:
+                with open(e.src, "rb") as f:
+                    self._set_digest(e.dst, hashlib.sha256(f.read()).digest())
+
+
+    def update_from_tar(self, data: bytes, remember: bool = False) -> List[MemFile]:
         """UpdateFromTarReader(r, untar=false) (mem_fs.go:165-255): merge the headers of an (uncompressed) layer tar
         into the tree; hard links in a second pass; nothing is written to disk.  Returns the merged layer in key
         order (the reference only logs its count)."""
         layer: Dict[str, MemFile] = {}
         hardlinks: Dict[str, Header] = {}
-        for m in read_tar(data):
+        members = read_tar(data)
+        for m in members:
             hdr = m.hdr
             path = go_clean(self.root + "/" + hdr.name)  # filepath.Join(fs.tree.src, hdr.Name)
             if posixpath.basename(path).startswith(WHITEOUT_META_PREFIX):
@@ -812,6 +842,12 @@ class MemFS:
         for path in sorted(hardlinks, key=os.fsencode):  # Go ranges over a map: order is unspecified, result is not affected
             hdr = hardlinks[path]
             self._maybe_add(layer, abs_path(hdr.name), abs_path(hdr.name), hdr, False)
+        if remember:
+            for m in members:
+                dst = abs_path(m.hdr.name)
+                if m.hdr.typeflag == TYPE_REG and m.data_len and dst in layer and not layer[dst].whiteout \
+                        and layer[dst].hdr.typeflag == TYPE_REG:
+                    self._set_digest(dst, hashlib.sha256(data[m.data_off:m.data_off + m.data_len]).digest())
         self.layers.append(layer)
         return [layer[k] for k in sorted(layer, key=os.fsencode)]
 

@@ -240,3 +240,114 @@ def test_update_from_tar_verifies_blob_and_chunks_files(ctx, tmp_path, arena_mib
                 h.update_from_tar(eng, NOW, f.fileno())
             assert "exceeds the arena" in str(ei.value)
     h.close()
+
+
+def test_content_aware_scan_catches_same_second_same_size_edits(tmp_path):
+    """SURVEY section 8f-3.  The reference's scan trusts mtime (1 s resolution) + size, which is why it sync()s and sleeps a
+    second first (mem_fs.go:291-311).  With MKHOST_SCAN_CONTENT files the metadata calls unchanged are re-hashed
+    on the GPU (one SHA-256 stream per file) and compared with the digest remembered at commit / ingest time.
+    Flag clear => the reference's behaviour, checked too."""
+    import io
+    import tarfile
+    from makisu_b200 import host
+    from makisu_b200.abi import Engine
+    from oracle import layer_tar as lt
+    rng = np.random.default_rng(11)
+    root = tmp_path / "root"
+    T = 1_500_000_000
+    _mk(root, "d/a.txt", b"A" * 5000)
+    _mk(root, "d/b.bin", rng.integers(0, 256, 300_000, dtype=np.uint8).tobytes())
+    _mk(root, "d/big.bin", rng.integers(0, 256, 5_000_000, dtype=np.uint8).tobytes())   # larger than one 2 MiB arena
+    _mk(root, "e/c.txt", b"c")
+    _mk(root, "e/empty", b"")
+    for d, _, _ in os.walk(root):
+        os.utime(d, (T, T))
+    o = lt.MemFS(lambda: NOW, str(root))
+    h = host.MemFS(str(root))
+    with Engine(device=0, device_arena_bytes=8 << 20, n_host_arenas=2, host_arena_bytes=8 << 20, max_extents=1 << 12) as eng:
+        l1 = o.add_layer_by_scan()
+        o.remember_content(l1)
+        g1 = h.commit_scan(eng, NOW, flags=host.MKHOST_FILE_DIGESTS)
+        assert g1["tar_digest"] == lt.tar_digest(l1) and g1["n_entries"] == len(l1) == 7
+
+        def edit(rel, off):
+            p = root / rel
+            st = os.lstat(p)
+            with open(p, "r+b") as f:
+                f.seek(off)
+                b = f.read(1)
+                f.seek(off)
+                f.write(bytes([b[0] ^ 0x5A]))
+            os.utime(p, ns=(st.st_atime_ns, st.st_mtime_ns))
+
+        edit("d/b.bin", 123_456)
+        edit("d/big.bin", 4_999_999)                                # last byte of a file that spans arenas
+        # the reference's scan: metadata identical => nothing to commit (the edit is missed)
+        assert o.add_layer_by_scan() == []
+        assert h.commit_scan(eng, NOW)["n_entries"] == 0
+    # the digest pass streams through 2 MiB arenas: big.bin continues across submits
+    with Engine(device=0, device_arena_bytes=2 << 20, n_host_arenas=2, host_arena_bytes=2 << 20, max_extents=1 << 12) as small, \
+            Engine(device=0, device_arena_bytes=8 << 20, n_host_arenas=2, host_arena_bytes=8 << 20, max_extents=1 << 12) as eng:
+        l3 = o.add_layer_by_scan(content_aware=True)
+        o.remember_content(l3)
+        assert [e.dst for e in l3] == ["/d", "/d/b.bin", "/d/big.bin"]
+        g3 = h.commit_scan(eng, NOW, flags=host.MKHOST_SCAN_CONTENT)
+        assert g3["n_entries"] == 3 and g3["tar_digest"] == lt.tar_digest(l3)
+        # nothing changed since: both empty, through the small-arena engine this time (exercises stream continuation)
+        assert o.add_layer_by_scan(content_aware=True) == []
+        assert h.commit_scan(small, NOW, flags=host.MKHOST_SCAN_CONTENT)["n_entries"] == 0
+        edit("d/big.bin", 0)
+        l5 = o.add_layer_by_scan(content_aware=True)
+        assert [e.dst for e in l5] == ["/d", "/d/big.bin"]
+        with pytest.raises(host.HostError) as ei:                  # the commit itself still needs the file in one arena
+            h.commit_scan(small, NOW, flags=host.MKHOST_SCAN_CONTENT)
+        assert "exceeds the arena" in str(ei.value)
+    h.close()
+
+    # base layer ingested from a tar (digests remembered per member), files "untarred" with the same metadata, then
+    # one of them edited in place
+    root2 = tmp_path / "root2"
+    body_a, body_b = rng.integers(0, 256, 70_000, dtype=np.uint8).tobytes(), b"config=1\n" * 100
+    buf = io.BytesIO()
+    with tarfile.open(fileobj=buf, mode="w", format=tarfile.PAX_FORMAT) as tf:
+        for name, typ, data in [("opt/", tarfile.DIRTYPE, b""), ("opt/app.bin", tarfile.REGTYPE, body_a),
+                                ("opt/app.conf", tarfile.REGTYPE, body_b)]:
+            ti = tarfile.TarInfo(name)
+            ti.type, ti.mode, ti.mtime, ti.uid, ti.gid = typ, (0o755 if typ == tarfile.DIRTYPE else 0o644), T, os.getuid(), os.getgid()
+            ti.size = len(data)
+            tf.addfile(ti, io.BytesIO(data) if data else None)
+    data = buf.getvalue()
+    _mk(root2, "opt/app.bin", body_a, mtime=T)
+    _mk(root2, "opt/app.conf", body_b, mtime=T)
+    os.chmod(root2 / "opt", 0o755)
+    os.utime(root2 / "opt", (T, T))
+    (tmp_path / "base.tar").write_bytes(data)
+    o2 = lt.MemFS(lambda: NOW, str(root2))
+    h2 = host.MemFS(str(root2))
+    with Engine(device=0, device_arena_bytes=8 << 20, n_host_arenas=2, host_arena_bytes=8 << 20, max_extents=1 << 12) as eng:
+        assert len(o2.update_from_tar(data, remember=True)) == 3
+        with open(tmp_path / "base.tar", "rb") as f:
+            got = h2.update_from_tar(eng, NOW, f.fileno(), flags=host.MKHOST_FILE_DIGESTS)
+        import hashlib
+        assert got["n_entries"] == 3 and got["tar_digest"] == "sha256:" + hashlib.sha256(data).hexdigest()
+        # the digests of the regular members are remembered in the tree
+        assert h2.file_digest("/opt/app.bin") == hashlib.sha256(body_a).digest() == o2.tree.children["opt"].children["app.bin"].mf.digest
+        assert h2.file_digest("/opt/app.conf") == hashlib.sha256(body_b).digest()
+        assert h2.file_digest("/opt") is None and h2.file_digest("/nope") is None
+        # Scanning a root other than "/" after an ingest: the reference records AbsPath(hdr.Name) as the node's src
+        # (mem_fs.go:224), so isOnDisk (mem_fs.go:49-57) looks for /opt/app.bin on the HOST, whites the child out and
+        # the walk re-adds it from disk.  Both implementations reproduce that; the re-added files carry fresh digests.
+        l = o2.add_layer_by_scan(content_aware=True)
+        o2.remember_content(l)
+        g = h2.commit_scan(eng, NOW, flags=host.MKHOST_SCAN_CONTENT)
+        assert g["n_entries"] == len(l) and g["tar_digest"] == lt.tar_digest(l)
+        st = os.lstat(root2 / "opt/app.conf")
+        with open(root2 / "opt/app.conf", "r+b") as f:
+            f.write(b"config=2")
+        os.utime(root2 / "opt/app.conf", ns=(st.st_atime_ns, st.st_mtime_ns))
+        assert o2.add_layer_by_scan() == [] and h2.commit_scan(eng, NOW)["n_entries"] == 0          # missed by metadata
+        l = o2.add_layer_by_scan(content_aware=True)
+        assert [e.dst for e in l] == ["/opt", "/opt/app.conf"]
+        g = h2.commit_scan(eng, NOW, flags=host.MKHOST_SCAN_CONTENT)
+        assert g["n_entries"] == 2 and g["tar_digest"] == lt.tar_digest(l)
+    h2.close()
