@@ -183,6 +183,8 @@ uint32_t mksnap_ctx_crc32(const mksnap_result *res);
 int mksnap_get_chunks(mksnap_t *h, uint64_t *ends, uint8_t *digests, uint64_t capacity);
 /* sorted-unique 32-byte digest table */
 int mksnap_get_table(mksnap_t *h, uint8_t *table, uint64_t capacity_rows);
+/* rows the handle's table currently holds: result.n_unique after finish / allgather, this rank's range after exchange */
+uint64_t mksnap_table_rows(mksnap_t *h);
 /* stream digests, row = stream slot: the TarDigest bytes of
  * lib/builder/step/common.go:86 (hex-encode and prefix "sha256:" on the host). */
 int mksnap_get_stream_digests(mksnap_t *h, uint8_t *digests, uint64_t capacity);
@@ -197,6 +199,19 @@ int mksnap_comm_init(mksnap_t *h, const uint8_t id[128], int32_t n_ranks, int32_
  * device, XOR-combine the CRC partials.  *out is identical on every rank and
  * equal to what a single GPU would produce for the whole context. */
 int mksnap_allgather_tables(mksnap_t *h, mksnap_result *out);
+/* The scalable form of the same step: the global table stays RANGE-PARTITIONED.  Rank r ends up owning the digests
+ * whose big-endian 64-bit prefix p has floor(p * n_ranks / 2^64) == r: slices of the per-rank tables travel once
+ * (ncclSend/ncclRecv all-to-all over NVLink), every rank sorts only its range, Merkle level 0 is computed where the
+ * rows are (a group of 256 consecutive global rows by the rank owning its first row, the missing rows of a group
+ * that straddles a range end come from an all-gather of every rank's first 255 rows), level-1 digests are
+ * all-gathered and the upper levels run everywhere.  *out (root, CRC, counters, n_unique = GLOBAL unique rows) is
+ * identical on every rank and equal to the single-GPU result; afterwards mksnap_get_table returns THIS rank's range
+ * (ascending; the ranges of ranks 0..n-1 concatenated are the global table).  Work per rank stays ~constant as
+ * n_ranks grows, where mksnap_allgather_tables sorts n_ranks times more rows on every rank. */
+int mksnap_exchange_tables(mksnap_t *h, mksnap_result *out);
+/* The same exchange between n handles of ONE process on ONE device (device copies instead of NCCL; no comm_init):
+ * handle i plays rank i, outs[i] receives its result.  Used to run the exchange logic for any n on a single GPU. */
+int mksnap_exchange_tables_local(mksnap_t **handles, int32_t n, mksnap_result *outs);
 
 /* ---- utilities --------------------------------------------------------- */
 /* Deterministic synthetic content, generated on the device into slot bytes

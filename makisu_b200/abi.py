@@ -82,7 +82,10 @@ SYMBOLS = [
     ("mksnap_get_stream_digests", C.c_int, [_P, _P, C.c_uint64]),
     ("mksnap_comm_unique_id", C.c_int, [_P]),
     ("mksnap_comm_init", C.c_int, [_P, _P, C.c_int32, C.c_int32]),
+    ("mksnap_table_rows", C.c_uint64, [_P]),
     ("mksnap_allgather_tables", C.c_int, [_P, C.POINTER(Result)]),
+    ("mksnap_exchange_tables", C.c_int, [_P, C.POINTER(Result)]),
+    ("mksnap_exchange_tables_local", C.c_int, [C.POINTER(_P), C.c_int32, C.POINTER(Result)]),
     ("mksnap_synth_fill", C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64]),
     ("mksnap_memset", C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int]),
     ("mksnap_device_download", C.c_int, [_P, C.c_uint32, C.c_uint64, _P, C.c_uint64]),
@@ -231,6 +234,9 @@ class Engine:
         self._ck(self.lib.mksnap_get_table(self.h, t.ctypes.data, n), "mksnap_get_table")
         return t[:n]
 
+    def table_rows(self) -> int:
+        return int(self.lib.mksnap_table_rows(self.h))
+
     def get_stream_digests(self, n: int):
         import numpy as np
         t = np.empty((max(n, 1), 32), dtype=np.uint8)
@@ -262,6 +268,24 @@ class Engine:
         r = Result()
         self._ck(self.lib.mksnap_allgather_tables(self.h, C.byref(r)), "mksnap_allgather_tables")
         return r
+
+    def exchange_tables(self) -> Result:
+        """Range-partitioned form of the exchange step (NCCL all-to-all); get_table then returns this rank's range."""
+        r = Result()
+        self._ck(self.lib.mksnap_exchange_tables(self.h, C.byref(r)), "mksnap_exchange_tables")
+        return r
+
+    @staticmethod
+    def exchange_tables_local(engines) -> list:
+        """The same exchange between engines of this process on one device (engine i = rank i)."""
+        n = len(engines)
+        hs = (_P * n)(*[e.h for e in engines])
+        outs = (Result * n)()
+        rc = engines[0].lib.mksnap_exchange_tables_local(hs, n, outs)
+        if rc:
+            msgs = [(e.lib.mksnap_last_error(e.h) or b"").decode() for e in engines]
+            raise MksnapError(rc, "mksnap_exchange_tables_local", "; ".join(m for m in msgs if m))
+        return [outs[i] for i in range(n)]
 
 
 def gear_table():
