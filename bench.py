@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--batch-mib", type=int, default=1024, help="pinned host arena size for the e2e path")
     ap.add_argument("--host-pool", type=int, default=8, help="distinct pinned arenas cycled by the e2e path")
     ap.add_argument("--cpu-sample-mib", type=int, default=1536)
+    ap.add_argument("--merge", default="exchange", choices=["exchange", "allgather"],
+                    help="N>1: range-partitioned all-to-all exchange (default) or all-gather of whole tables")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="uniform", choices=["uniform", "dup", "zipf"],
@@ -403,13 +405,34 @@ def main():
     eng.sync()
     ext = lay["ext"]
 
+    merge = {"mode": args.merge}
+
     def one_step():
         eng.begin()
         eng.lib.mksnap_device_submit(eng.h, 0, used, ext_ptr(ext), n_ext, None, 0)
         res = eng.finish()
         if world > 1:
-            res = eng.allgather_tables()
+            res = eng.exchange_tables() if merge["mode"] == "exchange" else eng.allgather_tables()
         return res
+
+    if world > 1 and merge["mode"] == "exchange":
+        # self-check before anything is timed: the range-partitioned exchange must give the root, CRC and counters of the
+        # all-gather merge on this very workload; if any rank disagrees every rank falls back to the all-gather.
+        merge["mode"] = "allgather"
+        ra = one_step()
+        merge["mode"] = "exchange"
+        try:
+            rx = one_step()
+            ok = (bytes(rx.root) == bytes(ra.root) and rx.n_unique == ra.n_unique and rx.crc_pure == ra.crc_pure
+                  and rx.n_chunks == ra.n_chunks)
+        except Exception as ex:  # noqa: BLE001
+            print("exchange failed:", ex, file=sys.stderr)
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            merge["mode"] = "allgather"
+            merge["note"] = "exchange self-check failed, fell back to all-gather"
 
     # ---- correctness gate on a sample (stdlib zlib / hashlib, not the oracle) ----
     gate_files = min(args.files, 8)
@@ -499,7 +522,7 @@ def main():
         {"name": "K1b k_select_cuts+scan", "bound": "latency", "ms": kern["ms_select"]},
         {"name": "K3 radix sort+unique", "bound": "hbm(small)", "ms": kern["ms_sort"]},
         {"name": "merkle root", "bound": "latency", "ms": kern["ms_root"]},
-        {"name": "nccl all-gather+merge", "bound": "nvlink(small)", "ms": kern["ms_gather"]},
+        {"name": "nccl table exchange (" + merge["mode"] + ")", "bound": "nvlink(small)", "ms": kern["ms_gather"]},
     ]
     for k in kernels:
         if k.get("algorithmic_GBps"):
@@ -560,7 +583,7 @@ def main():
                 eng2._ck(eng2.lib.mksnap_arena_submit(eng2.h, aid, blay["used"], ext_ptr(e), len(e), None, 0), "submit")
             r = eng2.finish()
             if world > 1:
-                r = eng2.allgather_tables()
+                r = eng2.exchange_tables() if merge["mode"] == "exchange" else eng2.allgather_tables()
             return r
 
         e2e_step()
@@ -629,7 +652,8 @@ def main():
             "config": {"workload": f"{args.files} files x {args.file_kib} KiB ({ctx_bytes / GiB:.2f} GiB) per GPU, "
                                    f"{args.dirs} dirs, BASELINE configs[2]",
                        "per_step": "crc32 cacheID + gear32 CDC + chunk SHA-256 + sort/unique + merkle root"
-                                   + (" + nccl allgather/merge" if world > 1 else ""),
+                                   + ((" + nccl " + merge["mode"] + " of the tables" + (" [" + merge["note"] + "]" if "note" in merge else ""))
+                                      if world > 1 else ""),
                        "l2": "inputs (48.8 GiB) >> L2 (126 MB): no flush needed", "sharding": f"files by rank, dp{world}",
                        "host_affinity": affinity_note,
                        "n_chunks": int(res.n_chunks), "n_unique": int(res.n_unique), "cache_id": "%x" % eng.ctx_crc32(res),

@@ -1,5 +1,6 @@
 """-m gpu, needs >= 2 GPUs (skipped otherwise): two processes, one per GPU, each digests its shard, then
-mksnap_allgather_tables (NCCL over NVLink) -- every rank must hold the single-GPU result of the whole context."""
+mksnap_allgather_tables (NCCL over NVLink) -- every rank must hold the single-GPU result of the whole context -- and
+mksnap_exchange_tables (ncclSend/ncclRecv all-to-all): same root and counters, the table range-partitioned."""
 import os
 import zlib
 
@@ -49,7 +50,14 @@ def _worker(rank, world, idfile, q):
     eng.device_submit(0, arena.size, ext)
     eng.finish()
     res = eng.allgather_tables()
-    q.put((rank, eng.ctx_crc32(res), res.n_chunks, res.n_unique, res.n_files, bytes(res.root), eng.get_table(res.n_unique).tobytes()))
+    gathered = (eng.ctx_crc32(res), res.n_chunks, res.n_unique, res.n_files, bytes(res.root), eng.get_table(res.n_unique).tobytes())
+    # the same shard again, merged the scalable way: ncclSend/ncclRecv all-to-all, the table stays range-partitioned
+    eng.begin()
+    eng.device_submit(0, arena.size, ext)
+    eng.finish()
+    rx = eng.exchange_tables()
+    exchanged = (eng.ctx_crc32(rx), rx.n_chunks, rx.n_unique, rx.n_files, bytes(rx.root), eng.get_table(eng.table_rows()).tobytes())
+    q.put((rank, gathered, exchanged))
     eng.close()
 
 
@@ -74,7 +82,14 @@ def test_two_gpus_equal_single(tmp_path):
     names, files, lens = _context()
     want_crc = zlib.crc32(b"".join(n + f.tobytes() for n, f in zip(names, files)))
     single = olib.chunk_table(np.concatenate(files), np.concatenate([[0], np.cumsum(lens)[:-1]]), lens)
-    for rank, crc, n_chunks, n_unique, n_files, root, table in res:
+    for rank, (crc, n_chunks, n_unique, n_files, root, table), _ in res:
         assert crc == want_crc
         assert (n_chunks, n_unique, n_files) == (single["n_chunks"], single["n_unique"], len(files))
         assert root == single["root"] and table == single["table"].tobytes()
+    ranges = {}
+    for rank, _, (crc, n_chunks, n_unique, n_files, root, rows) in res:
+        assert crc == want_crc and root == single["root"]
+        assert (n_chunks, n_unique, n_files) == (single["n_chunks"], single["n_unique"], len(files))
+        ranges[rank] = rows
+    assert b"".join(ranges[r] for r in sorted(ranges)) == single["table"].tobytes()
+    assert all(len(v) for v in ranges.values())
