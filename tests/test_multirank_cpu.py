@@ -1,6 +1,8 @@
 """CPU, world_size 2 over gloo: the host side of the N>1 path -- LPT sharding, position-independent CRC
 partials, header + padded-row all-gather, merge -- gives exactly the single-rank result.  The per-rank
-digests come from the oracle here (no GPU); on the GPU box tests/test_gpu_multi.py does the same with NCCL."""
+digests come from the oracle here (no GPU); on the GPU box tests/test_gpu_multi.py does the same with NCCL.
+Second half: the range-partitioned exchange (mksnap_exchange_tables) -- every transport step as a gloo collective,
+world sizes 2 and 3 -- and its single-process model on awkward distributions."""
 import os
 import zlib
 
@@ -101,3 +103,100 @@ def test_lpt_shard_properties():
         sh = shard.lpt_shard(lens, n)
         assert sorted(i for s in sh for i in s) == list(range(len(lens)))
         assert shard.imbalance(lens, sh) < 1.0 + max(lens) / (lens.sum() / n) + 1e-9
+
+
+# ---- range-partitioned exchange (mksnap_exchange_tables): the host logic over gloo -------------------------------
+def _sha(b: bytes) -> bytes:
+    import hashlib
+    return hashlib.sha256(b).digest()
+
+
+def _exchange_worker(rank, world, port, q):
+    """Every transport step of the exchange as a gloo collective; the per-rank arithmetic is shard.range_bounds /
+    shard.level0_plan -- the functions the device code (x_phase1..5 in mksnap.cu) restates."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    names, files, lens = _context()
+    _, table = _rank_result(rank, world, names, files, lens)
+    b = shard.range_bounds(table, world)
+    # 1 all-to-all of the slices
+    outbox = [table[b[j]:b[j + 1]].tobytes() for j in range(world)]
+    boxes = [None] * world
+    dist.all_gather_object(boxes, outbox)
+    got = sorted({boxes[k][rank][i:i + 32] for k in range(world) for i in range(0, len(boxes[k][rank]), 32)})
+    mine = np.frombuffer(b"".join(got), dtype=np.uint8).reshape(-1, 32)                 # 2 my range of the global table
+    recs = [None] * world                                                               # 3 rows per range + heads
+    dist.all_gather_object(recs, (int(mine.shape[0]), mine[:shard.HEAD_ROWS].tobytes()))
+    all_u = [r[0] for r in recs]
+    p = shard.level0_plan(all_u, rank)                                                  # 4 level 0 of the groups I own
+    l1 = [_sha(mine[p["lead"] + 256 * g:p["lead"] + 256 * (g + 1)].tobytes()) for g in range(p["full"])]
+    if p["tail_own"]:
+        tail, need, k = [mine[p["lead"] + 256 * p["full"]:].tobytes()], p["borrowed"], rank + 1
+        while need:
+            take = min(need, all_u[k])
+            tail.append(recs[k][1][:32 * take])
+            need -= take
+            k += 1
+        l1.append(_sha(b"".join(tail)))
+    assert len(l1) == p["groups"]
+    alll1 = [None] * world                                                              # 5 level-1 all-gather, upper levels
+    dist.all_gather_object(alll1, l1)
+    cur = [d for part in alll1 for d in part]
+    if sum(all_u) == 0:
+        cur = [_sha(b"")]
+    while len(cur) > 1:
+        cur = [_sha(b"".join(cur[i:i + 256])) for i in range(0, len(cur), 256)]
+    q.put((rank, cur[0].hex(), sum(all_u), mine.tobytes()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_ranks_equal_single_rank(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 17 * world) % 1000
+    ps = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=150) for _ in range(world))
+    for p in ps:
+        p.join(30)
+        assert p.exitcode == 0
+    names, files, lens = _context()
+    single = olib.chunk_table(np.concatenate(files), np.concatenate([[0], np.cumsum(lens)[:-1]]), lens)
+    for rank, root, n_unique, rows in res:
+        assert root == single["root"].hex() and n_unique == single["n_unique"]
+    assert b"".join(r[3] for r in res) == single["table"].tobytes()      # the ranges, in rank order, are the table
+
+
+def test_exchange_model_edge_cases():
+    """shard.exchange_tables_model against the oracle's Merkle root: empty ranks, ranks below one group, one row in
+    total, nothing at all, groups straddling several ranks, all digests on one rank (skew), duplicates across ranks."""
+    import ctypes
+    rng = np.random.default_rng(1)
+
+    def mk(n, skew=False):
+        a = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        if skew:
+            a[:, 0] = rng.integers(0, 3, n)
+        u = sorted({bytes(r) for r in a})
+        return np.frombuffer(b"".join(u), dtype=np.uint8).reshape(-1, 32) if u else np.zeros((0, 32), np.uint8)
+    cases = [([1000], False), ([700, 900], False), ([0, 5, 300, 0], False), ([10, 0, 3, 700, 256, 255, 1, 0], False),
+             ([600] * 4, True), ([0, 0, 0], False), ([1, 0, 0, 0, 0], False), ([4000] * 8, False), ([256, 0], False),
+             ([512, 256, 256], True), ([255, 1], False), ([1] * 7, False)]
+    for sizes, skew in cases:
+        tabs = [mk(n, skew) for n in sizes]
+        if len(tabs) > 1 and tabs[0].shape[0] > 3 and tabs[1].shape[0]:
+            u = sorted({bytes(r) for r in tabs[1]} | {bytes(r) for r in tabs[0][:3]})
+            tabs[1] = np.frombuffer(b"".join(u), dtype=np.uint8).reshape(-1, 32)
+        root, ranges = shard.exchange_tables_model(tabs, _sha)
+        union = sorted({bytes(r) for t in tabs for r in t})
+        cat = np.frombuffer(b"".join(union), dtype=np.uint8).reshape(-1, 32) if union else np.zeros((0, 32), np.uint8)
+        out = (ctypes.c_uint8 * 32)()
+        olib.L().mko_merkle_root(np.ascontiguousarray(cat).ctypes.data if union else None, len(union), out)
+        assert bytes(out) == root, sizes
+        assert b"".join(x.tobytes() for x in ranges) == b"".join(union)
+        for r, x in enumerate(ranges):                      # every row sits on the rank that owns its prefix
+            assert all(shard.range_owner(int.from_bytes(bytes(row[:8]), "big"), len(tabs)) == r for row in x)
