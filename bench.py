@@ -181,6 +181,29 @@ def ext_ptr(a: np.ndarray):
 
 # ----------------------------------------------------------------------------------------------------
 def clocks_sampler(dev_index: int, stop: threading.Event, out: list):
+    """SM clock + throttle reasons of this rank's GPU DURING the timed region.  NVML polled every 20 ms (a timed region
+    is only a few hundred ms; spawning nvidia-smi can take longer than that on an 8-GPU box); nvidia-smi -lms as the
+    fallback when NVML cannot be used.  Rows: [sm_mhz, sm_max_mhz, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap]."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(dev_index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        bits = [0x8, 0x40, 0x20, 0x4]  # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    except Exception:
+        h = None
+    if h is not None:
+        while not stop.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                out.append([str(sm), str(mx)] + [("Active" if r & b else "Not Active") for b in bits])
+            except Exception:
+                break
+            stop.wait(0.02)
+        return
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     try:
