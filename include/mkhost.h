@@ -132,6 +132,26 @@ int mkhost_memfs_update_from_tar(mkhost_memfs *m, mksnap_t *eng, int64_t now_uni
 size_t mkhost_memfs_describe_update_from_tar(mkhost_memfs *m, int64_t now_unix, int tar_fd, char *out, size_t cap,
                                              char *err, size_t errlen);
 
+/* CopyOperation.Execute (lib/snapshot/copy_op.go:82-147) with fileio.Copier (lib/fileio/copy.go): what a COPY/ADD step
+ * does to the file system when it runs with --modifyfs.  op->dst is used as the on-disk destination exactly like the
+ * reference does (resolved against op->work_dir when relative).  mode selects the Copier of copy_op.go:98-124:
+ * MKHOST_COPY_CHOWN (--chown: op->uid/gid), MKHOST_COPY_INTERNAL (--from=<stage>: no blacklist, owners preserved),
+ * MKHOST_COPY_PRESERVE_OWNER (--from --archive).  mode 0 = copy from the build context (owner root).
+ * MKHOST_COPY_DEFERRED runs the traversal (directories, symlinks, chmod of existing targets) first and writes the
+ * regular files afterwards from buffers read once -- the path mkhost_memfs_commit_copy_ops(…, MKHOST_MATERIALIZE)
+ * takes with its arena; here the buffers are plain reads, so the deferred machinery can be exercised without a GPU. */
+#define MKHOST_COPY_CHOWN 1u
+#define MKHOST_COPY_INTERNAL 2u
+#define MKHOST_COPY_PRESERVE_OWNER 4u
+#define MKHOST_COPY_DEFERRED 8u
+int mkhost_copy_op_execute(const mkhost_copy_op *op, uint32_t mode, const char *const *blacklist, size_t n_blacklist,
+                           char *err, size_t errlen);
+/* flag for mkhost_memfs_commit_copy_ops: also perform the copy (as mkhost_copy_op_execute with `copy_mode` 0 / CHOWN
+ * decided by MKHOST_MATERIALIZE_CHOWN), writing regular files from the arena the layer is packed in: the context is
+ * read once for the copy, the layer, its digest and its chunk table. */
+#define MKHOST_MATERIALIZE 8u
+#define MKHOST_MATERIALIZE_CHOWN 16u
+
 /* cache.Manager wire format (lib/cache/cache_manager.go:34-35,239-252).  key = "makisu_builder_cache_" + cacheID;
  * entry = "<tarHex>,<gzipHex>" (createEntry), or "MAKISU_CACHE_EMPTY" for a nil pair (tar_hex == NULL).
  * parse = parseEntry: error when there is no ',', otherwise SplitN(entry, ",", 2) -- no hex validation, like

@@ -56,6 +56,7 @@ SYMBOLS = [
                                                C.c_size_t]),
     ("mkhost_memfs_describe_update_from_tar", C.c_size_t, [_P, C.c_int64, C.c_int, C.c_char_p, C.c_size_t, C.c_char_p,
                                                            C.c_size_t]),
+    ("mkhost_copy_op_execute", C.c_int, [C.POINTER(CopyOp), C.c_uint32, C.POINTER(C.c_char_p), C.c_size_t, C.c_char_p, C.c_size_t]),
     ("mkhost_cache_key", C.c_size_t, [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]),
     ("mkhost_cache_entry_create", C.c_size_t, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     ("mkhost_cache_entry_parse", C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
@@ -173,6 +174,9 @@ def copy_step_cache_id(eng: abi.Engine, seed: str, directive: str, args: str, co
 MKHOST_NO_TAR_DIGEST = 1
 MKHOST_FILE_DIGESTS = 2   # remember per-file SHA-256 in the MemFS tree
 MKHOST_SCAN_CONTENT = 4   # content-aware AddLayerByScan (implies FILE_DIGESTS)
+MKHOST_MATERIALIZE = 8    # commit_copy_ops also performs the copy onto the file system, from the arena
+MKHOST_MATERIALIZE_CHOWN = 16
+MKHOST_COPY_CHOWN, MKHOST_COPY_INTERNAL, MKHOST_COPY_PRESERVE_OWNER, MKHOST_COPY_DEFERRED = 1, 2, 4, 8
 
 
 def commit_copy_ops(eng: abi.Engine, root_dir: str, now_unix: int, ops: Sequence[CopyOperation], n_threads: int = 0,
@@ -295,3 +299,12 @@ def cache_chunk_entry_parse(entry: str):
     if load().mkhost_cache_chunk_entry_parse(entry.encode(), root, C.byref(n), err, len(err)):
         raise HostError(err.value.decode())
     return bytes(root), n.value
+
+
+def copy_op_execute(op: "CopyOperation", mode: int = 0, blacklist: Sequence[str] = ()) -> None:
+    """CopyOperation.Execute (lib/snapshot/copy_op.go:82-147) through fileio.Copier's rules."""
+    err = C.create_string_buffer(1024)
+    arr, keep = _ops([op])
+    bl = _strs(list(blacklist))
+    if load().mkhost_copy_op_execute(arr, mode, bl, len(blacklist), err, len(err)):
+        raise HostError(err.value.decode())

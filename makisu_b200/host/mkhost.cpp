@@ -954,6 +954,356 @@ struct MemTarSource : TarSource {
 };
 
 // ---------------------------------------------------------------------------------------------------
+// fileio.Copier (lib/fileio/copy.go:30-400) + CopyOperation.Execute (lib/snapshot/copy_op.go:82-147) +
+// evalSymlinks (lib/snapshot/utils.go:249-324): the file copy a COPY/ADD step performs when it modifies the file
+// system.  `deferred` (ours): regular-file contents are not copied during the traversal but recorded, so the layer
+// packer -- which reads the same sources into its arena anyway -- can write them from memory (one read of the
+// context instead of one for the copy and one for the layer).
+// ---------------------------------------------------------------------------------------------------
+struct CopyOwner {
+    bool set = false;
+    int64_t uid = 0, gid = 0;
+    bool overwrite = false;
+};
+struct DeferredFile {
+    std::string dst;
+    struct stat st;
+    size_t copier = 0; // which Copier (owner rules) finishes it
+};
+
+void ck_sys(int rc, const std::string &what, const std::string &path)
+{
+    if (rc != 0)
+        throw HostError(errno_str(what, path));
+}
+
+class Copier
+{
+  public:
+    Copier(std::vector<std::string> blacklist, CopyOwner dir_owner, CopyOwner children_owner,
+           std::multimap<std::string, DeferredFile> *deferred = nullptr, size_t tag = 0)
+        : blacklist_(std::move(blacklist)), dir_owner_(dir_owner), children_owner_(children_owner), deferred_(deferred), tag_(tag)
+    {
+    }
+
+    void copy_file(const std::string &source, const std::string &target) // copy.go:122-131
+    {
+        std::string dir = go_clean(target);
+        const size_t sl = dir.rfind('/');
+        dir = sl == std::string::npos ? "." : (sl == 0 ? "/" : dir.substr(0, sl));
+        mkdir_all(dir);
+        copy_one(source, target);
+    }
+
+    void copy_dir(const std::string &source, const std::string &target) // copy.go:142-156
+    {
+        if (blacklisted(source))
+            return;
+        mkdir_all(target);
+        copy_dir_contents(source, target, target);
+    }
+
+    // copy.go:195-230 with the bytes coming from memory (or, when `data` is null, from src)
+    void finish_regular(const struct stat &st, const std::string &src, const std::string &dst, const uint8_t *data, uint64_t len)
+    {
+        int rfd = -1;
+        if (!data) {
+            rfd = open(src.c_str(), O_RDONLY | O_CLOEXEC);
+            if (rfd < 0)
+                throw HostError(errno_str("open", dst)); // the reference reports dst here (copy.go:198)
+        }
+        const int wfd = open(dst.c_str(), O_WRONLY | O_CREAT | O_CLOEXEC, 0777);
+        if (wfd < 0) {
+            if (rfd >= 0)
+                close(rfd);
+            throw HostError(errno_str("create", dst));
+        }
+        std::string err;
+        if (truncate(dst.c_str(), 0) != 0)
+            err = errno_str("truncate", dst);
+        auto write_all = [&](const uint8_t *p, uint64_t n) {
+            while (n && err.empty()) {
+                ssize_t w = write(wfd, p, n);
+                if (w < 0) {
+                    if (errno == EINTR)
+                        continue;
+                    err = errno_str("copy " + src + " to", dst);
+                    break;
+                }
+                p += w;
+                n -= (uint64_t)w;
+            }
+        };
+        if (err.empty()) {
+            if (data) {
+                write_all(data, len);
+            } else {
+                std::vector<uint8_t> buf(1 << 20);
+                for (;;) {
+                    ssize_t r = read(rfd, buf.data(), buf.size());
+                    if (r < 0) {
+                        if (errno == EINTR)
+                            continue;
+                        err = errno_str("copy " + src + " to", dst);
+                        break;
+                    }
+                    if (r == 0)
+                        break;
+                    write_all(buf.data(), (uint64_t)r);
+                    if (!err.empty())
+                        break;
+                }
+            }
+        }
+        close(wfd);
+        if (rfd >= 0)
+            close(rfd);
+        if (!err.empty())
+            throw HostError(err);
+        int64_t uid = st.st_uid, gid = st.st_gid;
+        if (children_owner_.set && children_owner_.overwrite) {
+            uid = children_owner_.uid;
+            gid = children_owner_.gid;
+        }
+        ck_sys(chown(dst.c_str(), (uid_t)uid, (gid_t)gid), "chown", dst);
+        ck_sys(chmod(dst.c_str(), st.st_mode & 07777), "chmod", dst); // after chown: setuid/setgid survive
+    }
+
+  private:
+    std::vector<std::string> blacklist_;
+    CopyOwner dir_owner_, children_owner_;
+    std::multimap<std::string, DeferredFile> *deferred_;
+    size_t tag_;
+
+    bool blacklisted(const std::string &p) const
+    {
+        const std::string a = abs_path(p);
+        const size_t sl = a.rfind('/');
+        const std::string dir = (sl == 0 ? std::string("/") : a.substr(0, sl)) + "/";
+        for (const auto &anc : blacklist_) {
+            const std::string b = abs_path(anc);
+            if (a == b || b == "/" || dir.compare(0, b.size() + 1, b + "/") == 0)
+                return true;
+        }
+        return false;
+    }
+
+    static bool exists(const std::string &p, struct stat *st = nullptr)
+    {
+        struct stat tmp;
+        if (lstat(p.c_str(), st ? st : &tmp) == 0)
+            return true;
+        if (errno != ENOENT)
+            throw HostError(errno_str("lstat", p));
+        return false;
+    }
+
+    void copy_one(const std::string &src, const std::string &dst) // copyFile, copy.go:163-193
+    {
+        struct stat st;
+        if (lstat(src.c_str(), &st) != 0)
+            throw HostError(errno_str("lstat", src));
+        if (blacklisted(src)) {
+            // the reference only logs in this branch and carries on
+        } else if (is_special(st)) {
+            return;
+        }
+        if (S_ISLNK(st.st_mode)) {
+            if (exists(dst))
+                ck_sys(remove(dst.c_str()), "remove existing file", dst);
+            const std::string target = read_link(src);
+            ck_sys(symlink(target.c_str(), dst.c_str()), "write link " + dst + " with content", target);
+            return;
+        }
+        if (exists(dst))
+            ck_sys(chmod(dst.c_str(), 0777), "chmod", dst);
+        if (deferred_) {
+            deferred_->emplace(src, DeferredFile{dst, st, tag_});
+            return;
+        }
+        finish_regular(st, src, dst, nullptr, 0);
+    }
+
+    void copy_dir_contents(const std::string &src, const std::string &dst, const std::string &orig_dst) // copy.go:252-283
+    {
+        for (const auto &name : sorted_names(src)) {
+            const std::string cur_src = go_join(src, name);
+            if (blacklisted(cur_src) || cur_src == orig_dst)
+                continue;
+            const std::string cur_dst = go_join(dst, name);
+            struct stat st;
+            if (lstat(cur_src.c_str(), &st) != 0)
+                throw HostError(errno_str("lstat", cur_src));
+            if (S_ISDIR(st.st_mode)) {
+                copy_dir_one(cur_src, cur_dst);
+                copy_dir_contents(cur_src, cur_dst, orig_dst);
+            } else {
+                copy_one(cur_src, cur_dst);
+            }
+        }
+    }
+
+    void copy_dir_one(const std::string &src, const std::string &dst) // copyDir, copy.go:286-329
+    {
+        struct stat st, dst_st;
+        if (lstat(src.c_str(), &st) != 0)
+            throw HostError(errno_str("lstat", src));
+        if (!S_ISDIR(st.st_mode))
+            throw HostError("source " + src + " is not a directory");
+        if (blacklisted(src))
+            return;
+        if (!exists(dst, &dst_st))
+            ck_sys(mkdir(dst.c_str(), st.st_mode & 07777), "mkdir", dst);
+        else if (!S_ISDIR(dst_st.st_mode))
+            throw HostError("dst is not a directory");
+        ck_sys(chmod(dst.c_str(), st.st_mode & 07777), "chmod", dst);
+        int64_t uid = st.st_uid, gid = st.st_gid;
+        if (children_owner_.set && children_owner_.overwrite) {
+            uid = children_owner_.uid;
+            gid = children_owner_.gid;
+        }
+        ck_sys(chown(dst.c_str(), (uid_t)uid, (gid_t)gid), "chown", dst);
+    }
+
+    void mkdir_all(const std::string &dst) // copy.go:334-399
+    {
+        if (dst.empty())
+            throw HostError("empty dst directory");
+        std::string a = go_clean(dst);
+        if (a[0] != '/') {
+            char cwd[4096];
+            if (!getcwd(cwd, sizeof cwd))
+                throw HostError("failed to get absolute path of " + dst);
+            a = go_join(cwd, a);
+        }
+        std::string prev = "/";
+        const auto parts = split_path(a);
+        for (size_t i = 0; i + 1 < parts.size(); ++i) {
+            const std::string cur = go_join(prev, parts[i]);
+            if (!exists(cur)) {
+                ck_sys(mkdir(cur.c_str(), 0755), "mkdir " + cur + " with default mode 0755", cur);
+                ck_sys(chown(cur.c_str(), 0, 0), "chown " + cur + " with default owner (0:0)", cur);
+            }
+            prev = cur;
+        }
+        if (!exists(a)) {
+            ck_sys(mkdir(a.c_str(), 0755), "mkdir " + a + " with default mode 0755", a);
+            if (dir_owner_.set)
+                ck_sys(chown(a.c_str(), (uid_t)dir_owner_.uid, (gid_t)dir_owner_.gid), "chown", a);
+            else
+                ck_sys(chown(a.c_str(), 0, 0), "chown", a);
+        } else if (dir_owner_.set && dir_owner_.overwrite) {
+            ck_sys(chown(a.c_str(), (uid_t)dir_owner_.uid, (gid_t)dir_owner_.gid), "chown", a);
+        }
+    }
+};
+
+// lib/snapshot/utils.go:249-324
+std::string walk_link(const std::string &path, const std::string &root, int &walked, bool &islink)
+{
+    islink = false;
+    if (walked > 255)
+        throw HostError("eval symlinks: too many links");
+    const std::string full = go_join(root, path);
+    struct stat st;
+    if (lstat(full.c_str(), &st) != 0)
+        throw HostError(errno_str("lstat", full));
+    if (!S_ISLNK(st.st_mode))
+        return path;
+    std::string target = read_link(full);
+    const bool has_root = target.compare(0, root.size(), root) == 0;
+    if (!has_root && !target.empty() && target[0] == '/')
+        throw HostError("link points outside of root: " + full + " -> " + target);
+    ++walked;
+    islink = true;
+    return has_root ? target.substr(root.size()) : target;
+}
+
+std::string walk_links(const std::string &path, const std::string &root, int &walked)
+{
+    const size_t sl = path.rfind('/');
+    const std::string dir = sl == std::string::npos ? "" : path.substr(0, sl + 1);
+    const std::string file = sl == std::string::npos ? path : path.substr(sl + 1);
+    bool islink;
+    if (dir.empty())
+        return walk_link(file, root, walked, islink);
+    if (file.empty()) {
+        auto trim = [](std::string s) {
+            while (!s.empty() && s.back() == '/')
+                s.pop_back();
+            return s;
+        };
+        if (trim(dir) == trim(root))
+            return dir;
+        return walk_links(dir.substr(0, dir.size() - 1), root, walked);
+    }
+    const std::string newdir = walk_links(dir, root, walked);
+    const std::string np = walk_link(newdir.empty() ? file : go_join(newdir, file), root, walked, islink);
+    if (!islink || (!np.empty() && np[0] == '/'))
+        return np;
+    return go_join(newdir, np);
+}
+
+std::string eval_symlinks(std::string p, const std::string &src_root)
+{
+    if (p.empty())
+        return p;
+    int walked = 0;
+    for (;;) {
+        const int before = walked;
+        const std::string np = walk_links(p, src_root, walked);
+        if (before == walked)
+            return abs_path(np);
+        p = np;
+    }
+}
+
+// CopyOperation.Execute for one operation.  op.dst must already be resolved against the working directory.
+void execute_copy_op(const mkhost_copy_op &c, uint32_t mode, const std::vector<std::string> &blacklist,
+                     std::multimap<std::string, DeferredFile> *deferred, std::vector<Copier> *copiers)
+{
+    const bool chown_flag = mode & MKHOST_COPY_CHOWN, internal = mode & MKHOST_COPY_INTERNAL,
+               preserve = mode & MKHOST_COPY_PRESERVE_OWNER;
+    if (chown_flag && preserve)
+        throw HostError("both chown and archive are true");
+    std::string dst = c.dst ? c.dst : "";
+    const bool dir_fmt = (!dst.empty() && dst.back() == '/') || dst == "." || dst == "..";
+    if (dst.empty() || dst[0] != '/') {
+        if (!c.work_dir || c.work_dir[0] != '/')
+            throw HostError("check copy param: dst is not absolute path, must specify absolute working directory");
+        const std::string d = go_join(c.work_dir, dst);
+        dst = dir_fmt ? d + "/" : d;
+    }
+    for (size_t k = 0; k < c.n_srcs; ++k) {
+        std::string src = eval_symlinks(rel_path(c.srcs[k]), c.src_root);
+        src = go_join(c.src_root, src);
+        struct stat st;
+        if (lstat(src.c_str(), &st) != 0)
+            throw HostError(errno_str("lstat", src));
+        const std::vector<std::string> bl = internal ? std::vector<std::string>{} : blacklist;
+        CopyOwner dir_owner, kids;
+        if (chown_flag) {
+            dir_owner = CopyOwner{true, c.uid, c.gid, false};
+            kids = CopyOwner{true, c.uid, c.gid, true};
+        } else if (!internal) {
+            dir_owner = CopyOwner{true, 0, 0, false};
+            kids = CopyOwner{true, 0, 0, true};
+        } else if (preserve) {
+            dir_owner = CopyOwner{true, (int64_t)st.st_uid, (int64_t)st.st_gid, false};
+        }
+        Copier copier(bl, dir_owner, kids, deferred, copiers ? copiers->size() : 0);
+        if (S_ISDIR(st.st_mode))
+            copier.copy_dir(src, dst);
+        else if (dir_fmt)
+            copier.copy_file(src, go_join(dst, path_base(src)));
+        else
+            copier.copy_file(src, dst);
+        if (copiers)
+            copiers->push_back(copier);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // MemFS (copy-op path): lib/snapshot/mem_fs.go, mem_layer.go
 // ---------------------------------------------------------------------------------------------------
 struct MemFile {
@@ -1033,6 +1383,8 @@ class MemFS
     }
 
     void set_now(int64_t now_unix) { now_ = now_unix; }
+    const std::string &root() const { return root_; }
+    const std::vector<std::string> &blacklist() const { return blacklist_; }
 
     std::map<std::string, MemFile> add_layer_by_copy_ops(const mkhost_copy_op *ops, size_t n)
     {
@@ -1409,7 +1761,8 @@ std::string describe_layer_text(const std::map<std::string, MemFile> &layer)
 
 // MemFS.commitLayer (mem_fs.go:424-433) + tario.WriteEntry, with the arena as the tar.Writer sink
 void commit_layer(mksnap_t *eng, const std::map<std::string, MemFile> &layer, int n_threads, int tar_fd, uint32_t flags,
-                  mkhost_layer_result *out, MemFS *remember = nullptr)
+                  mkhost_layer_result *out, MemFS *remember = nullptr,
+                  const std::function<void(const std::vector<ReadJob> &)> &on_read = nullptr)
 {
     const bool want_tar_digest = !(flags & MKHOST_NO_TAR_DIGEST);
     const bool file_digests = remember && (flags & (MKHOST_FILE_DIGESTS | MKHOST_SCAN_CONTENT));
@@ -1434,6 +1787,8 @@ void commit_layer(mksnap_t *eng, const std::map<std::string, MemFile> &layer, in
     // bytes, so of 64): stream 0 continues across submits, the device keeps the SHA-256 midstate.
     auto flush = [&](bool last) {
         run_reads(jobs, n_threads);
+        if (on_read)
+            on_read(jobs); // MKHOST_MATERIALIZE: the bytes just read are also the copy's payload
         if (tar_fd >= 0) { // hand the tar bytes on before the arena is recycled
             uint64_t w = 0;
             while (w < pos) {
@@ -1787,13 +2142,73 @@ size_t mkhost_memfs_describe_scan(mkhost_memfs *m, int64_t now_unix, char *out, 
     }
 }
 
+int mkhost_copy_op_execute(const mkhost_copy_op *op, uint32_t mode, const char *const *blacklist, size_t n_blacklist,
+                           char *err, size_t errlen)
+{
+    try {
+        if (!op || op->n_srcs == 0)
+            throw HostError("check copy param: srcs cannot be empty");
+        std::vector<std::string> bl;
+        for (size_t i = 0; i < n_blacklist; ++i)
+            bl.emplace_back(blacklist[i]);
+        std::multimap<std::string, DeferredFile> deferred;
+        std::vector<Copier> copiers;
+        execute_copy_op(*op, mode, bl, (mode & MKHOST_COPY_DEFERRED) ? &deferred : nullptr, &copiers);
+        for (const auto &kv : deferred) { // stand-in for the arena: one read of each source, written from memory
+            std::vector<uint8_t> buf((size_t)kv.second.st.st_size);
+            std::vector<ReadJob> job{ReadJob{kv.first, 0, (uint64_t)buf.size(), buf.data()}};
+            run_reads(job, 1);
+            copiers[kv.second.copier].finish_regular(kv.second.st, kv.first, kv.second.dst, buf.data(), buf.size());
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, e.what());
+        return -1;
+    }
+}
+
 int mkhost_memfs_commit_copy_ops(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops,
                                  int n_threads, int tar_fd, uint32_t flags, mkhost_layer_result *out, char *err,
                                  size_t errlen)
 {
     try {
         m->fs.set_now(now_unix);
-        commit_layer(eng, m->fs.add_layer_by_copy_ops(ops, n_ops), n_threads, tar_fd, flags, out, &m->fs);
+        if (!(flags & MKHOST_MATERIALIZE)) {
+            commit_layer(eng, m->fs.add_layer_by_copy_ops(ops, n_ops), n_threads, tar_fd, flags, out, &m->fs);
+            return 0;
+        }
+        // the copy onto the file system (CopyOperation.Execute) and the layer share one read of the
+        // context.  Directories, symlinks and chmods first; regular files are written from the arena as it fills;
+        // what the layer did not need to read (entries the tree already holds) is copied from disk at the end.
+        std::multimap<std::string, DeferredFile> deferred;
+        std::vector<Copier> copiers;
+        const uint32_t mode = (flags & MKHOST_MATERIALIZE_CHOWN) ? MKHOST_COPY_CHOWN : 0u;
+        for (size_t i = 0; i < n_ops; ++i) {
+            mkhost_copy_op on_disk = ops[i];
+            std::string dst = ops[i].dst ? ops[i].dst : "";
+            const bool dir_fmt = (!dst.empty() && dst.back() == '/') || dst == "." || dst == "..";
+            if (dst.empty() || dst[0] != '/') {
+                if (!ops[i].work_dir || ops[i].work_dir[0] != '/')
+                    throw HostError("check copy param: dst is not absolute path, must specify absolute working directory");
+                dst = go_join(ops[i].work_dir, dst);
+            }
+            dst = go_join(m->fs.root(), dst) + (dir_fmt ? "/" : ""); // image path -> path under the MemFS root ("/" in a real build)
+            on_disk.dst = dst.c_str();
+            execute_copy_op(on_disk, mode, m->fs.blacklist(), &deferred, &copiers);
+        }
+        auto write_from_arena = [&](const std::vector<ReadJob> &jobs) {
+            for (const auto &j : jobs) {
+                if (j.file_off != 0)
+                    continue;
+                auto range = deferred.equal_range(j.path);
+                for (auto it = range.first; it != range.second; ++it)
+                    copiers[it->second.copier].finish_regular(it->second.st, j.path, it->second.dst, j.dst, j.len);
+                deferred.erase(range.first, range.second);
+            }
+        };
+        commit_layer(eng, m->fs.add_layer_by_copy_ops(ops, n_ops), n_threads, tar_fd, flags, out, &m->fs, write_from_arena);
+        for (const auto &kv : deferred)
+            copiers[kv.second.copier].finish_regular(kv.second.st, kv.first, kv.second.dst, nullptr, 0);
         return 0;
     } catch (const std::exception &e) {
         set_err(err, errlen, std::string("failed to generate diff layer: ") + e.what());

@@ -1,0 +1,98 @@
+"""-m gpu.  Written after this round's GPU budget was spent: these two checks have run on the CPU side only (the code
+they exercise compiles and its host logic is covered by the CPU suite).  The file sorts last so that the verified GPU
+tests run first.
+
+  * the range-partitioned exchange over a 1-rank NCCL communicator (ncclSend/ncclRecv to self inside a group); the same
+    code was run with NCCL at 2, 4 and 8 ranks (tests/test_gpu_multi.py, bench.py self-check) and with the in-process
+    transport at 1..8 ranks (tests/test_gpu_exchange.py)
+  * mkhost_memfs_commit_copy_ops(..., MKHOST_MATERIALIZE): the COPY step's file copy (CopyOperation.Execute,
+    lib/snapshot/copy_op.go:82-147) fed from the arena the layer is packed in; the Copier itself
+    and its deferred mode are verified on the CPU (tests/test_host_copier_cpu.py)."""
+import os
+import stat
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+NOW = 1_600_000_000
+
+
+def test_nccl_exchange_world_of_one():
+    from makisu_b200.abi import Engine, Extent, MKSNAP_X_CDC, MKSNAP_X_CRC
+    fb = 1 << 20
+
+    def ext(i):
+        e = Extent()
+        e.arena_off, e.len, e.crc_suffix, e.flags = i * fb, fb, (199 - i) * fb, MKSNAP_X_CDC | MKSNAP_X_CRC
+        return e
+    with Engine(device=0, device_arena_bytes=256 << 20, max_extents=4096) as e:
+        e.comm_init(Engine.comm_unique_id(), 1, 0)
+        e.begin()
+        e.synth_fill(0, 0, 200 * fb, 99)
+        e.device_submit(0, 200 * fb, [ext(i) for i in range(200)])
+        r = e.finish()
+        table = e.get_table(r.n_unique).copy()
+        x = e.exchange_tables()
+        assert (x.n_chunks, x.n_unique, bytes(x.root), e.ctx_crc32(x)) == (r.n_chunks, r.n_unique, bytes(r.root), e.ctx_crc32(r))
+        assert e.table_rows() == r.n_unique
+        np.testing.assert_array_equal(e.get_table(e.table_rows()), table)
+
+
+def _tree(root):
+    out = {}
+    for d, dirs, files in os.walk(root):
+        for n in sorted(dirs + files):
+            p = os.path.join(d, n)
+            st = os.lstat(p)
+            rel = os.path.relpath(p, root)
+            if stat.S_ISLNK(st.st_mode):
+                out[rel] = ("l", os.readlink(p))
+            elif stat.S_ISDIR(st.st_mode):
+                out[rel] = ("d", stat.S_IMODE(st.st_mode), st.st_uid, st.st_gid)
+            else:
+                out[rel] = ("f", stat.S_IMODE(st.st_mode), st.st_uid, st.st_gid, open(p, "rb").read())
+    return out
+
+
+@pytest.mark.skipif(os.geteuid() != 0, reason="chown needs root")
+def test_commit_copy_ops_materializes_from_the_arena(tmp_path):
+    from makisu_b200 import host
+    from makisu_b200.abi import Engine
+    from oracle import copier as oc
+    from oracle import layer_tar as lt
+    rng = np.random.default_rng(3)
+    ctx = tmp_path / "ctx"
+    (ctx / "app" / "sub").mkdir(parents=True)
+    for rel, n, mode in [("app/a.bin", 700_000, 0o644), ("app/sub/b.bin", 3_000_000, 0o755), ("app/empty", 0, 0o600),
+                         ("conf.txt", 900, 0o640)]:
+        p = ctx / rel
+        p.write_bytes(rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+        os.chmod(p, mode)
+        os.utime(p, (1_500_000_000, 1_500_000_000))
+    os.symlink("a.bin", ctx / "app" / "link")
+    for d, _, _ in os.walk(ctx):
+        os.utime(d, (1_500_000_000, 1_500_000_000))
+    roots = {k: tmp_path / k for k in ("fused", "plain", "oracle")}
+    for r in roots.values():
+        r.mkdir()
+        os.chmod(r, 0o755)
+    ops = [host.CopyOperation(["/app"], str(ctx), "/", "/srv/app/", 5, 6), host.CopyOperation(["/conf.txt"], str(ctx), "/", "/etc/conf.txt", 7, 8)]
+    with Engine(device=0, device_arena_bytes=16 << 20, n_host_arenas=2, host_arena_bytes=16 << 20, max_extents=1 << 12) as eng:
+        fused = host.MemFS(str(roots["fused"])).commit_copy_ops(
+            eng, NOW, ops, flags=host.MKHOST_MATERIALIZE | host.MKHOST_MATERIALIZE_CHOWN)
+        plain = host.MemFS(str(roots["plain"])).commit_copy_ops(eng, NOW, ops)
+    assert fused == plain                                           # the layer, its digest and chunk table do not change
+    assert _tree(str(roots["plain"])) == {}                         # without the flag nothing is written
+    # what CopyOperation.Execute (--chown) would have put on disk, by the oracle's Copier
+    oc.execute_copy_op(str(ctx), ["/app"], str(roots["oracle"]) + "/srv/app/", 5, 6, True, False, False, [])
+    oc.execute_copy_op(str(ctx), ["/conf.txt"], str(roots["oracle"]) + "/etc/conf.txt", 7, 8, True, False, False, [])
+    got, want = _tree(str(roots["fused"])), _tree(str(roots["oracle"]))
+    assert got == want
+    assert got["srv/app/sub/b.bin"][1:4] == (0o755, 5, 6) and got["etc/conf.txt"][1:4] == (0o640, 7, 8)
+    assert got["srv/app/link"] == ("l", "a.bin") and got["srv/app"] == ("d", 0o755, 5, 6)
+    # and the layer equals the oracle's for the same ops
+    fs = lt.MemFS(lambda: NOW, str(roots["oracle"]))
+    entries = fs.add_layer_by_copy_ops([lt.CopyOperation.new(["/app"], str(ctx), "/", "/srv/app/", uid=5, gid=6),
+                                        lt.CopyOperation.new(["/conf.txt"], str(ctx), "/", "/etc/conf.txt", uid=7, gid=8)])
+    assert fused["tar_digest"] == lt.tar_digest(entries)
