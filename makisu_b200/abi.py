@@ -109,7 +109,7 @@ def load() -> C.CDLL:
         raise FileNotFoundError(
             f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  makisu_b200 has no CPU fallback.")
-    lib = C.CDLL(path)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)  # libmkhost resolves mksnap_* against it
     for name, res, args in SYMBOLS:
         fn = getattr(lib, name)  # AttributeError here = ABI drift
         fn.restype = res
