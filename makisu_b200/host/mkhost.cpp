@@ -931,12 +931,13 @@ struct MemTarSource : TarSource {
     }
     const uint8_t *place(const uint8_t *, uint64_t nb, bool, uint64_t *arena_off) override
     {
-        const uint64_t padded = align_up(nb, 512);
-        if (n - pos < padded)
+        // the data must be complete; a stream that ends inside the zero padding after it is a clean io.EOF for the
+        // go1.14 Reader (next(): tryReadFull of the padding returns io.EOF), i.e. the archive simply ends here
+        if (n - pos < nb)
             throw TarErr("unexpected EOF");
         const uint8_t *b = p + pos;
         *arena_off = pos;
-        pos += padded;
+        pos = std::min<uint64_t>(n, pos + align_up(nb, 512));
         return b;
     }
     void end_marker(const uint8_t *) override
@@ -1967,8 +1968,11 @@ struct ArenaTarSource : TarSource {
         consumed += done;
         return done;
     }
+    bool eof = false; // the stream ended inside the padding of the last member: clean end (see MemTarSource::place)
     bool read_header(uint8_t out[512]) override
     {
+        if (eof)
+            return false;
         const uint64_t r = read_full(out, 512);
         if (r == 0)
             return false;
@@ -1985,7 +1989,8 @@ struct ArenaTarSource : TarSource {
             flush(false);
         memcpy(a + pos, hdr, 512);
         pos += 512;
-        if (read_full(a + pos, padded) < padded)
+        const uint64_t got = read_full(a + pos, padded);
+        if (got < nb)
             throw TarErr("unexpected EOF");
         *arena_off = pos;
         if (file_content) {
@@ -1994,7 +1999,9 @@ struct ArenaTarSource : TarSource {
                 rngs.push_back(mksnap_range{pos, nb, ++n_file_streams, 0});
         }
         const uint8_t *body = a + pos;
-        pos += padded;
+        pos += got;
+        if (got < padded)
+            eof = true; // ended inside the padding: the go1.14 Reader reports a clean io.EOF on the next Next()
         return body;
     }
     void raw(const uint8_t *p, uint64_t n)

@@ -93,3 +93,97 @@ def test_absolute_symlink_outside_root_is_an_error_in_both(tmp_path):
     with pytest.raises(host.HostError) as ei:
         host.describe_layer(str(root), 0, [host.CopyOperation(["/"], str(ctx), "/", "/x/")])
     assert "trim" in str(ei.value)
+
+
+# ---- tar ingest (UpdateFromTarReader): random archives in three formats, then random byte damage -----------------
+def _random_tar(rng, fmt):
+    import io
+    import tarfile
+    buf = io.BytesIO()
+    names = set()
+    with tarfile.open(fileobj=buf, mode="w", format=fmt) as tf:
+        dirs = [""]
+        for _ in range(int(rng.integers(1, 25))):
+            base = "".join(rng.choice(list("abcXY01._-é"), size=int(rng.integers(1, 40 if fmt != tarfile.USTAR_FORMAT else 12))))
+            if base in (".", "..") or base.startswith(".wh."):
+                continue
+            parent = dirs[int(rng.integers(0, len(dirs)))]
+            name = (parent + "/" if parent else "") + base
+            if name in names:
+                continue
+            names.add(name)
+            ti = tarfile.TarInfo(name)
+            ti.mtime = int(rng.integers(0, 2**31))
+            ti.uid, ti.gid = int(rng.integers(0, 70000)), int(rng.integers(0, 70000))
+            ti.mode = int(rng.choice([0o644, 0o755, 0o4755, 0o600, 0o100644, 0o40755]))
+            r = rng.random()
+            data = b""
+            if r < 0.25:
+                ti.type, ti.name = tarfile.DIRTYPE, name + "/"
+                dirs.append(name)
+            elif r < 0.35:
+                ti.type, ti.linkname = tarfile.SYMTYPE, "../" * int(rng.integers(0, 3)) + "t" * int(rng.integers(1, 120 if fmt != tarfile.USTAR_FORMAT else 60))
+            elif r < 0.45 and names:
+                ti.type, ti.linkname = tarfile.LNKTYPE, sorted(names)[int(rng.integers(0, len(names)))]
+            elif r < 0.5:
+                ti.type = tarfile.FIFOTYPE
+            else:
+                data = bytes(rng.integers(0, 256, int(rng.integers(0, 3000)), dtype=np.uint8))
+                ti.size = len(data)
+            try:
+                tf.addfile(ti, io.BytesIO(data) if data else None)
+            except ValueError:      # USTAR cannot express this member (name too long / non-ASCII): leave it out
+                names.discard(name)
+    return buf.getvalue()
+
+
+def _ingest_both(root, data):
+    import tempfile
+    o_err = h_err = None
+    want = got = None
+    try:
+        want = [f"{e.hdr.typeflag.decode()} {e.hdr.mode:o} {e.hdr.uid} {e.hdr.gid} {e.hdr.size} {e.hdr.mtime_ns // 10**9} "
+                f"{e.dst} {e.hdr.name} {e.src}" for e in lt.MemFS(lambda: 1_600_000_000, root).update_from_tar(data)]
+    except (ValueError, UnicodeError) as e:
+        o_err = e
+    h = host.MemFS(root)
+    with tempfile.TemporaryFile() as f:
+        f.write(data)
+        f.seek(0)
+        try:
+            got = h.describe_update_from_tar(1_600_000_000, f.fileno())
+        except host.HostError as e:
+            h_err = e
+    h.close()
+    return want, got, o_err, h_err
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_random_tars_ingest_like_the_oracle_and_tarfile(tmp_path, seed):
+    import io
+    import tarfile
+    rng = np.random.default_rng(1000 + seed)
+    fmt = [tarfile.USTAR_FORMAT, tarfile.PAX_FORMAT, tarfile.GNU_FORMAT][seed % 3]
+    data = _random_tar(rng, fmt)
+    ms = lt.read_tar(data)
+    infos = tarfile.open(fileobj=io.BytesIO(data)).getmembers()
+    assert [m.hdr.name.rstrip("/") for m in ms] == [i.name.rstrip("/") for i in infos]
+    assert [(m.hdr.typeflag, m.hdr.uid, m.hdr.gid, m.hdr.mtime_ns // 10**9, m.hdr.linkname) for m in ms] == \
+        [(i.type, i.uid, i.gid, int(i.mtime), i.linkname) for i in infos]
+    assert [m.data_len for m in ms if m.hdr.typeflag == b"0"] == [i.size for i in infos if i.isreg()]
+    root = str(tmp_path)
+    want, got, o_err, h_err = _ingest_both(root, data)
+    assert o_err is None and h_err is None and got == want
+    # damage: flip one byte somewhere in the first members, or cut the stream -- both must agree on accept/reject, and
+    # on the result when they accept (a flipped body byte is not the parser's business)
+    for k in range(6):
+        bad = bytearray(data)
+        if k % 2 == 0:
+            pos = int(rng.integers(0, min(len(bad), 4096)))
+            bad[pos] ^= 1 << int(rng.integers(0, 8))
+        else:
+            bad = bad[:int(rng.integers(1, len(bad)))]
+        want, got, o_err, h_err = _ingest_both(root, bytes(bad))
+        assert (o_err is None) == (h_err is None), (k, o_err, h_err)
+        if o_err is None:
+            assert got == want
