@@ -444,7 +444,8 @@ void ck(mksnap_t *eng, int rc, const char *what)
 // ---------------------------------------------------------------------------------------------------
 struct Hdr {
     std::string name, linkname;
-    int64_t mode = 0, uid = 0, gid = 0, size = 0, mtime_ns = 0;
+    int64_t mode = 0, uid = 0, gid = 0, size = 0;
+    __int128 mtime_ns = 0; // time.Time holds any int64 second count: a base-256 mtime field can exceed int64 nanoseconds
     char typeflag = '0';
 };
 
@@ -528,7 +529,7 @@ void template_v7plus(uint8_t *b, const Hdr &h, const std::string &name, const st
     fmt_octal(b + 108, 8, h.uid);
     fmt_octal(b + 116, 8, h.gid);
     fmt_octal(b + 124, 12, h.size);
-    fmt_octal(b + 136, 12, h.mtime_ns / 1000000000ll);
+    fmt_octal(b + 136, 12, (int64_t)(h.mtime_ns / 1000000000ll));
     fmt_string(b + 265, 32, "");
     fmt_string(b + 297, 32, "");
     fmt_octal(b + 329, 8, 0);
@@ -577,7 +578,7 @@ std::string encode_header(Hdr h)
     verify_numeric(h.uid, 8, "uid");
     verify_numeric(h.gid, 8, "gid");
     verify_numeric(h.size, 12, "size");
-    verify_numeric(h.mtime_ns / 1000000000ll, 12, "mtime");
+    verify_numeric((int64_t)(h.mtime_ns / 1000000000ll), 12, "mtime");
     if ((h.typeflag == '0' || h.typeflag == '3' || h.typeflag == '4' || h.typeflag == '6') && !h.name.empty() &&
         h.name.back() == '/')
         throw HostError("archive/tar: filename may not have trailing slash");
@@ -630,12 +631,12 @@ std::string encode_header(Hdr h)
 // strconv.go parseNumeric/parseOctal/parsePAXTime, format.go getFormat).  Used by UpdateFromTarReader.
 // Sparse members (GNU 'S', PAX GNU.sparse.*) are rejected: docker layers do not carry them.
 // ---------------------------------------------------------------------------------------------------
-int64_t floor_sec(int64_t ns) // Time.Truncate(1s) compares equal iff the floored seconds are equal
+int64_t floor_sec(__int128 ns) // Time.Truncate(1s) compares equal iff the floored seconds are equal
 {
-    int64_t s = ns / 1000000000ll;
+    __int128 s = ns / 1000000000ll;
     if (ns % 1000000000ll < 0)
         --s;
-    return s;
+    return (int64_t)s;
 }
 
 constexpr uint32_t GO_MODE_DIR = 1u << 31, GO_MODE_SYMLINK = 1u << 27, GO_MODE_DEVICE = 1u << 26,
@@ -745,11 +746,11 @@ int64_t parse_int10(const std::string &v)
     return neg ? -x : x;
 }
 
-int64_t parse_pax_time(const std::string &s) // seconds[.fraction] -> ns, fraction truncated to 9 digits
+__int128 parse_pax_time(const std::string &s) // seconds[.fraction] -> ns, fraction truncated to 9 digits
 {
     const size_t dot = s.find('.');
     const std::string ss = s.substr(0, dot), sn = dot == std::string::npos ? "" : s.substr(dot + 1);
-    const int64_t secs = parse_int10(ss);
+    const __int128 secs = parse_int10(ss);
     if (sn.empty())
         return secs * 1000000000ll;
     int64_t ns = 0;
@@ -853,7 +854,7 @@ std::vector<TarMember> read_tar(TarSource &src)
         h.uid = parse_numeric(blk + 108, 8);
         h.gid = parse_numeric(blk + 116, 8);
         h.size = parse_numeric(blk + 124, 12);
-        h.mtime_ns = parse_numeric(blk + 136, 12) * 1000000000ll;
+        h.mtime_ns = (__int128)parse_numeric(blk + 136, 12) * 1000000000ll;
         h.typeflag = (char)blk[156];
         h.linkname = c_string(blk + 157, 100);
         if (fmt != V7) {
@@ -1355,7 +1356,7 @@ class MemFS
             if (m & S_ISUID) h.mode |= 04000;
             if (m & S_ISGID) h.mode |= 02000;
             if (m & S_ISVTX) h.mode |= 01000;
-            h.mtime_ns = (int64_t)st->st_mtim.tv_sec * 1000000000ll + st->st_mtim.tv_nsec;
+            h.mtime_ns = (__int128)st->st_mtim.tv_sec * 1000000000ll + st->st_mtim.tv_nsec;
             h.uid = st->st_uid;
             h.gid = st->st_gid;
             if (S_ISREG(m)) { h.typeflag = '0'; h.size = st->st_size; }
@@ -1644,7 +1645,7 @@ class MemFS
                 cp = go_join(cp, parts[k]);
             cp = abs_path(cp);
             Hdr hdr = create_header("", cp, nullptr, &last_ancestor->mf.hdr);
-            hdr.mtime_ns = now_ * 1000000000ll; // clk.Now()
+            hdr.mtime_ns = (__int128)now_ * 1000000000ll; // clk.Now()
             hdr.uid = uid;
             hdr.gid = gid;
             add_header(layer, "", cp, hdr);
