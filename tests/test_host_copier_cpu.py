@@ -8,6 +8,7 @@ import os
 import shutil
 import stat
 
+import numpy as np
 import pytest
 
 from makisu_b200 import host
@@ -195,3 +196,58 @@ def test_infinite_loop_guard(tmp_path):
     a, b = _tree(str(tmp_path / "oracle" / "src" / "target")), _tree(str(tmp_path / "cpp" / "src" / "target"))
     assert a == b and a["sub/f1"][4] == b"one" and "target" not in a
     shutil.rmtree(tmp_path)
+
+
+def _random_tree(root, rng, depth=0, fifos=True):
+    for _ in range(int(rng.integers(1, 7))):
+        nm = "".join(rng.choice(list("abAB01._-"), size=int(rng.integers(1, 9))))
+        p = os.path.join(root, nm)
+        if nm in (".", "..") or os.path.lexists(p):
+            continue
+        r = rng.random()
+        if r < 0.3 and depth < 3:
+            os.mkdir(p)
+            os.chmod(p, int(rng.choice([0o755, 0o700, 0o2775, 0o1777])))
+            os.chown(p, int(rng.integers(0, 5)), int(rng.integers(0, 5)))
+            _random_tree(p, rng, depth + 1, fifos)
+        elif r < 0.42:
+            os.symlink("some/target" if rng.random() < 0.5 else "../up", p)
+        elif r < 0.47 and fifos:
+            os.mkfifo(p)
+        else:
+            with open(p, "wb") as f:
+                f.write(bytes(rng.integers(0, 256, int(rng.integers(0, 3000)), dtype=np.uint8)))
+            os.chown(p, int(rng.integers(0, 5)), int(rng.integers(0, 5)))
+            os.chmod(p, int(rng.choice([0o644, 0o600, 0o755, 0o4755, 0o2711])))
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_trees_onto_random_destinations(tmp_path, seed):
+    """Random source tree copied onto a random, partly colliding destination tree with a random owner mode: the three
+    runs (oracle, C++, C++ deferred) must leave identical trees, or fail alike (a directory landing on a file, ...)."""
+    mode = [0, host.MKHOST_COPY_CHOWN, host.MKHOST_COPY_INTERNAL, host.MKHOST_COPY_INTERNAL | host.MKHOST_COPY_PRESERVE_OWNER][seed % 4]
+    trees, errs = [], []
+    for impl in ("oracle", "cpp", "cpp_deferred"):
+        rng = np.random.default_rng(700 + seed)                        # identical scenario for every implementation
+        base = tmp_path / impl
+        src, dst = base / "src", base / "dst"
+        src.mkdir(parents=True)
+        dst.mkdir()
+        _random_tree(str(src), rng)
+        _random_tree(str(dst), rng, fifos=False)                        # same name alphabet => collisions happen (no FIFOs: opening one blocks)
+        try:
+            if impl == "oracle":
+                oc.execute_copy_op(str(src), ["/"], str(dst) + "/", 3, 4, bool(mode & host.MKHOST_COPY_CHOWN),
+                                   bool(mode & host.MKHOST_COPY_INTERNAL), bool(mode & host.MKHOST_COPY_PRESERVE_OWNER), [])
+            else:
+                m = mode | (host.MKHOST_COPY_DEFERRED if impl == "cpp_deferred" else 0)
+                host.copy_op_execute(host.CopyOperation(["/"], str(src), "/", str(dst) + "/", 3, 4), m)
+            errs.append(None)
+        except (OSError, host.HostError) as e:
+            errs.append(e)
+        trees.append(_tree(str(dst)))
+    assert [e is None for e in errs] == [errs[0] is None] * 3, errs
+    if errs[0] is None:
+        assert trees[0] == trees[1] == trees[2]
+    else:
+        assert trees[0] == trees[1]                                     # both stop at the same entry (same traversal order)
