@@ -1572,19 +1572,29 @@ int mksnap_exchange_tables(mksnap_t *h, mksnap_result *out)
     CK(h, cudaStreamSynchronize(s));
     if ((rc = x_phase2(h, x)))
         return rc;
-    // all-to-all of the slices
-    if ((r = h->nccl.GroupStart()))
-        return fail(h, MKSNAP_E_NCCL, "ncclGroupStart: %s", h->nccl.GetErrorString(r));
-    for (int k = 0; k < R && !r; ++k) {
-        const uint64_t ns = x.hdr[GH_WORDS + k], nr = x.recv_off[k + 1] - x.recv_off[k];
-        if (ns)
-            r = h->nccl.Send(h->d_table + x.bounds[k] * 32, ns * 32, /*ncclUint8*/ 1, k, h->comm, s);
-        if (nr && !r)
-            r = h->nccl.Recv(h->d_concat + x.recv_off[k] * 32, nr * 32, 1, k, h->comm, s);
+    // all-to-all of the slices: my own slice is a device copy, the others one ncclSend/ncclRecv group
+    {
+        const uint64_t self_rows = x.hdr[GH_WORDS + x.rank];
+        if (self_rows)
+            CK(h, cudaMemcpyAsync(h->d_concat + x.recv_off[x.rank] * 32, h->d_table + x.bounds[x.rank] * 32, self_rows * 32,
+                                  cudaMemcpyDeviceToDevice, s));
     }
-    const int r2 = h->nccl.GroupEnd();
-    if (r || r2)
-        return fail(h, MKSNAP_E_NCCL, "ncclSend/ncclRecv: %s", h->nccl.GetErrorString(r ? r : r2));
+    if (R > 1) {
+        if ((r = h->nccl.GroupStart()))
+            return fail(h, MKSNAP_E_NCCL, "ncclGroupStart: %s", h->nccl.GetErrorString(r));
+        for (int k = 0; k < R && !r; ++k) {
+            if (k == x.rank)
+                continue;
+            const uint64_t ns = x.hdr[GH_WORDS + k], nr = x.recv_off[k + 1] - x.recv_off[k];
+            if (ns)
+                r = h->nccl.Send(h->d_table + x.bounds[k] * 32, ns * 32, /*ncclUint8*/ 1, k, h->comm, s);
+            if (nr && !r)
+                r = h->nccl.Recv(h->d_concat + x.recv_off[k] * 32, nr * 32, 1, k, h->comm, s);
+        }
+        const int r2 = h->nccl.GroupEnd();
+        if (r || r2)
+            return fail(h, MKSNAP_E_NCCL, "ncclSend/ncclRecv: %s", h->nccl.GetErrorString(r ? r : r2));
+    }
     if ((rc = x_phase3(h, x, s)))
         return rc;
     // records: rows in every range + heads

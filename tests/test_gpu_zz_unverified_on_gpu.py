@@ -2,9 +2,10 @@
 they exercise compiles and its host logic is covered by the CPU suite).  The file sorts last so that the verified GPU
 tests run first.
 
-  * the range-partitioned exchange over a 1-rank NCCL communicator (ncclSend/ncclRecv to self inside a group); the same
-    code was run with NCCL at 2, 4 and 8 ranks (tests/test_gpu_multi.py, bench.py self-check) and with the in-process
-    transport at 1..8 ranks (tests/test_gpu_exchange.py)
+  * the range-partitioned exchange over a 1-rank NCCL communicator (header / record / level-1 all-gathers of one
+    rank; the rank's own slice is a device copy); the same code was run with NCCL at 2, 4 and 8 ranks
+    (tests/test_gpu_multi.py, bench.py self-check) and with the in-process transport at 1..8 ranks
+    (tests/test_gpu_exchange.py)
   * mkhost_memfs_commit_copy_ops(..., MKHOST_MATERIALIZE): the COPY step's file copy (CopyOperation.Execute,
     lib/snapshot/copy_op.go:82-147) fed from the arena the layer is packed in; the Copier itself
     and its deferred mode are verified on the CPU (tests/test_host_copier_cpu.py)."""
