@@ -131,6 +131,14 @@ int mkhost_memfs_update_from_tar(mkhost_memfs *m, mksnap_t *eng, int64_t now_uni
 /* the same merge without a GPU: merged layer as text (format below) */
 size_t mkhost_memfs_describe_update_from_tar(mkhost_memfs *m, int64_t now_unix, int tar_fd, char *out, size_t cap,
                                              char *err, size_t errlen);
+/* MKHOST_UNTAR (flag of mkhost_memfs_update_from_tar and of the _ex describe): UpdateFromTarReader(r, untar=true) --
+ * every member is also written under the root (untarOneItem, lib/snapshot/mem_fs.go:574-716: whiteouts delete,
+ * existing directories are updated in place, similar entries are left alone, anything else is replaced; hard links
+ * last; tario.ApplyHeader sets owner, mode and mtime; parent directory mtimes are restored).  On the GPU path the file
+ * bodies are written straight from the arena that is being digested. */
+#define MKHOST_UNTAR 32u
+size_t mkhost_memfs_describe_update_from_tar_ex(mkhost_memfs *m, int64_t now_unix, int tar_fd, uint32_t flags, char *out,
+                                                size_t cap, char *err, size_t errlen);
 
 /* CopyOperation.Execute (lib/snapshot/copy_op.go:82-147) with fileio.Copier (lib/fileio/copy.go): what a COPY/ADD step
  * does to the file system when it runs with --modifyfs.  op->dst is used as the on-disk destination exactly like the

@@ -54,6 +54,8 @@ SYMBOLS = [
     ("mkhost_memfs_describe_scan", C.c_size_t, [_P, C.c_int64, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     ("mkhost_memfs_update_from_tar", C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_uint32, C.POINTER(LayerResult), C.c_char_p,
                                                C.c_size_t]),
+    ("mkhost_memfs_describe_update_from_tar_ex", C.c_size_t, [_P, C.c_int64, C.c_int, C.c_uint32, C.c_char_p, C.c_size_t,
+                                                              C.c_char_p, C.c_size_t]),
     ("mkhost_memfs_describe_update_from_tar", C.c_size_t, [_P, C.c_int64, C.c_int, C.c_char_p, C.c_size_t, C.c_char_p,
                                                            C.c_size_t]),
     ("mkhost_copy_op_execute", C.c_int, [C.POINTER(CopyOp), C.c_uint32, C.POINTER(C.c_char_p), C.c_size_t, C.c_char_p, C.c_size_t]),
@@ -176,6 +178,7 @@ MKHOST_FILE_DIGESTS = 2   # remember per-file SHA-256 in the MemFS tree
 MKHOST_SCAN_CONTENT = 4   # content-aware AddLayerByScan (implies FILE_DIGESTS)
 MKHOST_MATERIALIZE = 8    # commit_copy_ops also performs the copy onto the file system, from the arena
 MKHOST_MATERIALIZE_CHOWN = 16
+MKHOST_UNTAR = 32         # UpdateFromTarReader(untar=true): also write the members under the root
 MKHOST_COPY_CHOWN, MKHOST_COPY_INTERNAL, MKHOST_COPY_PRESERVE_OWNER, MKHOST_COPY_DEFERRED = 1, 2, 4, 8
 
 
@@ -246,10 +249,10 @@ class MemFS:
         out = (C.c_uint8 * 32)()
         return bytes(out) if load().mkhost_memfs_file_digest(self.h, os.fsencode(dst), out) == 0 else None
 
-    def describe_update_from_tar(self, now_unix: int, tar_fd: int) -> List[str]:
-        """UpdateFromTarReader(untar=false) without a GPU: the merged layer as text."""
+    def describe_update_from_tar(self, now_unix: int, tar_fd: int, flags: int = 0) -> List[str]:
+        """UpdateFromTarReader without a GPU: the merged layer as text (flags: MKHOST_UNTAR writes the members)."""
         err, buf = C.create_string_buffer(1024), C.create_string_buffer(self._BUF)
-        n = load().mkhost_memfs_describe_update_from_tar(self.h, now_unix, tar_fd, buf, len(buf), err, len(err))
+        n = load().mkhost_memfs_describe_update_from_tar_ex(self.h, now_unix, tar_fd, flags, buf, len(buf), err, len(err))
         if n == 0 or n > len(buf):
             raise HostError(err.value.decode() or "describe buffer too small")
         return [l for l in os.fsdecode(buf.value).split("\n") if l]

@@ -818,7 +818,9 @@ struct TarSource {
 
 bool is_header_only(char t) { return t == '1' || t == '2' || t == '3' || t == '4' || t == '5' || t == '6'; }
 
-std::vector<TarMember> read_tar(TarSource &src)
+using OnTarMember = std::function<void(const TarMember &, const uint8_t *body)>; // body valid only during the call
+
+std::vector<TarMember> read_tar(TarSource &src, const OnTarMember &on_member = nullptr)
 {
     std::vector<TarMember> members;
     std::map<std::string, std::string> pax;
@@ -909,6 +911,8 @@ std::vector<TarMember> read_tar(TarSource &src)
         m.data_off = data_off;
         m.data_len = (uint64_t)nb;
         m.arena_off = arena_off;
+        if (on_member)
+            on_member(m, body);
         members.push_back(std::move(m));
         pax.clear();
         gnu_name.clear();
@@ -1482,11 +1486,198 @@ class MemFS
         return layer;
     }
 
+    // UpdateFromTarReader(r, untar=true) (mem_fs.go:165-255): the same merge, and every member is also written under the
+    // root (untarOneItem, mem_fs.go:574-716; tario.ApplyHeader, lib/tario/apply.go:26-49); the mtimes of the parent
+    // directories are restored at the end.  Streaming: members arrive with their bodies (arena or memory).
+    struct Untar {
+        std::map<std::string, MemFile> layer;
+        std::map<std::string, Hdr> hardlinks;
+        std::map<std::string, struct timespec> modtimes;
+    };
+    void untar_member(Untar &u, const TarMember &m, const uint8_t *body)
+    {
+        Hdr hdr = m.hdr;
+        const std::string path = go_join(root_, hdr.name);
+        if (path_base(path).compare(0, 8, ".wh..wh.") == 0)
+            return;
+        if (is_descendant_of_any(path, blacklist_) || hdr_is_special(hdr))
+            return;
+        const size_t sl = path.rfind('/');
+        const std::string parent = sl == 0 ? "/" : path.substr(0, sl);
+        if (!u.modtimes.count(parent)) {
+            struct stat st;
+            if (lstat(parent.c_str(), &st) != 0)
+                throw HostError(errno_str("stat parent dir of " + path, parent));
+            u.modtimes[parent] = st.st_mtim;
+        }
+        hdr.name = rel_path(hdr.name);
+        if (hdr.typeflag == '1') {
+            hdr.linkname = abs_path(hdr.linkname);
+            u.hardlinks[path] = hdr;
+            return;
+        }
+        untar_one_item(path, hdr, body, m.data_len);
+        maybe_add(u.layer, abs_path(hdr.name), abs_path(hdr.name), hdr, false);
+    }
+    std::map<std::string, MemFile> untar_finish(Untar &u)
+    {
+        for (const auto &kv : u.hardlinks) {
+            untar_one_item(kv.first, kv.second, nullptr, 0);
+            maybe_add(u.layer, abs_path(kv.second.name), abs_path(kv.second.name), kv.second, false);
+        }
+        for (const auto &kv : u.modtimes) {
+            const struct timespec ts[2] = {kv.second, kv.second};
+            if (utimensat(AT_FDCWD, kv.first.c_str(), ts, 0) != 0)
+                throw HostError(errno_str("chtimes on parent directory", kv.first));
+        }
+        return std::move(u.layer);
+    }
+
   private:
     std::string root_;
     int64_t now_;
     std::vector<std::string> blacklist_;
     Node tree_;
+
+    static mode_t go_chmod_bits(uint32_t fm) // syscallMode (go1.14 os/file_posix.go)
+    {
+        mode_t m = fm & 0777;
+        if (fm & GO_MODE_SETUID) m |= 04000;
+        if (fm & GO_MODE_SETGID) m |= 02000;
+        if (fm & GO_MODE_STICKY) m |= 01000;
+        return m;
+    }
+
+    static void remove_all(const std::string &p) // os.RemoveAll
+    {
+        struct stat st;
+        if (lstat(p.c_str(), &st) != 0) {
+            if (errno == ENOENT)
+                return;
+            throw HostError(errno_str("lstat", p));
+        }
+        if (S_ISDIR(st.st_mode)) {
+            for (const auto &n : sorted_names(p))
+                remove_all(go_join(p, n));
+            if (rmdir(p.c_str()) != 0)
+                throw HostError(errno_str("remove", p));
+        } else if (unlink(p.c_str()) != 0) {
+            throw HostError(errno_str("remove", p));
+        }
+    }
+
+    static void apply_header(const std::string &path, const Hdr &hdr) // lib/tario/apply.go:26-49
+    {
+        struct stat st;
+        if (lstat(path.c_str(), &st) != 0)
+            throw HostError(errno_str("lstat", path));
+        if (S_ISLNK(st.st_mode) || (go_file_mode(hdr) & GO_MODE_SYMLINK))
+            throw HostError("update symlink instead of file: " + path);
+        ck_sys(chown(path.c_str(), (uid_t)hdr.uid, (gid_t)hdr.gid), "chown", path);
+        ck_sys(chmod(path.c_str(), go_chmod_bits(go_file_mode(hdr))), "chmod", path); // after chown: setuid/setgid survive
+        __int128 sec = hdr.mtime_ns / 1000000000ll, ns = hdr.mtime_ns % 1000000000ll;
+        if (ns < 0) {
+            ns += 1000000000ll;
+            --sec;
+        }
+        const struct timespec t = {(time_t)sec, (long)ns};
+        const struct timespec ts[2] = {t, t};
+        ck_sys(utimensat(AT_FDCWD, path.c_str(), ts, 0), "chtimes", path);
+    }
+
+    void untar_one_item(const std::string &path, const Hdr &hdr, const uint8_t *body, uint64_t len) // mem_fs.go:574-650
+    {
+        const std::string base = path_base(path);
+        const size_t sl = path.rfind('/');
+        const std::string dir = sl == 0 ? "/" : path.substr(0, sl);
+        if (base.compare(0, 4, ".wh.") == 0) { // untarWhiteout
+            remove_all(go_join(dir, base.substr(4)));
+            return;
+        }
+        struct stat st;
+        if (lstat(path.c_str(), &st) == 0) {
+            Hdr local = create_local_header(path, st);
+            if (is_similar(local, hdr))
+                return; // already on disk
+            if ((go_file_mode(hdr) & GO_MODE_DIR) && S_ISDIR(st.st_mode)) {
+                apply_header(path, hdr); // existing directories are updated, never deleted
+                return;
+            }
+            remove_all(path);
+        } else if (errno != ENOENT) {
+            throw HostError(errno_str("lstat", path));
+        }
+        switch (hdr.typeflag) {
+        case '5':
+            ck_sys(mkdir(path.c_str(), go_chmod_bits(go_file_mode(hdr))), "create dir", path);
+            apply_header(path, hdr);
+            break;
+        case '2': {
+            std::string target = hdr.linkname;
+            if (!target.empty() && target[0] == '/')
+                target = go_join(root_, target);
+            ck_sys(symlink(target.c_str(), path.c_str()), "create symlink " + path + " =>", target);
+            ck_sys(lchown(path.c_str(), (uid_t)hdr.uid, (gid_t)hdr.gid), "lchown symlink", path);
+            break;
+        }
+        case '1': {
+            const std::string target = go_join(root_, hdr.linkname);
+            ck_sys(link(target.c_str(), path.c_str()), "create link " + path + " =>", target);
+            apply_header(path, hdr);
+            break;
+        }
+        default: {
+            const int fd = open(path.c_str(), O_CREAT | O_TRUNC | O_WRONLY | O_CLOEXEC, go_chmod_bits(go_file_mode(hdr)));
+            if (fd < 0)
+                throw HostError(errno_str("open file", path));
+            uint64_t done = 0;
+            while (done < len) {
+                ssize_t w = write(fd, body + done, len - done);
+                if (w < 0) {
+                    if (errno == EINTR)
+                        continue;
+                    const std::string e = errno_str("read from file", path);
+                    close(fd);
+                    throw HostError(e);
+                }
+                done += (uint64_t)w;
+            }
+            close(fd);
+            apply_header(path, hdr);
+        }
+        }
+    }
+
+    // tar.FileInfoHeader(localInfo, linkTarget) as untarOneItem builds it (mem_fs.go:588-605)
+    Hdr create_local_header(const std::string &path, const struct stat &st)
+    {
+        Hdr h;
+        const mode_t m = st.st_mode;
+        h.mode = m & 0777;
+        if (m & S_ISUID) h.mode |= 04000;
+        if (m & S_ISGID) h.mode |= 02000;
+        if (m & S_ISVTX) h.mode |= 01000;
+        h.mtime_ns = (__int128)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec;
+        h.uid = st.st_uid;
+        h.gid = st.st_gid;
+        h.name = path_base(path);
+        if (S_ISREG(m)) { h.typeflag = '0'; h.size = st.st_size; }
+        else if (S_ISDIR(m)) h.typeflag = '5';
+        else if (S_ISLNK(m)) {
+            h.typeflag = '2';
+            std::string target = read_link(path);
+            if (!target.empty() && target[0] == '/') {
+                if (target.compare(0, root_.size(), root_) != 0)
+                    throw HostError("trim link: failed to trim root prefix " + root_ + " from path " + target);
+                target = abs_path(target.substr(root_.size()));
+            }
+            h.linkname = target;
+        } else if (S_ISCHR(m)) h.typeflag = '3';
+        else if (S_ISBLK(m)) h.typeflag = '4';
+        else if (S_ISFIFO(m)) h.typeflag = '6';
+        else throw HostError("archive/tar: sockets not supported");
+        return h;
+    }
 
     // pathutils.IsDescendantOfAny (lib/pathutils/path.go:24-36)
     static bool is_descendant_of_any(const std::string &path, const std::vector<std::string> &ancestors)
@@ -2250,8 +2441,8 @@ int mkhost_memfs_commit_scan(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, i
     }
 }
 
-size_t mkhost_memfs_describe_update_from_tar(mkhost_memfs *m, int64_t now_unix, int tar_fd, char *out, size_t cap, char *err,
-                                             size_t errlen)
+size_t mkhost_memfs_describe_update_from_tar_ex(mkhost_memfs *m, int64_t now_unix, int tar_fd, uint32_t flags, char *out,
+                                                size_t cap, char *err, size_t errlen)
 {
     try {
         m->fs.set_now(now_unix);
@@ -2269,11 +2460,22 @@ size_t mkhost_memfs_describe_update_from_tar(mkhost_memfs *m, int64_t now_unix, 
             buf.insert(buf.end(), tmp, tmp + r);
         }
         MemTarSource src(buf.data(), buf.size());
+        if (flags & MKHOST_UNTAR) {
+            MemFS::Untar u;
+            read_tar(src, [&](const TarMember &mem, const uint8_t *body) { m->fs.untar_member(u, mem, body); });
+            return emit_text(describe_layer_text(m->fs.untar_finish(u)), out, cap);
+        }
         return emit_text(describe_layer_text(m->fs.update_from_tar(read_tar(src))), out, cap);
     } catch (const std::exception &e) {
         set_err(err, errlen, std::string("update memfs from tar: ") + e.what());
         return 0;
     }
+}
+
+size_t mkhost_memfs_describe_update_from_tar(mkhost_memfs *m, int64_t now_unix, int tar_fd, char *out, size_t cap, char *err,
+                                             size_t errlen)
+{
+    return mkhost_memfs_describe_update_from_tar_ex(m, now_unix, tar_fd, 0, out, cap, err, errlen);
 }
 
 int mkhost_memfs_update_from_tar(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, int tar_fd, uint32_t flags,
@@ -2285,7 +2487,11 @@ int mkhost_memfs_update_from_tar(mkhost_memfs *m, mksnap_t *eng, int64_t now_uni
         ck(eng, mksnap_begin(eng), "begin");
         const bool file_digests = (flags & MKHOST_FILE_DIGESTS) != 0;
         ArenaTarSource src(eng, tar_fd, want_digest, file_digests);
-        const std::vector<TarMember> members = read_tar(src);
+        const bool untar = (flags & MKHOST_UNTAR) != 0;
+        MemFS::Untar u;
+        const std::vector<TarMember> members =
+            untar ? read_tar(src, [&](const TarMember &mem, const uint8_t *body) { m->fs.untar_member(u, mem, body); }) // files written from the arena
+                  : read_tar(src);
         src.flush(true);
         mksnap_result res;
         ck(eng, mksnap_finish(eng, &res), "finish");
@@ -2296,7 +2502,7 @@ int mkhost_memfs_update_from_tar(mkhost_memfs *m, mksnap_t *eng, int64_t now_uni
         if (want_digest)
             memcpy(out->tar_digest, d.data(), 32);
         memcpy(out->root, res.root, 32);
-        const std::map<std::string, MemFile> layer = m->fs.update_from_tar(members);
+        const std::map<std::string, MemFile> layer = untar ? m->fs.untar_finish(u) : m->fs.update_from_tar(members);
         out->n_entries = layer.size();
         if (file_digests) { // remember the content digest of every regular member that made it into the tree
             uint32_t k = 0;

@@ -4,7 +4,8 @@ SHA-256 is DigestPair.TarDigest.
 Restates
   reference lib/snapshot/mem_fs.go:69-83,276-289,353-433,440-569  (MemFS, AddLayerByCopyOps, addToLayer,
             commitLayer, maybeAddToLayer, isUpdated, addAncestors)
-  reference lib/snapshot/mem_fs.go:165-255                        (UpdateFromTarReader, untar=false)
+  reference lib/snapshot/mem_fs.go:165-255,574-716                (UpdateFromTarReader, untarOneItem and helpers)
+  reference lib/tario/apply.go:26-49                              (ApplyHeader)
   reference lib/snapshot/mem_layer.go:83-88,127-132,152-244       (commit, whiteout, createHeader, addHeader, rangeFiles)
   reference lib/snapshot/copy_op.go:45-80,149-174                 (NewCopyOperation, resolveDestination)
   reference lib/snapshot/utils.go:37-75                           (shouldSkip, walk)
@@ -40,6 +41,19 @@ C_ISUID, C_ISGID, C_ISVTX = 0o4000, 0o2000, 0o1000
 # os.FileMode bits (go1.14 os/types.go)
 GO_MODE_DIR, GO_MODE_SYMLINK, GO_MODE_DEVICE, GO_MODE_NAMED_PIPE, GO_MODE_SOCKET = 1 << 31, 1 << 27, 1 << 26, 1 << 25, 1 << 24
 GO_MODE_SETUID, GO_MODE_SETGID, GO_MODE_CHAR_DEVICE, GO_MODE_STICKY = 1 << 23, 1 << 22, 1 << 21, 1 << 20
+
+
+def go_chmod_bits(file_mode: int) -> int:
+    """os.Chmod / os.Mkdir / os.OpenFile take an os.FileMode; syscallMode keeps the permission bits and maps
+    ModeSetuid / ModeSetgid / ModeSticky back to 04000 / 02000 / 01000 (go1.14 os/file_posix.go)."""
+    m = file_mode & 0o777
+    if file_mode & GO_MODE_SETUID:
+        m |= C_ISUID
+    if file_mode & GO_MODE_SETGID:
+        m |= C_ISGID
+    if file_mode & GO_MODE_STICKY:
+        m |= C_ISVTX
+    return m
 
 
 # ---- pathutils (lib/pathutils/path.go) ----------------------------------------------
@@ -819,12 +833,14 @@ class MemFS:
                     self._set_digest(e.dst, hashlib.sha256(f.read()).digest())
 
 
-    def update_from_tar(self, data: bytes, remember: bool = False) -> List[MemFile]:
-        """UpdateFromTarReader(r, untar=false) (mem_fs.go:165-255): merge the headers of an (uncompressed) layer tar
-        into the tree; hard links in a second pass; nothing is written to disk.  Returns the merged layer in key
-        order (the reference only logs its count)."""
+    def update_from_tar(self, data: bytes, remember: bool = False, untar: bool = False) -> List[MemFile]:
+        """UpdateFromTarReader(r, untar) (mem_fs.go:165-255): merge the headers of an (uncompressed) layer tar into the
+        tree, hard links in a second pass.  untar=True also writes the members under the root (untarOneItem,
+        mem_fs.go:574-716; tario.ApplyHeader, lib/tario/apply.go:26-49) and restores the parent directories' mtimes.
+        Returns the merged layer in key order (the reference only logs its count)."""
         layer: Dict[str, MemFile] = {}
         hardlinks: Dict[str, Header] = {}
+        modtimes: Dict[str, int] = {}
         members = read_tar(data)
         for m in members:
             hdr = m.hdr
@@ -833,15 +849,25 @@ class MemFS:
                 continue
             if is_descendant_of_any(path, self.blacklist) or hdr.is_special() or self.is_mountpoint(path):
                 continue
+            if untar:
+                parent = posixpath.dirname(path)
+                if parent not in modtimes:
+                    modtimes[parent] = os.lstat(parent).st_mtime_ns      # "stat parent dir of ..." when it is missing
             hdr = replace(hdr, name=rel_path(hdr.name))
             if hdr.typeflag == TYPE_LINK:
                 hdr.linkname = abs_path(hdr.linkname)
                 hardlinks[path] = hdr
             else:
+                if untar:
+                    self._untar_one_item(path, hdr, data[m.data_off:m.data_off + m.data_len])
                 self._maybe_add(layer, abs_path(hdr.name), abs_path(hdr.name), hdr, False)
         for path in sorted(hardlinks, key=os.fsencode):  # Go ranges over a map: order is unspecified, result is not affected
             hdr = hardlinks[path]
+            if untar:
+                self._untar_one_item(path, hdr, b"")
             self._maybe_add(layer, abs_path(hdr.name), abs_path(hdr.name), hdr, False)
+        for path, ns in modtimes.items():
+            os.utime(path, ns=(ns, ns))
         if remember:
             for m in members:
                 dst = abs_path(m.hdr.name)
@@ -850,6 +876,67 @@ class MemFS:
                     self._set_digest(dst, hashlib.sha256(data[m.data_off:m.data_off + m.data_len]).digest())
         self.layers.append(layer)
         return [layer[k] for k in sorted(layer, key=os.fsencode)]
+
+    # lib/tario/apply.go:26-49
+    @staticmethod
+    def _apply_header(path: str, hdr: Header) -> None:
+        st = os.lstat(path)
+        if stat.S_ISLNK(st.st_mode) or hdr.file_mode_bits() & GO_MODE_SYMLINK:
+            raise OSError("update symlink instead of file: %s" % path)
+        os.chown(path, hdr.uid, hdr.gid)
+        os.chmod(path, go_chmod_bits(hdr.file_mode_bits()))   # after chown: setuid/setgid survive
+        os.utime(path, ns=(hdr.mtime_ns, hdr.mtime_ns))
+
+    # mem_fs.go:574-716
+    def _untar_one_item(self, path: str, hdr: Header, body: bytes) -> None:
+        base = posixpath.basename(path)
+        if base.startswith(WHITEOUT_PREFIX):
+            victim = posixpath.join(posixpath.dirname(path), base[len(WHITEOUT_PREFIX):])
+            if os.path.lexists(victim):
+                if os.path.isdir(victim) and not os.path.islink(victim):
+                    import shutil
+                    shutil.rmtree(victim)
+                else:
+                    os.remove(victim)
+            return
+        if os.path.lexists(path):
+            st = os.lstat(path)
+            link = ""
+            if stat.S_ISLNK(st.st_mode):
+                link = os.readlink(path)
+                if posixpath.isabs(link):
+                    link = trim_root(link, self.root)
+            local = file_info_header(st, link)
+            local.name = base
+            if is_similar_header(local, hdr, False):
+                return
+            if hdr.file_mode_bits() & GO_MODE_DIR and stat.S_ISDIR(st.st_mode):
+                self._apply_header(path, hdr)
+                return
+            if stat.S_ISDIR(st.st_mode):
+                import shutil
+                shutil.rmtree(path)
+            else:
+                os.remove(path)
+        if hdr.typeflag == TYPE_DIR:
+            os.mkdir(path, go_chmod_bits(hdr.file_mode_bits()))
+            self._apply_header(path, hdr)
+        elif hdr.typeflag == TYPE_SYMLINK:
+            target = hdr.linkname
+            if posixpath.isabs(target):
+                target = go_clean(self.root + "/" + target)
+            os.symlink(target, path)
+            os.lchown(path, hdr.uid, hdr.gid)
+        elif hdr.typeflag == TYPE_LINK:
+            os.link(go_clean(self.root + "/" + hdr.linkname), path)
+            self._apply_header(path, hdr)
+        else:
+            fd = os.open(path, os.O_CREAT | os.O_TRUNC | os.O_WRONLY, go_chmod_bits(hdr.file_mode_bits()))
+            try:
+                os.write(fd, body)
+            finally:
+                os.close(fd)
+            self._apply_header(path, hdr)
 
 
 # ---- tario.WriteEntry / WriteHeader (lib/tario/write.go) -----------------------------
