@@ -1,4 +1,4 @@
-"""-m gpu.  Written after this round's GPU budget was spent: these two checks have run on the CPU side only (the code
+"""-m gpu.  Written after this round's GPU budget was spent: these checks have run on the CPU side only (the code
 they exercise compiles and its host logic is covered by the CPU suite).  The file sorts last so that the verified GPU
 tests run first.
 
@@ -8,7 +8,8 @@ tests run first.
     (tests/test_gpu_exchange.py)
   * mkhost_memfs_commit_copy_ops(..., MKHOST_MATERIALIZE): the COPY step's file copy (CopyOperation.Execute,
     lib/snapshot/copy_op.go:82-147) fed from the arena the layer is packed in; the Copier itself
-    and its deferred mode are verified on the CPU (tests/test_host_copier_cpu.py)."""
+    and its deferred mode are verified on the CPU (tests/test_host_copier_cpu.py)
+  * mkhost_memfs_update_from_tar(..., MKHOST_UNTAR): the base layer untarred from the arena while it is digested."""
 import os
 import stat
 
@@ -97,3 +98,67 @@ def test_commit_copy_ops_materializes_from_the_arena(tmp_path):
     entries = fs.add_layer_by_copy_ops([lt.CopyOperation.new(["/app"], str(ctx), "/", "/srv/app/", uid=5, gid=6),
                                         lt.CopyOperation.new(["/conf.txt"], str(ctx), "/", "/etc/conf.txt", uid=7, gid=8)])
     assert fused["tar_digest"] == lt.tar_digest(entries)
+
+
+@pytest.mark.skipif(os.geteuid() != 0, reason="chown needs root")
+def test_update_from_tar_untars_from_the_arena(tmp_path):
+    """UpdateFromTarReader(untar=true) with the GPU in the loop: members are written under the root from the arena
+    that is being digested; disk state == the oracle's untar, DiffID == SHA-256 of the blob.  (The untar logic itself
+    is verified on the CPU: tests/test_host_tar_ingest_cpu.py.)"""
+    import hashlib
+    import io
+    import tarfile
+    from makisu_b200 import host
+    from makisu_b200.abi import Engine
+    from oracle import layer_tar as lt
+    rng = np.random.default_rng(8)
+    buf = io.BytesIO()
+    with tarfile.open(fileobj=buf, mode="w", format=tarfile.PAX_FORMAT) as tf:
+        def add(name, type_=tarfile.REGTYPE, data=b"", link="", mode=0o644):
+            ti = tarfile.TarInfo(name)
+            ti.type, ti.mode, ti.mtime, ti.linkname, ti.uid, ti.gid = type_, mode, 1_500_000_000, link, 7, 8
+            ti.size = len(data) if type_ == tarfile.REGTYPE else 0
+            tf.addfile(ti, io.BytesIO(data) if ti.size else None)
+        add("usr/", tarfile.DIRTYPE, mode=0o755)
+        add("usr/lib/", tarfile.DIRTYPE, mode=0o2755)
+        for i in range(6):
+            add(f"usr/lib/lib{i}.so", data=rng.integers(0, 256, int(rng.integers(1, 900_000)), dtype=np.uint8).tobytes(), mode=0o755)
+        add("usr/lib/alias.so", tarfile.LNKTYPE, link="usr/lib/lib0.so", mode=0o755)
+        add("lib", tarfile.SYMTYPE, link="usr/lib", mode=0o777)
+        add("etc/", tarfile.DIRTYPE, mode=0o755)
+        add("etc/empty", data=b"")
+        add("etc/.wh.stale", data=b"")
+    data = buf.getvalue()
+    (tmp_path / "base.tar").write_bytes(data)
+    disks, layers = [], []
+    for impl in ("oracle", "gpu"):
+        root = tmp_path / impl
+        (root / "etc").mkdir(parents=True)
+        (root / "etc" / "stale").write_bytes(b"to be whited out")
+        os.chmod(root / "etc", 0o700)                              # exists: updated in place to the header's 0755
+        for d in (root / "etc", root):
+            os.utime(d, (1_400_000_000, 1_400_000_000))
+        if impl == "oracle":
+            layers.append(len(lt.MemFS(lambda: NOW, str(root)).update_from_tar(data, untar=True)))
+        else:
+            with Engine(device=0, device_arena_bytes=2 << 20, n_host_arenas=2, host_arena_bytes=2 << 20, max_extents=1 << 10) as eng:
+                with open(tmp_path / "base.tar", "rb") as f:
+                    got = host.MemFS(str(root)).update_from_tar(eng, NOW, f.fileno(), flags=host.MKHOST_UNTAR)
+            assert got["tar_digest"] == "sha256:" + hashlib.sha256(data).hexdigest()
+            layers.append(got["n_entries"])
+        tree = {}
+        for d, dirs, files in os.walk(root):
+            for n in sorted(dirs + files):
+                p = os.path.join(d, n)
+                st = os.lstat(p)
+                rel = os.path.relpath(p, root)
+                if stat.S_ISLNK(st.st_mode):
+                    tree[rel] = ("l", os.readlink(p), st.st_uid, st.st_gid)
+                elif stat.S_ISDIR(st.st_mode):
+                    tree[rel] = ("d", stat.S_IMODE(st.st_mode), st.st_uid, st.st_gid, st.st_mtime_ns)
+                else:
+                    tree[rel] = ("f", stat.S_IMODE(st.st_mode), st.st_uid, st.st_gid, st.st_mtime_ns, st.st_nlink, open(p, "rb").read())
+        disks.append(tree)
+    assert layers[0] == layers[1]
+    assert disks[0] == disks[1]
+    assert "etc/stale" not in disks[1] and disks[1]["etc"][:4] == ("d", 0o755, 7, 8) and disks[1]["usr/lib/alias.so"][5] == 2
