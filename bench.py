@@ -8,7 +8,8 @@
 
 A "step" = one pass of the hot path over one build context per GPU:
   CRC-32 context fingerprint (cacheID, bit-exact reference arithmetic) + Gear-32 CDC + per-chunk SHA-256
-  + sort/unique + Merkle root [+ NCCL all-gather/merge of the per-rank tables when N > 1].
+  + sort/unique + Merkle root [+ the NCCL table exchange when N > 1: range-partitioned all-to-all by default
+  (checked untimed against the all-gather merge first, fallback to it on disagreement), --merge allgather for the other].
 Workload = BASELINE.json configs[2]: 100k files x 512 KiB (48.83 GiB) synthetic, per GPU (weak scaling:
 the file list shards by rank, every rank owns a full-size shard).  Inputs are 48.8 GiB >> 126 MB L2, so no
 L2 flush is needed between timed iterations.
@@ -18,6 +19,8 @@ value  : device-resident arena (bytes already in HBM), wall time around K steps 
 e2e    : same work through mksnap_arena_acquire/submit with PINNED HOST arenas: every step copies the whole
          context host->device in batches (overlapped with compute) and reads the result struct back.
 TarDigest (serial SHA-256 per layer stream) is reported separately in "tar_digest" (DESIGN.md section 5).
+cpu_baseline    : the reference-equivalent CPU path (single thread like the reference's goroutines) on a bounded sample.
+cpu_best_effort : all host threads doing the SAME work as the GPU step (CRC-32 + Gear CDC + SHA-NI chunk SHA-256).
 """
 from __future__ import annotations
 
