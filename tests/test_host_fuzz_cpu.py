@@ -224,3 +224,93 @@ def test_random_header_fields_with_repaired_checksum(tmp_path, seed):
             assert got == want
             accepted += 1
     assert accepted > 0
+
+
+# ---- stateful: random sequences of MemFS operations on both implementations ---------------------------------------
+@pytest.mark.skipif(os.geteuid() != 0, reason="chown needs root")
+@pytest.mark.parametrize("seed", range(14))
+def test_random_memfs_operation_sequences(tmp_path, seed):
+    """ingest (untar or not) / edit the disk / scan / copy ops, in random order, on the oracle's MemFS and the C++ one
+    (each on its own root built by the same seeded steps).  Every step must return the same layer, or fail on both."""
+    import shutil
+    import tarfile
+    import tempfile
+    NOW = 1_600_000_000
+    T = 1_450_000_000
+    logs = []
+    for impl in ("oracle", "cpp"):
+        rng = np.random.default_rng(31000 + seed)
+        root, ctx = tmp_path / impl / "root", tmp_path / impl / "ctx"
+        root.mkdir(parents=True)
+        ctx.mkdir()
+        _random_tree(str(ctx), rng)
+        for d, dirs, files in os.walk(ctx):
+            for n in dirs + files:
+                os.utime(os.path.join(d, n), (T, T), follow_symlinks=False)
+        os.utime(ctx, (T, T))
+        os.utime(root, (T, T))
+        fs = lt.MemFS(lambda: NOW, str(root)) if impl == "oracle" else host.MemFS(str(root))
+        log = []
+        for step in range(7):
+            op = ["ingest", "untar", "edit", "scan", "copy", "scan"][int(rng.integers(0, 6))]
+            try:
+                if op in ("ingest", "untar"):
+                    data = _random_tar(rng, [tarfile.USTAR_FORMAT, tarfile.PAX_FORMAT, tarfile.GNU_FORMAT][int(rng.integers(0, 3))])
+                    if impl == "oracle":
+                        layer = fs.update_from_tar(data, untar=(op == "untar"))
+                        out = [e.dst for e in layer]
+                    else:
+                        with tempfile.TemporaryFile() as f:
+                            f.write(data)
+                            f.seek(0)
+                            out = [l.split(" ")[6] for l in fs.describe_update_from_tar(NOW, f.fileno(), host.MKHOST_UNTAR if op == "untar" else 0)]
+                elif op == "edit":
+                    names = sorted(os.listdir(root))
+                    k = rng.random()
+                    if names and k < 0.4:
+                        victim = root / names[int(rng.integers(0, len(names)))]
+                        if victim.is_dir() and not victim.is_symlink():
+                            shutil.rmtree(victim)
+                        else:
+                            victim.unlink()
+                    else:
+                        p = root / ("new%d" % step)
+                        p.write_bytes(bytes(rng.integers(0, 256, int(rng.integers(0, 2000)), dtype=np.uint8)))
+                        os.chmod(p, 0o640)
+                        os.utime(p, (T + step, T + step))
+                    os.utime(root, (T + step, T + step))
+                    out = ["edited"]
+                elif op == "scan":
+                    if impl == "oracle":
+                        out = [e.dst + ("!" if e.whiteout else "") for e in fs.add_layer_by_scan()]
+                    else:
+                        out = []
+                        for l in fs.describe_scan(NOW):
+                            parts = l.split(" ")
+                            out.append(parts[6] + ("!" if os.path.basename(parts[7].rstrip("/")).startswith(".wh.") else ""))
+                else:
+                    dst = ["/app/", "/srv/x/y/", "/new%d" % step][int(rng.integers(0, 3))]
+                    srcs = ["/"] if dst.endswith("/") else None
+                    if srcs is None:
+                        files = [n for n in sorted(os.listdir(ctx)) if (ctx / n).is_file() and not (ctx / n).is_symlink()]
+                        if not files:
+                            log.append((op, "skip"))
+                            continue
+                        srcs = ["/" + files[0]]
+                    if impl == "oracle":
+                        out = [e.dst for e in fs.add_layer_by_copy_ops([lt.CopyOperation.new(srcs, str(ctx), "/", dst, uid=2, gid=3)])]
+                    else:
+                        out = [l.split(" ")[6] for l in fs.describe_copy_ops(NOW, [host.CopyOperation(srcs, str(ctx), "/", dst, 2, 3)])]
+                log.append((op, out))
+            except (OSError, ValueError, host.HostError):
+                log.append((op, "err"))
+            # an aborted untar leaves wall-clock mtimes on directories: pin them so that the next scan cannot depend on
+            # whether the two runs crossed a second boundary at different steps
+            for d, dirs, _ in os.walk(root):
+                for n in dirs:
+                    if not os.path.islink(os.path.join(d, n)):
+                        os.utime(os.path.join(d, n), (T + 100 + step, T + 100 + step))
+        if impl == "cpp":
+            fs.close()
+        logs.append(log)
+    assert logs[0] == logs[1]
