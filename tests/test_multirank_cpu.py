@@ -200,3 +200,32 @@ def test_exchange_model_edge_cases():
         assert b"".join(x.tobytes() for x in ranges) == b"".join(union)
         for r, x in enumerate(ranges):                      # every row sits on the rank that owns its prefix
             assert all(shard.range_owner(int.from_bytes(bytes(row[:8]), "big"), len(tabs)) == r for row in x)
+
+
+def test_level0_plan_invariants():
+    """For any distribution of range sizes: every global Merkle group is owned by exactly one rank, the groups appear in
+    rank order, a rank never borrows more than 255 rows and never beyond the end of the table -- the facts x_phase4/5 in
+    mksnap.cu rely on (hypothesis-free sweep: all size vectors of length <= 4 over a set of boundary values, plus random)."""
+    import itertools
+    vals = [0, 1, 2, 255, 256, 257, 511, 512, 513, 1000]
+    vecs = [list(v) for n in (1, 2, 3) for v in itertools.product(vals, repeat=n)]
+    vecs += [list(v) for v in itertools.product([0, 1, 255, 256, 257, 700], repeat=4)]
+    rng = np.random.default_rng(0)
+    vecs += [list(map(int, rng.integers(0, 3000, int(rng.integers(1, 9))))) for _ in range(2000)]
+    for all_u in vecs:
+        U = sum(all_u)
+        owned = []
+        for r in range(len(all_u)):
+            p = shard.level0_plan(all_u, r)
+            assert p["U"] == U and p["g0"] == sum(all_u[:r])
+            assert 0 <= p["borrowed"] <= 255 and p["lead"] <= 255
+            if p["groups"]:
+                first = (p["g0"] + p["lead"]) // 256
+                assert (p["g0"] + p["lead"]) % 256 == 0 and p["lead"] < all_u[r]
+                owned += list(range(first, first + p["groups"]))
+                end = p["g0"] + all_u[r] + p["borrowed"]
+                assert end <= U and (end % 256 == 0 or end == U)             # the tail group is complete or is the last one
+                assert p["borrowed"] <= sum(all_u[r + 1:])
+            else:
+                assert p["full"] == p["tail_own"] == p["borrowed"] == 0
+        assert owned == list(range((U + 255) // 256)), all_u
