@@ -212,6 +212,10 @@ int mksnap_exchange_tables(mksnap_t *h, mksnap_result *out);
 /* The same exchange between n handles of ONE process on ONE device (device copies instead of NCCL; no comm_init):
  * handle i plays rank i, outs[i] receives its result.  Used to run the exchange logic for any n on a single GPU. */
 int mksnap_exchange_tables_local(mksnap_t **handles, int32_t n, mksnap_result *outs);
+/* Host arithmetic of the exchange, no device needed: given the rows every rank holds after the all-to-all, which
+ * groups of 256 global rows does `rank` hash?  out = {U total rows, g0 first global row of the rank, lead rows that
+ * belong to a predecessor's group, full groups, own rows in the tail group, rows borrowed from successors, groups}. */
+int mksnap_exchange_plan(const uint64_t *rows_per_rank, int32_t n_ranks, int32_t rank, uint64_t out[7]);
 
 /* ---- utilities --------------------------------------------------------- */
 /* Deterministic synthetic content, generated on the device into slot bytes

@@ -86,6 +86,7 @@ SYMBOLS = [
     ("mksnap_allgather_tables", C.c_int, [_P, C.POINTER(Result)]),
     ("mksnap_exchange_tables", C.c_int, [_P, C.POINTER(Result)]),
     ("mksnap_exchange_tables_local", C.c_int, [C.POINTER(_P), C.c_int32, C.POINTER(Result)]),
+    ("mksnap_exchange_plan", C.c_int, [C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
     ("mksnap_synth_fill", C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64]),
     ("mksnap_memset", C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int]),
     ("mksnap_device_download", C.c_int, [_P, C.c_uint32, C.c_uint64, _P, C.c_uint64]),
@@ -286,6 +287,17 @@ class Engine:
             msgs = [(e.lib.mksnap_last_error(e.h) or b"").decode() for e in engines]
             raise MksnapError(rc, "mksnap_exchange_tables_local", "; ".join(m for m in msgs if m))
         return [outs[i] for i in range(n)]
+
+
+def exchange_plan(rows_per_rank, rank: int) -> dict:
+    """mksnap_exchange_plan: the device code's own statement of shard.level0_plan (host arithmetic only)."""
+    n = len(rows_per_rank)
+    arr = (C.c_uint64 * n)(*[int(x) for x in rows_per_rank])
+    out = (C.c_uint64 * 7)()
+    rc = load().mksnap_exchange_plan(arr, n, rank, out)
+    if rc:
+        raise MksnapError(rc, "mksnap_exchange_plan", "")
+    return dict(zip(["U", "g0", "lead", "full", "tail_own", "borrowed", "groups"], [int(v) for v in out]))
 
 
 def gear_table():

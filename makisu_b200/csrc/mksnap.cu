@@ -1344,6 +1344,17 @@ static XPlan x_plan(const std::vector<uint64_t> &all_u, int rank)
     return p;
 }
 
+// introspection (no device work): which Merkle groups rank `rank` hashes given every rank's range size.
+// out = {U, g0, lead, full, tail_own, borrowed, groups}; the same arithmetic as shard.level0_plan.
+int mksnap_exchange_plan(const uint64_t *rows_per_rank, int32_t n_ranks, int32_t rank, uint64_t out[7])
+{
+    if (!rows_per_rank || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+        return MKSNAP_E_INVAL;
+    const XPlan p = x_plan(std::vector<uint64_t>(rows_per_rank, rows_per_rank + n_ranks), rank);
+    out[0] = p.U; out[1] = p.g0; out[2] = p.lead; out[3] = p.full; out[4] = p.tail_own; out[5] = p.borrowed; out[6] = p.groups;
+    return 0;
+}
+
 struct XState { // host-side state of one rank between phases
     int R = 0, rank = 0;
     std::vector<uint64_t> bounds;  // R+1

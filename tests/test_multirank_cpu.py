@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from makisu_b200 import shard
+from makisu_b200 import abi, shard
 from oracle import lib as olib
 
 
@@ -217,6 +217,7 @@ def test_level0_plan_invariants():
         owned = []
         for r in range(len(all_u)):
             p = shard.level0_plan(all_u, r)
+            assert abi.exchange_plan(all_u, r) == p                          # the C++ statement inside libmksnap (x_plan)
             assert p["U"] == U and p["g0"] == sum(all_u[:r])
             assert 0 <= p["borrowed"] <= 255 and p["lead"] <= 255
             if p["groups"]:
