@@ -1087,611 +1087,6 @@ int mksnap_stats(mksnap_t *h, mksnap_stats_t *out)
     *out = h->stats;
     return 0;
 }
-
-// ---------------------------------------------------------------------------
-// multi-GPU exchange (NCCL, dlopen'ed)
-// ---------------------------------------------------------------------------
-static int nccl_load(NcclApi &api, std::string &err)
-{
-    if (api.lib)
-        return 0;
-    const char *names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char *nm : names) {
-        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-        if (api.lib)
-            break;
-    }
-    if (!api.lib) {
-        const char *env = getenv("MKSNAP_NCCL_LIB");
-        if (env)
-            api.lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
-    }
-    if (!api.lib) {
-        err = std::string("cannot dlopen libnccl.so.2 (set MKSNAP_NCCL_LIB): ") + dlerror();
-        return MKSNAP_E_NCCL;
-    }
-    api.GetUniqueId = (int (*)(void *))dlsym(api.lib, "ncclGetUniqueId");
-    api.CommInitRank = (int (*)(void **, int, Id128, int))dlsym(api.lib, "ncclCommInitRank");
-    api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(api.lib, "ncclAllGather");
-    api.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))dlsym(api.lib, "ncclSend");
-    api.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))dlsym(api.lib, "ncclRecv");
-    api.GroupStart = (int (*)())dlsym(api.lib, "ncclGroupStart");
-    api.GroupEnd = (int (*)())dlsym(api.lib, "ncclGroupEnd");
-    api.CommDestroy = (int (*)(void *))dlsym(api.lib, "ncclCommDestroy");
-    api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
-    if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) {
-        err = "libnccl is missing required symbols";
-        return MKSNAP_E_NCCL;
-    }
-    return 0;
-}
-
-int mksnap_comm_unique_id(uint8_t id[128])
-{
-    static NcclApi api;
-    std::string err;
-    int rc = nccl_load(api, err);
-    if (rc) {
-        g_create_error = err;
-        return rc;
-    }
-    int r = api.GetUniqueId(id);
-    if (r) {
-        g_create_error = std::string("ncclGetUniqueId: ") + (api.GetErrorString ? api.GetErrorString(r) : "?");
-        return MKSNAP_E_NCCL;
-    }
-    return 0;
-}
-
-int mksnap_comm_init(mksnap_t *h, const uint8_t id[128], int32_t n_ranks, int32_t rank)
-{
-    if (!h || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks)
-        return MKSNAP_E_INVAL;
-    CK(h, cudaSetDevice(h->cfg.device));
-    int rc = nccl_load(h->nccl, h->err);
-    if (rc)
-        return rc;
-    Id128 uid;
-    memcpy(uid.b, id, 128);
-    int r = h->nccl.CommInitRank(&h->comm, n_ranks, uid, rank);
-    if (r)
-        return fail(h, MKSNAP_E_NCCL, "ncclCommInitRank: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(r) : "?");
-    h->n_ranks = n_ranks;
-    h->rank = rank;
-    if (n_ranks > 1) { // the merged table can hold every rank's rows
-        CK(h, cudaStreamSynchronize(h->s_comp));
-        int rc2 = alloc_table_buffers(h, h->max_chunks * (uint64_t)n_ranks);
-        if (rc2)
-            return rc2;
-    }
-    CK(h, cudaMalloc(&h->d_gcount, (size_t)n_ranks * GH_WORDS * sizeof(unsigned long long)));
-    return 0;
-}
-
-// header for the first all-gather: one row of GH_WORDS u64 per rank
-struct GatherHeader {
-    unsigned long long w[GH_WORDS];
-};
-__global__ void k_pack_header(unsigned long long *dst, GatherHeader hd)
-{
-    if (threadIdx.x < GH_WORDS)
-        dst[threadIdx.x] = hd.w[threadIdx.x];
-}
-
-// copy rank r's rows from the padded gather buffer to a dense buffer
-__global__ void k_dense_rows(const uint8_t *__restrict__ gathered, uint64_t pad_rows, uint64_t rank_off, uint64_t n,
-                             uint64_t r, uint8_t *__restrict__ dense)
-{
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * 2)
-        return;
-    reinterpret_cast<uint4 *>(dense + rank_off * 32)[t] =
-        reinterpret_cast<const uint4 *>(gathered + r * pad_rows * 32)[t];
-}
-
-int mksnap_allgather_tables(mksnap_t *h, mksnap_result *out)
-{
-    if (!h || !out)
-        return MKSNAP_E_INVAL;
-    if (!h->finished)
-        return fail(h, MKSNAP_E_STATE, "allgather before finish");
-    if (!h->comm)
-        return fail(h, MKSNAP_E_STATE, "allgather without comm_init");
-    CK(h, cudaSetDevice(h->cfg.device));
-    cudaStream_t s = h->s_comp;
-    const int R = h->n_ranks;
-    CK(h, cudaEventRecord(h->ev_fin[2], s));
-    // 1) header: table rows, CRC partial and the additive counters of every rank
-    unsigned long long *mine = h->d_gcount + (size_t)h->rank * GH_WORDS;
-    GatherHeader hd;
-    memset(&hd, 0, sizeof hd);
-    hd.w[0] = h->n_unique;
-    hd.w[1] = h->last_result.crc_pure;
-    hd.w[2] = h->last_result.crc_bytes;
-    hd.w[3] = h->last_result.cdc_bytes;
-    hd.w[4] = h->last_result.n_chunks;
-    hd.w[5] = h->last_result.n_files;
-    hd.w[6] = h->last_result.n_streams;
-    k_pack_header<<<1, 32, 0, s>>>(mine, hd);
-    LAUNCH_OK(h);
-    int r = h->nccl.AllGather(mine, h->d_gcount, GH_WORDS, /*ncclUint64*/ 5, h->comm, s);
-    if (r)
-        return fail(h, MKSNAP_E_NCCL, "ncclAllGather(header): %s", h->nccl.GetErrorString(r));
-    std::vector<unsigned long long> hc((size_t)R * GH_WORDS);
-    CK(h, cudaMemcpyAsync(hc.data(), h->d_gcount, hc.size() * 8, cudaMemcpyDeviceToHost, s));
-    CK(h, cudaStreamSynchronize(s));
-    uint64_t total = 0, pad = 0;
-    uint32_t crc = 0;
-    mksnap_result sum;
-    memset(&sum, 0, sizeof sum);
-    for (int k = 0; k < R; k++) {
-        const unsigned long long *w = &hc[(size_t)k * GH_WORDS];
-        total += w[0];
-        pad = std::max<uint64_t>(pad, w[0]);
-        crc ^= (uint32_t)w[1];
-        sum.crc_bytes += w[2];
-        sum.cdc_bytes += w[3];
-        sum.n_chunks += w[4];
-        sum.n_files += w[5];
-        sum.n_streams += w[6];
-    }
-    if (total > h->table_cap)
-        return fail(h, MKSNAP_E_CAPACITY, "gathered table of %llu rows exceeds max_chunks %llu", (unsigned long long)total,
-                    (unsigned long long)h->table_cap);
-    if (total > h->concat_rows) {
-        cudaFree(h->d_concat);
-        h->d_concat = nullptr;
-        h->concat_rows = total;
-        CK(h, cudaMalloc(&h->d_concat, std::max<uint64_t>(total, 1) * 32));
-    }
-    pad = std::max<uint64_t>(pad, 1);
-    if ((uint64_t)R * pad > h->gather_rows) {
-        cudaFree(h->d_gather);
-        h->d_gather = nullptr;
-        h->gather_rows = (uint64_t)R * pad;
-        CK(h, cudaMalloc(&h->d_gather, h->gather_rows * 32));
-    }
-    // 2) padded rows.  My rows go in place first (sendbuff = my slot of recvbuff).
-    uint8_t *myrows = h->d_gather + (uint64_t)h->rank * pad * 32;
-    if (h->n_unique)
-        CK(h, cudaMemcpyAsync(myrows, h->d_table, h->n_unique * 32, cudaMemcpyDeviceToDevice, s));
-    r = h->nccl.AllGather(myrows, h->d_gather, pad * 32, /*ncclUint8*/ 1, h->comm, s);
-    if (r)
-        return fail(h, MKSNAP_E_NCCL, "ncclAllGather(rows): %s", h->nccl.GetErrorString(r));
-    // 3) dense concat into d_sorted (scratch), then sort+unique -> d_table, root
-    uint64_t off = 0;
-    for (int k = 0; k < R; k++) {
-        const uint64_t n = hc[(size_t)k * GH_WORDS];
-        if (n) {
-            k_dense_rows<<<(uint32_t)((2 * n + 255) / 256), 256, 0, s>>>(h->d_gather, pad, off, n, (uint64_t)k,
-                                                                        h->d_concat);
-            LAUNCH_OK(h);
-        }
-        off += n;
-    }
-    int rc = sort_unique_root(h, h->d_concat, total, s);
-    if (rc)
-        return rc;
-    rc = merkle_root(h, s);
-    if (rc)
-        return rc;
-    CK(h, cudaEventRecord(h->ev_fin[3], s));
-    CK(h, cudaStreamSynchronize(s));
-    CK(h, cudaEventElapsedTime(&h->stats.ms_gather, h->ev_fin[2], h->ev_fin[3]));
-    *out = sum;
-    out->crc_pure = crc;
-    out->n_unique = h->n_unique;
-    memcpy(out->root, h->root, 32);
-    return 0;
-}
-
-// ---------------------------------------------------------------------------
-// Range-partitioned exchange.  mksnap_allgather_tables makes every rank sort the union (cost grows with R);
-// here rank r keeps only the digests whose big-endian 64-bit prefix p has floor(p*R / 2^64) == r:
-//   1  cut my sorted-unique table at the R+1 range boundaries, all-to-all the slices (ncclSend/ncclRecv group)
-//   2  sort + unique what arrived -> my range of the GLOBAL table (u_r rows)
-//   3  all-gather u_r and every rank's first 255 rows
-//   4  Merkle level 0: a group of 256 consecutive global rows is hashed by the rank owning its first row; rows
-//      missing at the end of my range come from the heads of the ranks that follow
-//   5  all-gather the level-1 digests, upper levels on every rank -> the root a single table would give
-// The host logic is stated in makisu_b200/shard.py (exchange_tables_model) and tested there against the oracle.
-// The phases are written per handle; the transport between them is either NCCL (one process per GPU) or plain
-// device copies between handles of one process (mksnap_exchange_tables_local: same code path, any R on one GPU).
-// ---------------------------------------------------------------------------
-constexpr uint64_t XHEAD_ROWS = 255;
-constexpr uint64_t XREC_BYTES = 32 + XHEAD_ROWS * 32; // u64 count + 24 pad + 255 rows = 8192
-
-__global__ void k_range_bounds(const uint8_t *__restrict__ table, uint64_t n, uint32_t R, unsigned long long *bounds)
-{
-    const uint32_t j = threadIdx.x;
-    if (j > R)
-        return;
-    uint64_t lo = 0, hi = n;
-    while (lo < hi) { // first row whose owner is >= j
-        const uint64_t mid = lo + (hi - lo) / 2;
-        const uint8_t *q = table + mid * 32;
-        unsigned long long key = 0;
-        for (int b = 0; b < 8; ++b)
-            key = (key << 8) | q[b];
-        if (__umul64hi(key, (unsigned long long)R) >= j)
-            hi = mid;
-        else
-            lo = mid + 1;
-    }
-    bounds[j] = lo;
-}
-
-struct XPlan { // level0_plan of shard.py
-    uint64_t U = 0, g0 = 0, lead = 0, full = 0, tail_own = 0, borrowed = 0, groups = 0;
-};
-static XPlan x_plan(const std::vector<uint64_t> &all_u, int rank)
-{
-    XPlan p;
-    for (size_t k = 0; k < all_u.size(); ++k) {
-        p.U += all_u[k];
-        if ((int)k < rank)
-            p.g0 += all_u[k];
-    }
-    const uint64_t u = all_u[rank], first_mult = (p.g0 + 255) / 256 * 256;
-    if (p.U == 0 || first_mult >= p.g0 + u)
-        return p;
-    p.lead = first_mult - p.g0;
-    const uint64_t owned = u - p.lead;
-    p.full = owned / 256;
-    p.tail_own = owned % 256;
-    p.borrowed = p.tail_own ? std::min<uint64_t>(256 - p.tail_own, p.U - (p.g0 + u)) : 0;
-    p.groups = p.full + (p.tail_own ? 1 : 0);
-    return p;
-}
-
-// introspection (no device work): which Merkle groups rank `rank` hashes given every rank's range size.
-// out = {U, g0, lead, full, tail_own, borrowed, groups}; the same arithmetic as shard.level0_plan.
-int mksnap_exchange_plan(const uint64_t *rows_per_rank, int32_t n_ranks, int32_t rank, uint64_t out[7])
-{
-    if (!rows_per_rank || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks)
-        return MKSNAP_E_INVAL;
-    const XPlan p = x_plan(std::vector<uint64_t>(rows_per_rank, rows_per_rank + n_ranks), rank);
-    out[0] = p.U; out[1] = p.g0; out[2] = p.lead; out[3] = p.full; out[4] = p.tail_own; out[5] = p.borrowed; out[6] = p.groups;
-    return 0;
-}
-
-struct XState { // host-side state of one rank between phases
-    int R = 0, rank = 0;
-    std::vector<uint64_t> bounds;  // R+1
-    std::vector<uint64_t> hdr;     // GH_WORDS + R words: counters, then rows sent to each rank
-    std::vector<uint64_t> all_hdr; // R * (GH_WORDS + R)
-    std::vector<uint64_t> recv_off; // R+1
-    std::vector<uint64_t> all_u;
-    uint64_t pad_l1 = 1;
-};
-
-static int x_ensure(mksnap *h, int R)
-{
-    if (h->x_ranks >= R)
-        return 0;
-    cudaFree(h->d_xbounds); cudaFree(h->d_xhdr); cudaFree(h->d_xrec); cudaFree(h->d_xtail);
-    h->d_xbounds = h->d_xhdr = nullptr;
-    h->d_xrec = h->d_xtail = nullptr;
-    CK(h, cudaMalloc(&h->d_xbounds, (size_t)(R + 1) * 8));
-    CK(h, cudaMalloc(&h->d_xhdr, (size_t)R * (GH_WORDS + R) * 8));
-    CK(h, cudaMalloc(&h->d_xrec, (size_t)R * XREC_BYTES));
-    CK(h, cudaMalloc(&h->d_xtail, 256 * 32));
-    h->x_ranks = R;
-    return 0;
-}
-
-// phase 1: where my table is cut; my header row
-static int x_phase1(mksnap *h, XState &x, cudaStream_t s)
-{
-    const int R = x.R;
-    if (R > 1024)
-        return fail(h, MKSNAP_E_INVAL, "exchange supports at most 1024 ranks");
-    int rc = x_ensure(h, R);
-    if (rc)
-        return rc;
-    k_range_bounds<<<1, 1024, 0, s>>>(h->d_table, h->n_unique, (uint32_t)R, h->d_xbounds);
-    LAUNCH_OK(h);
-    x.bounds.assign(R + 1, 0);
-    CK(h, cudaMemcpyAsync(x.bounds.data(), h->d_xbounds, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost, s));
-    CK(h, cudaStreamSynchronize(s));
-    x.hdr.assign(GH_WORDS + R, 0);
-    x.hdr[0] = h->n_unique;
-    x.hdr[1] = h->last_result.crc_pure;
-    x.hdr[2] = h->last_result.crc_bytes;
-    x.hdr[3] = h->last_result.cdc_bytes;
-    x.hdr[4] = h->last_result.n_chunks;
-    x.hdr[5] = h->last_result.n_files;
-    x.hdr[6] = h->last_result.n_streams;
-    for (int j = 0; j < R; ++j)
-        x.hdr[GH_WORDS + j] = x.bounds[j + 1] - x.bounds[j];
-    return 0;
-}
-
-// phase 2 (after the header all-gather): receive layout
-static int x_phase2(mksnap *h, XState &x)
-{
-    const int R = x.R, W = GH_WORDS + R;
-    x.recv_off.assign(R + 1, 0);
-    for (int k = 0; k < R; ++k)
-        x.recv_off[k + 1] = x.recv_off[k] + x.all_hdr[(size_t)k * W + GH_WORDS + x.rank];
-    const uint64_t total = x.recv_off[R];
-    if (total > h->table_cap)
-        return fail(h, MKSNAP_E_CAPACITY, "range of %llu rows exceeds the table capacity %llu (skewed digests?)",
-                    (unsigned long long)total, (unsigned long long)h->table_cap);
-    if (std::max<uint64_t>(total, 1) > h->concat_rows) {
-        cudaFree(h->d_concat);
-        h->d_concat = nullptr;
-        h->concat_rows = std::max<uint64_t>(total, 1);
-        CK(h, cudaMalloc(&h->d_concat, h->concat_rows * 32));
-    }
-    return 0;
-}
-
-// phase 3 (after the all-to-all): my range of the global table; my record for the second all-gather
-static int x_phase3(mksnap *h, XState &x, cudaStream_t s)
-{
-    int rc = sort_unique_root(h, h->d_concat, x.recv_off[x.R], s);
-    if (rc)
-        return rc;
-    uint8_t *rec = h->d_xrec + (size_t)x.rank * XREC_BYTES;
-    const unsigned long long u = h->n_unique;
-    CK(h, cudaMemsetAsync(rec, 0, 32, s));
-    CK(h, cudaMemcpyAsync(rec, &u, 8, cudaMemcpyHostToDevice, s));
-    const uint64_t head = std::min<uint64_t>(u, XHEAD_ROWS);
-    if (head)
-        CK(h, cudaMemcpyAsync(rec + 32, h->d_table, head * 32, cudaMemcpyDeviceToDevice, s));
-    CK(h, cudaStreamSynchronize(s)); // `u` is a stack variable
-    return 0;
-}
-
-// phase 4 (after the record all-gather; x.all_u filled): Merkle level 0 of the groups I own -> my slot of d_gather
-static int x_phase4(mksnap *h, XState &x, cudaStream_t s)
-{
-    const int R = x.R;
-    uint64_t pad = 1;
-    for (int k = 0; k < R; ++k)
-        pad = std::max<uint64_t>(pad, x_plan(x.all_u, k).groups);
-    x.pad_l1 = pad;
-    if ((uint64_t)R * pad > h->gather_rows) {
-        cudaFree(h->d_gather);
-        h->d_gather = nullptr;
-        h->gather_rows = (uint64_t)R * pad;
-        CK(h, cudaMalloc(&h->d_gather, h->gather_rows * 32));
-    }
-    const XPlan p = x_plan(x.all_u, x.rank);
-    uint8_t *mine = h->d_gather + (uint64_t)x.rank * pad * 32;
-    if (p.full) {
-        CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, s));
-        k_sha256_ranges<true><<<sha_grid(h), SHA_THREADS, 0, s>>>(h->d_table + p.lead * 32, nullptr, nullptr, nullptr, p.full,
-                                                                  nullptr, 0, 8192, p.full * 8192, mine, &h->d_sc->work, nullptr,
-                                                                  1u, nullptr, nullptr, nullptr, nullptr);
-        LAUNCH_OK(h);
-    }
-    if (p.tail_own) {
-        CK(h, cudaMemcpyAsync(h->d_xtail, h->d_table + (p.lead + p.full * 256) * 32, p.tail_own * 32, cudaMemcpyDeviceToDevice, s));
-        uint64_t need = p.borrowed, at = p.tail_own;
-        for (int k = x.rank + 1; need && k < R; ++k) {
-            const uint64_t take = std::min<uint64_t>(need, x.all_u[k]);
-            if (take)
-                CK(h, cudaMemcpyAsync(h->d_xtail + at * 32, h->d_xrec + (size_t)k * XREC_BYTES + 32, take * 32,
-                                      cudaMemcpyDeviceToDevice, s));
-            at += take;
-            need -= take;
-        }
-        if (need)
-            return fail(h, MKSNAP_E_STATE, "internal: exchange ran out of rows for the last group");
-        CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, s));
-        k_sha256_ranges<true><<<1, SHA_THREADS, 0, s>>>(h->d_xtail, nullptr, nullptr, nullptr, 1, nullptr, 0, 8192, at * 32,
-                                                        mine + p.full * 32, &h->d_sc->work, nullptr, 1u, nullptr, nullptr,
-                                                        nullptr, nullptr);
-        LAUNCH_OK(h);
-    }
-    return 0;
-}
-
-// phase 5 (after the level-1 all-gather): upper levels, result
-static int x_phase5(mksnap *h, XState &x, cudaStream_t s, mksnap_result *out)
-{
-    const int R = x.R, W = GH_WORDS + R;
-    const XPlan me = x_plan(x.all_u, x.rank);
-    if (me.U == 0) {
-        int rc = merkle_from(h, h->d_table, 0, s); // SHA-256 of nothing
-        if (rc)
-            return rc;
-    } else {
-        const uint64_t n1 = (me.U + 255) / 256;
-        if (n1 > h->concat_rows) {
-            cudaFree(h->d_concat);
-            h->d_concat = nullptr;
-            h->concat_rows = n1;
-            CK(h, cudaMalloc(&h->d_concat, n1 * 32));
-        }
-        uint64_t off = 0;
-        for (int k = 0; k < R; ++k) {
-            const uint64_t n = x_plan(x.all_u, k).groups;
-            if (n) {
-                k_dense_rows<<<(uint32_t)((2 * n + 255) / 256), 256, 0, s>>>(h->d_gather, x.pad_l1, off, n, (uint64_t)k, h->d_concat);
-                LAUNCH_OK(h);
-            }
-            off += n;
-        }
-        if (off != n1)
-            return fail(h, MKSNAP_E_STATE, "internal: exchange level-1 count %llu != %llu", (unsigned long long)off,
-                        (unsigned long long)n1);
-        if (n1 == 1) {
-            CK(h, cudaMemcpyAsync(h->root, h->d_concat, 32, cudaMemcpyDeviceToHost, s));
-        } else {
-            int rc = merkle_from(h, h->d_concat, n1, s);
-            if (rc)
-                return rc;
-        }
-    }
-    CK(h, cudaStreamSynchronize(s));
-    mksnap_result sum;
-    memset(&sum, 0, sizeof sum);
-    uint32_t crc = 0;
-    for (int k = 0; k < R; ++k) {
-        const uint64_t *w = &x.all_hdr[(size_t)k * W];
-        crc ^= (uint32_t)w[1];
-        sum.crc_bytes += w[2];
-        sum.cdc_bytes += w[3];
-        sum.n_chunks += w[4];
-        sum.n_files += w[5];
-        sum.n_streams += w[6];
-    }
-    *out = sum;
-    out->crc_pure = crc;
-    out->n_unique = me.U; // GLOBAL unique rows; mksnap_get_table now returns this rank's range (h->n_unique rows)
-    memcpy(out->root, h->root, 32);
-    return 0;
-}
-
-static int x_check(mksnap *h, mksnap_result *out)
-{
-    if (!h || !out)
-        return MKSNAP_E_INVAL;
-    if (!h->finished)
-        return fail(h, MKSNAP_E_STATE, "exchange before finish");
-    return 0;
-}
-
-int mksnap_exchange_tables(mksnap_t *h, mksnap_result *out)
-{
-    int rc = x_check(h, out);
-    if (rc)
-        return rc;
-    if (!h->comm)
-        return fail(h, MKSNAP_E_STATE, "exchange without comm_init");
-    if (!h->nccl.Send || !h->nccl.Recv || !h->nccl.GroupStart || !h->nccl.GroupEnd)
-        return fail(h, MKSNAP_E_NCCL, "libnccl lacks ncclSend/ncclRecv/ncclGroupStart/ncclGroupEnd");
-    CK(h, cudaSetDevice(h->cfg.device));
-    cudaStream_t s = h->s_comp;
-    XState x;
-    x.R = h->n_ranks;
-    x.rank = h->rank;
-    const int R = x.R, W = GH_WORDS + R;
-    CK(h, cudaEventRecord(h->ev_fin[2], s));
-    if ((rc = x_phase1(h, x, s)))
-        return rc;
-    // header all-gather
-    CK(h, cudaMemcpyAsync(h->d_xhdr + (size_t)x.rank * W, x.hdr.data(), (size_t)W * 8, cudaMemcpyHostToDevice, s));
-    int r = h->nccl.AllGather(h->d_xhdr + (size_t)x.rank * W, h->d_xhdr, (size_t)W, /*ncclUint64*/ 5, h->comm, s);
-    if (r)
-        return fail(h, MKSNAP_E_NCCL, "ncclAllGather(header): %s", h->nccl.GetErrorString(r));
-    x.all_hdr.assign((size_t)R * W, 0);
-    CK(h, cudaMemcpyAsync(x.all_hdr.data(), h->d_xhdr, x.all_hdr.size() * 8, cudaMemcpyDeviceToHost, s));
-    CK(h, cudaStreamSynchronize(s));
-    if ((rc = x_phase2(h, x)))
-        return rc;
-    // all-to-all of the slices: my own slice is a device copy, the others one ncclSend/ncclRecv group
-    {
-        const uint64_t self_rows = x.hdr[GH_WORDS + x.rank];
-        if (self_rows)
-            CK(h, cudaMemcpyAsync(h->d_concat + x.recv_off[x.rank] * 32, h->d_table + x.bounds[x.rank] * 32, self_rows * 32,
-                                  cudaMemcpyDeviceToDevice, s));
-    }
-    if (R > 1) {
-        if ((r = h->nccl.GroupStart()))
-            return fail(h, MKSNAP_E_NCCL, "ncclGroupStart: %s", h->nccl.GetErrorString(r));
-        for (int k = 0; k < R && !r; ++k) {
-            if (k == x.rank)
-                continue;
-            const uint64_t ns = x.hdr[GH_WORDS + k], nr = x.recv_off[k + 1] - x.recv_off[k];
-            if (ns)
-                r = h->nccl.Send(h->d_table + x.bounds[k] * 32, ns * 32, /*ncclUint8*/ 1, k, h->comm, s);
-            if (nr && !r)
-                r = h->nccl.Recv(h->d_concat + x.recv_off[k] * 32, nr * 32, 1, k, h->comm, s);
-        }
-        const int r2 = h->nccl.GroupEnd();
-        if (r || r2)
-            return fail(h, MKSNAP_E_NCCL, "ncclSend/ncclRecv: %s", h->nccl.GetErrorString(r ? r : r2));
-    }
-    if ((rc = x_phase3(h, x, s)))
-        return rc;
-    // records: rows in every range + heads
-    r = h->nccl.AllGather(h->d_xrec + (size_t)x.rank * XREC_BYTES, h->d_xrec, XREC_BYTES, 1, h->comm, s);
-    if (r)
-        return fail(h, MKSNAP_E_NCCL, "ncclAllGather(records): %s", h->nccl.GetErrorString(r));
-    x.all_u.assign(R, 0);
-    CK(h, cudaMemcpy2DAsync(x.all_u.data(), 8, h->d_xrec, XREC_BYTES, 8, R, cudaMemcpyDeviceToHost, s));
-    CK(h, cudaStreamSynchronize(s));
-    if ((rc = x_phase4(h, x, s)))
-        return rc;
-    r = h->nccl.AllGather(h->d_gather + (uint64_t)x.rank * x.pad_l1 * 32, h->d_gather, x.pad_l1 * 32, 1, h->comm, s);
-    if (r)
-        return fail(h, MKSNAP_E_NCCL, "ncclAllGather(level 1): %s", h->nccl.GetErrorString(r));
-    if ((rc = x_phase5(h, x, s, out)))
-        return rc;
-    CK(h, cudaEventRecord(h->ev_fin[3], s));
-    CK(h, cudaStreamSynchronize(s));
-    CK(h, cudaEventElapsedTime(&h->stats.ms_gather, h->ev_fin[2], h->ev_fin[3]));
-    return 0;
-}
-
-// The same exchange between R handles of ONE process (all on the same device): the transport is device copies.
-// Lets one GPU run the exchange logic for any R (tests), and lets a process that drives several engines merge them.
-int mksnap_exchange_tables_local(mksnap_t **hs, int32_t n, mksnap_result *outs)
-{
-    if (!hs || !outs || n < 1)
-        return MKSNAP_E_INVAL;
-    std::vector<XState> xs(n);
-    int rc;
-    for (int i = 0; i < n; ++i) {
-        if ((rc = x_check(hs[i], outs + i)))
-            return rc;
-        if (hs[i]->cfg.device != hs[0]->cfg.device)
-            return fail(hs[i], MKSNAP_E_INVAL, "local exchange needs all handles on one device");
-    }
-    CK(hs[0], cudaSetDevice(hs[0]->cfg.device));
-    const int R = n, W = GH_WORDS + R;
-    for (int i = 0; i < n; ++i) {
-        xs[i].R = R;
-        xs[i].rank = i;
-        if ((rc = x_phase1(hs[i], xs[i], hs[i]->s_comp)))
-            return rc;
-    }
-    for (int i = 0; i < n; ++i) {
-        xs[i].all_hdr.assign((size_t)R * W, 0);
-        for (int k = 0; k < n; ++k)
-            memcpy(&xs[i].all_hdr[(size_t)k * W], xs[k].hdr.data(), (size_t)W * 8);
-        if ((rc = x_phase2(hs[i], xs[i])))
-            return rc;
-    }
-    for (int i = 0; i < n; ++i) // all-to-all: rank i pulls its slice from every rank k
-        for (int k = 0; k < n; ++k) {
-            const uint64_t nr = xs[i].recv_off[k + 1] - xs[i].recv_off[k];
-            if (nr)
-                CK(hs[i], cudaMemcpyAsync(hs[i]->d_concat + xs[i].recv_off[k] * 32, hs[k]->d_table + xs[k].bounds[i] * 32, nr * 32,
-                                          cudaMemcpyDeviceToDevice, hs[i]->s_comp));
-        }
-    for (int i = 0; i < n; ++i)
-        CK(hs[i], cudaStreamSynchronize(hs[i]->s_comp)); // every slice has left d_table before phase 3 overwrites it
-    for (int i = 0; i < n; ++i)
-        if ((rc = x_phase3(hs[i], xs[i], hs[i]->s_comp)))
-            return rc;
-    for (int i = 0; i < n; ++i) {
-        xs[i].all_u.assign(R, 0);
-        for (int k = 0; k < n; ++k) {
-            xs[i].all_u[k] = hs[k]->n_unique;
-            if (k != i)
-                CK(hs[i], cudaMemcpyAsync(hs[i]->d_xrec + (size_t)k * XREC_BYTES, hs[k]->d_xrec + (size_t)k * XREC_BYTES, XREC_BYTES,
-                                          cudaMemcpyDeviceToDevice, hs[i]->s_comp));
-        }
-        if ((rc = x_phase4(hs[i], xs[i], hs[i]->s_comp)))
-            return rc;
-    }
-    for (int i = 0; i < n; ++i)
-        CK(hs[i], cudaStreamSynchronize(hs[i]->s_comp));
-    for (int i = 0; i < n; ++i) {
-        const uint64_t pad = xs[i].pad_l1; // identical on every rank (function of all_u)
-        for (int k = 0; k < n; ++k)
-            if (k != i)
-                CK(hs[i], cudaMemcpyAsync(hs[i]->d_gather + (uint64_t)k * pad * 32, hs[k]->d_gather + (uint64_t)k * pad * 32, pad * 32,
-                                          cudaMemcpyDeviceToDevice, hs[i]->s_comp));
-        if ((rc = x_phase5(hs[i], xs[i], hs[i]->s_comp, outs + i)))
-            return rc;
-    }
-    return 0;
-}
+#include "mksnap_comm.inc"
 
 } // extern "C"
