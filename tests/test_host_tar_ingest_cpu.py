@@ -360,3 +360,42 @@ def test_untar_random_archives_cpp_equals_oracle(tmp_path, seed):
         drop = lambda t: {k: (v[:4] if v[0] == "d" else v) for k, v in t.items()}  # noqa: E731
         a, b = drop(a), drop(b)
     assert a == b
+
+
+REF_LAYER = "/root/reference/testdata/files/alpine/test_layer.tar"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LAYER), reason="the reference checkout is only present in the build container")
+def test_reference_layer_archive_end_to_end(tmp_path):
+    """The reference's own gzipped layer (testutil.SampleLayerTarDigest, lib/utils/testutil/constants.go:28): gunzip ->
+    the Go-written tar (SHA-256 4ac76077...caba).  Reader == tarfile, C++ merge == oracle merge, and an
+    untar by both leaves identical trees whose hard links share inodes (372 of the 390 members are hard links)."""
+    import hashlib
+    raw = open(REF_LAYER, "rb").read()
+    assert hashlib.sha256(raw).hexdigest() == "393ccd5c4dd90344c9d725125e13f636ce0087c62f5ca89050faaacbb9e3ed5b"
+    data = gzip.decompress(raw)
+    assert hashlib.sha256(data).hexdigest().startswith("4ac76077") and len(data) == 1_308_672
+    ms = _check_against_tarfile(data)
+    assert len(ms) == 390
+    root = tmp_path / "merge"
+    root.mkdir()
+    _both(root, [], [data])[1].close()
+    if os.geteuid() != 0:
+        return
+    disks = []
+    for impl in ("oracle", "cpp"):
+        r = tmp_path / impl
+        r.mkdir()
+        os.utime(r, (1_400_000_000, 1_400_000_000))
+        if impl == "oracle":
+            n = len(lt.MemFS(lambda: NOW, str(r)).update_from_tar(data, untar=True))
+        else:
+            fs = host.MemFS(str(r))
+            with _pipe_fd(data) as f:
+                n = len(fs.describe_update_from_tar(NOW, f.fileno(), host.MKHOST_UNTAR))
+            fs.close()
+        assert n == 390
+        disks.append(_disk(r))
+    assert disks[0] == disks[1]
+    busybox = [v for k, v in disks[0].items() if k == "bin/busybox" or k.endswith("/busybox")]
+    assert busybox and busybox[0][5] > 300                          # st_nlink: the applets are hard links to it
