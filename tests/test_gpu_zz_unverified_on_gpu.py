@@ -16,7 +16,10 @@ import stat
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+# non-strict xfail: a first GPU run may still shake something out here without turning the verified suite red; a pass
+# is reported as XPASS (then the marker goes and the test moves next to its verified siblings)
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: first GPU run pending")]
 NOW = 1_600_000_000
 
 
