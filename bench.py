@@ -299,6 +299,41 @@ def cpu_reference_pass(sample_mib: int, file_bytes: int):
                 sha_impl="SHA-NI" if L.mko_have_sha_ni() else "scalar")
 
 
+def cpu_reference_extras(file_bytes: int, threads: int):
+    """Two informational figures SURVEY section 8d asks for next to the CPU baseline (they do NOT enter cpu_baseline.value, which
+    stays the most favourable reading of the reference): SHA-256 without the x86 SHA extensions (Go 1.14's crypto/sha256
+    had none), and a deflate level-6 sink on `threads` threads over 1 MiB blocks standing in for pgzip (the reference
+    joins tar->sha256 and tar->pgzip per 32 KiB write, so its layer pass runs at the slower of the two)."""
+    import oracle.lib as o
+    L = o.L()
+    n = 64 << 20
+    buf = o.synth_fill(0, n, 0xC3)
+    out = (ctypes.c_uint8 * 32)()
+    t0 = time.perf_counter()
+    L.mko_sha256(buf.ctypes.data, n, out)                       # the scalar FIPS 180-4 restatement
+    sha_scalar = n / GiB / (time.perf_counter() - t0)
+    blocks = [bytes(buf[i:i + (1 << 20)]) for i in range(0, n, 1 << 20)] * max(1, threads // 8)
+    idx = iter(range(len(blocks)))
+    lock = threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                i = next(idx, None)
+            if i is None:
+                return
+            zlib.compress(blocks[i], 6)                          # releases the GIL
+    ths = [threading.Thread(target=work) for _ in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    gz = len(blocks) * (1 << 20) / GiB / (time.perf_counter() - t0)
+    return {"sha256_scalar_GiBps": sha_scalar, "deflate6_GiBps": gz, "deflate_threads": threads,
+            "note": "synthetic content is incompressible: deflate runs at its slowest here"}
+
+
 def cpu_same_work_pass(file_bytes: int, threads: int, files_per_thread: int = 192):
     """Best-effort CPU figure: the SAME work as one GPU step -- CRC-32 of every file, Gear CDC, SHA-256
     of every chunk (SHA-NI when present) -- on `threads` host threads over disjoint slices of files
@@ -661,6 +696,10 @@ def main():
                          f"crc32 pass {c['s_crc']:.2f}s (slicing-8) + tar SHA-256 pass {c['s_sha']:.2f}s ({c['sha_impl']}), single thread (the reference "
                          f"path is single-goroutine); gzip and the >=1 s sync() floor excluded",
                "host_cpus": os.cpu_count()}
+        try:
+            cpu["extras"] = cpu_reference_extras(file_bytes, max(1, min(len(os.sched_getaffinity(0)), 64)))
+        except Exception as ex:  # noqa: BLE001
+            cpu["extras"] = {"unavailable": repr(ex)}
         try:  # honesty figure: all host threads doing what the GPU step does (not the reference's algorithm)
             nt = max(1, min(len(os.sched_getaffinity(0)), 64))
             b = cpu_same_work_pass(file_bytes, nt)
