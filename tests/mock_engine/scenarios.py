@@ -1,0 +1,311 @@
+"""Scenarios run against the CPU mock engine (see run.py).  They drive the real libmkhost packers -- layer commit over
+several arenas, tar ingest, per-file digests, untar / materialise from the arena, content-aware scan -- and check the
+results against the oracle, exactly like the -m gpu host tests do on a B200."""
+import ctypes as C
+import hashlib
+import io
+import os
+import stat
+import tarfile
+
+import numpy as np
+
+from makisu_b200 import abi, host
+from oracle import copier as oc
+from oracle import ctx_crc
+from oracle import layer_tar as lt
+from oracle import lib as olib
+
+NOW = 1_600_000_000
+T = 1_500_000_000
+
+
+class MockEngine:
+    def __init__(self, mock, host_arena_bytes, n_host_arenas=2, max_extents=1 << 12):
+        self.mock = mock
+        cfg = abi.Config()
+        cfg.device, cfg.n_host_arenas, cfg.host_arena_bytes = 0, n_host_arenas, host_arena_bytes
+        cfg.device_arena_bytes, cfg.max_extents = host_arena_bytes, max_extents
+        self.h = C.c_void_p()
+        mock.mksnap_create.argtypes = [C.POINTER(abi.Config), C.POINTER(C.c_void_p)]
+        assert mock.mksnap_create(C.byref(cfg), C.byref(self.h)) == 0
+        mock.mock_submits.restype = C.c_uint64
+        mock.mock_submits.argtypes = [C.c_void_p]
+
+    def submits(self):
+        return int(self.mock.mock_submits(self.h))
+
+
+class MockEngineFactory:
+    def __init__(self, mock):
+        self.mock = mock
+
+    def __call__(self, host_arena_bytes, **kw):
+        return MockEngine(self.mock, host_arena_bytes, **kw)
+
+
+def _mk(root, rel, data=b"", mode=0o644, mtime=T):
+    p = os.path.join(root, rel)
+    os.makedirs(os.path.dirname(p), exist_ok=True)
+    with open(p, "wb") as f:
+        f.write(data)
+    os.chmod(p, mode)
+    os.utime(p, (mtime, mtime))
+    return p
+
+
+def _ctx(tmp, seed=42):
+    c = os.path.join(tmp, "ctx")
+    rng = np.random.default_rng(seed)
+    _mk(c, "Dockerfile", b"FROM scratch\nCOPY . /app/\n")
+    for d in range(3):
+        for i in range(6):
+            _mk(c, f"d{d}/f{i:03d}.bin", rng.integers(0, 256, int(rng.integers(0, 300_000)), dtype=np.uint8).tobytes())
+    _mk(c, "big.bin", rng.integers(0, 256, 1_500_000, dtype=np.uint8).tobytes())
+    _mk(c, "empty", b"")
+    _mk(c, "zeros", bytes(200_000))
+    os.symlink("big.bin", os.path.join(c, "link"))
+    for d, _, _ in os.walk(c):
+        os.utime(d, (T, T))
+    return c
+
+
+def _tree(root, mtimes=False):
+    out = {}
+    for d, dirs, files in os.walk(root):
+        for n in sorted(dirs + files):
+            p = os.path.join(d, n)
+            st = os.lstat(p)
+            rel = os.path.relpath(p, root)
+            if stat.S_ISLNK(st.st_mode):
+                out[rel] = ("l", os.readlink(p), st.st_uid, st.st_gid)
+            elif stat.S_ISDIR(st.st_mode):
+                out[rel] = ("d", stat.S_IMODE(st.st_mode), st.st_uid, st.st_gid) + ((st.st_mtime_ns,) if mtimes else ())
+            else:
+                out[rel] = ("f", stat.S_IMODE(st.st_mode), st.st_uid, st.st_gid) + ((st.st_mtime_ns, st.st_nlink) if mtimes else ()) \
+                    + (open(p, "rb").read(),)
+    return out
+
+
+def _layer_expectations(entries):
+    blob = b"".join(lt.layer_tar_chunks(entries))
+    arena = np.frombuffer(blob, dtype=np.uint8)
+    offs, lens, pos = [], [], 0
+    for e in entries:
+        pos += len(lt.entry_header_bytes(e))
+        if not e.whiteout and e.hdr.typeflag == lt.TYPE_REG and e.hdr.size:
+            offs.append(pos)
+            lens.append(e.hdr.size)
+            pos += (e.hdr.size + 511) // 512 * 512
+    return blob, olib.chunk_table(arena, offs, lens)
+
+
+def cache_id_and_commit(make_engine, tmp):
+    """cacheID through the packer (several arenas, files split across them) and a layer commit whose tar stream spans
+    many arenas (stream continuation), with tar emission -- against the oracle."""
+    ctx = _ctx(tmp)
+    seed = ctx_crc.from_step_cache_id(ctx_crc.plan_seed(True, False), "scratch")
+    eng = make_engine(1 << 20)                                    # 1 MiB arenas: big.bin alone needs two
+    for args, paths in [(". /app/", ["."]), ("d1 d2 big.bin /x/", ["d1", "d2", "big.bin"]), ("d*/f00?.bin /y/", ["d*/f00?.bin"])]:
+        assert host.copy_step_cache_id(eng, seed, "COPY", args, ctx, paths) == ctx_crc.copy_step_cache_id(seed, "COPY", args, ctx, paths)
+    assert eng.submits() > 6
+    root = os.path.join(tmp, "root")
+    os.mkdir(root)
+    os.chmod(root, 0o755)
+    fs = lt.MemFS(lambda: NOW, root)
+    entries = fs.add_layer_by_copy_ops([lt.CopyOperation.new(["/"], ctx, "/", "/app/", uid=3, gid=4)])
+    blob, want = _layer_expectations(entries)
+    for arena_bytes in (8 << 20, 2 << 20):                        # one arena / many arenas (big.bin = 1.5 MB fits 2 MiB)
+        eng = make_engine(arena_bytes)
+        tar_path = os.path.join(tmp, "layer%d.tar" % arena_bytes)
+        with open(tar_path, "wb") as f:
+            got = host.commit_copy_ops(eng, root, NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 3, 4)], tar_fd=f.fileno())
+        assert open(tar_path, "rb").read() == blob
+        assert got["tar_digest"] == "sha256:" + hashlib.sha256(blob).hexdigest() == lt.tar_digest(entries)
+        assert (got["n_entries"], got["tar_bytes"]) == (len(entries), len(blob))
+        assert (got["n_chunks"], got["n_unique"], got["root"]) == (want["n_chunks"], want["n_unique"], want["root"])
+    assert eng.submits() >= 3
+    try:                                                          # an entry larger than the arena is refused loudly
+        host.commit_copy_ops(make_engine(1 << 20), root, NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 3, 4)])
+        raise AssertionError("expected a capacity error")
+    except host.HostError as e:
+        assert "exceeds the arena" in str(e)
+
+
+def _base_tar(rng):
+    buf = io.BytesIO()
+    with tarfile.open(fileobj=buf, mode="w", format=tarfile.PAX_FORMAT) as tf:
+        def add(name, type_=tarfile.REGTYPE, data=b"", link="", mode=0o644):
+            ti = tarfile.TarInfo(name)
+            ti.type, ti.mode, ti.mtime, ti.linkname, ti.uid, ti.gid = type_, mode, T, link, 7, 8
+            ti.size = len(data) if type_ == tarfile.REGTYPE else 0
+            tf.addfile(ti, io.BytesIO(data) if ti.size else None)
+        add("usr/", tarfile.DIRTYPE, mode=0o755)
+        add("usr/lib/", tarfile.DIRTYPE, mode=0o2755)
+        shared = rng.integers(0, 256, 300_000, dtype=np.uint8).tobytes()
+        for i in range(8):
+            add(f"usr/lib/lib{i}.so", data=rng.integers(0, 256, int(rng.integers(1, 400_000)), dtype=np.uint8).tobytes(), mode=0o755)
+        add("usr/lib/copy_a.bin", data=shared)
+        add("usr/lib/" + "d" * 150 + "/", tarfile.DIRTYPE, mode=0o755)
+        add("usr/lib/" + "d" * 150 + "/copy_b.bin", data=shared)
+        add("usr/lib/alias.so", tarfile.LNKTYPE, link="usr/lib/lib0.so", mode=0o755)
+        add("lib", tarfile.SYMTYPE, link="usr/lib", mode=0o777)
+        add("etc/", tarfile.DIRTYPE, mode=0o755)
+        add("etc/empty", data=b"")
+        add("etc/.wh.stale", data=b"")
+        add("dev/null", tarfile.CHRTYPE)
+    return buf.getvalue()
+
+
+def ingest_untar_and_file_digests(make_engine, tmp):
+    """mkhost_memfs_update_from_tar: DiffID + chunk table over 1 MiB arenas, record padding after the end marker,
+    a pipe as the source, per-file digests, and MKHOST_UNTAR writing the members from the arena."""
+    rng = np.random.default_rng(5)
+    data = _base_tar(rng)
+    assert len(data) % 10240 == 0
+    tar_path = os.path.join(tmp, "base.tar")
+    open(tar_path, "wb").write(data)
+    members = [m for m in lt.read_tar(data) if m.hdr.typeflag == lt.TYPE_REG and m.data_len]
+    want = olib.chunk_table(np.frombuffer(data, dtype=np.uint8), [m.data_off for m in members], [m.data_len for m in members])
+    # 1. untar=false, FILE_DIGESTS
+    root = os.path.join(tmp, "r1")
+    os.mkdir(root)
+    o = lt.MemFS(lambda: NOW, root)
+    want_layer = o.update_from_tar(data, remember=True)
+    eng = make_engine(1 << 20)
+    h = host.MemFS(root)
+    with open(tar_path, "rb") as f:
+        got = h.update_from_tar(eng, NOW, f.fileno(), flags=host.MKHOST_FILE_DIGESTS)
+    assert eng.submits() >= 3
+    assert got["tar_digest"] == "sha256:" + hashlib.sha256(data).hexdigest() and got["tar_bytes"] == len(data)
+    assert got["n_entries"] == len(want_layer)
+    assert (got["n_chunks"], got["n_unique"], got["root"]) == (want["n_chunks"], want["n_unique"], want["root"])
+    assert got["n_unique"] < got["n_chunks"]
+    for m in members:
+        dst = lt.abs_path(m.hdr.name)
+        assert h.file_digest(dst) == hashlib.sha256(data[m.data_off:m.data_off + m.data_len]).digest(), dst
+    assert h.file_digest("/etc/empty") is None and h.file_digest("/usr") is None
+    # 2. through a pipe, digest left to the caller
+    r, w = os.pipe()
+    import threading
+    t = threading.Thread(target=lambda: (os.write(w, data), os.close(w)))
+    t.start()
+    piped = host.MemFS(root).update_from_tar(make_engine(1 << 20), NOW, r, flags=host.MKHOST_NO_TAR_DIGEST)
+    t.join()
+    os.close(r)
+    assert piped["root"] == got["root"] and piped["tar_digest"] == "sha256:" + "00" * 32
+    # 3. untar=true from the arena == the oracle's untar
+    disks, counts = [], []
+    for impl in ("oracle", "engine"):
+        rr = os.path.join(tmp, "untar_" + impl)
+        os.makedirs(os.path.join(rr, "etc"))
+        open(os.path.join(rr, "etc", "stale"), "wb").write(b"to be whited out")
+        os.chmod(os.path.join(rr, "etc"), 0o700)
+        for d in (os.path.join(rr, "etc"), rr):
+            os.utime(d, (1_400_000_000, 1_400_000_000))
+        if impl == "oracle":
+            counts.append(len(lt.MemFS(lambda: NOW, rr).update_from_tar(data, untar=True)))
+        else:
+            with open(tar_path, "rb") as f:
+                g = host.MemFS(rr).update_from_tar(make_engine(1 << 20), NOW, f.fileno(), flags=host.MKHOST_UNTAR)
+            assert g["tar_digest"] == got["tar_digest"] and g["root"] == got["root"]
+            counts.append(g["n_entries"])
+        disks.append(_tree(rr, mtimes=True))
+    assert counts[0] == counts[1] and disks[0] == disks[1]
+    assert "etc/stale" not in disks[1] and disks[1]["usr/lib/alias.so"][5] == 2
+    # 4. a truncated blob is refused
+    open(tar_path, "wb").write(data[:5000])
+    try:
+        with open(tar_path, "rb") as f:
+            host.MemFS(root).update_from_tar(make_engine(1 << 20), NOW, f.fileno())
+        raise AssertionError("expected unexpected EOF")
+    except host.HostError as e:
+        assert "unexpected EOF" in str(e)
+
+
+def content_aware_scan(make_engine, tmp):
+    """MKHOST_FILE_DIGESTS at commit, then MKHOST_SCAN_CONTENT: same-second same-size edits are caught; the digest pass
+    streams a file larger than an arena across submits."""
+    rng = np.random.default_rng(11)
+    root = os.path.join(tmp, "root")
+    _mk(root, "d/a.txt", b"A" * 5000)
+    _mk(root, "d/b.bin", rng.integers(0, 256, 300_000, dtype=np.uint8).tobytes())
+    _mk(root, "d/big.bin", rng.integers(0, 256, 2_500_000, dtype=np.uint8).tobytes())
+    _mk(root, "e/c.txt", b"c")
+    _mk(root, "e/empty", b"")
+    for d, _, _ in os.walk(root):
+        os.utime(d, (T, T))
+    o = lt.MemFS(lambda: NOW, root)
+    h = host.MemFS(root)
+    eng = make_engine(4 << 20)
+    l1 = o.add_layer_by_scan()
+    o.remember_content(l1)
+    g1 = h.commit_scan(eng, NOW, flags=host.MKHOST_FILE_DIGESTS)
+    assert g1["tar_digest"] == lt.tar_digest(l1) and g1["n_entries"] == len(l1) == 7
+
+    def edit(rel, off):
+        p = os.path.join(root, rel)
+        st = os.lstat(p)
+        with open(p, "r+b") as f:
+            f.seek(off)
+            b = f.read(1)
+            f.seek(off)
+            f.write(bytes([b[0] ^ 0x5A]))
+        os.utime(p, ns=(st.st_atime_ns, st.st_mtime_ns))
+    edit("d/b.bin", 123_456)
+    edit("d/big.bin", 2_499_999)
+    assert o.add_layer_by_scan() == [] and h.commit_scan(eng, NOW)["n_entries"] == 0       # the reference misses it
+    l3 = o.add_layer_by_scan(content_aware=True)
+    o.remember_content(l3)
+    assert [e.dst for e in l3] == ["/d", "/d/b.bin", "/d/big.bin"]
+    g3 = h.commit_scan(eng, NOW, flags=host.MKHOST_SCAN_CONTENT)
+    assert g3["n_entries"] == 3 and g3["tar_digest"] == lt.tar_digest(l3)
+    small = make_engine(1 << 20)                                  # big.bin (2.5 MB) streams through 1 MiB arenas
+    assert o.add_layer_by_scan(content_aware=True) == []
+    assert h.commit_scan(small, NOW, flags=host.MKHOST_SCAN_CONTENT)["n_entries"] == 0
+    assert small.submits() >= 4
+    edit("d/big.bin", 0)
+    assert [e.dst for e in o.add_layer_by_scan(content_aware=True)] == ["/d", "/d/big.bin"]
+    try:
+        h.commit_scan(small, NOW, flags=host.MKHOST_SCAN_CONTENT)
+        raise AssertionError("expected a capacity error")
+    except host.HostError as e:
+        assert "exceeds the arena" in str(e)
+
+
+def materialize_from_the_arena(make_engine, tmp):
+    """MKHOST_MATERIALIZE: the COPY step's file copy fed from the arena of the layer commit == CopyOperation.Execute by
+    the oracle's Copier; the layer itself is unchanged."""
+    rng = np.random.default_rng(3)
+    ctx = os.path.join(tmp, "ctx")
+    os.makedirs(os.path.join(ctx, "app", "sub"))
+    for rel, n, mode in [("app/a.bin", 700_000, 0o644), ("app/sub/b.bin", 1_200_000, 0o755), ("app/empty", 0, 0o600), ("conf.txt", 900, 0o640)]:
+        p = os.path.join(ctx, rel)
+        open(p, "wb").write(rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+        os.chmod(p, mode)
+        os.utime(p, (T, T))
+    os.symlink("a.bin", os.path.join(ctx, "app", "link"))
+    for d, _, _ in os.walk(ctx):
+        os.utime(d, (T, T))
+    roots = {k: os.path.join(tmp, k) for k in ("fused", "plain", "oracle")}
+    for r in roots.values():
+        os.mkdir(r)
+        os.chmod(r, 0o755)
+    ops = [host.CopyOperation(["/app"], ctx, "/", "/srv/app/", 5, 6), host.CopyOperation(["/conf.txt"], ctx, "/", "/etc/conf.txt", 7, 8)]
+    eng = make_engine(2 << 20)                                    # the layer spans two arenas
+    fused = host.MemFS(roots["fused"]).commit_copy_ops(eng, NOW, ops, flags=host.MKHOST_MATERIALIZE | host.MKHOST_MATERIALIZE_CHOWN)
+    plain = host.MemFS(roots["plain"]).commit_copy_ops(make_engine(2 << 20), NOW, ops)
+    assert fused == plain and _tree(roots["plain"]) == {}
+    oc.execute_copy_op(ctx, ["/app"], roots["oracle"] + "/srv/app/", 5, 6, True, False, False, [])
+    oc.execute_copy_op(ctx, ["/conf.txt"], roots["oracle"] + "/etc/conf.txt", 7, 8, True, False, False, [])
+    got, want = _tree(roots["fused"]), _tree(roots["oracle"])
+    assert got == want
+    assert got["srv/app/sub/b.bin"][1:4] == (0o755, 5, 6) and got["etc/conf.txt"][1:4] == (0o640, 7, 8)
+    assert got["srv/app/link"][:2] == ("l", "a.bin") and got["srv/app"] == ("d", 0o755, 5, 6)
+    fs = lt.MemFS(lambda: NOW, roots["oracle"])
+    entries = fs.add_layer_by_copy_ops([lt.CopyOperation.new(["/app"], ctx, "/", "/srv/app/", uid=5, gid=6),
+                                        lt.CopyOperation.new(["/conf.txt"], ctx, "/", "/etc/conf.txt", uid=7, gid=8)])
+    assert fused["tar_digest"] == lt.tar_digest(entries)
+    # a second commit of the same ops: nothing new for the layer except re-added ancestors, files copied from disk
+    again = host.MemFS(roots["fused"]).commit_copy_ops(make_engine(2 << 20), NOW, ops, flags=host.MKHOST_MATERIALIZE | host.MKHOST_MATERIALIZE_CHOWN)
+    assert again["n_entries"] == fused["n_entries"] and _tree(roots["fused"]) == want

@@ -1,5 +1,6 @@
-"""-m gpu.  Written after this round's GPU budget was spent: these checks have run on the CPU side only (the code
-they exercise compiles and its host logic is covered by the CPU suite).  The file sorts last so that the verified GPU
+"""-m gpu.  Written after this round's GPU budget was spent: these checks have run on the CPU side only (the host code
+they exercise is verified against the CPU mock engine, tests/test_host_mock_engine_cpu.py, which replays the same
+scenarios with the oracle's arithmetic behind the mksnap_* entry points).  The file sorts last so that the verified GPU
 tests run first.
 
   * the range-partitioned exchange over a 1-rank NCCL communicator (header / record / level-1 all-gathers of one
