@@ -12,4 +12,4 @@ g++ -O1 -g -std=c++17 -fPIC -shared -pthread -fsanitize=address,undefined -fno-o
 export LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)"
 export ASAN_OPTIONS=detect_leaks=0
 python -m pytest tests/test_host_cpu.py tests/test_host_tar_ingest_cpu.py tests/test_host_copier_cpu.py \
-    tests/test_host_fuzz_cpu.py -q 2>&1 | grep -E "runtime error|AddressSanitizer|SUMMARY|passed|failed"
+    tests/test_host_fuzz_cpu.py tests/test_host_mock_engine_cpu.py -q 2>&1 | grep -E "runtime error|AddressSanitizer|SUMMARY|passed|failed"

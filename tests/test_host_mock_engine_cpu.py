@@ -30,3 +30,4 @@ def test_host_packers_against_the_mock_engine(mock_so, tmp_path, scenario):
     r = subprocess.run([sys.executable, "-m", "tests.mock_engine.run", mock_so, scenario, str(tmp_path)], cwd=ROOT,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "SCENARIO-OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
+    assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr, r.stderr[-6000:]  # tests/run_host_sanitized.sh
