@@ -309,3 +309,41 @@ def materialize_from_the_arena(make_engine, tmp):
     # a second commit of the same ops: nothing new for the layer except re-added ancestors, files copied from disk
     again = host.MemFS(roots["fused"]).commit_copy_ops(make_engine(2 << 20), NOW, ops, flags=host.MKHOST_MATERIALIZE | host.MKHOST_MATERIALIZE_CHOWN)
     assert again["n_entries"] == fused["n_entries"] and _tree(roots["fused"]) == want
+
+
+def random_trees_small_arenas(make_engine, tmp):
+    """Arena-boundary arithmetic: random build contexts committed and fingerprinted through arenas of 8 KiB .. 1 MiB
+    (every flush condition is hit: entry does not fit the remainder, trailer does not fit, file split across arenas for
+    the CRC stream at 16-byte granularity) -- tar bytes, TarDigest, chunk table root and cacheID against the oracle."""
+    from tests.test_host_fuzz_cpu import _random_tree
+    seedid = ctx_crc.from_step_cache_id(ctx_crc.plan_seed(True, False), "scratch")
+    for seed in range(10):
+        rng = np.random.default_rng(77 + seed)
+        ctx = os.path.join(tmp, "ctx%d" % seed)
+        os.mkdir(ctx)
+        _random_tree(ctx, rng)
+        with open(os.path.join(ctx, "blob"), "wb") as f:          # one file that spans several small arenas in the CRC stream
+            f.write(bytes(rng.integers(0, 256, 40_000 + seed, dtype=np.uint8)))
+        for d, dirs, files in os.walk(ctx):
+            for n in dirs + files:
+                os.utime(os.path.join(d, n), (T, T), follow_symlinks=False)
+        os.utime(ctx, (T, T))
+        root = os.path.join(tmp, "root%d" % seed)
+        os.mkdir(root)
+        os.chmod(root, 0o755)
+        try:
+            entries = lt.MemFS(lambda: NOW, root).add_layer_by_copy_ops([lt.CopyOperation.new(["/"], ctx, "/", "/app/", uid=1, gid=2)])
+            want_id = ctx_crc.copy_step_cache_id(seedid, "COPY", ". /app/", ctx, ["."])
+        except (OSError, ValueError):
+            continue                                              # e.g. an absolute symlink out of the tree: both sides refuse (test_host_fuzz_cpu)
+        blob, want = _layer_expectations(entries)
+        for arena in (8 << 10, 12 << 10, 64 << 10, 1 << 20):
+            assert host.copy_step_cache_id(make_engine(arena), seedid, "COPY", ". /app/", ctx, ["."]) == want_id, (seed, arena)
+            if arena < 48 << 10:
+                continue                                          # the 40 kB blob must fit one arena for the layer
+            tar_path = os.path.join(tmp, "t%d_%d.tar" % (seed, arena))
+            with open(tar_path, "wb") as f:
+                got = host.commit_copy_ops(make_engine(arena), root, NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 1, 2)],
+                                           tar_fd=f.fileno())
+            assert open(tar_path, "rb").read() == blob, (seed, arena)
+            assert got["tar_digest"] == lt.tar_digest(entries) and got["root"] == want["root"] and got["n_chunks"] == want["n_chunks"]
