@@ -154,6 +154,11 @@ size_t mkhost_memfs_describe_update_from_tar_ex(mkhost_memfs *m, int64_t now_uni
 #define MKHOST_COPY_DEFERRED 8u
 int mkhost_copy_op_execute(const mkhost_copy_op *op, uint32_t mode, const char *const *blacklist, size_t n_blacklist,
                            char *err, size_t errlen);
+/* evalSymlinks(p, srcRoot) (lib/snapshot/utils.go:249-324): the root-relative path after following every symlink on
+ * it, links confined to src_root (absolute targets must carry the root prefix, which is trimmed), at most 255 links.
+ * Both CopyOperation.Execute (copy_op.go:86) and MemFS.addToLayer (mem_fs.go:380) resolve each source through it.
+ * Returns the number of bytes needed including NUL (nothing written if > cap), 0 on error. */
+size_t mkhost_eval_symlinks(const char *path, const char *src_root, char *out, size_t cap, char *err, size_t errlen);
 /* flag for mkhost_memfs_commit_copy_ops: also perform the copy (as mkhost_copy_op_execute with `copy_mode` 0 / CHOWN
  * decided by MKHOST_MATERIALIZE_CHOWN), writing regular files from the arena the layer is packed in: the context is
  * read once for the copy, the layer, its digest and its chunk table. */

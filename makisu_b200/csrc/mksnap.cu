@@ -854,10 +854,12 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     }
     CK(h, cudaEventRecord(h->ev[4], sk));
     if (n_rng) {
+        // K4: warp pairs, 32 streams each, spread one pair per SM first (a pair then owns its two sub-partitions)
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, sk));
-        k_sha256_ranges<false><<<(uint32_t)std::min<uint64_t>(sha_grid(h), (n_rng + 3) / 4), SHA_THREADS, 0, sk>>>(
-            d_arena, m.d_rstart, m.d_rlen, nullptr, n_rng, nullptr, 0, 0, 0, h->d_stream_digests, &h->d_sc->work, nullptr,
-            1u, m.d_rstream, m.d_rflags, h->d_stream_state, nullptr);
+        const uint32_t pairs = (uint32_t)((n_rng + 31) / 32);
+        k_sha256_streams<<<std::min<uint32_t>(pairs, (uint32_t)h->sm_count * 2), SS_THREADS, 0, sk>>>(
+            d_arena, m.d_rstart, m.d_rlen, (uint32_t)n_rng, m.d_rstream, m.d_rflags, h->d_stream_state, h->d_stream_digests,
+            &h->d_sc->work, 32u);
         LAUNCH_OK(h);
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, sk));
     }

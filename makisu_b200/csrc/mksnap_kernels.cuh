@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "mksnap_sha_stream.cuh" // K4: serial-stream SHA-256 (warp pairs)
+
 namespace mk {
 
 // ------------------------------------------------------------------------
@@ -1112,13 +1114,7 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16], 
 
 constexpr int SHA_THREADS = 128;
 
-// midstate of a serial stream that continues in a later submit
-struct StreamState {
-    uint32_t st[8];
-    unsigned long long bytes; // bytes compressed so far (multiple of 64)
-    uint32_t open;            // 1 = a piece with MKSNAP_R_MORE was seen and the stream is not finished
-    uint32_t pad;
-};
+// StreamState (midstate of a serial stream that continues in a later submit): mksnap_sha_stream.cuh
 
 // mode 0: ranges from (start[], len[]) arrays, count read from *n_dev (or n_host if n_dev==nullptr)
 // mode 1: uniform ranges of `uni_len` bytes over [0, uni_total) of `data` (Merkle levels)

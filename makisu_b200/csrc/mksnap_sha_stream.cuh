@@ -1,0 +1,287 @@
+// mksnap_sha_stream.cuh -- K4: SHA-256 of SERIAL streams (TarDigest, per-file digests), sm_100a.
+//
+// Replaces the tarDigester sink of lib/builder/step/common.go:44-55 (`sha256.New()` behind the tar.Writer):
+// one stream = one Merkle-Damgard chain, so a stream cannot be split; what bounds it on a GPU is the time ONE
+// warp needs per 64-byte block.  On B200 the rotate/logic ops (SHF, LOP3) issue on the half-rate ALU pipe: a
+// warp instruction occupies it for 2 cycles whatever the number of active lanes.  A block costs
+//   rounds   64 x (6 SHF + 4 LOP3)        = 640 ALU-pipe ops = 1280 cycles
+//   schedule 48 x (6 SHF/SHR + 2 LOP3)    = 384 ALU-pipe ops =  768 cycles  (+ byte swaps, loads, K adds)
+// With both in one warp (the round-1 kernel, lane per stream) a stream gets one block per >2000 cycles, and that
+// kernel also waited for its un-prefetched global loads: 34.5 MB/s measured.
+//
+// Here a CTA is a PAIR of warps on two different SM sub-partitions (each with its own ALU pipe):
+//   warp 1 ("schedule")  owns the pieces: fetches work, prefetches the next block of every lane one iteration
+//                        ahead (ld.global.nc, 4 x 16 B per lane), byte-swaps, builds the padding blocks,
+//                        expands W[0..63] and stores W[t]+K[t] to shared memory ([t][lane]: conflict-free);
+//   warp 0 ("rounds")    runs nothing but the 64-round chain: per round one LDS (prefetched by the unrolled
+//                        code), 6 SHF + 4 LOP3 + the additions; the state never leaves its registers.
+// Lane l of both warps works on the same stream, 32 streams per pair, double-buffered hand-over through two
+// named barriers per buffer (bar.sync / bar.arrive, 64 threads).  The rounds warp is the bound:
+// 1280 cycles per block = 98 MB/s per stream at 1965 MHz, 3.1 GB/s per pair, independent of how many of the 32
+// lanes carry a stream; pairs are spread one per SM first so a pair owns its sub-partitions.
+// Lanes pull the next piece from a global counter when theirs ends (ragged per-file streams).
+//
+// Bit-exactness: FIPS 180-4; checked against hashlib and the oracle in tests/test_gpu_parity.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mk {
+
+// midstate of a serial stream that continues in a later submit
+struct StreamState {
+    uint32_t st[8];
+    unsigned long long bytes; // bytes compressed so far (multiple of 64)
+    uint32_t open;            // 1 = a piece with MKSNAP_R_MORE was seen and the stream is not finished
+    uint32_t pad;
+};
+
+constexpr int SS_THREADS = 64;
+constexpr uint32_t SS_ACTIVE = 1u, SS_START_IV = 2u, SS_START_RESUME = 4u, SS_FINAL = 8u, SS_PARK = 16u, SS_EXIT = 32u;
+
+struct SsShared {
+    uint32_t kw[2][64][32]; // W[t] + K[t] of the block in flight, [buffer][t][lane]
+    uint32_t ctrl[2][32];
+    uint32_t sid[2][32];
+};
+
+__device__ __forceinline__ void ss_bar_sync(uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void ss_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ uint32_t ss_rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+__device__ __forceinline__ uint4 ss_ldg(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __constant__ uint32_t SS_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+// One piece per (start[i], len[i], stream[i], flags[i]); start multiple of 16.  Digest of a finished stream goes to
+// row stream[i] of `out`; a piece with flag bit 0 (MKSNAP_R_MORE, len multiple of 64) parks the midstate in
+// sstate[stream[i]] instead.  max_lanes: lanes of a pair that take pieces (32 normally; a tuning knob).
+__global__ void __launch_bounds__(SS_THREADS)
+k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ start, const uint64_t *__restrict__ len,
+                 uint32_t n, const uint32_t *__restrict__ rng_stream, const uint32_t *__restrict__ rng_flags,
+                 StreamState *__restrict__ sstate, uint8_t *__restrict__ out, uint32_t *__restrict__ work_counter,
+                 uint32_t max_lanes)
+{
+    __shared__ SsShared sh;
+    const uint32_t lane = threadIdx.x & 31;
+    // named barriers: 1+b = "buffer b is full", 3+b = "buffer b is empty"
+    if (threadIdx.x < 32) {
+        // ------------------------------ rounds warp ------------------------------
+        uint32_t st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t b = it & 1u;
+            ss_bar_sync(1 + b);
+            const uint32_t c = sh.ctrl[b][lane];
+            if (c & SS_EXIT)
+                break; // warp-uniform
+            const uint32_t sid = sh.sid[b][lane];
+            if (c & SS_START_IV) {
+                st[0] = 0x6a09e667; st[1] = 0xbb67ae85; st[2] = 0x3c6ef372; st[3] = 0xa54ff53a;
+                st[4] = 0x510e527f; st[5] = 0x9b05688c; st[6] = 0x1f83d9ab; st[7] = 0x5be0cd19;
+            }
+            if (c & SS_START_RESUME) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    st[k] = sstate[sid].st[k];
+            }
+            uint32_t a = st[0], bb = st[1], cc = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+            const uint32_t *kw = &sh.kw[b][0][lane];
+#pragma unroll
+            for (int t = 0; t < 64; ++t) {
+                const uint32_t x = h + kw[t * 32]; // off the critical path: h and kw are old
+                const uint32_t y = x + d;
+                const uint32_t S1 = ss_rotr(e, 6) ^ ss_rotr(e, 11) ^ ss_rotr(e, 25);
+                const uint32_t ch = (e & f) ^ (~e & g);
+                const uint32_t S0 = ss_rotr(a, 2) ^ ss_rotr(a, 13) ^ ss_rotr(a, 22);
+                const uint32_t mj = (a & bb) ^ (a & cc) ^ (bb & cc);
+                const uint32_t z = S0 + mj + x; // also off the e-chain
+                // e-chain per round: SHF -> LOP3 (S1) -> one add; ch + y is ready when S1 is
+                const uint32_t chy = ch + y, chz = ch + z;
+                h = g; g = f; f = e;
+                e = S1 + chy;
+                d = cc; cc = bb; bb = a;
+                a = S1 + chz;
+            }
+            if (c & SS_ACTIVE) {
+                st[0] += a; st[1] += bb; st[2] += cc; st[3] += d;
+                st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+            }
+            if (c & SS_FINAL) {
+                uint4 o0, o1;
+                o0.x = __byte_perm(st[0], 0, 0x0123); o0.y = __byte_perm(st[1], 0, 0x0123);
+                o0.z = __byte_perm(st[2], 0, 0x0123); o0.w = __byte_perm(st[3], 0, 0x0123);
+                o1.x = __byte_perm(st[4], 0, 0x0123); o1.y = __byte_perm(st[5], 0, 0x0123);
+                o1.z = __byte_perm(st[6], 0, 0x0123); o1.w = __byte_perm(st[7], 0, 0x0123);
+                uint4 *dst = reinterpret_cast<uint4 *>(out + (uint64_t)sid * 32);
+                dst[0] = o0;
+                dst[1] = o1;
+            }
+            if (c & SS_PARK) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    sstate[sid].st[k] = st[k];
+            }
+            ss_bar_arrive(3 + b);
+        }
+        return;
+    }
+
+    // ------------------------------ schedule warp ------------------------------
+    const uint8_t *p = nullptr; // next block to take
+    uint64_t total = 0, done = 0, prior = 0;
+    uint32_t sid = 0;
+    bool more = false, first = false;
+    uint32_t phase = 0; // 0 idle, 1 data blocks, 2 needs the extra length block
+    bool exhausted = lane >= max_lanes;
+    uint4 pre[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t b = it & 1u;
+        // ---- refill idle lanes (warp-aggregated fetch) ----
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, phase == 0 && !exhausted);
+        if (need) {
+            uint32_t basei = 0;
+            const uint32_t leader = __ffs(need) - 1;
+            if (lane == leader)
+                basei = atomicAdd(work_counter, __popc(need));
+            basei = __shfl_sync(0xFFFFFFFFu, basei, leader);
+            if (phase == 0 && !exhausted) {
+                const uint32_t idx = basei + __popc(need & ((1u << lane) - 1u));
+                if (idx < n) {
+                    p = data + start[idx];
+                    total = len[idx];
+                    sid = rng_stream[idx];
+                    more = (rng_flags[idx] & 1u) != 0;
+                    done = 0;
+                    prior = 0;
+                    first = true;
+                    phase = 1;
+                    if (sstate[sid].open)
+                        prior = sstate[sid].bytes | (1ull << 63); // bit 63: resume the parked midstate
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if ((uint64_t)(16 * k) < total)
+                            pre[k] = ss_ldg(reinterpret_cast<const uint4 *>(p) + k);
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        const bool any = __any_sync(0xFFFFFFFFu, phase != 0);
+        if (it >= 2)
+            ss_bar_sync(3 + b); // the rounds warp is done with buffer b
+        if (!any) {
+            sh.ctrl[b][lane] = SS_EXIT;
+            ss_bar_arrive(1 + b);
+            break;
+        }
+
+        // ---- this lane's block -> w[0..15] ----
+        uint32_t w[16];
+        uint32_t ctrl = 0;
+        const bool resume = (prior >> 63) != 0;
+        const uint64_t prior_b = prior & ~(1ull << 63);
+        if (phase != 0) {
+            ctrl = SS_ACTIVE;
+            if (first)
+                ctrl |= resume ? SS_START_RESUME : SS_START_IV;
+            first = false;
+        }
+        const uint64_t rem = total - done;
+        if (phase == 1) {
+            w[0] = pre[0].x; w[1] = pre[0].y; w[2] = pre[0].z; w[3] = pre[0].w;
+            w[4] = pre[1].x; w[5] = pre[1].y; w[6] = pre[1].z; w[7] = pre[1].w;
+            w[8] = pre[2].x; w[9] = pre[2].y; w[10] = pre[2].z; w[11] = pre[2].w;
+            w[12] = pre[3].x; w[13] = pre[3].y; w[14] = pre[3].z; w[15] = pre[3].w;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                w[i] = __byte_perm(w[i], 0, 0x0123);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                w[i] = 0;
+        }
+        const bool tail = (phase == 1 && rem < 64) || phase == 2;
+        if (__any_sync(0xFFFFFFFFu, tail)) { // rare: some lane is at the end of its stream
+            if (phase == 1 && rem < 64) {
+                // final data block: keep `rem` bytes, append 0x80, zero the rest
+                const uint32_t rb = (uint32_t)rem;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int32_t k = (int32_t)rb - 4 * i; // valid bytes in this word
+                    const uint32_t keep = k >= 4 ? 0xFFFFFFFFu : (k <= 0 ? 0u : ~(0xFFFFFFFFu >> (8 * k)));
+                    uint32_t v = w[i] & keep;
+                    if (k >= 0 && k < 4)
+                        v |= 0x80000000u >> (8 * k);
+                    w[i] = v;
+                }
+                if (rb < 56) {
+                    w[14] = (uint32_t)(((prior_b + total) * 8) >> 32);
+                    w[15] = (uint32_t)((prior_b + total) * 8);
+                    ctrl |= SS_FINAL;
+                    phase = 0;
+                } else {
+                    phase = 2;
+                }
+            } else if (phase == 2) {
+                w[14] = (uint32_t)(((prior_b + total) * 8) >> 32);
+                w[15] = (uint32_t)((prior_b + total) * 8);
+                ctrl |= SS_FINAL;
+                phase = 0;
+            }
+            if (ctrl & SS_FINAL)
+                sstate[sid].open = 0;
+        }
+        if (phase == 1) { // a full data block was taken (rem >= 64)
+            p += 64;
+            done += 64;
+            if (done == total && more) { // piece boundary of a stream that continues: park the midstate
+                ctrl |= SS_PARK;
+                sstate[sid].bytes = prior_b + total;
+                sstate[sid].open = 1;
+                phase = 0;
+            } else {
+                // prefetch the next block while this one is expanded (the only global-memory latency on the path)
+                const uint64_t left = total - done;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((uint64_t)(16 * k) < left)
+                        pre[k] = ss_ldg(reinterpret_cast<const uint4 *>(p) + k);
+            }
+        }
+        sh.ctrl[b][lane] = ctrl;
+        sh.sid[b][lane] = sid;
+
+        // ---- message schedule: W[t] + K[t] for the 64 rounds ----
+        uint32_t *kw = &sh.kw[b][0][lane];
+#pragma unroll
+        for (int t = 0; t < 64; ++t) {
+            uint32_t wt;
+            if (t < 16) {
+                wt = w[t];
+            } else {
+                const uint32_t w15 = w[(t + 1) & 15], w2 = w[(t + 14) & 15];
+                const uint32_t s0 = ss_rotr(w15, 7) ^ ss_rotr(w15, 18) ^ (w15 >> 3);
+                const uint32_t s1 = ss_rotr(w2, 17) ^ ss_rotr(w2, 19) ^ (w2 >> 10);
+                wt = w[t & 15] + s0 + w[(t + 9) & 15] + s1;
+                w[t & 15] = wt;
+            }
+            kw[t * 32] = wt + SS_K[t];
+        }
+        ss_bar_arrive(1 + b);
+    }
+}
+
+} // namespace mk

@@ -59,6 +59,7 @@ SYMBOLS = [
     ("mkhost_memfs_describe_update_from_tar", C.c_size_t, [_P, C.c_int64, C.c_int, C.c_char_p, C.c_size_t, C.c_char_p,
                                                            C.c_size_t]),
     ("mkhost_copy_op_execute", C.c_int, [C.POINTER(CopyOp), C.c_uint32, C.POINTER(C.c_char_p), C.c_size_t, C.c_char_p, C.c_size_t]),
+    ("mkhost_eval_symlinks", C.c_size_t, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
     ("mkhost_cache_key", C.c_size_t, [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]),
     ("mkhost_cache_entry_create", C.c_size_t, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     ("mkhost_cache_entry_parse", C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]),
@@ -311,3 +312,12 @@ def copy_op_execute(op: "CopyOperation", mode: int = 0, blacklist: Sequence[str]
     bl = _strs(list(blacklist))
     if load().mkhost_copy_op_execute(arr, mode, bl, len(blacklist), err, len(err)):
         raise HostError(err.value.decode())
+
+
+def eval_symlinks(path: str, src_root: str) -> str:
+    """evalSymlinks(p, srcRoot) (lib/snapshot/utils.go:249-324)."""
+    err, buf = C.create_string_buffer(1024), C.create_string_buffer(8192)
+    n = load().mkhost_eval_symlinks(os.fsencode(path), os.fsencode(src_root), buf, len(buf), err, len(err))
+    if n == 0 or n > len(buf):
+        raise HostError(err.value.decode() or "path too long")
+    return os.fsdecode(buf.value)

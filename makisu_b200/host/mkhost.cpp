@@ -156,6 +156,16 @@ size_t mkhost_memfs_describe_scan(mkhost_memfs *m, int64_t now_unix, char *out, 
     }
 }
 
+size_t mkhost_eval_symlinks(const char *path, const char *src_root, char *out, size_t cap, char *err, size_t errlen)
+{
+    try {
+        return emit_text(eval_symlinks(path ? path : "", src_root ? src_root : ""), out, cap);
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("eval symlinks for ") + (path ? path : "") + ": " + e.what());
+        return 0;
+    }
+}
+
 int mkhost_copy_op_execute(const mkhost_copy_op *op, uint32_t mode, const char *const *blacklist, size_t n_blacklist,
                            char *err, size_t errlen)
 {

@@ -150,7 +150,7 @@ class Copier:
 def _walk_link(path: str, root: str, walked: List[int]):
     if walked[0] > 255:
         raise OSError("eval symlinks: too many links")
-    full = go_clean(posixpath.join(root, path))
+    full = go_clean(root + "/" + path)  # filepath.Join(root, path): an absolute `path` stays UNDER root
     st = os.lstat(full)
     if not stat.S_ISLNK(st.st_mode):
         return path, False
@@ -177,12 +177,12 @@ def _walk_links(path: str, root: str, walked: List[int]) -> str:
             return d
         return _walk_links(d[:-1], root, walked)
     newdir = _walk_links(d, root, walked)
-    newpath, islink = _walk_link(go_clean(posixpath.join(newdir, f)) if newdir else f, root, walked)
+    newpath, islink = _walk_link(go_clean(newdir + "/" + f) if newdir else f, root, walked)
     if not islink:
         return newpath
     if newpath.startswith("/"):
         return newpath
-    return go_clean(posixpath.join(newdir, newpath))
+    return go_clean(newdir + "/" + newpath) if newdir else go_clean(newpath)
 
 
 def eval_symlinks(p: str, src_root: str) -> str:

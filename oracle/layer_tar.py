@@ -703,6 +703,10 @@ class MemFS:
     def _add_ancestors(self, layer, dst: str, inclusive: bool, depth: int, uid: int, gid: int) -> str:
         if depth >= 1024:
             raise ValueError(f"symlink loop at {dst}")
+        if depth == 0:  # the reference recurses 1024 deep before it gives up; CPython's default limit is 1000 frames
+            import sys
+            if sys.getrecursionlimit() < 4000:
+                sys.setrecursionlimit(4000)
         last_ancestor = self.tree
         cur = self.tree
         parts = split_path(dst)
@@ -762,9 +766,10 @@ class MemFS:
                 resolved += "/"
             c.dst = resolved
         for s in c.srcs:
-            # evalSymlinks: synthetic/test contexts carry no symlinked *sources*; identity + AbsPath
-            s = abs_path(s) if s else ""
-            src = posixpath.normpath(c.src_root + "/" + s) if s else c.src_root
+            # mem_fs.go:380-384: src, err = evalSymlinks(src, c.srcRoot); src = filepath.Join(c.srcRoot, src)
+            from .copier import eval_symlinks  # local import: copier.py imports this module
+            s = eval_symlinks(s, c.src_root)
+            src = go_clean(c.src_root + "/" + s) if s else c.src_root
 
             def visit(cur_src: str, st: os.stat_result, src=src):
                 if cur_src == src:

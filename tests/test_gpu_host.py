@@ -351,3 +351,35 @@ def test_content_aware_scan_catches_same_second_same_size_edits(tmp_path):
         g = h2.commit_scan(eng, NOW, flags=host.MKHOST_SCAN_CONTENT)
         assert g["n_entries"] == 2 and g["tar_digest"] == lt.tar_digest(l)
     h2.close()
+
+
+def test_commit_copy_of_symlinked_sources(eng, tmp_path):
+    """COPY linkdir /dst, COPY link.txt /dst2/ (mem_fs.go:380-384: sources go through evalSymlinks before the walk):
+    the committed layer holds the link TARGETS' content; TarDigest equals the oracle's stream and SHA-256 of the
+    emitted tar, and the archive lists the resolved names."""
+    import hashlib
+    import tarfile
+    from makisu_b200 import host
+    from oracle import layer_tar as lt
+    c = str(tmp_path / "ctx")
+    rng = np.random.default_rng(9)
+    _mk(c, "real/a.bin", rng.integers(0, 256, 200_000, dtype=np.uint8).tobytes())
+    _mk(c, "real/sub/b.bin", rng.integers(0, 256, 70_000, dtype=np.uint8).tobytes())
+    _mk(c, "file.txt", b"F" * 3000)
+    os.symlink("real", os.path.join(c, "linkdir"))
+    os.symlink("file.txt", os.path.join(c, "link.txt"))
+    for d, _, _ in os.walk(c):
+        os.utime(d, (1_500_000_000, 1_500_000_000))
+    root = tmp_path / "root"
+    root.mkdir()
+    ops_h = [host.CopyOperation(["/linkdir"], c, "/", "/dst", 1, 2), host.CopyOperation(["/link.txt"], c, "/", "/dst2/", 1, 2)]
+    ops_o = [lt.CopyOperation.new(["/linkdir"], c, "/", "/dst", uid=1, gid=2),
+             lt.CopyOperation.new(["/link.txt"], c, "/", "/dst2/", uid=1, gid=2)]
+    tar_path = tmp_path / "layer.tar"
+    with open(tar_path, "wb") as f:
+        got = host.commit_copy_ops(eng, str(root), NOW, ops_h, tar_fd=f.fileno())
+    entries = lt.MemFS(lambda: NOW, str(root)).add_layer_by_copy_ops(ops_o)
+    assert got["tar_digest"] == lt.tar_digest(entries)
+    assert got["tar_digest"] == "sha256:" + hashlib.sha256(open(tar_path, "rb").read()).hexdigest()
+    names = [m.name for m in tarfile.open(tar_path).getmembers()]
+    assert names == ["dst", "dst/a.bin", "dst/sub", "dst/sub/b.bin", "dst2", "dst2/file.txt"]

@@ -1,15 +1,13 @@
-"""-m gpu.  Written after this round's GPU budget was spent: these checks have run on the CPU side only (the host code
-they exercise is verified against the CPU mock engine, tests/test_host_mock_engine_cpu.py, which replays the same
-scenarios with the oracle's arithmetic behind the mksnap_* entry points).  The file sorts last so that the verified GPU
-tests run first.
+"""-m gpu.  Arena-fed host paths and the world-of-one NCCL exchange.  (Round 1 wrote these after its GPU budget was
+spent and marked them non-strict xfail; all three passed on the driver's B200 run (GPUTEST_r01: 3 xpassed), so the
+markers are gone and failures here are failures.)
 
   * the range-partitioned exchange over a 1-rank NCCL communicator (header / record / level-1 all-gathers of one
-    rank; the rank's own slice is a device copy); the same code was run with NCCL at 2, 4 and 8 ranks
+    rank; the rank's own slice is a device copy); the same code runs with NCCL at 2, 4 and 8 ranks
     (tests/test_gpu_multi.py, bench.py self-check) and with the in-process transport at 1..8 ranks
     (tests/test_gpu_exchange.py)
   * mkhost_memfs_commit_copy_ops(..., MKHOST_MATERIALIZE): the COPY step's file copy (CopyOperation.Execute,
-    lib/snapshot/copy_op.go:82-147) fed from the arena the layer is packed in; the Copier itself
-    and its deferred mode are verified on the CPU (tests/test_host_copier_cpu.py)
+    lib/snapshot/copy_op.go:82-147) fed from the arena the layer is packed in
   * mkhost_memfs_update_from_tar(..., MKHOST_UNTAR): the base layer untarred from the arena while it is digested."""
 import os
 import stat
@@ -17,10 +15,7 @@ import stat
 import numpy as np
 import pytest
 
-# non-strict xfail: a first GPU run may still shake something out here without turning the verified suite red; a pass
-# is reported as XPASS (then the marker goes and the test moves next to its verified siblings)
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: first GPU run pending")]
+pytestmark = pytest.mark.gpu
 NOW = 1_600_000_000
 
 

@@ -2,7 +2,7 @@
 (tests/mock_engine/mock_mksnap.cpp: every digest computed by the oracle, the same call contract enforced).  Each
 scenario runs in a fresh process that loads the mock with RTLD_GLOBAL before libmkhost, so the real host code -- arena
 flushing, stream continuation, ranges per file, untar / materialise from the arena -- executes exactly as it does on
-a B200, minus the kernels.  These are the CPU twins of tests/test_gpu_host.py and tests/test_gpu_zz_unverified_on_gpu.py."""
+a B200, minus the kernels.  These are the CPU twins of tests/test_gpu_host.py and tests/test_gpu_host_arena_paths.py."""
 import os
 import subprocess
 import sys
