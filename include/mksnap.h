@@ -150,6 +150,24 @@ int mksnap_begin(mksnap_t *h);
  * with mksnap_arena_submit. */
 int mksnap_arena_acquire(mksnap_t *h, void **host_ptr, uint64_t *capacity, int32_t *arena_id);
 
+/* Give an acquired arena back without submitting it (error unwinding in a packer: a file vanished, a damaged
+ * archive).  mksnap_begin() also reclaims every arena that was acquired and never submitted. */
+int mksnap_arena_release(mksnap_t *h, int32_t arena_id);
+
+/* Capacities of this handle, so that a packer can flush an arena BEFORE a table limit is hit (a context of 500k tiny
+ * files fills max_extents long before it fills a 1 GiB arena; the reference handles any file count,
+ * add_copy_step.go:153-169). */
+typedef struct {
+    uint64_t max_extents;        /* extents, and ranges, per submit */
+    uint64_t max_streams;        /* serial-stream slots per session */
+    uint64_t max_chunks;         /* chunk-table rows per session */
+    uint64_t host_arena_bytes;
+    uint64_t device_arena_bytes;
+    uint32_t n_host_arenas;
+    uint32_t n_device_slots;
+} mksnap_limits;
+int mksnap_get_limits(const mksnap_t *h, mksnap_limits *out);
+
 /* Async: copy arena[0,used) host->device, then run CRC over MKSNAP_X_CRC
  * extents, CDC + per-chunk SHA-256 over MKSNAP_X_CDC extents and one serial
  * SHA-256 per range.  Returns once everything is enqueued; the arena becomes

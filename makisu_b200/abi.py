@@ -62,6 +62,12 @@ class Stats(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
+class Limits(C.Structure):
+    _fields_ = [("max_extents", C.c_uint64), ("max_streams", C.c_uint64), ("max_chunks", C.c_uint64),
+                ("host_arena_bytes", C.c_uint64), ("device_arena_bytes", C.c_uint64), ("n_host_arenas", C.c_uint32),
+                ("n_device_slots", C.c_uint32)]
+
+
 # every symbol include/mksnap.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = [
@@ -71,6 +77,8 @@ SYMBOLS = [
     ("mksnap_last_error", C.c_char_p, [_P]),
     ("mksnap_begin", C.c_int, [_P]),
     ("mksnap_arena_acquire", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
+    ("mksnap_arena_release", C.c_int, [_P, C.c_int32]),
+    ("mksnap_get_limits", C.c_int, [_P, C.POINTER(Limits)]),
     ("mksnap_arena_submit", C.c_int, [_P, C.c_int32, C.c_uint64, C.POINTER(Extent), C.c_uint64, C.POINTER(Range), C.c_uint64]),
     ("mksnap_device_arena", C.c_int, [_P, C.c_uint32, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     ("mksnap_device_upload", C.c_int, [_P, C.c_uint32, C.c_uint64, _P, C.c_uint64]),
@@ -105,7 +113,7 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("MKSNAP_LIB", str(LIB_PATH))
+    path = str(LIB_PATH)  # the in-tree build only: no environment override, nothing else may stand in for the engine
     if not os.path.exists(path):
         raise FileNotFoundError(
             f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -180,6 +188,14 @@ class Engine:
         ptr, cap, aid = _P(), C.c_uint64(), C.c_int32()
         self._ck(self.lib.mksnap_arena_acquire(self.h, C.byref(ptr), C.byref(cap), C.byref(aid)), "mksnap_arena_acquire")
         return ptr.value, cap.value, aid.value
+
+    def arena_release(self, arena_id: int):
+        self._ck(self.lib.mksnap_arena_release(self.h, arena_id), "mksnap_arena_release")
+
+    def limits(self) -> Limits:
+        out = Limits()
+        self._ck(self.lib.mksnap_get_limits(self.h, C.byref(out)), "mksnap_get_limits")
+        return out
 
     @staticmethod
     def _tables(extents, ranges):

@@ -114,7 +114,8 @@ struct mksnap {
     uint64_t max_streams = 0;
     uint8_t *d_stream_digests = nullptr;
     StreamState *d_stream_state = nullptr;
-    std::vector<uint8_t> stream_open; // host shadow: stream slot has a parked midstate
+    std::vector<uint32_t> stream_stamp; // submit epoch that last used the stream slot (one piece per stream per submit)
+    uint32_t stamp_epoch = 0;
     uint64_t n_streams = 0;
     uint64_t stream_base = 0; // bytes of arenas submitted before the current one
     uint64_t crc_bytes = 0;
@@ -537,7 +538,7 @@ static int create_impl(mksnap *h)
     CK(h, cudaMalloc(&h->d_stream_digests, h->max_streams * 32));
     CK(h, cudaMalloc(&h->d_stream_state, h->max_streams * sizeof(StreamState)));
     CK(h, cudaMemset(h->d_stream_state, 0, h->max_streams * sizeof(StreamState)));
-    h->stream_open.assign(h->max_streams, 0);
+    h->stream_stamp.assign(h->max_streams, 0);
 
     {
         int rc = alloc_table_buffers(h, mc);
@@ -646,7 +647,8 @@ int mksnap_begin(mksnap_t *h)
     CK(h, cudaStreamSynchronize(h->s_comp));
     CK(h, cudaMemsetAsync(h->d_sc, 0, sizeof(SessionCounters), h->s_comp));
     CK(h, cudaMemsetAsync(h->d_stream_state, 0, h->max_streams * sizeof(StreamState), h->s_comp));
-    std::fill(h->stream_open.begin(), h->stream_open.end(), 0);
+    for (auto &a : h->arenas) // an arena acquired but never submitted (a packer that failed half way) is reclaimed here
+        a.acquired = false;
     h->n_streams = 0;
     h->stream_base = 0;
     h->crc_bytes = 0;
@@ -681,6 +683,30 @@ int mksnap_arena_acquire(mksnap_t *h, void **host_ptr, uint64_t *capacity, int32
         return 0;
     }
     return fail(h, MKSNAP_E_STATE, "all %u host arenas are acquired and not yet submitted", n);
+}
+
+int mksnap_arena_release(mksnap_t *h, int32_t arena_id)
+{
+    if (!h)
+        return MKSNAP_E_INVAL;
+    if (arena_id < 0 || (size_t)arena_id >= h->arenas.size() || !h->arenas[arena_id].acquired)
+        return fail(h, MKSNAP_E_STATE, "arena %d was not acquired", arena_id);
+    h->arenas[arena_id].acquired = false;
+    return 0;
+}
+
+int mksnap_get_limits(const mksnap_t *h, mksnap_limits *out)
+{
+    if (!h || !out)
+        return MKSNAP_E_INVAL;
+    out->max_extents = h->cfg.max_extents;
+    out->max_streams = h->max_streams;
+    out->max_chunks = h->max_chunks;
+    out->host_arena_bytes = h->cfg.host_arena_bytes;
+    out->device_arena_bytes = h->cfg.device_arena_bytes;
+    out->n_host_arenas = (uint32_t)h->arenas.size();
+    out->n_device_slots = h->n_slots;
+    return 0;
 }
 
 static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_extent *ext, uint64_t n_ext,
@@ -730,6 +756,10 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     if (big_slots > h->table_cap) // the cut lists of the big files live in the (idle) radix key buffer
         return fail(h, MKSNAP_E_CAPACITY, "big-file cut lists need %llu slots, max_chunks allows %llu",
                     (unsigned long long)big_slots, (unsigned long long)h->table_cap);
+    if (++h->stamp_epoch == 0) { // epoch wrapped: forget every stamp
+        std::fill(h->stream_stamp.begin(), h->stream_stamp.end(), 0);
+        h->stamp_epoch = 1;
+    }
     for (uint64_t i = 0; i < n_rng; i++) {
         if ((rng[i].arena_off & 15) || rng[i].arena_off > used || rng[i].len > used - rng[i].arena_off)
             return fail(h, MKSNAP_E_INVAL, "range %llu out of bounds or not 16-byte aligned", (unsigned long long)i);
@@ -739,10 +769,10 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         if ((rng[i].flags & MKSNAP_R_MORE) && (rng[i].len == 0 || rng[i].len % 64))
             return fail(h, MKSNAP_E_INVAL, "range %llu: a piece with MKSNAP_R_MORE must be a non-empty multiple of 64 bytes",
                         (unsigned long long)i);
-        for (uint64_t j = 0; j < i; j++)
-            if (rng[j].stream == rng[i].stream)
-                return fail(h, MKSNAP_E_INVAL, "ranges %llu and %llu: one piece per stream per submit", (unsigned long long)j,
-                            (unsigned long long)i);
+        if (h->stream_stamp[rng[i].stream] == h->stamp_epoch)
+            return fail(h, MKSNAP_E_INVAL, "range %llu: stream slot %u already has a piece in this submit (one piece per stream per submit)",
+                        (unsigned long long)i, rng[i].stream);
+        h->stream_stamp[rng[i].stream] = h->stamp_epoch;
         m.h_rstart[i] = rng[i].arena_off;
         m.h_rlen[i] = rng[i].len;
         m.h_rstream[i] = rng[i].stream;

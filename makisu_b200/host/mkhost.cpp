@@ -427,9 +427,11 @@ int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, c
             total += g.kind == 'F' ? g.size : g.bytes.size();
         ck(eng, mksnap_begin(eng), "begin");
 
+        const mksnap_limits lim = engine_limits(eng);
         void *hp = nullptr;
         uint64_t cap = 0;
-        int32_t aid = -1;
+        ArenaLease lease(eng);
+        int32_t &aid = lease.id;
         uint64_t pos = 0;
         std::vector<mksnap_extent> ext;
         std::vector<ReadJob> jobs;
@@ -450,7 +452,8 @@ int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, c
             if (n == 0)
                 return;
             uint64_t o = align_up(pos, 16);
-            if (o + n > cap) {
+            if (o + n > cap || ext.size() >= lim.max_extents) { // the extent table fills before the arena on tiny files
+
                 flush();
                 acquire();
                 o = 0;
@@ -471,7 +474,7 @@ int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, c
             uint64_t done = 0; // CRC is linear: a file may be split across arenas at any 16-byte boundary
             while (done < g.size) {
                 uint64_t o = align_up(pos, 512);
-                if (o + 4096 > cap) {
+                if (o + 4096 > cap || ext.size() >= lim.max_extents) {
                     flush();
                     acquire();
                     o = 0;

@@ -102,6 +102,28 @@ int mksnap_arena_acquire(mksnap_t *h, void **host_ptr, uint64_t *capacity, int32
     return 0;
 }
 
+int mksnap_arena_release(mksnap_t *h, int32_t arena_id)
+{
+    if (!h)
+        return MKSNAP_E_INVAL;
+    if (arena_id < 0 || (size_t)arena_id >= h->arenas.size() || !h->acquired[arena_id])
+        return fail(h, MKSNAP_E_STATE, "arena was not acquired");
+    h->acquired[arena_id] = false;
+    return 0;
+}
+
+int mksnap_get_limits(const mksnap_t *h, mksnap_limits *out)
+{
+    if (!h || !out)
+        return MKSNAP_E_INVAL;
+    memset(out, 0, sizeof *out);
+    out->max_extents = out->max_streams = h->cfg.max_extents;
+    out->host_arena_bytes = h->cfg.host_arena_bytes;
+    out->device_arena_bytes = h->cfg.device_arena_bytes;
+    out->n_host_arenas = (uint32_t)h->arenas.size();
+    return 0;
+}
+
 int mksnap_arena_submit(mksnap_t *h, int32_t arena_id, uint64_t used, const mksnap_extent *ext, uint64_t n_ext,
                         const mksnap_range *rng, uint64_t n_rng)
 {

@@ -347,3 +347,64 @@ def random_trees_small_arenas(make_engine, tmp):
                                            tar_fd=f.fileno())
             assert open(tar_path, "rb").read() == blob, (seed, arena)
             assert got["tar_digest"] == lt.tar_digest(entries) and got["root"] == want["root"] and got["n_chunks"] == want["n_chunks"]
+
+
+def table_limits_and_arena_leases(make_engine, tmp):
+    """(a) a context of many tiny files fills max_extents long before it fills an arena -- the packers
+    flush early instead of failing with E_CAPACITY (the reference handles any file count, add_copy_step.go:153-169);
+    (b) a packer that throws between acquire and submit gives its arena back (ArenaLease): the handle survives more
+    failures than it has arenas."""
+    ctx = os.path.join(tmp, "tiny")
+    rng = np.random.default_rng(11)
+    for i in range(300):
+        _mk(ctx, "d%02d/f%04d" % (i % 7, i), rng.integers(0, 256, int(rng.integers(0, 40)), dtype=np.uint8).tobytes())
+    for d, _, _ in os.walk(ctx):
+        os.utime(d, (T, T))
+    seed = ctx_crc.from_step_cache_id(ctx_crc.plan_seed(True, False), "scratch")
+    eng = make_engine(1 << 20, max_extents=16)                      # 300 files x 2 extents each >> 16
+    assert host.copy_step_cache_id(eng, seed, "COPY", ". /app/", ctx, ["."]) == ctx_crc.copy_step_cache_id(seed, "COPY", ". /app/", ctx, ["."])
+    assert eng.submits() >= 300 * 2 // 16
+    root = os.path.join(tmp, "root")
+    os.mkdir(root)
+    entries = lt.MemFS(lambda: NOW, root).add_layer_by_copy_ops([lt.CopyOperation.new(["/"], ctx, "/", "/app/")])
+    blob, want = _layer_expectations(entries)
+    eng = make_engine(1 << 20, max_extents=16)
+    got = host.commit_copy_ops(eng, root, NOW, [host.CopyOperation(["/"], ctx, "/", "/app/")])
+    assert got["tar_digest"] == lt.tar_digest(entries) and got["root"] == want["root"] and got["n_chunks"] == want["n_chunks"]
+    # per-file digests: one stream slot per file is a session-wide need, refused with a clear message when too small
+    h = host.MemFS(root)
+    try:
+        h.commit_copy_ops(make_engine(1 << 20, max_extents=16), NOW, [host.CopyOperation(["/"], ctx, "/", "/app/")],
+                          flags=host.MKHOST_FILE_DIGESTS)
+        raise AssertionError("expected a capacity error")
+    except host.HostError as e:
+        assert "stream slot per regular file" in str(e)
+    h2 = host.MemFS(root)
+    got2 = h2.commit_copy_ops(make_engine(1 << 20, max_extents=512), NOW, [host.CopyOperation(["/"], ctx, "/", "/app/")],
+                              flags=host.MKHOST_FILE_DIGESTS)
+    assert got2["tar_digest"] == got["tar_digest"]
+    # (b) failures between acquire and submit: a damaged archive, n_host_arenas + 2 times on ONE handle, then a good one
+    rng = np.random.default_rng(5)
+    data = _base_tar(rng)
+    bad = bytearray(data)
+    victim = [m for m in lt.read_tar(data) if m.hdr.typeflag == lt.TYPE_REG and m.data_len][3]
+    bad[victim.data_off - 512 + 150] ^= 0x55                        # break a header checksum a few members in
+    eng = make_engine(1 << 20, n_host_arenas=2)
+    for _ in range(4):
+        r, w = os.pipe()
+        import threading
+        t = threading.Thread(target=lambda: (os.write(w, bytes(bad)), os.close(w)))
+        t.start()
+        try:
+            host.MemFS(root).update_from_tar(eng, NOW, r)
+            raise AssertionError("expected a damaged-archive error")
+        except host.HostError:
+            pass
+        finally:
+            os.close(r)
+            t.join()
+    good = os.path.join(tmp, "good.tar")
+    open(good, "wb").write(data)
+    with open(good, "rb") as f:
+        ok = host.MemFS(root).update_from_tar(eng, NOW, f.fileno())
+    assert ok["tar_digest"] == "sha256:" + hashlib.sha256(data).hexdigest()

@@ -161,3 +161,39 @@ def test_update_from_tar_untars_from_the_arena(tmp_path):
     assert layers[0] == layers[1]
     assert disks[0] == disks[1]
     assert "etc/stale" not in disks[1] and disks[1]["etc"][:4] == ("d", 0o755, 7, 8) and disks[1]["usr/lib/alias.so"][5] == 2
+
+
+def test_failed_packers_give_their_arena_back(tmp_path):
+    """A packer that throws between mksnap_arena_acquire and mksnap_arena_submit (damaged archive) must not cost the
+    handle an arena: n_host_arenas + 2 failed ingests on one engine, then a good one (mksnap.cu:641)."""
+    import hashlib
+    import threading
+    from makisu_b200 import host
+    from makisu_b200.abi import Engine
+    from oracle import layer_tar as lt
+    from tests.mock_engine.scenarios import _base_tar
+    data = _base_tar(np.random.default_rng(5))
+    victim = [m for m in lt.read_tar(data) if m.hdr.typeflag == lt.TYPE_REG and m.data_len][3]
+    bad = bytearray(data)
+    bad[victim.data_off - 512 + 150] ^= 0x55
+    root = tmp_path / "r"
+    root.mkdir()
+    with Engine(device=0, device_arena_bytes=4 << 20, n_host_arenas=2, host_arena_bytes=1 << 20, max_extents=4096) as eng:
+        for _ in range(4):
+            r, w = os.pipe()
+            t = threading.Thread(target=lambda: (os.write(w, bytes(bad)), os.close(w)))
+            t.start()
+            with pytest.raises(host.HostError):
+                host.MemFS(str(root)).update_from_tar(eng, NOW, r)
+            os.close(r)
+            t.join()
+        good = tmp_path / "good.tar"
+        good.write_bytes(data)
+        with open(good, "rb") as f:
+            ok = host.MemFS(str(root)).update_from_tar(eng, NOW, f.fileno())
+        assert ok["tar_digest"] == "sha256:" + hashlib.sha256(data).hexdigest()
+        # explicit release through the C-ABI
+        ptr, cap, aid = (eng.begin(), eng.arena_acquire())[1]
+        eng.arena_release(aid)
+        with pytest.raises(Exception):
+            eng.arena_release(aid)
