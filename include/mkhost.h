@@ -114,6 +114,23 @@ int mkhost_memfs_commit_copy_ops(mkhost_memfs *m, mksnap_t *eng, int64_t now_uni
                                  size_t errlen);
 int mkhost_memfs_commit_scan(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, int n_threads, int tar_fd, uint32_t flags,
                              mkhost_layer_result *out, char *err, size_t errlen);
+/* Several consecutive layers of ONE build committed in one engine session.  Equivalent to calling
+ * mkhost_memfs_commit_copy_ops once per layer, in order (same entries, same tar bytes to each layer's tar_fd, same
+ * TarDigest per layer) -- but every pinned arena carries a piece of EVERY unfinished layer, so the serial SHA-256
+ * chains (one per layer, lib/builder/step/common.go:44-55) advance together on the device instead of one after the
+ * other.  This is what makes TarDigest on the GPU worthwhile: one chain runs at ~0.09 GB/s, 256 chains at ~23 GB/s.
+ * The reference commits layer by layer (build_node.go:102-107); COPY/ADD steps that do not modify the file system
+ * (no RUN in between) can be deferred and committed together, which is what a cgo caller would do.
+ * outs[i].tar_digest / tar_bytes / n_entries are per layer; root / n_chunks / n_unique describe the chunk table of the
+ * whole batch (one session).  flags: MKHOST_NO_TAR_DIGEST only.  tar_fd < 0: that layer's tar is not emitted. */
+typedef struct {
+    const mkhost_copy_op *ops;
+    size_t n_ops;
+    int tar_fd;
+} mkhost_layer_spec;
+int mkhost_memfs_commit_layers(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, const mkhost_layer_spec *layers,
+                               size_t n_layers, int n_threads, uint32_t flags, mkhost_layer_result *outs, char *err,
+                               size_t errlen);
 /* the same two without a GPU: entry list as text (format below); they DO merge the layer into the tree */
 size_t mkhost_memfs_describe_copy_ops(mkhost_memfs *m, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops, char *out,
                                       size_t cap, char *err, size_t errlen);

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 
+#define SS_PROFILE 1
 #include "mksnap_sha_stream.cuh"
 
 using namespace mk;
@@ -119,7 +120,7 @@ int main(int argc, char **argv)
                 CK(cudaMemset(d_work, 0, 4));
                 CK(cudaEventRecord(e0));
                 k_sha256_streams<<<grid, SS_THREADS>>>(d_data, d_start, d_len, (uint32_t)n, d_sid, d_flags, d_ss, d_out, d_work,
-                                                       (uint32_t)max_lanes);
+                                                       (uint32_t)max_lanes, 1u);
                 CK(cudaEventRecord(e1));
                 CK(cudaDeviceSynchronize());
                 float ms;
@@ -139,6 +140,12 @@ int main(int argc, char **argv)
                 host_sha256(m.data(), len[i], ref);
                 if (memcmp(ref, out.data() + 32 * i, 32)) bad++;
             }
+            unsigned long long prof[8];
+            CK(cudaMemcpyFromSymbol(prof, mk::ss_prof, sizeof prof));
+            if (n <= 64 || n == 9472)
+                printf("    CTA0: rounds warp %.0f cyc/block (%.0f waiting), schedule warp %.0f cyc/block (%.0f waiting), %llu blocks, %.0f MHz\n",
+                       (double)prof[0] / prof[4], (double)prof[1] / prof[4], (double)prof[2] / prof[4], (double)prof[3] / prof[4], prof[4],
+                       (double)prof[0] / best / 1e3);
             double bytes = 0;
             for (int i = 0; i < n; ++i) bytes += len[i];
             printf("lanes/pair %2d  streams %6d  grid %4d  L %8llu  %8.3f ms  per-stream %7.1f MB/s  aggregate %8.2f GB/s  %s\n",

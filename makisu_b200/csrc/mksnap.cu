@@ -889,7 +889,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         const uint32_t pairs = (uint32_t)((n_rng + 31) / 32);
         k_sha256_streams<<<std::min<uint32_t>(pairs, (uint32_t)h->sm_count * 2), SS_THREADS, 0, sk>>>(
             d_arena, m.d_rstart, m.d_rlen, (uint32_t)n_rng, m.d_rstream, m.d_rflags, h->d_stream_state, h->d_stream_digests,
-            &h->d_sc->work, 32u);
+            &h->d_sc->work, 32u, 1u);
         LAUNCH_OK(h);
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, sk));
     }

@@ -45,9 +45,20 @@ struct SsShared {
     uint32_t sid[2][32];
 };
 
+#ifdef SS_PROFILE
+// microbenchmark only (k4_microbench.cu): [0] rounds-warp cycles, [1] of which waiting for a full buffer,
+// [2] schedule-warp cycles, [3] of which waiting for an empty buffer, [4] blocks; CTA 0 only
+__device__ unsigned long long ss_prof[8];
+#endif
 __device__ __forceinline__ void ss_bar_sync(uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void ss_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ uint32_t ss_rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+__device__ __forceinline__ uint32_t ss_add(uint32_t a, uint32_t b, uint32_t one)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
 __device__ __forceinline__ uint4 ss_ldg(const uint4 *p)
 {
     uint4 r;
@@ -72,7 +83,7 @@ __global__ void __launch_bounds__(SS_THREADS)
 k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ start, const uint64_t *__restrict__ len,
                  uint32_t n, const uint32_t *__restrict__ rng_stream, const uint32_t *__restrict__ rng_flags,
                  StreamState *__restrict__ sstate, uint8_t *__restrict__ out, uint32_t *__restrict__ work_counter,
-                 uint32_t max_lanes)
+                 uint32_t max_lanes, const uint32_t one /* = 1, see ss_add */)
 {
     __shared__ SsShared sh;
     const uint32_t lane = threadIdx.x & 31;
@@ -80,9 +91,18 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
     if (threadIdx.x < 32) {
         // ------------------------------ rounds warp ------------------------------
         uint32_t st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#ifdef SS_PROFILE
+        long long p_wait = 0, p_t0 = clock64();
+#endif
         for (uint32_t it = 0;; ++it) {
             const uint32_t b = it & 1u;
+#ifdef SS_PROFILE
+            const long long p_a = clock64();
+#endif
             ss_bar_sync(1 + b);
+#ifdef SS_PROFILE
+            p_wait += clock64() - p_a;
+#endif
             const uint32_t c = sh.ctrl[b][lane];
             if (c & SS_EXIT)
                 break; // warp-uniform
@@ -100,19 +120,21 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
             const uint32_t *kw = &sh.kw[b][0][lane];
 #pragma unroll
             for (int t = 0; t < 64; ++t) {
-                const uint32_t x = h + kw[t * 32]; // off the critical path: h and kw are old
-                const uint32_t y = x + d;
+                // Every addition is an IMAD (a*1+b with the 1 in a register ptxas knows nothing about) so that the
+                // half-rate ALU pipe carries only the 6 SHF + 4 LOP3 of the round; the e-chain per round is
+                // SHF -> LOP3 -> one IMAD.
+                const uint32_t x = ss_add(h, kw[t * 32], one); // off the critical path: h and kw are old
+                const uint32_t y = ss_add(x, d, one);
                 const uint32_t S1 = ss_rotr(e, 6) ^ ss_rotr(e, 11) ^ ss_rotr(e, 25);
                 const uint32_t ch = (e & f) ^ (~e & g);
                 const uint32_t S0 = ss_rotr(a, 2) ^ ss_rotr(a, 13) ^ ss_rotr(a, 22);
                 const uint32_t mj = (a & bb) ^ (a & cc) ^ (bb & cc);
-                const uint32_t z = S0 + mj + x; // also off the e-chain
-                // e-chain per round: SHF -> LOP3 (S1) -> one add; ch + y is ready when S1 is
-                const uint32_t chy = ch + y, chz = ch + z;
+                const uint32_t z = ss_add(ss_add(S0, mj, one), x, one); // also off the e-chain
+                const uint32_t chy = ss_add(ch, y, one), chz = ss_add(ch, z, one);
                 h = g; g = f; f = e;
-                e = S1 + chy;
+                e = ss_add(S1, chy, one);
                 d = cc; cc = bb; bb = a;
-                a = S1 + chz;
+                a = ss_add(S1, chz, one);
             }
             if (c & SS_ACTIVE) {
                 st[0] += a; st[1] += bb; st[2] += cc; st[3] += d;
@@ -135,6 +157,12 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
             }
             ss_bar_arrive(3 + b);
         }
+#ifdef SS_PROFILE
+        if (blockIdx.x == 0 && lane == 0) {
+            ss_prof[0] = (unsigned long long)(clock64() - p_t0);
+            ss_prof[1] = (unsigned long long)p_wait;
+        }
+#endif
         return;
     }
 
@@ -147,6 +175,9 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
     bool exhausted = lane >= max_lanes;
     uint4 pre[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
 
+#ifdef SS_PROFILE
+    long long p_wait = 0, p_t0 = clock64();
+#endif
     for (uint32_t it = 0;; ++it) {
         const uint32_t b = it & 1u;
         // ---- refill idle lanes (warp-aggregated fetch) ----
@@ -180,11 +211,24 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
             }
         }
         const bool any = __any_sync(0xFFFFFFFFu, phase != 0);
+#ifdef SS_PROFILE
+        const long long p_a = clock64();
+#endif
         if (it >= 2)
             ss_bar_sync(3 + b); // the rounds warp is done with buffer b
+#ifdef SS_PROFILE
+        p_wait += clock64() - p_a;
+#endif
         if (!any) {
             sh.ctrl[b][lane] = SS_EXIT;
             ss_bar_arrive(1 + b);
+#ifdef SS_PROFILE
+            if (blockIdx.x == 0 && lane == 0) {
+                ss_prof[2] = (unsigned long long)(clock64() - p_t0);
+                ss_prof[3] = (unsigned long long)p_wait;
+                ss_prof[4] = it;
+            }
+#endif
             break;
         }
 
@@ -275,10 +319,10 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
                 const uint32_t w15 = w[(t + 1) & 15], w2 = w[(t + 14) & 15];
                 const uint32_t s0 = ss_rotr(w15, 7) ^ ss_rotr(w15, 18) ^ (w15 >> 3);
                 const uint32_t s1 = ss_rotr(w2, 17) ^ ss_rotr(w2, 19) ^ (w2 >> 10);
-                wt = w[t & 15] + s0 + w[(t + 9) & 15] + s1;
+                wt = ss_add(ss_add(w[t & 15], s0, one), ss_add(w[(t + 9) & 15], s1, one), one);
                 w[t & 15] = wt;
             }
-            kw[t * 32] = wt + SS_K[t];
+            kw[t * 32] = ss_add(wt, SS_K[t], one);
         }
         ss_bar_arrive(1 + b);
     }

@@ -26,6 +26,10 @@ class CopyOp(C.Structure):
                 ("work_dir", C.c_char_p), ("dst", C.c_char_p), ("uid", C.c_int32), ("gid", C.c_int32)]
 
 
+class LayerSpec(C.Structure):
+    _fields_ = [("ops", C.POINTER(CopyOp)), ("n_ops", C.c_size_t), ("tar_fd", C.c_int)]
+
+
 class LayerResult(C.Structure):
     _fields_ = [("tar_digest", C.c_uint8 * 32), ("root", C.c_uint8 * 32), ("n_entries", C.c_uint64),
                 ("tar_bytes", C.c_uint64), ("n_chunks", C.c_uint64), ("n_unique", C.c_uint64)]
@@ -47,6 +51,8 @@ SYMBOLS = [
     ("mkhost_memfs_file_digest", C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint8)]),
     ("mkhost_memfs_commit_copy_ops", C.c_int, [_P, _P, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_int, C.c_int, C.c_uint32,
                                                C.POINTER(LayerResult), C.c_char_p, C.c_size_t]),
+    ("mkhost_memfs_commit_layers", C.c_int, [_P, _P, C.c_int64, C.POINTER(LayerSpec), C.c_size_t, C.c_int, C.c_uint32,
+                                             C.POINTER(LayerResult), C.c_char_p, C.c_size_t]),
     ("mkhost_memfs_commit_scan", C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.POINTER(LayerResult),
                                            C.c_char_p, C.c_size_t]),
     ("mkhost_memfs_describe_copy_ops", C.c_size_t, [_P, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_char_p, C.c_size_t,
@@ -244,6 +250,21 @@ class MemFS:
                                                C.byref(out), err, len(err)):
             raise HostError(err.value.decode())
         return _layer_dict(out)
+
+    def commit_layers(self, eng: abi.Engine, now_unix: int, layers: Sequence[Sequence[CopyOperation]], n_threads: int = 0,
+                      tar_fds: Optional[Sequence[int]] = None, flags: int = 0):
+        """Consecutive layers of one build in ONE engine session (all TarDigest chains advance together)."""
+        err = C.create_string_buffer(1024)
+        n = len(layers)
+        specs, keep, outs = (LayerSpec * max(1, n))(), [], (LayerResult * max(1, n))()
+        for i, ops in enumerate(layers):
+            arr, k = _ops(ops)
+            keep.append((arr, k))
+            specs[i].ops, specs[i].n_ops = arr, len(ops)
+            specs[i].tar_fd = tar_fds[i] if tar_fds is not None else -1
+        if load().mkhost_memfs_commit_layers(self.h, eng.h, now_unix, specs, n, n_threads, flags, outs, err, len(err)):
+            raise HostError(err.value.decode())
+        return [_layer_dict(outs[i]) for i in range(n)]
 
     def file_digest(self, dst: str) -> Optional[bytes]:
         """SHA-256 the tree remembers for the regular file at dst, or None."""

@@ -240,6 +240,32 @@ int mkhost_memfs_commit_copy_ops(mkhost_memfs *m, mksnap_t *eng, int64_t now_uni
     }
 }
 
+int mkhost_memfs_commit_layers(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, const mkhost_layer_spec *specs, size_t n_layers,
+                               int n_threads, uint32_t flags, mkhost_layer_result *outs, char *err, size_t errlen)
+{
+    try {
+        if (!m || !eng || (!specs && n_layers) || (!outs && n_layers))
+            throw HostError("null argument");
+        if (flags & ~(uint32_t)MKHOST_NO_TAR_DIGEST)
+            throw HostError("commit layers: only MKHOST_NO_TAR_DIGEST is supported for a batch");
+        m->fs.set_now(now_unix);
+        // the layer maps are built in order -- each AddLayerByCopyOps sees the tree its predecessors left
+        // (mem_fs.go:276-289) -- and only then packed together
+        std::vector<std::map<std::string, MemFile>> maps;
+        maps.reserve(n_layers);
+        for (size_t i = 0; i < n_layers; ++i)
+            maps.push_back(m->fs.add_layer_by_copy_ops(specs[i].ops, specs[i].n_ops));
+        std::vector<BatchLayer> bl;
+        for (size_t i = 0; i < n_layers; ++i)
+            bl.push_back(BatchLayer{&maps[i], specs[i].tar_fd});
+        commit_layers_batch(eng, bl, n_threads, flags, outs);
+        return 0;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("failed to generate diff layers: ") + e.what());
+        return -1;
+    }
+}
+
 int mkhost_memfs_commit_scan(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, int n_threads, int tar_fd, uint32_t flags,
                              mkhost_layer_result *out, char *err, size_t errlen)
 {

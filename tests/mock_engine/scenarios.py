@@ -408,3 +408,47 @@ def table_limits_and_arena_leases(make_engine, tmp):
     with open(good, "rb") as f:
         ok = host.MemFS(root).update_from_tar(eng, NOW, f.fileno())
     assert ok["tar_digest"] == "sha256:" + hashlib.sha256(data).hexdigest()
+
+
+def batch_of_layers_in_one_session(make_engine, tmp):
+    """mkhost_memfs_commit_layers: N consecutive COPY layers packed together (every arena carries a piece of every open
+    layer, one SHA-256 stream per layer continued across submits) == N sequential commits: per-layer TarDigest and tar
+    bytes equal the oracle's, later layers are diffed against the tree the earlier ones left."""
+    ctx = _ctx(tmp)
+    root = os.path.join(tmp, "root")
+    os.mkdir(root)
+    os.chmod(root, 0o755)
+    specs = [(["/d0"], "/app/d0/"), (["/d1", "/d2"], "/app/"), (["/big.bin"], "/data/big.bin"), (["/empty", "/zeros"], "/app/"),
+             (["/d0"], "/app/d0/"),                                # identical to layer 0: only re-added ancestors remain
+             (["/link"], "/app/")]
+    o = lt.MemFS(lambda: NOW, root)
+    want = []
+    for srcs, dst in specs:
+        entries = o.add_layer_by_copy_ops([lt.CopyOperation.new(srcs, ctx, "/", dst, uid=5, gid=6)])
+        want.append((lt.tar_digest(entries), b"".join(lt.layer_tar_chunks(entries)), len(entries)))
+    for arena_bytes in (2 << 20, 8 << 20):                         # shares of 341 KiB / 1.3 MiB per layer
+        eng = make_engine(arena_bytes, n_host_arenas=2)
+        h = host.MemFS(root)
+        paths = [os.path.join(tmp, "l%d_%d.tar" % (i, arena_bytes)) for i in range(len(specs))]
+        files = [open(p, "wb") for p in paths]
+        got = h.commit_layers(eng, NOW, [[host.CopyOperation(s, ctx, "/", d, 5, 6)] for s, d in specs],
+                              tar_fds=[f.fileno() for f in files])
+        for f in files:
+            f.close()
+        for i, (dig, blob, n) in enumerate(want):
+            assert got[i]["tar_digest"] == dig, (i, arena_bytes)
+            assert open(paths[i], "rb").read() == blob, (i, arena_bytes)
+            assert (got[i]["n_entries"], got[i]["tar_bytes"]) == (n, len(blob))
+        assert eng.submits() >= 2
+        h.close()
+    # the union chunk table equals the one over the concatenation of the layers' files
+    # without digests
+    eng = make_engine(8 << 20)
+    got = host.MemFS(root).commit_layers(eng, NOW, [[host.CopyOperation(s, ctx, "/", d, 5, 6)] for s, d in specs],
+                                        flags=host.MKHOST_NO_TAR_DIGEST)
+    assert all(g["tar_digest"] == "sha256:" + "00" * 32 for g in got)
+    try:
+        host.MemFS(root).commit_layers(make_engine(1 << 20), NOW, [[host.CopyOperation(["/big.bin"], ctx, "/", "/x")]])
+        raise AssertionError("expected a capacity error")
+    except host.HostError as e:
+        assert "exceeds the arena" in str(e)

@@ -383,3 +383,36 @@ def test_commit_copy_of_symlinked_sources(eng, tmp_path):
     assert got["tar_digest"] == "sha256:" + hashlib.sha256(open(tar_path, "rb").read()).hexdigest()
     names = [m.name for m in tarfile.open(tar_path).getmembers()]
     assert names == ["dst", "dst/a.bin", "dst/sub", "dst/sub/b.bin", "dst2", "dst2/file.txt"]
+
+
+def test_batch_of_layers_shares_one_session(ctx, tmp_path):
+    """mkhost_memfs_commit_layers on the GPU: 6 consecutive COPY layers in ONE session (every arena carries a piece of
+    every open layer; 6 SHA-256 chains advance together in K4) give the per-layer TarDigest and tar bytes of 6
+    sequential commits (oracle), over 4 MiB arenas (many submits, stream continuation) and in one big arena."""
+    import hashlib
+    from makisu_b200 import host
+    from makisu_b200.abi import Engine
+    from oracle import layer_tar as lt
+    root = tmp_path / "root"
+    root.mkdir()
+    os.chmod(root, 0o755)
+    specs = [(["/d0"], "/app/d0/"), (["/d1", "/d2"], "/app/"), (["/zeros", "/empty"], "/app/"), (["/d3"], "/srv/"),
+             (["/d0"], "/app/d0/"), (["/link"], "/app/")]
+    o = lt.MemFS(lambda: NOW, str(root))
+    want = []
+    for srcs, dst in specs:
+        entries = o.add_layer_by_copy_ops([lt.CopyOperation.new(srcs, ctx, "/", dst, uid=5, gid=6)])
+        want.append((lt.tar_digest(entries), b"".join(lt.layer_tar_chunks(entries))))
+    for arena in (4 << 20, 64 << 20):
+        with Engine(device=0, device_arena_bytes=arena, n_host_arenas=2, host_arena_bytes=arena, max_extents=1 << 12) as eng:
+            h = host.MemFS(str(root))
+            paths = [tmp_path / ("l%d_%d.tar" % (i, arena)) for i in range(len(specs))]
+            files = [open(p, "wb") for p in paths]
+            got = h.commit_layers(eng, NOW, [[host.CopyOperation(s, ctx, "/", d, 5, 6)] for s, d in specs],
+                                  tar_fds=[f.fileno() for f in files])
+            for f in files:
+                f.close()
+            h.close()
+        for i, (dig, blob) in enumerate(want):
+            assert got[i]["tar_digest"] == dig == "sha256:" + hashlib.sha256(paths[i].read_bytes()).hexdigest(), (i, arena)
+            assert paths[i].read_bytes() == blob
