@@ -64,6 +64,10 @@ def parse():
                     help="uniform = BASELINE configs[2] (the bench line); dup = configs[4] (80 %% repeated content); "
                          "zipf = configs[3] (Zipf-sized files 10 B..1 GiB, LPT-sharded by rank)")
     ap.add_argument("--tar-files", type=int, default=256, help="files in the TarDigest side measurement")
+    ap.add_argument("--strong", action="store_true", help="run the strong-scaling legs at N=1 too (always run at N>1)")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-deliverables", action="store_true", help="skip the {cacheID, TarDigest} same-deliverables leg")
+    ap.add_argument("--deliv-one-layer-mib", type=int, default=256, help="sample size of the ONE-layer TarDigest run")
     return ap.parse_args()
 
 
@@ -175,6 +179,88 @@ def special_layout(args, rank, world):
     names = [b"z/f%07d.bin" % i for i in mine]
     info = {"n_files_total": int(len(sizes)), "imbalance": shard.imbalance(sizes, shards), "largest_file": int(sizes.max())}
     return layout_from_files(names, off, ml.astype(np.uint64), data_end), info
+
+
+def global_sharded_layout(names, sizes, rank, world, region_of=None, region_bytes=0, n_regions=0):
+    """ONE global context (stream = name_i || content_i, i ascending) whose files are LPT-sharded over `world` ranks:
+    the strong-scaling form of the path.  A rank packs its own files (512-aligned, or -- dup --
+    the shared pool regions they point at) and their names; crc_suffix is GLOBAL, so the XOR of the rank partials is
+    the cacheID of the whole context and the exchanged table is the table of the whole context at every N."""
+    from makisu_b200 import shard
+    sizes = np.asarray(sizes, dtype=np.uint64)
+    n = len(names)
+    nlen = np.array([len(x) for x in names], dtype=np.uint64)
+    seg = np.empty(2 * n, dtype=np.uint64)
+    seg[0::2], seg[1::2] = nlen, sizes
+    total = int(seg.sum())
+    suffix = (np.uint64(total) - np.cumsum(seg)).astype(np.uint64)
+    shards = shard.lpt_shard(sizes.tolist(), world) if world > 1 else [list(range(n))]
+    mine = np.array(shards[rank], dtype=np.int64)
+    ml = sizes[mine]
+    if region_of is None:
+        pad = (ml + np.uint64(511)) // np.uint64(512) * np.uint64(512)
+        off = (np.cumsum(pad) - pad).astype(np.uint64)
+        data_end = int(pad.sum())
+        fill = data_end
+    else:
+        off = (np.asarray(region_of)[mine].astype(np.uint64) * np.uint64(region_bytes))
+        data_end = fill = n_regions * region_bytes
+    mlen = nlen[mine]
+    mpad = (mlen + np.uint64(15)) // np.uint64(16) * np.uint64(16)
+    moff = (np.cumsum(mpad) - mpad).astype(np.uint64)
+    blob = bytearray(int(mpad.sum()))
+    for j, i in enumerate(mine):
+        x = names[i]
+        blob[int(moff[j]):int(moff[j]) + len(x)] = x
+    blob += b"\0" * (-len(blob) % 512)
+    meta_base = (data_end + 511) // 512 * 512
+    ext = np.zeros(2 * len(mine), dtype=EXT_DT)
+    ext["arena_off"][0::2] = moff + np.uint64(meta_base)
+    ext["len"][0::2] = mlen
+    ext["flags"][0::2] = 1
+    ext["crc_suffix"][0::2] = suffix[2 * mine]
+    ext["arena_off"][1::2] = off
+    ext["len"][1::2] = ml
+    ext["flags"][1::2] = 3
+    ext["crc_suffix"][1::2] = suffix[2 * mine + 1]
+    loads = [int(sizes[np.array(s_, dtype=np.int64)].sum()) if len(s_) else 0 for s_ in shards]
+    info = {"n_files_total": n, "bytes_total": int(sizes.sum()), "files_this_rank": int(len(mine)),
+            "imbalance_max_over_mean": max(loads) / (sum(loads) / len(loads)) if sum(loads) else 1.0,
+            "largest_file": int(sizes.max()) if n else 0}
+    return dict(blob=bytes(blob), meta_base=meta_base, ext=ext, used=meta_base + len(blob), stream_len=total,
+                data_bytes=int(ml.sum()), fill_bytes=int(fill)), info
+
+
+def strong_contexts(args):
+    """The fixed-size contexts of BASELINE configs[2..4], as (names, sizes, region_of, n_regions) generators."""
+    fb = args.file_kib << 10
+
+    def uniform():
+        names = [b"d%03d/f%06d.bin" % (i * args.dirs // args.files, i) for i in range(args.files)]
+        return names, np.full(args.files, fb, dtype=np.uint64), None, 0
+
+    def dup():
+        rng = np.random.default_rng(0xC5)
+        pool = max(1, args.files // 5)
+        pick = rng.integers(0, pool, args.files)
+        pick[:pool] = np.arange(pool)
+        names = [b"d%03d/f%06d.bin" % (i % args.dirs, i) for i in range(args.files)]
+        return names, np.full(args.files, fb, dtype=np.uint64), pick, pool
+
+    def zipf():
+        rng = np.random.default_rng(0xC4)
+        target = args.files * fb
+        sizes, tot = [], 0
+        while tot < target:
+            z = np.clip(rng.zipf(1.1, 4096).astype(np.float64) * 10, 10, 1 << 30).astype(np.int64)
+            for v in z:
+                if tot >= target:
+                    break
+                sizes.append(int(v))
+                tot += int(v)
+        names = [b"z/f%07d.bin" % i for i in range(len(sizes))]
+        return names, np.array(sizes, dtype=np.uint64), None, 0
+    return {"uniform": uniform, "dup": dup, "zipf": zipf}
 
 
 def ext_ptr(a: np.ndarray):
@@ -666,13 +752,178 @@ def main():
                        f"2 device slots, H2D overlapped with kernels; api = mksnap_arena_acquire/submit/finish"}
         launches_e2e = int(s1.kernel_launches - s0.kernel_launches) // n_e2e
         e2e["gpu_launches_per_step"] = launches_e2e
+
+        # ---- same deliverables as the reference: {cacheID, TarDigest per layer}, host buffers, H2D in the timed region ----
+        # The reference commits one layer per step (common.go:67-111); TarDigest is one serial SHA-256 chain per layer.
+        # Every pinned arena is split into L equal regions = the pieces of L layer streams (MKSNAP_R_MORE until the last
+        # batch), next to the CRC extents of the cacheID: what mkhost_memfs_commit_layers submits for L layers.
+        def stream_ranges(L, b, nb, span):
+            reg = span // L // 64 * 64
+            r = (Range * L)()
+            for i in range(L):
+                r[i].arena_off = i * reg
+                r[i].len = reg if i < L - 1 else span - reg * (L - 1)
+                r[i].stream, r[i].flags = i, (1 if b < nb - 1 else 0)
+            return r
+
+        def deliv_step(L, nb, with_table, span, check=None):
+            eng2.begin()
+            seen = []
+            for b in range(nb):
+                ptr, cap, aid = eng2.arena_acquire()
+                seen.append(ptr)
+                e = per_batch_ext[b] if with_table else per_batch_crc[b]
+                eng2._ck(eng2.lib.mksnap_arena_submit(eng2.h, aid, blay["used"], ext_ptr(e), len(e), stream_ranges(L, b, nb, span), L),
+                         "submit")
+            r = eng2.finish()
+            d = eng2.get_stream_digests(L)
+            if check is not None:  # untimed: stdlib SHA-256 over the same pinned bytes
+                reg = span // L // 64 * 64
+                for i in check:
+                    hh = hashlib.sha256()
+                    ln = reg if i < L - 1 else span - reg * (L - 1)
+                    for ptr in seen:
+                        hh.update(ctypes.string_at(ptr + i * reg, ln))
+                    assert hh.digest() == d[i].tobytes(), "TarDigest stream %d of %d mismatch" % (i, L)
+            return r
+
+        per_batch_crc = []
+        for e in per_batch_ext:
+            c = e.copy()
+            c["flags"] = 1
+            per_batch_crc.append(c)
+        deliv = {"unit": "GiB/s", "what": "cacheID (CRC-32 of the context stream) + one TarDigest (serial SHA-256) per layer, "
+                 "pinned host arenas -> H2D -> kernels -> digests read back; layers = equal slices of the context "
+                 "(C3 has 256 directories: 256 = one COPY per directory)", "runs": []}
+        if not args.no_deliverables:
+            span = blay["data_bytes"]
+            for L, with_table in ((256, False), (256, True), (1024, False)):
+                if L + 16 > len(blay["ext"]):
+                    continue
+                deliv_step(L, min(2, n_batches), with_table, span, check=[0, L - 1])
+                barrier()
+                t0 = time.perf_counter()
+                deliv_step(L, n_batches, with_table, span)
+                barrier()
+                dtd = max_over_ranks(time.perf_counter() - t0)
+                deliv["runs"].append({"layers": L, "chunk_table_too": with_table, "bytes_per_gpu": e2e_bytes, "s": dtd,
+                                      "value": world * e2e_bytes / GiB / dtd, "sample": "full context"})
+            # ONE layer: one chain for the whole context is latency-bound (~0.09 GB/s): bounded sample, extrapolated
+            one_span = min(span, args.deliv_one_layer_mib << 20) // 64 * 64
+            deliv_step(1, 1, False, one_span, check=[0])
+            barrier()
+            t0 = time.perf_counter()
+            deliv_step(1, 1, False, one_span)
+            barrier()
+            dt1 = max_over_ranks(time.perf_counter() - t0)
+            deliv["runs"].append({"layers": 1, "chunk_table_too": False, "bytes_per_gpu": one_span, "s": dt1,
+                                  "value": world * one_span / GiB / dt1,
+                                  "sample": f"first {one_span >> 20} MiB of one batch: a single SHA-256 chain cannot be split; "
+                                            f"the whole context as ONE layer would take ~{e2e_bytes / one_span * dt1:.0f} s"})
+        # ---- strong scaling end to end: the SAME fixed context (args.files files in total) split over the N ranks ----
+        if (world > 1 or args.strong) and not args.no_strong:
+            counts = [args.files // world + (1 if r_ < args.files % world else 0) for r_ in range(world)]
+
+            def rank_plan(r_):
+                nbf_, k_ = divmod(counts[r_], files_per_batch)
+                slp = context_layout(k_, file_bytes, 1, r_)["stream_len"] if k_ else 0
+                return nbf_, k_, nbf_ * blay["stream_len"] + slp
+            plans = [rank_plan(r_) for r_ in range(world)]
+            total_stream = sum(p_[2] for p_ in plans)
+            after = total_stream - sum(p_[2] for p_ in plans[:rank])
+            nbf, k_last, _ = plans[rank]
+            sexts = []
+            for _ in range(nbf):
+                after -= blay["stream_len"]
+                e = blay["ext"].copy()
+                e["crc_suffix"] += np.uint64(after)
+                sexts.append((e, blay["used"], None))
+            if k_last:
+                lp = context_layout(k_last, file_bytes, 1, rank)
+                after -= lp["stream_len"]
+                e = lp["ext"].copy()
+                e["crc_suffix"] += np.uint64(after)
+                sexts.append((e, lp["used"], lp))
+
+            def strong_e2e_step():
+                eng2.begin()
+                for e, used_b, lp in sexts:
+                    ptr, cap, aid = eng2.arena_acquire()
+                    if lp is not None:  # the names of a partial batch are packed behind its last file
+                        ctypes.memmove(ptr + lp["meta_base"], lp["blob"], len(lp["blob"]))
+                    eng2._ck(eng2.lib.mksnap_arena_submit(eng2.h, aid, used_b, ext_ptr(e), len(e), None, 0), "submit")
+                r_ = eng2.finish()
+                if world > 1:
+                    r_ = eng2.exchange_tables() if merge["mode"] == "exchange" else eng2.allgather_tables()
+                return r_
+            strong_e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                strong_e2e_step()
+            barrier()
+            dse = max_over_ranks(time.perf_counter() - t0) / n_e2e
+            e2e["strong"] = {"value": args.files * file_bytes / GiB / dse, "unit": "GiB/s", "ms_per_step": dse * 1e3,
+                             "context_GiB": args.files * file_bytes / GiB, "files_per_rank": counts[rank],
+                             "note": "the ONE 100k-file context of BASELINE configs[2] split over the N ranks, pinned host arenas, "
+                                     "H2D inside the timed region, table exchange included"}
         eng2.close()
 
+    # ---- strong scaling: ONE fixed-size context sharded over the N ranks (BASELINE configs[2],[3],[4]) ----
+    strong = None
+    if (world > 1 or args.strong) and args.workload == "uniform" and not args.no_strong:
+        strong = {"what": "one GLOBAL context LPT-sharded by file over the N ranks (whole files; global crc_suffix); a step = "
+                          "every rank digests its shard + the table exchange; value = bytes of the WHOLE context / max-over-ranks time",
+                  "runs": {}}
+        fb = file_bytes
+        for kind, gen in strong_contexts(args).items():
+            names, sizes, region_of, n_regions = gen()
+            slay, sinfo = global_sharded_layout(names, sizes, rank, world, region_of, fb, n_regions)
+            sa = (slay["used"] + (1 << 20)) // 512 * 512
+            ne = len(slay["ext"])
+            se = Engine(device=local, device_arena_bytes=sa, n_host_arenas=0, max_extents=ne + 16,
+                        max_chunks=max(sa, slay["data_bytes"]) // 4096 + ne + 1024)
+            if world > 1:
+                uid = [Engine.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(uid, src=0)
+                se.comm_init(uid[0], world, rank)
+            # dup: the pool (same bytes on every rank: seed and offsets are global); else the rank's own files
+            se.synth_fill(0, 0, (slay["fill_bytes"] + 15) // 16 * 16, 0x5C0 + (0 if kind == "dup" else 1000 * rank))
+            se.device_upload(0, slay["meta_base"], np.frombuffer(slay["blob"], dtype=np.uint8))
+            se.sync()
+
+            def sstep():
+                se.begin()
+                se.lib.mksnap_device_submit(se.h, 0, slay["used"], ext_ptr(slay["ext"]), ne, None, 0)
+                r_ = se.finish()
+                if world > 1:
+                    r_ = se.exchange_tables() if merge["mode"] == "exchange" else se.allgather_tables()
+                return r_
+            for _ in range(max(1, args.warmup)):
+                sstep()
+            barrier()
+            t0 = time.perf_counter()
+            n_s = max(2, args.steps)
+            for _ in range(n_s):
+                sr = sstep()
+            barrier()
+            dts = max_over_ranks(time.perf_counter() - t0) / n_s
+            sst = se.stats()
+            run = {"value": sinfo["bytes_total"] / GiB / dts, "unit": "GiB/s", "ms_per_step": dts * 1e3, "steps": n_s,
+                   "context_GiB": sinfo["bytes_total"] / GiB, "n_files": sinfo["n_files_total"],
+                   "imbalance_max_over_mean": sinfo["imbalance_max_over_mean"], "largest_file": sinfo["largest_file"],
+                   "n_chunks": int(sr.n_chunks), "n_unique": int(sr.n_unique),
+                   "dedup_ratio_unique_over_total": int(sr.n_unique) / int(sr.n_chunks) if sr.n_chunks else None,
+                   "cache_id": "%x" % se.ctx_crc32(sr), "root": bytes(sr.root).hex(),
+                   "rank0_ms": {"crc": sst.ms_crc, "gear": sst.ms_gear, "select": sst.ms_select, "sha": sst.ms_sha,
+                                "sort": sst.ms_sort, "root": sst.ms_root, "exchange": sst.ms_gather}}
+            strong["runs"][kind] = run
+            se.close()
     # ---- TarDigest side measurement: serial SHA-256 streams (one per layer) ----
     tar = None
     if rank == 0 and args.tar_files > 0:
         nf = min(args.tar_files, args.files)
-        for streams in (1, 64):
+        for streams in (1, 64, 256):
             per = nf // streams
             rng_ = (Range * streams)()
             for s_ in range(streams):
@@ -709,6 +960,15 @@ def main():
         except Exception as ex:  # noqa: BLE001
             cpu_best = {"unavailable": repr(ex)}
 
+    deliverables = None
+    if e2e is not None:
+        deliverables = deliv
+        if cpu is not None:  # the reference path's time does not depend on the layer count: one goroutine, layer after layer
+            deliverables["cpu_reference_GiBps"] = cpu["value"]
+            deliverables["cpu_reference_s_for_context"] = ctx_bytes / GiB / cpu["value"]
+            deliverables["cpu_note"] = "oracle port, 1 thread, CRC pass + tar SHA-256 pass (cpu_baseline), extrapolated from its sample"
+            for r_ in deliverables["runs"]:
+                r_["speedup_vs_cpu_reference"] = r_["value"] / cpu["value"]
     if rank == 0:
         line = {
             "metric": "snapshot_hash_throughput", "value": value, "unit": "GiB/s", "n_gpus": world, "steps": args.steps,
@@ -726,6 +986,7 @@ def main():
                        "workload_kind": args.workload, "workload_info": wl_info,
                        "root": bytes(res.root).hex()},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "cpu_best_effort": cpu_best, "e2e": e2e,
+            "deliverables": deliverables, "strong": strong,
             "gpu_launches": launches,
             "gpu_launches_per_step": launches // max(1, args.steps), "tar_digest": tar,
             "clocks": summarize_clocks(rows),

@@ -230,3 +230,47 @@ def test_level0_plan_invariants():
             else:
                 assert p["full"] == p["tail_own"] == p["borrowed"] == 0
         assert owned == list(range((U + 255) // 256)), all_u
+
+
+def test_bench_global_sharded_layout_reassembles_the_global_stream():
+    """bench.py's strong-scaling layout: every rank's extents carry GLOBAL crc_suffix values, so sorting the union of
+    all ranks' extents by suffix (descending) must give back name_0, content_0, name_1, ... of the one global context,
+    for any rank count; dup contexts point several files at one shared pool region."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(3)
+    names = [b"d%02d/f%04d" % (i % 5, i) for i in range(97)]
+    sizes = rng.integers(0, 5000, 97).astype(np.uint64)
+    total = int(sizes.sum()) + sum(len(n) for n in names)
+    for world in (1, 2, 3, 8):
+        rows, seen_files = [], 0
+        for rank in range(world):
+            lay, info = bench.global_sharded_layout(names, sizes, rank, world)
+            assert info["bytes_total"] == int(sizes.sum()) and lay["stream_len"] == total
+            e = lay["ext"]
+            seen_files += len(e) // 2
+            for k in range(len(e)):
+                if e["flags"][k] == 1:  # a name: its bytes sit in the meta blob
+                    o = int(e["arena_off"][k]) - lay["meta_base"]
+                    rows.append((int(e["crc_suffix"][k]), "n", lay["blob"][o:o + int(e["len"][k])]))
+                else:
+                    assert int(e["arena_off"][k]) % 512 == 0 and int(e["arena_off"][k]) + int(e["len"][k]) <= lay["meta_base"]
+                    rows.append((int(e["crc_suffix"][k]), "f", int(e["len"][k])))
+        assert seen_files == len(names)
+        rows.sort(key=lambda r: -r[0])
+        after = total
+        for i, nm in enumerate(names):
+            s_n, kind_n, val_n = rows[2 * i]
+            s_f, kind_f, val_f = rows[2 * i + 1]
+            after -= len(nm)
+            assert (kind_n, val_n, s_n) == ("n", nm, after)
+            after -= int(sizes[i])
+            assert (kind_f, val_f, s_f) == ("f", int(sizes[i]), after)
+        assert after == 0
+    # dup: files share pool regions
+    pick = rng.integers(0, 10, 97)
+    lay, info = bench.global_sharded_layout(names, np.full(97, 1024, np.uint64), 1, 4, pick, 1024, 10)
+    assert lay["fill_bytes"] == 10 * 1024 and set(int(x) // 1024 for x in lay["ext"]["arena_off"][1::2]) <= set(range(10))
