@@ -187,7 +187,9 @@ int mksnap_device_submit(mksnap_t *h, uint32_t slot, uint64_t used,
                          const mksnap_range *ranges, uint64_t n_ranges);
 
 /* Finish the session: sort + unique the chunk digests, Merkle root, wait for
- * the device, fill *out. */
+ * the device, fill *out.  On a handle that is one rank of SEVERAL (mksnap_comm_init with n_ranks > 1) out->root is
+ * left zeroed: the content address is the root of the global table, which mksnap_exchange_tables /
+ * mksnap_allgather_tables return. */
 int mksnap_finish(mksnap_t *h, mksnap_result *out);
 
 /* cacheID arithmetic: the value checksum.Sum32() returns at
