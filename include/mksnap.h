@@ -75,6 +75,14 @@ typedef struct {
  * being submitted and must be multiples of 16. */
 #define MKSNAP_X_CRC 1u /* part of the CRC-32 context stream */
 #define MKSNAP_X_CDC 2u /* chunk + digest this extent as one file */
+/* A file larger than one arena (tario.WriteEntry copies any size, lib/tario/write.go:45): its pieces travel in
+ * consecutive submits.  Every piece but the last carries MKSNAP_X_MORE, must be the LAST CDC extent of its submit and
+ * states in `reserved` how many bytes of the file follow in later submits (saturate at 0xFFFFFFFF); every piece but
+ * the first carries MKSNAP_X_CONT, must be the FIRST CDC extent of the next submit and start at arena offset >=
+ * mksnap_limits.carry_bytes (the engine copies the chunk left open at the end of the previous piece in front of it).
+ * Chunks and digests are exactly those of the undivided file.  CRC extents need none of this: they split anywhere. */
+#define MKSNAP_X_MORE 4u
+#define MKSNAP_X_CONT 8u
 typedef struct {
     uint64_t arena_off;
     uint64_t len;
@@ -85,7 +93,7 @@ typedef struct {
      * per walked path, no separators. */
     uint64_t crc_suffix;
     uint32_t flags;
-    uint32_t reserved;
+    uint32_t reserved; /* MKSNAP_X_MORE: bytes of this file in later submits (saturated); otherwise 0 */
 } mksnap_extent;
 
 /* A piece of a serial SHA-256 stream (replaces the tarDigester sha256.New() sink of
@@ -165,6 +173,7 @@ typedef struct {
     uint64_t device_arena_bytes;
     uint32_t n_host_arenas;
     uint32_t n_device_slots;
+    uint64_t carry_bytes;        /* earliest arena offset of a MKSNAP_X_CONT extent (max chunk size, 512-aligned) */
 } mksnap_limits;
 int mksnap_get_limits(const mksnap_t *h, mksnap_limits *out);
 

@@ -16,6 +16,8 @@ LIB_PATH = _HERE / "lib" / "libmksnap.so"
 
 MKSNAP_X_CRC = 1
 MKSNAP_X_CDC = 2
+MKSNAP_X_MORE = 4   # CDC extent whose file continues in the next submit (reserved = bytes that follow)
+MKSNAP_X_CONT = 8   # CDC extent that continues the MORE extent of the previous submit
 
 ERRORS = {0: "OK", -1: "E_INVAL", -2: "E_CUDA", -3: "E_NOMEM", -4: "E_CAPACITY", -5: "E_STATE", -6: "E_NCCL"}
 
@@ -65,7 +67,7 @@ class Stats(C.Structure):
 class Limits(C.Structure):
     _fields_ = [("max_extents", C.c_uint64), ("max_streams", C.c_uint64), ("max_chunks", C.c_uint64),
                 ("host_arena_bytes", C.c_uint64), ("device_arena_bytes", C.c_uint64), ("n_host_arenas", C.c_uint32),
-                ("n_device_slots", C.c_uint32)]
+                ("n_device_slots", C.c_uint32), ("carry_bytes", C.c_uint64)]
 
 
 # every symbol include/mksnap.h declares: (name, restype, argtypes)

@@ -120,6 +120,9 @@ struct mksnap {
     uint64_t n_streams = 0;
     uint64_t stream_base = 0; // bytes of arenas submitted before the current one
     uint64_t crc_bytes = 0;
+    bool open_file = false;      // the last submit ended with a MKSNAP_X_MORE extent: the next must start with its continuation
+    uint8_t *d_carry = nullptr;  // open chunk of that file (k_carry_out -> k_carry_in)
+    uint64_t carry_cap = 0;
 
     // sort / table
     uint64_t *d_keys[2] = {nullptr, nullptr};
@@ -525,6 +528,8 @@ static int create_impl(mksnap *h)
     h->pool_cap = (uint32_t)pc;
     CK(h, cudaMalloc(&h->d_pool, (uint64_t)h->pool_cap * 4));
     CK(h, cudaMalloc(&h->d_pool_count, 4));
+    h->carry_cap = ((uint64_t)h->prm.max_size + 511) / 512 * 512;
+    CK(h, cudaMalloc(&h->d_carry, h->carry_cap));
     CK(h, cudaMalloc(&h->d_counts, mx * 4));
     CK(h, cudaMalloc(&h->d_bases, mx * 4));
 
@@ -625,6 +630,7 @@ void mksnap_destroy(mksnap_t *h)
             cudaEventDestroy(m.ev_done);
     }
     cudaFree(h->d_consts); cudaFree(h->d_gear); cudaFree(h->d_sc); cudaFreeHost(h->h_sc);
+    cudaFree(h->d_carry);
     cudaFree(h->d_tiles); cudaFree(h->d_pool); cudaFree(h->d_pool_count); cudaFree(h->d_counts); cudaFree(h->d_bases);
     cudaFree(h->d_scan_tmp);
     cudaFree(h->d_order); cudaFree(h->d_chunk_start); cudaFree(h->d_chunk_len); cudaFree(h->d_chunk_end); cudaFree(h->d_digests);
@@ -653,6 +659,7 @@ int mksnap_begin(mksnap_t *h)
     h->n_streams = 0;
     h->stream_base = 0;
     h->crc_bytes = 0;
+    h->open_file = false;
     h->n_unique = 0;
     h->finished = false;
     h->in_session = true;
@@ -707,6 +714,7 @@ int mksnap_get_limits(const mksnap_t *h, mksnap_limits *out)
     out->device_arena_bytes = h->cfg.device_arena_bytes;
     out->n_host_arenas = (uint32_t)h->arenas.size();
     out->n_device_slots = h->n_slots;
+    out->carry_bytes = h->carry_cap;
     return 0;
 }
 
@@ -727,7 +735,8 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         CK(h, cudaEventSynchronize(m.ev_done));
         m.in_flight = false;
     }
-    uint64_t n_crc = 0, n_files = 0, pieces = 0, cdc_bytes = 0, crc_bytes = 0, big_slots = 0;
+    uint64_t n_crc = 0, n_files = 0, pieces = 0, cdc_bytes = 0, crc_bytes = 0, big_slots = 0, cont_off = 0;
+    bool have_cont = false, have_more = false;
     for (uint64_t i = 0; i < n_ext; i++) {
         const mksnap_extent &x = ext[i];
         if ((x.arena_off & 15) || x.arena_off > used || x.len > used - x.arena_off)
@@ -744,16 +753,41 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
             n_crc++;
         }
         if (x.flags & MKSNAP_X_CDC) {
+            const bool cont = (x.flags & MKSNAP_X_CONT) != 0, more = (x.flags & MKSNAP_X_MORE) != 0;
+            if (cont) {
+                if (n_files != 0 || !h->open_file)
+                    return fail(h, MKSNAP_E_STATE, "extent %llu: MKSNAP_X_CONT must be the first CDC extent of the submit that follows a MKSNAP_X_MORE extent",
+                                (unsigned long long)i);
+                if (x.arena_off < h->carry_cap)
+                    return fail(h, MKSNAP_E_INVAL, "extent %llu: a continuation starts at arena offset >= %llu (room for the open chunk)",
+                                (unsigned long long)i, (unsigned long long)h->carry_cap);
+                have_cont = true;
+                cont_off = x.arena_off;
+            }
+            if (have_more)
+                return fail(h, MKSNAP_E_INVAL, "extent %llu: a MKSNAP_X_MORE extent must be the last CDC extent of its submit", (unsigned long long)i);
+            if (more) {
+                if (x.len == 0 || x.reserved == 0)
+                    return fail(h, MKSNAP_E_INVAL, "extent %llu: MKSNAP_X_MORE needs a non-empty piece and the bytes that follow in `reserved`",
+                                (unsigned long long)i);
+                have_more = true;
+            }
             m.h_files[n_files].off = x.arena_off;
             m.h_files[n_files].len = x.len;
             m.h_files[n_files].scratch = big_slots;
-            if (x.len >= SELECT_BIG_FILE)
-                big_slots += x.len / h->prm.min_size + 2;
+            m.h_files[n_files].more_after = more ? x.reserved : 0u;
+            m.h_files[n_files].cont = cont ? 1u : 0u;
+            if (x.len + (cont ? h->carry_cap : 0) >= SELECT_BIG_FILE)
+                big_slots += (x.len + h->carry_cap) / h->prm.min_size + 2;
             cdc_bytes += x.len;
             n_files++;
+        } else if (x.flags & (MKSNAP_X_MORE | MKSNAP_X_CONT)) {
+            return fail(h, MKSNAP_E_INVAL, "extent %llu: MKSNAP_X_MORE / MKSNAP_X_CONT apply to MKSNAP_X_CDC extents", (unsigned long long)i);
         }
     }
     m.h_piece_base[n_crc] = (uint32_t)pieces;
+    if (h->open_file && !have_cont)
+        return fail(h, MKSNAP_E_STATE, "the previous submit left a file open (MKSNAP_X_MORE): this one must start with its MKSNAP_X_CONT extent");
     if (big_slots > h->table_cap) // the cut lists of the big files live in the (idle) radix key buffer
         return fail(h, MKSNAP_E_CAPACITY, "big-file cut lists need %llu slots, max_chunks allows %llu",
                     (unsigned long long)big_slots, (unsigned long long)h->table_cap);
@@ -816,6 +850,10 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
 
     // ---- compute stream ----
     CK(h, cudaStreamWaitEvent(sk, h->ev_copy_done, 0));
+    if (have_cont) { // prepend the open chunk of the file that continues here (before anything scans the arena)
+        k_carry_in<<<1, 256, 0, sk>>>(h->d_carry, d_arena, cont_off, m.d_files, 0u, h->d_sc);
+        LAUNCH_OK(h);
+    }
     CK(h, cudaEventRecord(h->ev[0], sk));
     if (n_crc && pieces) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>(h->sm_count, (pieces + 31) / 32);
@@ -840,7 +878,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         const bool big_files = big_slots != 0;
         if (big_files) {
             k_select_cuts_big<<<(uint32_t)n_files, SELB_THREADS, 0, sk>>>(m.d_files, (uint32_t)n_files, h->prm, h->d_tiles,
-                                                                       h->d_pool, h->d_counts, h->d_keys[0]);
+                                                                       h->d_pool, h->d_counts, h->d_keys[0], h->d_sc);
             LAUNCH_OK(h);
         }
         int rc = scan_u32(h, h->d_counts, h->d_bases, n_files, sk);
@@ -882,6 +920,10 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         LAUNCH_OK(h);
         k_batch_end<<<1, 32, 0, sk>>>(h->d_sc);
         LAUNCH_OK(h);
+        if (have_more) { // park the open chunk before this slot is recycled
+            k_carry_out<<<1, 256, 0, sk>>>(d_arena, h->d_carry, h->carry_cap, h->d_sc);
+            LAUNCH_OK(h);
+        }
     }
     CK(h, cudaEventRecord(h->ev[4], sk));
     if (n_rng) {
@@ -903,6 +945,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     for (uint64_t i = 0; i < n_rng; i++)
         if (!(rng[i].flags & MKSNAP_R_MORE))
             h->n_streams = std::max<uint64_t>(h->n_streams, (uint64_t)rng[i].stream + 1);
+    h->open_file = have_more;
     h->stream_base += used;
     h->crc_bytes += crc_bytes;
     h->submit_idx++;
@@ -1012,6 +1055,10 @@ int mksnap_finish(mksnap_t *h, mksnap_result *out)
         return fail(h, MKSNAP_E_CAPACITY, "gear candidate pool overflow (capacity %u entries): pathologically dense candidates", h->pool_cap);
     if (h->h_sc->err & 4u)
         return fail(h, MKSNAP_E_CUDA, "k_gear_scan: dynamic shared memory does not start where the layout plan assumes");
+    if (h->h_sc->err & 8u)
+        return fail(h, MKSNAP_E_STATE, "internal: open chunk of a continued file exceeds the carry buffer");
+    if (h->open_file)
+        return fail(h, MKSNAP_E_STATE, "finish: the last submit left a file open (MKSNAP_X_MORE without its continuation)");
     if (h->h_sc->err & 2u)
         return fail(h, MKSNAP_E_CAPACITY, "chunk table overflow (max_chunks = %llu)", (unsigned long long)h->max_chunks);
     const uint64_t n = h->h_sc->n_chunks;

@@ -593,6 +593,8 @@ struct CdcFile {
     uint64_t off;
     uint64_t len;
     uint64_t scratch; // big files: first slot of this file's cut list in the scratch buffer (len/min + 2 slots)
+    uint32_t more_after; // bytes of this file that follow in LATER submits (saturated); 0 = the file ends in this piece
+    uint32_t cont;       // 1 = continues the open file of the previous submit (k_carry_in prepended the open chunk)
 };
 
 struct CdcParamsDev {
@@ -608,6 +610,8 @@ struct SessionCounters {
     uint32_t err;                  // 1 = candidate pool overflow, 2 = chunk table overflow
     uint32_t crc_acc;              // XOR accumulator of K0
     uint32_t work;                 // work-stealing counter of K2
+    unsigned long long carry_off;  // open chunk of a file that continues in the next submit: slot offset of its first byte
+    unsigned long long carry_len;  //   and its length (< max_size); consumed by k_carry_in of the next submit
     uint32_t len_bins[64];         // K2 work order: chunks of the batch per length class (2 KiB classes)
     uint32_t len_cursor[64];       //   slots handed out per class while the order is written
 };
@@ -616,16 +620,22 @@ constexpr uint32_t LEN_CLASS_SHIFT = 11;
 
 // One application of the cut rule from `prev`, reading tile records and candidates from
 // global memory.
-__device__ __forceinline__ uint64_t select_one_cut(uint64_t prev, uint64_t end, const CdcParamsDev &prm,
+// `more_after` > 0: the file continues in a later submit, `end` is only the end of this PIECE.  The rule is then
+// applied to the whole file (rem counts the bytes still to come); when it cannot be decided from the bytes at hand --
+// no qualifying candidate before `end` and the forced cut / file end lies beyond it -- CUT_OPEN is returned and the
+// open chunk [prev, end) is carried into the next submit (k_carry_in).
+constexpr uint64_t CUT_OPEN = ~0ull;
+__device__ __forceinline__ uint64_t select_one_cut(uint64_t prev, uint64_t end, uint32_t more_after, const CdcParamsDev &prm,
                                                    const TileRec *__restrict__ tiles, const uint32_t *__restrict__ pool)
 {
-    const uint64_t rem = end - prev;
+    const uint64_t rem = end - prev + more_after;
     if (rem <= prm.min_size)
-        return end;
-    const uint64_t limit_end = prev + (rem < prm.max_size ? rem : prm.max_size);
+        return more_after ? CUT_OPEN : end;
+    const uint64_t limit_end = prev + (rem < prm.max_size ? rem : prm.max_size); // may lie beyond `end`
+    const uint64_t scan_end = limit_end < end ? limit_end : end;
     const uint64_t lo = prev + prm.min_size - 1;
     const uint64_t normal_pos = prev + prm.normal_size - 1; // pos >= this: loose accepted
-    for (uint64_t t = lo / GEAR_TILE; t * GEAR_TILE < limit_end; ++t) {
+    for (uint64_t t = lo / GEAR_TILE; t * GEAR_TILE < scan_end; ++t) {
         const TileRec tr = tiles[t];
         const uint64_t tb = t * GEAR_TILE;
         for (uint32_t j = 0; j < tr.count; ++j) {
@@ -633,13 +643,13 @@ __device__ __forceinline__ uint64_t select_one_cut(uint64_t prev, uint64_t end, 
             const uint64_t pos = tb + (ent & 0x7FFFFFFFu);
             if (pos < lo)
                 continue;
-            if (pos >= limit_end)
-                return limit_end;
+            if (pos >= scan_end)
+                return limit_end <= end ? limit_end : CUT_OPEN;
             if (pos >= normal_pos || (ent >> 31))
                 return pos + 1;
         }
     }
-    return limit_end;
+    return limit_end <= end ? limit_end : CUT_OPEN;
 }
 
 constexpr uint64_t SELECT_BIG_FILE = 4ull << 20; // files at least this long get a CTA and shared-memory staging
@@ -668,7 +678,14 @@ k_select_cuts(const CdcFile *__restrict__ files, uint32_t n_files, CdcParamsDev 
         out = sc->n_chunks + bases[f];
     uint32_t n = 0;
     while (prev < end) {
-        const uint64_t cut = select_one_cut(prev, end, prm, tiles, pool);
+        const uint64_t cut = select_one_cut(prev, end, fl.more_after, prm, tiles, pool);
+        if (cut == CUT_OPEN) { // the file continues in the next submit: [prev, end) travels with it
+            if (PASS == 1) {
+                sc->carry_off = prev;
+                sc->carry_len = end - prev;
+            }
+            break;
+        }
         if (PASS == 1) {
             if (out + n < max_chunks) {
                 chunk_start[out + n] = prev;
@@ -753,7 +770,7 @@ __device__ __forceinline__ uint32_t sel_rule(const SelWin &w, const CdcParamsDev
 __global__ void __launch_bounds__(SELB_THREADS)
 k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParamsDev prm,
                   const TileRec *__restrict__ tiles, const uint32_t *__restrict__ pool,
-                  uint32_t *__restrict__ counts, uint64_t *__restrict__ cuts)
+                  uint32_t *__restrict__ counts, uint64_t *__restrict__ cuts, SessionCounters *__restrict__ sc)
 {
     constexpr int PASS = 0;
     const uint32_t f = blockIdx.x;
@@ -767,12 +784,13 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
     __shared__ uint32_t s_cand[SELB_CANDS];      // offset within the window | strict << 31
     __shared__ uint32_t s_next[SELB_CANDS];      // where the chain goes from each candidate
     __shared__ uint32_t s_w[SELB_THREADS / 32];
-    __shared__ unsigned long long s_prev;
+    __shared__ unsigned long long s_prev, s_open;
     __shared__ uint32_t s_n;
 
     const uint64_t end = fl.off + fl.len;
     if (threadIdx.x == 0) {
         s_prev = fl.off;
+        s_open = CUT_OPEN;
         s_n = 0;
     }
     __syncthreads();
@@ -836,7 +854,9 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
         w.cand = s_cand;
         w.ncand = s_off[nreg];
         w.wend = nreg * GEAR_TILE;
-        w.fend = (wbase + w.wend >= end) ? (uint32_t)(end - wbase) : 0xFFFFFFFFu;
+        // a piece whose file continues (more_after) has no file end in sight: the chain stops with NX_OUT near the
+        // piece end and the exact rule (select_one_cut with more_after) finishes from global memory
+        w.fend = (wbase + w.wend >= end && !fl.more_after) ? (uint32_t)(end - wbase) : 0xFFFFFFFFu;
         // ---- 2. next[] for every candidate, in parallel ----
         for (uint32_t q = threadIdx.x; q < w.ncand; q += SELB_THREADS) {
             const uint32_t prev = (s_cand[q] & 0x7FFFFFFFu) + 1;
@@ -877,20 +897,30 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
             }
             uint64_t prev64 = wbase + prev;
             if (!progressed && prev64 < end) {
-                // pathologically dense candidates: the staged window is too short for one search range.
-                // Make progress with one cut straight from global memory.
-                const uint64_t cut = select_one_cut(prev64, end, prm, tiles, pool);
-                my_cuts[n] = cut - fl.off;
-                ++n;
-                prev64 = cut;
+                // pathologically dense candidates (the staged window is too short for one search range), or the last
+                // stretch of a piece whose file continues in the next submit: one cut straight from global memory
+                const uint64_t cut = select_one_cut(prev64, end, fl.more_after, prm, tiles, pool);
+                if (cut == CUT_OPEN) {
+                    s_open = prev64;
+                    prev64 = end; // leave the loop; [s_open, end) is the open chunk
+                } else {
+                    my_cuts[n] = cut - fl.off;
+                    ++n;
+                    prev64 = cut;
+                }
             }
             s_prev = prev64;
             s_n = n;
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         counts[f] = s_n;
+        if (s_open != CUT_OPEN) {
+            sc->carry_off = s_open;
+            sc->carry_len = end - s_open;
+        }
+    }
     (void)PASS;
 }
 
@@ -936,6 +966,47 @@ __global__ void k_batch_begin(SessionCounters *sc, const uint32_t *counts, const
             sc->err |= 2u;
         sc->n_files += n_files;
         sc->cdc_bytes += cdc_bytes;
+    }
+}
+
+// A file larger than one arena (tario.WriteEntry streams any size, lib/tario/write.go:45).  The piece of such a file
+// ends with an OPEN chunk the cut rule cannot close without the bytes that follow (sc->carry_off/len, < max_size).
+// k_carry_out parks it in a side buffer at the end of its submit (the slot may be overwritten by the next H2D);
+// k_carry_in of the next submit copies it in FRONT of the continuation, which the packer placed at `cont_off` of the
+// new arena with at least max_size free bytes before it, and widens the file record to start at the open chunk.
+// k_carry_in runs on the compute stream after the new arena's H2D copy has landed.  One CTA each.
+__global__ void __launch_bounds__(256)
+k_carry_out(const uint8_t *__restrict__ src_slot, uint8_t *__restrict__ carry, uint64_t carry_cap, SessionCounters *__restrict__ sc)
+{
+    const uint64_t n = sc->carry_len, from = sc->carry_off;
+    if (n > carry_cap) {
+        if (threadIdx.x == 0)
+            sc->err |= 8u;
+        return;
+    }
+    for (uint64_t i = threadIdx.x; i < n; i += blockDim.x)
+        carry[i] = src_slot[from + i];
+}
+
+__global__ void __launch_bounds__(256)
+k_carry_in(const uint8_t *__restrict__ carry, uint8_t *__restrict__ dst_slot, uint64_t cont_off, CdcFile *__restrict__ files,
+           uint32_t cont_index, SessionCounters *__restrict__ sc)
+{
+    const uint64_t n = sc->carry_len;
+    if (n > cont_off) { // cannot happen: carry_len < max_size <= cont_off (checked at submit)
+        if (threadIdx.x == 0)
+            sc->err |= 8u;
+        return;
+    }
+    uint8_t *d = dst_slot + cont_off - n;
+    for (uint64_t i = threadIdx.x; i < n; i += blockDim.x)
+        d[i] = carry[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        files[cont_index].off = cont_off - n;
+        files[cont_index].len += n;
+        sc->carry_len = 0;
+        sc->carry_off = 0;
     }
 }
 

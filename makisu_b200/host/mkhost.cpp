@@ -225,6 +225,8 @@ int mkhost_memfs_commit_copy_ops(mkhost_memfs *m, mksnap_t *eng, int64_t now_uni
                 if (j.file_off != 0)
                     continue;
                 auto range = deferred.equal_range(j.path);
+                if (range.first == range.second || (uint64_t)range.first->second.st.st_size != j.len)
+                    continue; // a piece of a file larger than the arena: that file is copied from disk at the end
                 for (auto it = range.first; it != range.second; ++it)
                     copiers[it->second.copier].finish_regular(it->second.st, j.path, it->second.dst, j.dst, j.len);
                 deferred.erase(range.first, range.second);

@@ -35,6 +35,9 @@ struct mksnap {
     std::map<uint32_t, std::vector<uint8_t>> stream_digest;
     mksnap_result last;
     uint64_t submits = 0;
+    bool file_open = false;            // MKSNAP_X_MORE seen: the next submit must start with the continuation
+    uint64_t open_follow = 0;
+    std::vector<uint8_t> open_bytes;   // pieces of the file that spans submits
 };
 
 static std::string g_err;
@@ -79,6 +82,8 @@ int mksnap_begin(mksnap_t *h)
     h->digests.clear();
     h->open_streams.clear();
     h->stream_digest.clear();
+    h->file_open = false;
+    h->open_bytes.clear();
     std::fill(h->acquired.begin(), h->acquired.end(), false);
     return 0;
 }
@@ -121,6 +126,7 @@ int mksnap_get_limits(const mksnap_t *h, mksnap_limits *out)
     out->host_arena_bytes = h->cfg.host_arena_bytes;
     out->device_arena_bytes = h->cfg.device_arena_bytes;
     out->n_host_arenas = (uint32_t)h->arenas.size();
+    out->carry_bytes = 131072;
     return 0;
 }
 
@@ -140,6 +146,8 @@ int mksnap_arena_submit(mksnap_t *h, int32_t arena_id, uint64_t used, const mksn
     mko_cdc_default_params(&p);
     if (h->cfg.cdc.min_size)
         memcpy(&p, &h->cfg.cdc, sizeof p);
+    uint64_t n_cdc = 0;
+    bool saw_more = false;
     for (uint64_t i = 0; i < n_ext; ++i) {
         const mksnap_extent &e = ext[i];
         if (e.arena_off % 16 || e.arena_off + e.len > used)
@@ -149,17 +157,50 @@ int mksnap_arena_submit(mksnap_t *h, int32_t arena_id, uint64_t used, const mksn
             h->crc_bytes += e.len;
         }
         if (e.flags & MKSNAP_X_CDC) {
-            std::vector<uint64_t> ends((size_t)(e.len / p.min_size) + 2);
-            const size_t n = mko_cdc_cuts(a + e.arena_off, e.len, &p, ends.data(), ends.size());
+            const bool cont = e.flags & MKSNAP_X_CONT, more = e.flags & MKSNAP_X_MORE;
+            // a file that spans submits (same contract as the real engine): the pieces are buffered and the WHOLE file is
+            // chunked when its last piece arrives -- by definition what the engine's carried open chunk must reproduce
+            if (cont && (n_cdc != 0 || !h->file_open))
+                return fail(h, MKSNAP_E_STATE, "MKSNAP_X_CONT must be the first CDC extent after a MKSNAP_X_MORE extent");
+            if (cont && e.arena_off < 131072)
+                return fail(h, MKSNAP_E_INVAL, "a continuation starts at arena offset >= carry_bytes");
+            if (!cont && h->file_open)
+                return fail(h, MKSNAP_E_STATE, "the previous submit left a file open: its continuation must come first");
+            if (saw_more)
+                return fail(h, MKSNAP_E_INVAL, "a MKSNAP_X_MORE extent must be the last CDC extent of its submit");
+            if (more && (e.len == 0 || e.reserved == 0))
+                return fail(h, MKSNAP_E_INVAL, "MKSNAP_X_MORE needs a non-empty piece and the bytes that follow");
+            ++n_cdc;
+            h->cdc_bytes += e.len;
+            if (!cont)
+                h->n_files++;
+            const uint8_t *fp = a + e.arena_off;
+            uint64_t flen = e.len;
+            if (cont || more) {
+                if (cont && h->open_follow != e.len + (more ? e.reserved : 0) && h->open_follow != 0xFFFFFFFFull)
+                    return fail(h, MKSNAP_E_INVAL, "continuation length disagrees with the bytes announced by the previous piece");
+                h->open_bytes.insert(h->open_bytes.end(), fp, fp + e.len);
+                h->file_open = more;
+                h->open_follow = more ? e.reserved : 0;
+                saw_more = more;
+                if (more)
+                    continue;
+                fp = h->open_bytes.data();
+                flen = h->open_bytes.size();
+            }
+            std::vector<uint64_t> ends((size_t)(flen / p.min_size) + 2);
+            const size_t n = mko_cdc_cuts(fp, flen, &p, ends.data(), ends.size());
             uint64_t prev = 0;
             for (size_t j = 0; j < n; ++j) {
                 uint8_t d[32];
-                mko_sha256(a + e.arena_off + prev, ends[j] - prev, d);
+                mko_sha256(fp + prev, ends[j] - prev, d);
                 h->digests.insert(h->digests.end(), d, d + 32);
                 prev = ends[j];
             }
-            h->cdc_bytes += e.len;
-            h->n_files++;
+            if (cont)
+                h->open_bytes.clear();
+        } else if (e.flags & (MKSNAP_X_MORE | MKSNAP_X_CONT)) {
+            return fail(h, MKSNAP_E_INVAL, "MKSNAP_X_MORE / MKSNAP_X_CONT apply to CDC extents");
         }
     }
     std::set<uint32_t> seen;
@@ -201,6 +242,8 @@ int mksnap_finish(mksnap_t *h, mksnap_result *out)
         return fail(h, MKSNAP_E_STATE, "finish outside a session");
     if (!h->open_streams.empty())
         return fail(h, MKSNAP_E_STATE, "a stream was left open (last piece carried MKSNAP_R_MORE)");
+    if (h->file_open)
+        return fail(h, MKSNAP_E_STATE, "a file was left open (MKSNAP_X_MORE without its continuation)");
     memset(out, 0, sizeof *out);
     out->crc_pure = h->crc_pure;
     out->crc_bytes = h->crc_bytes;

@@ -125,8 +125,20 @@ def cache_id_and_commit(make_engine, tmp):
         assert (got["n_entries"], got["tar_bytes"]) == (len(entries), len(blob))
         assert (got["n_chunks"], got["n_unique"], got["root"]) == (want["n_chunks"], want["n_unique"], want["root"])
     assert eng.submits() >= 3
-    try:                                                          # an entry larger than the arena is refused loudly
-        host.commit_copy_ops(make_engine(1 << 20), root, NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 3, 4)])
+    # big.bin (1.5 MB) is larger than a 1 MiB arena: it travels in pieces (MKSNAP_X_MORE / MKSNAP_X_CONT, per-file
+    # stream continued) and everything equals the single-arena result -- tario.WriteEntry copies any size (write.go:45)
+    eng = make_engine(1 << 20)
+    tar_path = os.path.join(tmp, "layer_split.tar")
+    with open(tar_path, "wb") as f:
+        got = host.commit_copy_ops(eng, root, NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 3, 4)], tar_fd=f.fileno())
+    assert open(tar_path, "rb").read() == blob
+    assert got["tar_digest"] == lt.tar_digest(entries) and (got["n_entries"], got["tar_bytes"]) == (len(entries), len(blob))
+    assert (got["n_chunks"], got["n_unique"], got["root"]) == (want["n_chunks"], want["n_unique"], want["root"])
+    h = host.MemFS(root)
+    got = h.commit_copy_ops(make_engine(1 << 20), NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 3, 4)], flags=host.MKHOST_FILE_DIGESTS)
+    assert got["root"] == want["root"] and h.file_digest("/app/big.bin") == hashlib.sha256(open(os.path.join(ctx, "big.bin"), "rb").read()).digest()
+    try:                                                          # too small to carry a file across submits: refused loudly
+        host.commit_copy_ops(make_engine(128 << 10), root, NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 3, 4)])
         raise AssertionError("expected a capacity error")
     except host.HostError as e:
         assert "exceeds the arena" in str(e)
@@ -265,12 +277,11 @@ def content_aware_scan(make_engine, tmp):
     assert h.commit_scan(small, NOW, flags=host.MKHOST_SCAN_CONTENT)["n_entries"] == 0
     assert small.submits() >= 4
     edit("d/big.bin", 0)
-    assert [e.dst for e in o.add_layer_by_scan(content_aware=True)] == ["/d", "/d/big.bin"]
-    try:
-        h.commit_scan(small, NOW, flags=host.MKHOST_SCAN_CONTENT)
-        raise AssertionError("expected a capacity error")
-    except host.HostError as e:
-        assert "exceeds the arena" in str(e)
+    l4 = o.add_layer_by_scan(content_aware=True)
+    assert [e.dst for e in l4] == ["/d", "/d/big.bin"]
+    g4 = h.commit_scan(small, NOW, flags=host.MKHOST_SCAN_CONTENT)   # the 2.5 MB entry is committed in pieces (1 MiB arenas)
+    assert g4["n_entries"] == 2 and g4["tar_digest"] == lt.tar_digest(l4)
+    assert h.file_digest("/d/big.bin") == hashlib.sha256(open(os.path.join(root, "d/big.bin"), "rb").read()).digest()
 
 
 def materialize_from_the_arena(make_engine, tmp):

@@ -416,3 +416,39 @@ def test_batch_of_layers_shares_one_session(ctx, tmp_path):
         for i, (dig, blob) in enumerate(want):
             assert got[i]["tar_digest"] == dig == "sha256:" + hashlib.sha256(paths[i].read_bytes()).hexdigest(), (i, arena)
             assert paths[i].read_bytes() == blob
+
+
+def test_commit_layer_with_a_file_larger_than_the_arena(ctx, tmp_path):
+    """big.bin (11 MB) through 4 MiB pinned arenas: the packer splits the tar member (MKSNAP_X_MORE / MKSNAP_X_CONT), the
+    engine carries the open chunk, the TarDigest stream and the per-file digest across submits -- same TarDigest, tar
+    bytes, chunk table and file digest as the oracle over the undivided file (lib/tario/write.go:45 copies any size)."""
+    import hashlib
+    from makisu_b200 import host
+    from makisu_b200.abi import Engine
+    from oracle import layer_tar as lt
+    from oracle import lib as olib
+    root = tmp_path / "root"
+    root.mkdir()
+    os.chmod(root, 0o755)
+    entries = lt.MemFS(lambda: NOW, str(root)).add_layer_by_copy_ops([lt.CopyOperation.new(["/"], ctx, "/", "/app/", uid=3, gid=4)])
+    blob = b"".join(lt.layer_tar_chunks(entries))
+    arena = np.frombuffer(blob, dtype=np.uint8)
+    offs, lens, pos = [], [], 0
+    for e in entries:
+        pos += len(lt.entry_header_bytes(e))
+        if e.hdr.typeflag == lt.TYPE_REG and e.hdr.size:
+            offs.append(pos)
+            lens.append(e.hdr.size)
+            pos += (e.hdr.size + 511) // 512 * 512
+    want = olib.chunk_table(arena, offs, lens)
+    tar_path = tmp_path / "layer.tar"
+    with Engine(device=0, device_arena_bytes=4 << 20, n_host_arenas=2, host_arena_bytes=4 << 20, max_extents=1 << 12) as eng:
+        h = host.MemFS(str(root))
+        with open(tar_path, "wb") as f:
+            got = h.commit_copy_ops(eng, NOW, [host.CopyOperation(["/"], ctx, "/", "/app/", 3, 4)], tar_fd=f.fileno(),
+                                    flags=host.MKHOST_FILE_DIGESTS)
+        assert tar_path.read_bytes() == blob
+        assert got["tar_digest"] == lt.tar_digest(entries) == "sha256:" + hashlib.sha256(blob).hexdigest()
+        assert (got["n_chunks"], got["n_unique"], got["root"]) == (want["n_chunks"], want["n_unique"], want["root"])
+        assert h.file_digest("/app/big.bin") == hashlib.sha256(open(os.path.join(ctx, "big.bin"), "rb").read()).digest()
+        h.close()

@@ -233,3 +233,94 @@ def test_chunk_order_knob_is_result_neutral(oracle_lib, monkeypatch):
         assert root == want["root"] and n == want["n_chunks"] and u == want["n_unique"]
         np.testing.assert_array_equal(ends, want_ends)
         np.testing.assert_array_equal(dig, want["digests"])
+
+
+def _split_submit(e, files, pieces_of, carry, use_host_arenas):
+    """Drive one session: `files` = list of byte arrays in order; pieces_of[i] = piece lengths of file i (sum = len).
+    Every piece after the first of a file opens a new submit (MKSNAP_X_MORE / MKSNAP_X_CONT)."""
+    from makisu_b200.abi import Extent, MKSNAP_X_CDC, MKSNAP_X_CONT, MKSNAP_X_MORE
+    import ctypes
+    cap = e.limits().host_arena_bytes if use_host_arenas else e.limits().device_arena_bytes
+    arena = np.zeros(cap, dtype=np.uint8)
+    ext, pos = [], 0
+
+    def flush():
+        nonlocal arena, ext, pos
+        if use_host_arenas:
+            ptr, c, aid = e.arena_acquire()
+            ctypes.memmove(ptr, arena.ctypes.data, pos)
+            e.arena_submit(aid, pos, ext)
+        else:
+            e.sync()
+            e.device_upload(0, 0, arena[:pos])
+            e.device_submit(0, pos, ext)
+        arena = np.zeros(cap, dtype=np.uint8)
+        ext, pos = [], 0
+    e.begin()
+    for data, pieces in zip(files, pieces_of):
+        done = 0
+        for k, n in enumerate(pieces):
+            first, last = k == 0, k == len(pieces) - 1
+            if not first:
+                flush()
+                pos = carry
+            pos = (pos + 511) // 512 * 512
+            assert pos + n <= cap
+            arena[pos:pos + n] = data[done:done + n]
+            x = Extent()
+            x.arena_off, x.len, x.crc_suffix = pos, n, 0
+            x.flags = MKSNAP_X_CDC | (0 if first else MKSNAP_X_CONT) | (0 if last else MKSNAP_X_MORE)
+            x.reserved = 0 if last else min(len(data) - done - n, 0xFFFFFFFF)
+            ext.append(x)
+            pos += n
+            done += n
+        assert done == len(data)
+    flush()
+    return e.finish()
+
+
+@pytest.mark.parametrize("use_host_arenas", [False, True])
+def test_files_larger_than_an_arena_span_submits(oracle_lib, use_host_arenas):
+    """lib/tario/write.go:45 copies a file of ANY size; here a file larger than an arena travels in pieces
+    (MKSNAP_X_MORE / MKSNAP_X_CONT): the open chunk at the end of a piece is carried to the next submit, so chunk
+    count, every digest, the table and the root equal the oracle's over the UNDIVIDED files -- for random content,
+    zero runs (forced max-size cuts straddling the boundary), pieces shorter than min_size, three-way splits, a
+    >4 MiB file (CTA-per-file selection path) and small neighbours sharing the arenas."""
+    from makisu_b200.abi import Engine, MksnapError, Extent, MKSNAP_X_CDC, MKSNAP_X_MORE
+    rng = np.random.default_rng(2024)
+    big = _rand(rng, 9_000_000)
+    zr = _rand(rng, 1_500_000)
+    zr[200_000:900_000] = 0                                   # forced cuts across the split
+    files = [_rand(rng, 70_000), big, _rand(rng, 5), zr, _rand(rng, 300_000), _rand(rng, 600_000), _rand(rng, 131_072 * 3)]
+    pieces = [[70_000], [3_145_728, 3_145_728, 9_000_000 - 2 * 3_145_728], [5], [524_288 - 512, 512 * 3, 1_500_000 - 524_288 - 1024],
+              [300_000], [1024, 600_000 - 1024], [131_072, 131_072 * 2]]
+    arena, offs = pack([f for f in files])
+    want = oracle_lib.chunk_table(arena, offs, [len(f) for f in files])
+    kw = dict(n_host_arenas=2, host_arena_bytes=8 << 20) if use_host_arenas else {}
+    with Engine(device=0, device_arena_bytes=8 << 20, max_extents=256, **kw) as e:
+        carry = e.limits().carry_bytes
+        assert carry >= 131072 and carry % 512 == 0
+        res = _split_submit(e, files, pieces, carry, use_host_arenas)
+        assert (res.n_chunks, res.n_unique, bytes(res.root)) == (want["n_chunks"], want["n_unique"], want["root"])
+        assert res.n_files == len(files) and res.cdc_bytes == sum(len(f) for f in files)
+        ends, dig = e.get_chunks(res.n_chunks)
+        np.testing.assert_array_equal(dig, want["digests"])    # same chunks in the same order
+        # contract errors: a file left open at finish; a continuation that is missing
+        e.begin()
+        x = Extent()
+        x.arena_off, x.len, x.flags, x.reserved = 0, 4096, MKSNAP_X_CDC | MKSNAP_X_MORE, 100
+        if use_host_arenas:
+            ptr, c, aid = e.arena_acquire()
+            e.arena_submit(aid, 8192, [x])
+        else:
+            e.device_submit(0, 8192, [x])
+        y = Extent()
+        y.arena_off, y.len, y.flags = 0, 4096, MKSNAP_X_CDC
+        with pytest.raises(MksnapError):
+            if use_host_arenas:
+                ptr, c, aid = e.arena_acquire()
+                e.arena_submit(aid, 8192, [y])
+            else:
+                e.device_submit(0, 8192, [y])
+        with pytest.raises(MksnapError):
+            e.finish()
