@@ -80,8 +80,9 @@ int main(int argc, char **argv)
     fill<<<148 * 8, 256>>>((uint64_t *)d_data, (total_cap + 8192) / 8);
     CK(cudaDeviceSynchronize());
     int sm = 148;
-    const int ns[] = {1, 4, 16, 32, 33, 64, 256, 1024, 4736, 9472, 20000};
-    const int lanes[] = {32, 16, 8, 1};
+    const int ns[] = {1, 32, 256, 1024, 4736, 9472, 20000};
+    const int lanes[] = {32};
+    printf("schedule warp = warp %d of the CTA (%d threads)\n", SS_SCHED_WARP, SS_THREADS);
     for (int max_lanes : lanes)
         for (int n : ns) {
             // ragged lengths around L, L chosen so the run takes a few ms
@@ -143,9 +144,10 @@ int main(int argc, char **argv)
             unsigned long long prof[8];
             CK(cudaMemcpyFromSymbol(prof, mk::ss_prof, sizeof prof));
             if (n <= 64 || n == 9472)
-                printf("    CTA0: rounds warp %.0f cyc/block (%.0f waiting), schedule warp %.0f cyc/block (%.0f waiting), %llu blocks, %.0f MHz\n",
+                printf("    CTA0: rounds warp %.0f cyc/block (%.0f waiting), schedule warp %.0f cyc/block (%.0f waiting), %llu blocks, %.0f MHz; "
+                       "hw warp slots %llu / %llu (sm %llu)\n",
                        (double)prof[0] / prof[4], (double)prof[1] / prof[4], (double)prof[2] / prof[4], (double)prof[3] / prof[4], prof[4],
-                       (double)prof[0] / best / 1e3);
+                       (double)prof[0] / best / 1e3, prof[5] & 0xffffffffu, prof[6] & 0xffffffffu, prof[5] >> 32);
             double bytes = 0;
             for (int i = 0; i < n; ++i) bytes += len[i];
             printf("lanes/pair %2d  streams %6d  grid %4d  L %8llu  %8.3f ms  per-stream %7.1f MB/s  aggregate %8.2f GB/s  %s\n",

@@ -97,7 +97,7 @@ struct mksnap {
 
     TileRec *d_tiles = nullptr;
     CUtensorMap tm_main[MAX_SLOTS][3], tm_halo[MAX_SLOTS]; // per slot: arena viewed as [rows][128 B]
-    int gear_cfg = 3;
+    int gear_cfg = 0; // index into GEAR_SHAPES
     bool sha_fma = true;                                    // chunk SHA-256: additions on the FMA pipe                                       // index into the k_gear_scan instantiations
     uint32_t *d_pool = nullptr;
     uint32_t pool_cap = 0;
@@ -412,16 +412,34 @@ static int alloc_table_buffers(mksnap *h, uint64_t rows)
     return 0;
 }
 
-template <int GROUPS> static int launch_gear(mksnap *h, uint32_t slot, uint32_t n_regions, cudaStream_t sk)
+template <int GROUPS, int TW, int ST> static int launch_gear(mksnap *h, uint32_t slot, uint32_t n_regions, cudaStream_t sk)
 {
-    using Cfg = GearCfg<GROUPS>;
+    using Cfg = GearCfg<GROUPS, TW, ST>;
     const uint32_t n_tiles = (n_regions + Cfg::TILE_WARPS - 1) / Cfg::TILE_WARPS;
     const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)h->sm_count);
-    k_gear_scan<GROUPS><<<grid, Cfg::THREADS, Cfg::SMEM, sk>>>(h->tm_main[slot][0], h->tm_halo[slot], n_tiles, h->d_gear,
-                                                              h->prm.strict_lim, h->prm.loose_lim, h->d_tiles, h->d_pool,
-                                                              h->pool_cap, h->d_pool_count, &h->d_sc->err);
+    k_gear_scan<GROUPS, TW, ST><<<grid, Cfg::THREADS, Cfg::SMEM, sk>>>(h->tm_main[slot][0], h->tm_halo[slot], n_tiles, h->d_gear,
+                                                                      h->prm.strict_lim, h->prm.loose_lim, h->d_tiles, h->d_pool,
+                                                                      h->pool_cap, h->d_pool_count, &h->d_sc->err);
     LAUNCH_OK(h);
     return 0;
+}
+
+// the k_gear_scan shapes that are compiled in: {groups, warps per tile, stages}; MKSNAP_GEAR_CFG picks one by index
+struct GearShape {
+    int groups, tile_warps, stages;
+};
+static const GearShape GEAR_SHAPES[] = {{4, 6, 6}, {3, 8, 4}, {2, 8, 4}, {3, 7, 5}, {6, 4, 9}};
+constexpr int N_GEAR_SHAPES = 5;
+
+static int launch_gear_cfg(mksnap *h, uint32_t slot, uint32_t n_regions, cudaStream_t sk)
+{
+    switch (h->gear_cfg) {
+    case 1: return launch_gear<3, 8, 4>(h, slot, n_regions, sk);
+    case 2: return launch_gear<2, 8, 4>(h, slot, n_regions, sk);
+    case 3: return launch_gear<3, 7, 5>(h, slot, n_regions, sk);
+    case 4: return launch_gear<6, 4, 9>(h, slot, n_regions, sk);
+    default: return launch_gear<4, 6, 6>(h, slot, n_regions, sk);
+    }
 }
 
 extern "C" {
@@ -500,24 +518,28 @@ static int create_impl(mksnap *h)
         CK(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&enc, cudaEnableDefault, &qres));
         if (!enc || qres != cudaDriverEntryPointSuccess)
             return fail(h, MKSNAP_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+        const char *e = getenv("MKSNAP_GEAR_CFG"); // tuning knob: index into GEAR_SHAPES (0 = default)
+        if (e && e[0] >= '0' && e[0] < '0' + N_GEAR_SHAPES && !e[1])
+            h->gear_cfg = e[0] - '0';
         const uint64_t n_rows = (c.device_arena_bytes + SLOT_SLACK) / 128;
+        const uint32_t box_rows = (uint32_t)GEAR_SHAPES[h->gear_cfg].tile_warps * 32u;
         for (uint32_t s = 0; s < h->n_slots; s++) {
             int rc;
-            if ((rc = make_row_map(h, enc, &h->tm_main[s][0], h->d_slot[s], n_rows, GearCfg<3>::BOX_ROWS)) ||
+            if ((rc = make_row_map(h, enc, &h->tm_main[s][0], h->d_slot[s], n_rows, box_rows)) ||
                 (rc = make_row_map(h, enc, &h->tm_halo[s], h->d_slot[s], n_rows, 1)))
                 return rc;
         }
-        CK(h, cudaFuncSetAttribute(k_gear_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<2>::SMEM));
-        CK(h, cudaFuncSetAttribute(k_gear_scan<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<3>::SMEM));
+        CK(h, cudaFuncSetAttribute(k_gear_scan<4, 6, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<4, 6, 6>::SMEM));
+        CK(h, cudaFuncSetAttribute(k_gear_scan<3, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<3, 8, 4>::SMEM));
+        CK(h, cudaFuncSetAttribute(k_gear_scan<2, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<2, 8, 4>::SMEM));
+        CK(h, cudaFuncSetAttribute(k_gear_scan<3, 7, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<3, 7, 5>::SMEM));
+        CK(h, cudaFuncSetAttribute(k_gear_scan<6, 4, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<6, 4, 9>::SMEM));
         const char *e2 = getenv("MKSNAP_SHA_FMA"); // tuning knob: 0 = plain adds in the chunk SHA-256 kernel
         if (e2 && e2[0] == '0')
             h->sha_fma = false;
         const char *e3 = getenv("MKSNAP_SHA_ORDER"); // tuning knob: 0 = hash chunks in file order instead of longest first
         if (e3 && e3[0] == '0')
             h->sha_order = false;
-        const char *e = getenv("MKSNAP_GEAR_CFG"); // tuning knob: consumer warp groups per CTA (2 or 3, x8 warps)
-        if (e && (e[0] == '2' || e[0] == '3'))
-            h->gear_cfg = e[0] - '0';
     }
     // expected candidates = bytes >> loose_bits; 8x headroom (32x at the default 12 bits would be wasteful for
     // dense parameter sets), plus one private block per resident gear warp (x2)
@@ -865,7 +887,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     if (n_files) {
         const uint32_t n_regions = (uint32_t)((used + GEAR_TILE - 1) / GEAR_TILE);
         CK(h, cudaMemsetAsync(h->d_pool_count, 0, 4, sk));
-        int rc = h->gear_cfg == 2 ? launch_gear<2>(h, slot, n_regions, sk) : launch_gear<3>(h, slot, n_regions, sk);
+        int rc = launch_gear_cfg(h, slot, n_regions, sk);
         if (rc)
             return rc;
     }

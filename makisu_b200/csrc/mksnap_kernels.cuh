@@ -294,9 +294,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        // the suspend-time hint lets the hardware park the warp instead of re-issuing the probe: a spinning warp
+        // steals issue slots from the warps that have data (ncu, round 2: 20 % of all issued instructions were
+        // YIELD/SYNCS/BRA of this loop)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok)
-                     : "r"(bar), "r"(parity)
+                     : "r"(bar), "r"(parity), "r"(200000u)
                      : "memory");
     } while (!ok);
 }
@@ -342,49 +345,57 @@ template <int K> __device__ __forceinline__ uint32_t gear_addr(uint32_t word, ui
         hv[(k0) + 3] = h;                                           \
     }
 
-// Tiles are 8 warps x 32 rows x 128 B = 32 KiB (one TMA op); GEAR_GROUPS groups of 8 consumer warps take the
-// CTA's tiles round-robin, so the pipeline depth (stages) is independent of how many warps hide latency.
+// A tile is TILE_WARPS warps x 32 rows x 128 B (one TMA op); GROUPS groups of TILE_WARPS consumer warps take the
+// CTA's tiles round-robin, so the pipeline depth (STAGES) is independent of how many warps hide latency.  With G groups
+// consuming, STAGES - G stages are in flight from HBM: the round-1 shape (3 groups x 8 warps, 4 stages of 32 KiB)
+// left ONE 32 KiB stage in flight per SM -- 4.7 MB over the chip against the ~6.5 MB that 6.5 TB/s x ~1 us of loaded
+// latency needs -- and consumers spun on the full barrier; 4 groups x 6 warps with 6 stages of 24 KiB keeps the same 24
+// consumer warps and puts two stages (48 KiB per SM, 7.1 MB) in flight.
 // Shared-memory plan (ABSOLUTE shared-window addresses; the kernel has no static shared memory, so the dynamic
 // region starts at the architecture's reserved 1 KiB, s0 = 0x400):
-//   [s0, s0 + 3*32 KiB)    stages 0..2
+//   [0x400, 0x20000)       the first N_A stages
 //   [0x20000, 0x30000)     gear table, 256-byte stride: value v of lane l at 0x20000 + v*256 + l*4.  With the
 //                          table on a 64 KiB boundary ONE PRMT builds a lookup address
 //                          (bytes {lane*4, data byte, 0x02, 0x00}): no multiply/add per lookup.
-//   [0x30000, 0x38000)     stage 3
-//   0x38000 / 0x38400      halo rows (one 128 B row per stage) / mbarriers
-template <int GEAR_GROUPS> struct GearCfg {
-    static constexpr uint32_t STAGES = 4;
-    static constexpr uint32_t TILE_WARPS = 8;
+//   [0x30000, ...)         the remaining stages, then the halo rows (one 128 B row per stage) and the mbarriers
+template <int GEAR_GROUPS, int TW = 8, int ST = 4> struct GearCfg {
+    static constexpr uint32_t STAGES = ST;
+    static constexpr uint32_t TILE_WARPS = TW;
+    static constexpr uint32_t GROUPS = GEAR_GROUPS;
     static constexpr uint32_t ROWS = TILE_WARPS * 32;
     static constexpr uint32_t TILE_BYTES = ROWS * 128;
     static constexpr uint32_t BOX_ROWS = ROWS;
     static constexpr uint32_t CONSUMER_WARPS = GEAR_GROUPS * TILE_WARPS;
     static constexpr uint32_t THREADS = (CONSUMER_WARPS + 1) * 32;
+    static constexpr uint32_t A0_ABS = 0x400;
     static constexpr uint32_t GEAR_ABS = 0x20000;
-    static constexpr uint32_t STAGE3_ABS = 0x30000;
-    static constexpr uint32_t HALO_ABS = 0x38000;
-    static constexpr uint32_t BARS_ABS = 0x38400;
+    static constexpr uint32_t B0_ABS = 0x30000;
+    static constexpr uint32_t N_A = (GEAR_ABS - A0_ABS) / TILE_BYTES < STAGES ? (GEAR_ABS - A0_ABS) / TILE_BYTES : STAGES;
+    static constexpr uint32_t N_B = STAGES - N_A;
+    static constexpr uint32_t HALO_ABS = B0_ABS + N_B * TILE_BYTES;           // 1 KiB aligned (TILE_BYTES is)
+    static constexpr uint32_t BARS_ABS = HALO_ABS + ((STAGES * 128 + 1023) / 1024) * 1024;
     static constexpr uint32_t END_ABS = BARS_ABS + 2 * STAGES * 8;
     static constexpr uint32_t SMEM = END_ABS - 1024; // dynamic bytes to request when the region starts at 0x400
+    static_assert(TILE_BYTES % 1024 == 0 && ROWS <= 256, "tile = whole swizzle atoms, one TMA box");
     static_assert(END_ABS <= 227 * 1024 + 1024, "exceeds the 227 KiB per-CTA limit");
-    __device__ static uint32_t stage_addr(uint32_t s0, uint32_t s) { return s < 3 ? s0 + s * TILE_BYTES : STAGE3_ABS; }
+    __device__ static uint32_t stage_addr(uint32_t s0, uint32_t s) { return s < N_A ? s0 + s * TILE_BYTES : B0_ABS + (s - N_A) * TILE_BYTES; }
 };
 
-template <int GEAR_GROUPS>
-__global__ void __launch_bounds__((GEAR_GROUPS * 8 + 1) * 32, 1)
+template <int GEAR_GROUPS, int TW, int ST>
+__global__ void __launch_bounds__((GEAR_GROUPS * TW + 1) * 32, 1)
 k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
             uint32_t n_tiles, const uint32_t *__restrict__ gear, uint32_t strict_lim, uint32_t loose_lim,
             TileRec *__restrict__ tiles, uint32_t *__restrict__ pool, uint32_t pool_cap,
             uint32_t *__restrict__ pool_count, uint32_t *__restrict__ err_flag)
 {
-    using Cfg = GearCfg<GEAR_GROUPS>;
+    using Cfg = GearCfg<GEAR_GROUPS, TW, ST>;
     constexpr uint32_t GEAR_STAGES = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t s0 = smem_u32(smem_raw); // stages 0..2 live at the start of the dynamic region
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t bar_full = Cfg::BARS_ABS, bar_empty = bar_full + GEAR_STAGES * 8;
     const uint32_t halo_abs = Cfg::HALO_ABS;
-    if (s0 + 3 * Cfg::TILE_BYTES > Cfg::GEAR_ABS || (s0 & 1023u)) { // layout assumption violated: fail loudly
+    if (s0 + Cfg::N_A * Cfg::TILE_BYTES > Cfg::GEAR_ABS || (s0 & 1023u)) { // layout assumption violated: fail loudly
         if (threadIdx.x == 0)
             atomicExch(err_flag, 4u);
         return;
@@ -443,7 +454,7 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
         {
             uint32_t addr;
             if (wt == 0) {
-                addr = halo_abs + s * 128u + (((6u + (lane >> 4)) ^ s) << 4) + (lane & 15u);
+                addr = halo_abs + s * 128u + (((6u + (lane >> 4)) ^ (s & 7u)) << 4) + (lane & 15u);
             } else {
                 const uint32_t pr = wt * 32u - 1u; // previous row, chunks 6 and 7
                 addr = sb + pr * 128u + (((6u + (lane >> 4)) ^ (pr & 7u)) << 4) + (lane & 15u);
@@ -474,7 +485,9 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
 #pragma unroll
                 for (int i = 1; i < 16; ++i)
                     m = min(m, hv[i]);
-                if (m < loose_lim) { // ~0.4 % of lane-chunks; the warp pays for it ~12 % of the time
+                // ~0.4 % of lane-chunks hold a candidate, so ~12 % of the time some lane of the warp does: the vote makes
+                // the branch warp-uniform (no BSSY/BSYNC pair around it on the 88 % path)
+                if (__any_sync(0xFFFFFFFFu, m < loose_lim) && m < loose_lim) {
                     uint32_t bl = 0, bs = 0;
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
@@ -509,7 +522,7 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
                 L[i] += A << (i + 1);
                 m = min(m, L[i]);
             }
-            if (m < loose_lim) {
+            if (__any_sync(0xFFFFFFFFu, m < loose_lim) && m < loose_lim) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                     if (L[i] < loose_lim)

@@ -36,7 +36,10 @@ struct StreamState {
     uint32_t pad;
 };
 
-constexpr int SS_THREADS = 64;
+#ifndef SS_SCHED_WARP
+#define SS_SCHED_WARP 1 // which warp of the CTA is the schedule warp (the rounds warp is warp 0); others exit at once
+#endif
+constexpr int SS_THREADS = 32 * (SS_SCHED_WARP + 1);
 constexpr uint32_t SS_ACTIVE = 1u, SS_START_IV = 2u, SS_START_RESUME = 4u, SS_FINAL = 8u, SS_PARK = 16u, SS_EXIT = 32u;
 
 struct SsShared {
@@ -87,6 +90,16 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
 {
     __shared__ SsShared sh;
     const uint32_t lane = threadIdx.x & 31;
+    if ((threadIdx.x >> 5) != 0 && (threadIdx.x >> 5) != SS_SCHED_WARP)
+        return;
+#ifdef SS_PROFILE
+    if (blockIdx.x == 0 && lane == 0) {
+        uint32_t wid, sid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sid));
+        ss_prof[(threadIdx.x >> 5) ? 6 : 5] = ((unsigned long long)sid << 32) | wid;
+    }
+#endif
     // named barriers: 1+b = "buffer b is full", 3+b = "buffer b is empty"
     if (threadIdx.x < 32) {
         // ------------------------------ rounds warp ------------------------------
