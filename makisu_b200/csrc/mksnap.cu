@@ -906,7 +906,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         int rc = scan_u32(h, h->d_counts, h->d_bases, n_files, sk);
         if (rc)
             return rc;
-        k_batch_begin<<<1, 64, 0, sk>>>(h->d_sc, h->d_counts, h->d_bases, (uint32_t)n_files, h->max_chunks, cdc_bytes);
+        k_batch_begin<<<1, 64, 0, sk>>>(h->d_sc, h->d_counts, h->d_bases, (uint32_t)n_files, h->max_chunks, cdc_bytes, have_cont ? 1u : 0u);
         LAUNCH_OK(h);
         k_select_cuts<1><<<nb, 128, 0, sk>>>(m.d_files, (uint32_t)n_files, h->prm, h->d_tiles, h->d_pool, h->d_counts,
                                              h->d_bases, h->d_sc, h->max_chunks, h->stream_base, h->d_chunk_start,

@@ -965,7 +965,7 @@ k_expand_big_cuts(const CdcFile *__restrict__ files, uint32_t n_files, const uin
 
 // after the scan of counts: publish the batch chunk count / overflow
 __global__ void k_batch_begin(SessionCounters *sc, const uint32_t *counts, const uint32_t *bases, uint32_t n_files,
-                              uint64_t max_chunks, uint64_t cdc_bytes)
+                              uint64_t max_chunks, uint64_t cdc_bytes, uint32_t n_continued /* pieces of files counted earlier */)
 {
     if (blockIdx.x == 0 && threadIdx.x < LEN_CLASSES) {
         sc->len_bins[threadIdx.x] = 0;
@@ -977,7 +977,7 @@ __global__ void k_batch_begin(SessionCounters *sc, const uint32_t *counts, const
         sc->work = 0;
         if (sc->n_chunks + total > max_chunks)
             sc->err |= 2u;
-        sc->n_files += n_files;
+        sc->n_files += n_files - n_continued;
         sc->cdc_bytes += cdc_bytes;
     }
 }

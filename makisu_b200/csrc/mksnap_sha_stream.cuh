@@ -42,8 +42,12 @@ struct StreamState {
 constexpr int SS_THREADS = 32 * (SS_SCHED_WARP + 1);
 constexpr uint32_t SS_ACTIVE = 1u, SS_START_IV = 2u, SS_START_RESUME = 4u, SS_FINAL = 8u, SS_PARK = 16u, SS_EXIT = 32u;
 
+// W[t] + K[t] of the block in flight, [buffer][lane][t]: a lane's 64 words are contiguous (LDS.128 / STS.128, 16
+// instead of 64 shared-memory instructions per block and warp) and the lane stride is 68 words so that the 8 lanes of
+// one quarter-warp phase of a 128-bit access fall into 8 disjoint groups of 4 banks (68 mod 32 = 4): conflict-free.
+constexpr uint32_t SS_LANE_WORDS = 68;
 struct SsShared {
-    uint32_t kw[2][64][32]; // W[t] + K[t] of the block in flight, [buffer][t][lane]
+    uint4 kw[2][32 * SS_LANE_WORDS / 4];
     uint32_t ctrl[2][32];
     uint32_t sid[2][32];
 };
@@ -52,6 +56,7 @@ struct SsShared {
 // microbenchmark only (k4_microbench.cu): [0] rounds-warp cycles, [1] of which waiting for a full buffer,
 // [2] schedule-warp cycles, [3] of which waiting for an empty buffer, [4] blocks; CTA 0 only
 __device__ unsigned long long ss_prof[8];
+__device__ int ss_dbg; // 1: the schedule warp skips its global loads; 2: the rounds warp skips the rounds (timing only)
 #endif
 __device__ __forceinline__ void ss_bar_sync(uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void ss_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
@@ -69,15 +74,6 @@ __device__ __forceinline__ uint4 ss_ldg(const uint4 *p)
     return r;
 }
 
-__device__ __constant__ uint32_t SS_K[64] = {
-    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
-    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
-    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
-    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
-    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
-    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
-    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
-    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
 
 // One piece per (start[i], len[i], stream[i], flags[i]); start multiple of 16.  Digest of a finished stream goes to
 // row stream[i] of `out`; a piece with flag bit 0 (MKSNAP_R_MORE, len multiple of 64) parks the midstate in
@@ -130,13 +126,27 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
                     st[k] = sstate[sid].st[k];
             }
             uint32_t a = st[0], bb = st[1], cc = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
-            const uint32_t *kw = &sh.kw[b][0][lane];
+            // all 64 words of the block into registers before round 0: this warp is alone on its sub-partition, so
+            // a shared-memory load issued next to its use (ptxas's choice when the loads are left to it) stalls the
+            // round for the full ~30-cycle LDS latency -- 64 times per block (measured: 3250 cycles per block)
+            uint32_t kw[64];
+            {
+                const uint32_t base = (uint32_t)__cvta_generic_to_shared(&sh.kw[b][lane * (SS_LANE_WORDS / 4)]);
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(kw[4 * q]), "=r"(kw[4 * q + 1]), "=r"(kw[4 * q + 2]), "=r"(kw[4 * q + 3])
+                                 : "r"(base + 16u * q));
+            }
+#ifdef SS_PROFILE
+            if (ss_dbg != 2)
+#endif
 #pragma unroll
             for (int t = 0; t < 64; ++t) {
                 // Every addition is an IMAD (a*1+b with the 1 in a register ptxas knows nothing about) so that the
                 // half-rate ALU pipe carries only the 6 SHF + 4 LOP3 of the round; the e-chain per round is
                 // SHF -> LOP3 -> one IMAD.
-                const uint32_t x = ss_add(h, kw[t * 32], one); // off the critical path: h and kw are old
+                const uint32_t x = ss_add(h, kw[t], one); // off the critical path: h and kw are old
                 const uint32_t y = ss_add(x, d, one);
                 const uint32_t S1 = ss_rotr(e, 6) ^ ss_rotr(e, 11) ^ ss_rotr(e, 25);
                 const uint32_t ch = (e & f) ^ (~e & g);
@@ -214,6 +224,9 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
                     phase = 1;
                     if (sstate[sid].open)
                         prior = sstate[sid].bytes | (1ull << 63); // bit 63: resume the parked midstate
+#ifdef SS_PROFILE
+                    if (ss_dbg != 1)
+#endif
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if ((uint64_t)(16 * k) < total)
@@ -312,6 +325,9 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
             } else {
                 // prefetch the next block while this one is expanded (the only global-memory latency on the path)
                 const uint64_t left = total - done;
+#ifdef SS_PROFILE
+                if (ss_dbg != 1)
+#endif
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if ((uint64_t)(16 * k) < left)
@@ -322,7 +338,17 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
         sh.sid[b][lane] = sid;
 
         // ---- message schedule: W[t] + K[t] for the 64 rounds ----
-        uint32_t *kw = &sh.kw[b][0][lane];
+        constexpr uint32_t K[64] = {
+            0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+            0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+            0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+            0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+            0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+            0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+            0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+            0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+        const uint32_t kbase = (uint32_t)__cvta_generic_to_shared(&sh.kw[b][lane * (SS_LANE_WORDS / 4)]);
+        uint32_t o4[4];
 #pragma unroll
         for (int t = 0; t < 64; ++t) {
             uint32_t wt;
@@ -335,7 +361,11 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
                 wt = ss_add(ss_add(w[t & 15], s0, one), ss_add(w[(t + 9) & 15], s1, one), one);
                 w[t & 15] = wt;
             }
-            kw[t * 32] = ss_add(wt, SS_K[t], one);
+            o4[t & 3] = ss_add(wt, K[t], one);
+            if ((t & 3) == 3)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(kbase + 4u * (t - 3)), "r"(o4[0]), "r"(o4[1]), "r"(o4[2]),
+                             "r"(o4[3])
+                             : "memory");
         }
         ss_bar_arrive(1 + b);
     }
