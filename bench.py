@@ -64,6 +64,9 @@ def parse():
                     help="uniform = BASELINE configs[2] (the bench line); dup = configs[4] (80 %% repeated content); "
                          "zipf = configs[3] (Zipf-sized files 10 B..1 GiB, LPT-sharded by rank)")
     ap.add_argument("--tar-files", type=int, default=256, help="files in the TarDigest side measurement")
+    ap.add_argument("--fs-files", type=int, default=16384, help="files of the e2e_fs leg (real files on tmpfs); 0 = skip")
+    ap.add_argument("--fs-dir", default="/dev/shm")
+    ap.add_argument("--fs-threads", type=int, default=32)
     ap.add_argument("--strong", action="store_true", help="run the strong-scaling legs at N=1 too (always run at N>1)")
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-deliverables", action="store_true", help="skip the {cacheID, TarDigest} same-deliverables leg")
@@ -447,6 +450,90 @@ def cpu_same_work_pass(file_bytes: int, threads: int, files_per_thread: int = 19
     dt = time.perf_counter() - t0
     return dict(bytes=n_files * file_bytes, s=dt, n_files=n_files, chunks=sum(counts),
                 sha_impl="SHA-NI" if L.mko_have_sha_ni() else "scalar")
+
+
+def fs_leg(args, local, rank):
+    """e2e_fs: the same path from REAL FILES on tmpfs through the C++ host side (libmkhost: filepath.Walk-ordered
+    walker, parallel pread into the pinned arenas, tar headers) -- what a `makisu build` would actually drive:
+      cacheID          mkhost_context_crc32                      (add_copy_step.go:102-122)
+      commit           mkhost_memfs_commit_copy_ops, 1 layer     (common.go:67-111; chunk table, TarDigest left to the caller)
+      commit_layers    mkhost_memfs_commit_layers, one layer per directory WITH TarDigest (the reference's deliverables)
+    Gate: cacheID and TarDigest of a sub-context against the oracle's file-based restatement (zlib / hashlib)."""
+    import shutil
+    from concurrent.futures import ThreadPoolExecutor
+    from makisu_b200 import host
+    from makisu_b200.abi import Engine
+    from oracle import ctx_crc, layer_tar as lt
+    fb = args.file_kib << 10
+    n_files, n_dirs = args.fs_files, min(args.dirs, max(1, args.fs_files // 8))
+    base = os.path.join(args.fs_dir, "mkbench_r%d" % rank)
+    shutil.rmtree(base, ignore_errors=True)
+    ctx, root = os.path.join(base, "ctx"), os.path.join(base, "root")
+    os.makedirs(root)
+    for d in range(n_dirs):
+        os.makedirs(os.path.join(ctx, "d%03d" % d))
+    total = n_files * fb
+    threads = max(1, min(len(os.sched_getaffinity(0)), args.fs_threads))
+    arena = 1 << 30
+    t_create = time.perf_counter()
+    with Engine(device=local, device_arena_bytes=arena, n_host_arenas=4, host_arena_bytes=arena, n_device_slots=2,
+                max_extents=1 << 16, max_chunks=total // 4096 + n_files + (1 << 16)) as eng:
+        # content: device generator -> host -> files (written by a few threads; tmpfs)
+        per = (arena // fb)
+        def write_one(args_):
+            path, buf = args_
+            with open(path, "wb") as f:
+                f.write(buf)
+        with ThreadPoolExecutor(max_workers=min(16, threads)) as ex:
+            for b0 in range(0, n_files, per):
+                nb = min(per, n_files - b0)
+                eng.synth_fill(0, 0, nb * fb, 0xF5 + 1000 * rank + b0)
+                blob = eng.device_download(0, 0, nb * fb)
+                list(ex.map(write_one, [(os.path.join(ctx, "d%03d" % ((b0 + i) * n_dirs // n_files), "f%06d.bin" % (b0 + i)),
+                                         blob[i * fb:(i + 1) * fb]) for i in range(nb)]))
+        for d, _, _ in os.walk(ctx):
+            os.utime(d, (1_500_000_000, 1_500_000_000))
+        t_create = time.perf_counter() - t_create
+        seed = ctx_crc.from_step_cache_id(ctx_crc.plan_seed(True, False), "scratch")
+        prefix = (seed + "COPY" + ". /app/").encode()
+        # gate on a sub-context (2 directories): GPU vs the oracle's zlib / hashlib restatement
+        sub = ["d000", "d001"] if n_dirs > 1 else ["d000"]
+        want_id = ctx_crc.copy_step_cache_id(seed, "COPY", " ".join(sub) + " /app/", ctx, sub)
+        got_id = host.copy_step_cache_id(eng, seed, "COPY", " ".join(sub) + " /app/", ctx, sub)
+        assert got_id == want_id, ("e2e_fs cacheID gate", got_id, want_id)
+        o = lt.MemFS(lambda: 1_600_000_000, root)
+        want_td = [lt.tar_digest(o.add_layer_by_copy_ops([lt.CopyOperation.new(["/" + d], ctx, "/", "/app/%s/" % d)])) for d in sub]
+        got_l = host.MemFS(root).commit_layers(eng, 1_600_000_000, [[host.CopyOperation(["/" + d], ctx, "/", "/app/%s/" % d)] for d in sub],
+                                               n_threads=threads)
+        assert [g["tar_digest"] for g in got_l] == want_td, "e2e_fs TarDigest gate"
+        out = {"files": n_files, "file_kib": args.file_kib, "dirs": n_dirs, "GiB": total / GiB, "tmpfs": args.fs_dir,
+               "host_threads": threads, "create_s": t_create, "arena_MiB": arena >> 20,
+               "gate": "cacheID and per-layer TarDigest of %d directories equal the oracle's file-based restatement" % len(sub)}
+        host.context_crc32(eng, prefix, ctx, ["."], threads)  # warm: page cache, reader pool
+        best = {}
+        for rep in range(2):
+            t0 = time.perf_counter()
+            crc, slen = host.context_crc32(eng, prefix, ctx, ["."], threads)
+            t1 = time.perf_counter()
+            lay1 = host.MemFS(root).commit_copy_ops(eng, 1_600_000_000, [host.CopyOperation(["/"], ctx, "/", "/app/")], threads,
+                                                    flags=host.MKHOST_NO_TAR_DIGEST)
+            t2 = time.perf_counter()
+            layn = host.MemFS(root).commit_layers(eng, 1_600_000_000,
+                                                  [[host.CopyOperation(["/d%03d" % d], ctx, "/", "/app/d%03d/" % d)] for d in range(n_dirs)],
+                                                  n_threads=threads)
+            t3 = time.perf_counter()
+            for k, v in (("cacheid_s", t1 - t0), ("commit_1layer_no_tardigest_s", t2 - t1), ("commit_layers_with_tardigest_s", t3 - t2)):
+                best[k] = min(best.get(k, 1e30), v)
+        out.update(best)
+        out.update(cache_id="%x" % crc, n_layers=n_dirs, n_chunks=int(lay1["n_chunks"]),
+                   cacheid_GiBps=total / GiB / best["cacheid_s"],
+                   commit_1layer_no_tardigest_GiBps=total / GiB / best["commit_1layer_no_tardigest_s"],
+                   commit_layers_with_tardigest_GiBps=total / GiB / best["commit_layers_with_tardigest_s"],
+                   deliverables_GiBps=total / GiB / (best["cacheid_s"] + best["commit_layers_with_tardigest_s"]),
+                   deliverables_note="cacheID pass + commit of %d layers with TarDigest, back to back (the reference reads the context "
+                                     "once for each, add_copy_step.go:153 and common.go:69)" % n_dirs)
+    shutil.rmtree(base, ignore_errors=True)
+    return out
 
 
 def run_reference_arm(args, emit):
@@ -960,6 +1047,16 @@ def main():
         except Exception as ex:  # noqa: BLE001
             cpu_best = {"unavailable": repr(ex)}
 
+    e2e_fs = None
+    if rank == 0 and world == 1 and args.fs_files > 0 and args.workload == "uniform" and not args.no_e2e:
+        try:
+            e2e_fs = fs_leg(args, local, rank)
+            if cpu is not None:
+                e2e_fs["speedup_vs_cpu_reference_deliverables"] = e2e_fs["deliverables_GiBps"] / cpu["value"]
+        except AssertionError:
+            raise
+        except Exception as ex:  # noqa: BLE001  (tmpfs too small, ...): reported, not fatal for the contract line
+            e2e_fs = {"unavailable": repr(ex)}
     deliverables = None
     if e2e is not None:
         deliverables = deliv
@@ -986,7 +1083,7 @@ def main():
                        "workload_kind": args.workload, "workload_info": wl_info,
                        "root": bytes(res.root).hex()},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "cpu_best_effort": cpu_best, "e2e": e2e,
-            "deliverables": deliverables, "strong": strong,
+            "deliverables": deliverables, "e2e_fs": e2e_fs, "strong": strong,
             "gpu_launches": launches,
             "gpu_launches_per_step": launches // max(1, args.steps), "tar_digest": tar,
             "clocks": summarize_clocks(rows),
