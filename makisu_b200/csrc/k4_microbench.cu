@@ -117,7 +117,7 @@ int main(int argc, char **argv)
             CK(cudaMemcpy(d_flags, flags.data(), n * 4, cudaMemcpyHostToDevice));
             CK(cudaMemset(d_ss, 0, n * sizeof(StreamState)));
             const int pairs = (n + max_lanes - 1) / max_lanes;
-            const int grid = pairs < sm * 2 ? pairs : sm * 2;
+            const int grid = pairs < sm * 4 ? pairs : sm * 4;
             cudaEvent_t e0, e1;
             cudaEventCreate(&e0); cudaEventCreate(&e1);
             float best = 1e30f;

@@ -582,6 +582,7 @@ static int create_impl(mksnap *h)
     CK(h, cudaEventCreate(&h->ev_copy1));
     CK(h, cudaEventCreateWithFlags(&h->ev_copy_done, cudaEventDisableTiming));
     CK(h, cudaFuncSetAttribute(k_crc32_extents, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CRC_SMEM));
+    CK(h, cudaFuncSetAttribute(k_select_cuts_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELB_SMEM));
     CK(h, cudaStreamSynchronize(h->s_comp));
     memset(&h->stats, 0, sizeof h->stats);
     return 0;
@@ -899,7 +900,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         LAUNCH_OK(h);
         const bool big_files = big_slots != 0;
         if (big_files) {
-            k_select_cuts_big<<<(uint32_t)n_files, SELB_THREADS, 0, sk>>>(m.d_files, (uint32_t)n_files, h->prm, h->d_tiles,
+            k_select_cuts_big<<<(uint32_t)n_files, SELB_THREADS, SELB_SMEM, sk>>>(m.d_files, (uint32_t)n_files, h->prm, h->d_tiles,
                                                                        h->d_pool, h->d_counts, h->d_keys[0], h->d_sc);
             LAUNCH_OK(h);
         }
@@ -952,7 +953,7 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         // K4: warp pairs, 32 streams each, spread one pair per SM first (a pair then owns its two sub-partitions)
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, sk));
         const uint32_t pairs = (uint32_t)((n_rng + 31) / 32);
-        k_sha256_streams<<<std::min<uint32_t>(pairs, (uint32_t)h->sm_count * 2), SS_THREADS, 0, sk>>>(
+        k_sha256_streams<<<std::min<uint32_t>(pairs, (uint32_t)h->sm_count * 4), SS_THREADS, 0, sk>>>(
             d_arena, m.d_rstart, m.d_rlen, (uint32_t)n_rng, m.d_rstream, m.d_rflags, h->d_stream_state, h->d_stream_digests,
             &h->d_sc->work, 32u, 1u);
         LAUNCH_OK(h);

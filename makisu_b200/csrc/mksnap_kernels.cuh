@@ -720,9 +720,14 @@ k_select_cuts(const CdcFile *__restrict__ files, uint32_t n_files, CdcParamsDev 
 //      the chain goes (another candidate, a forced/end position, or "beyond this window");
 //   3. chase: one thread follows next[] from the current cut -- one shared-memory load per chunk.
 // The rule itself is sel_rule(): identical to select_one_cut() but over the staged list.
-constexpr uint32_t SELB_THREADS = 128;
-constexpr uint32_t SELB_REGIONS = 1024; // window = 4 MiB of file
-constexpr uint32_t SELB_CANDS = 4096;   // candidate capacity of a window (expected 1024 at the default mask)
+// Window size: every window costs two dependent round trips to global memory (tile records, then their candidates)
+// plus block barriers, and a CTA works alone on its file, so the cost per window is latency, not bandwidth: 128 threads
+// x 4 MiB windows spent ~50 us per window (13 ms per GiB file, round-1 Zipf workload); 512 threads x 16 MiB windows
+// amortise the same latencies over four times the bytes.
+constexpr uint32_t SELB_THREADS = 512;
+constexpr uint32_t SELB_REGIONS = 4096; // window = 16 MiB of file
+constexpr uint32_t SELB_CANDS = 16384;  // candidate capacity of a window (expected 4096 at the default mask)
+constexpr size_t SELB_SMEM = (SELB_REGIONS + 1 + 2 * SELB_CANDS) * sizeof(uint32_t); // s_off, s_cand, s_next (dynamic)
 constexpr uint32_t NX_CAND = 0u << 30;  // value = candidate index: cut = pos(value) + 1
 constexpr uint32_t NX_POS = 1u << 30;   // value = window-relative cut position that is not after a candidate
 constexpr uint32_t NX_OUT = 2u << 30;   // the search range leaves the staged window: restage
@@ -793,9 +798,10 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
     if (fl.len < SELECT_BIG_FILE)
         return;
     uint64_t *const my_cuts = cuts + fl.scratch;
-    __shared__ uint32_t s_off[SELB_REGIONS + 1]; // exclusive prefix of candidate counts per region
-    __shared__ uint32_t s_cand[SELB_CANDS];      // offset within the window | strict << 31
-    __shared__ uint32_t s_next[SELB_CANDS];      // where the chain goes from each candidate
+    extern __shared__ uint32_t selb_smem[];
+    uint32_t *const s_off = selb_smem;                      // [SELB_REGIONS + 1] exclusive prefix of candidate counts per region
+    uint32_t *const s_cand = s_off + SELB_REGIONS + 1;      // [SELB_CANDS] offset within the window | strict << 31
+    uint32_t *const s_next = s_cand + SELB_CANDS;           // [SELB_CANDS] where the chain goes from each candidate
     __shared__ uint32_t s_w[SELB_THREADS / 32];
     __shared__ unsigned long long s_prev, s_open;
     __shared__ uint32_t s_n;

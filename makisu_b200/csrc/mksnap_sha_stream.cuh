@@ -36,6 +36,9 @@ struct StreamState {
     uint32_t pad;
 };
 
+#ifndef SS_ADD_MODE
+#define SS_ADD_MODE 0 // 0: 3-input adds (IADD3), fewest instructions; 1: every add as IMAD (FMA pipe)
+#endif
 #ifndef SS_SCHED_WARP
 #define SS_SCHED_WARP 1 // which warp of the CTA is the schedule warp (the rounds warp is warp 0); others exit at once
 #endif
@@ -66,6 +69,15 @@ __device__ __forceinline__ uint32_t ss_add(uint32_t a, uint32_t b, uint32_t one)
     uint32_t d;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
     return d;
+}
+// a + b + c meant to become ONE IADD3.  There is no 3-input add in PTX; ptxas fuses two dependent adds, but the
+// compiler, left alone, shares the partial sum S1 + ch between the two state updates of a round (one instruction
+// fewer, one more on the dependent chain).  The empty asm makes the first operand opaque, so no subexpression is
+// shared across two ss_add3 calls, and costs no instruction.
+__device__ __forceinline__ uint32_t ss_add3(uint32_t a, uint32_t b, uint32_t c)
+{
+    asm("" : "+r"(a));
+    return (a + b) + c;
 }
 __device__ __forceinline__ uint4 ss_ldg(const uint4 *p)
 {
@@ -143,21 +155,38 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
 #endif
 #pragma unroll
             for (int t = 0; t < 64; ++t) {
-                // Every addition is an IMAD (a*1+b with the 1 in a register ptxas knows nothing about) so that the
-                // half-rate ALU pipe carries only the 6 SHF + 4 LOP3 of the round; the e-chain per round is
-                // SHF -> LOP3 -> one IMAD.
-                const uint32_t x = ss_add(h, kw[t], one); // off the critical path: h and kw are old
+                // Measured (k4_microbench, B200): a warp that is alone on its sub-partition issues one instruction per
+                // TWO cycles, whichever pipe it goes to (2430 cycles per block for 1185 instructions; 1577 for the
+                // schedule warp's ~800) -- so the per-stream rate is set by the INSTRUCTION COUNT of this loop, not by
+                // pipe balance: 6 SHF + 4 LOP3 + four additions per round.  The e-chain per round is
+                // SHF -> LOP3 -> IADD3; h + kw + d and S0 + mj + (h + kw) are ready before S1 is.
+#if SS_ADD_MODE == 1
+                const uint32_t x = ss_add(h, kw[t], one);
                 const uint32_t y = ss_add(x, d, one);
                 const uint32_t S1 = ss_rotr(e, 6) ^ ss_rotr(e, 11) ^ ss_rotr(e, 25);
                 const uint32_t ch = (e & f) ^ (~e & g);
                 const uint32_t S0 = ss_rotr(a, 2) ^ ss_rotr(a, 13) ^ ss_rotr(a, 22);
                 const uint32_t mj = (a & bb) ^ (a & cc) ^ (bb & cc);
-                const uint32_t z = ss_add(ss_add(S0, mj, one), x, one); // also off the e-chain
+                const uint32_t z = ss_add(ss_add(S0, mj, one), x, one);
                 const uint32_t chy = ss_add(ch, y, one), chz = ss_add(ch, z, one);
                 h = g; g = f; f = e;
                 e = ss_add(S1, chy, one);
                 d = cc; cc = bb; bb = a;
                 a = ss_add(S1, chz, one);
+#else
+                // four additions per round: with T1 = h + S1 + ch + kw the new state words are
+                //   e' = d + T1 = S1 + ch + (h + kw + d)         a' = T1 + S0 + mj = e' + (S0 + mj - d)
+                const uint32_t y = ss_add3(h, kw[t], d);
+                const uint32_t S1 = ss_rotr(e, 6) ^ ss_rotr(e, 11) ^ ss_rotr(e, 25);
+                const uint32_t ch = (e & f) ^ (~e & g);
+                const uint32_t S0 = ss_rotr(a, 2) ^ ss_rotr(a, 13) ^ ss_rotr(a, 22);
+                const uint32_t mj = (a & bb) ^ (a & cc) ^ (bb & cc);
+                const uint32_t w_ = ss_add3(S0, mj, 0u - d);
+                h = g; g = f; f = e;
+                e = ss_add3(S1, ch, y);
+                d = cc; cc = bb; bb = a;
+                a = e + w_;
+#endif
             }
             if (c & SS_ACTIVE) {
                 st[0] += a; st[1] += bb; st[2] += cc; st[3] += d;
@@ -358,10 +387,18 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
                 const uint32_t w15 = w[(t + 1) & 15], w2 = w[(t + 14) & 15];
                 const uint32_t s0 = ss_rotr(w15, 7) ^ ss_rotr(w15, 18) ^ (w15 >> 3);
                 const uint32_t s1 = ss_rotr(w2, 17) ^ ss_rotr(w2, 19) ^ (w2 >> 10);
+#if SS_ADD_MODE == 1
                 wt = ss_add(ss_add(w[t & 15], s0, one), ss_add(w[(t + 9) & 15], s1, one), one);
+#else
+                wt = ss_add3(ss_add3(w[t & 15], s0, w[(t + 9) & 15]), s1, 0u);
+#endif
                 w[t & 15] = wt;
             }
+#if SS_ADD_MODE == 1
             o4[t & 3] = ss_add(wt, K[t], one);
+#else
+            o4[t & 3] = wt + K[t];
+#endif
             if ((t & 3) == 3)
                 asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(kbase + 4u * (t - 3)), "r"(o4[0]), "r"(o4[1]), "r"(o4[2]),
                              "r"(o4[3])
