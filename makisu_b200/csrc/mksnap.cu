@@ -412,33 +412,41 @@ static int alloc_table_buffers(mksnap *h, uint64_t rows)
     return 0;
 }
 
-template <int GROUPS, int TW, int ST> static int launch_gear(mksnap *h, uint32_t slot, uint32_t n_regions, cudaStream_t sk)
+template <int GROUPS, int TW, int ST, bool RS> static int launch_gear(mksnap *h, uint32_t slot, uint32_t n_regions, cudaStream_t sk)
 {
     using Cfg = GearCfg<GROUPS, TW, ST>;
     const uint32_t n_tiles = (n_regions + Cfg::TILE_WARPS - 1) / Cfg::TILE_WARPS;
     const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)h->sm_count);
-    k_gear_scan<GROUPS, TW, ST><<<grid, Cfg::THREADS, Cfg::SMEM, sk>>>(h->tm_main[slot][0], h->tm_halo[slot], n_tiles, h->d_gear,
-                                                                      h->prm.strict_lim, h->prm.loose_lim, h->d_tiles, h->d_pool,
-                                                                      h->pool_cap, h->d_pool_count, &h->d_sc->err);
+    k_gear_scan<GROUPS, TW, ST, RS><<<grid, Cfg::THREADS, Cfg::SMEM, sk>>>(h->tm_main[slot][0], h->tm_halo[slot], n_tiles, h->d_gear,
+                                                                          h->prm.strict_lim, h->prm.loose_lim, h->d_tiles, h->d_pool,
+                                                                          h->pool_cap, h->d_pool_count, &h->d_sc->err);
     LAUNCH_OK(h);
     return 0;
 }
 
-// the k_gear_scan shapes that are compiled in: {groups, warps per tile, stages}; MKSNAP_GEAR_CFG picks one by index
+// the k_gear_scan shapes that are compiled in: {groups, warps per tile, stages, register staging}; MKSNAP_GEAR_CFG picks one
 struct GearShape {
-    int groups, tile_warps, stages;
+    int groups, tile_warps, stages, rs;
 };
-static const GearShape GEAR_SHAPES[] = {{4, 6, 6}, {3, 8, 4}, {2, 8, 4}, {3, 7, 5}, {6, 4, 9}};
-constexpr int N_GEAR_SHAPES = 5;
+static const GearShape GEAR_SHAPES[] = {{4, 6, 6, 0}, {3, 8, 4, 0}, {2, 8, 4, 0}, {3, 7, 5, 0}, {6, 4, 9, 0},
+                                        {4, 4, 9, 1}, {5, 4, 9, 1}, {3, 6, 6, 1}, {4, 5, 7, 1}};
+constexpr int N_GEAR_SHAPES = 9;
+
+#define MK_GEAR_SHAPES(X) X(4, 6, 6, false) X(3, 8, 4, false) X(2, 8, 4, false) X(3, 7, 5, false) X(6, 4, 9, false) \
+    X(4, 4, 9, true) X(5, 4, 9, true) X(3, 6, 6, true) X(4, 5, 7, true)
 
 static int launch_gear_cfg(mksnap *h, uint32_t slot, uint32_t n_regions, cudaStream_t sk)
 {
     switch (h->gear_cfg) {
-    case 1: return launch_gear<3, 8, 4>(h, slot, n_regions, sk);
-    case 2: return launch_gear<2, 8, 4>(h, slot, n_regions, sk);
-    case 3: return launch_gear<3, 7, 5>(h, slot, n_regions, sk);
-    case 4: return launch_gear<6, 4, 9>(h, slot, n_regions, sk);
-    default: return launch_gear<4, 6, 6>(h, slot, n_regions, sk);
+    case 1: return launch_gear<3, 8, 4, false>(h, slot, n_regions, sk);
+    case 2: return launch_gear<2, 8, 4, false>(h, slot, n_regions, sk);
+    case 3: return launch_gear<3, 7, 5, false>(h, slot, n_regions, sk);
+    case 4: return launch_gear<6, 4, 9, false>(h, slot, n_regions, sk);
+    case 5: return launch_gear<4, 4, 9, true>(h, slot, n_regions, sk);
+    case 6: return launch_gear<5, 4, 9, true>(h, slot, n_regions, sk);
+    case 7: return launch_gear<3, 6, 6, true>(h, slot, n_regions, sk);
+    case 8: return launch_gear<4, 5, 7, true>(h, slot, n_regions, sk);
+    default: return launch_gear<4, 6, 6, false>(h, slot, n_regions, sk);
     }
 }
 
@@ -529,11 +537,10 @@ static int create_impl(mksnap *h)
                 (rc = make_row_map(h, enc, &h->tm_halo[s], h->d_slot[s], n_rows, 1)))
                 return rc;
         }
-        CK(h, cudaFuncSetAttribute(k_gear_scan<4, 6, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<4, 6, 6>::SMEM));
-        CK(h, cudaFuncSetAttribute(k_gear_scan<3, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<3, 8, 4>::SMEM));
-        CK(h, cudaFuncSetAttribute(k_gear_scan<2, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<2, 8, 4>::SMEM));
-        CK(h, cudaFuncSetAttribute(k_gear_scan<3, 7, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<3, 7, 5>::SMEM));
-        CK(h, cudaFuncSetAttribute(k_gear_scan<6, 4, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<6, 4, 9>::SMEM));
+#define MK_SET_SMEM(G, T, S, R) \
+    CK(h, cudaFuncSetAttribute(k_gear_scan<G, T, S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<G, T, S>::SMEM));
+        MK_GEAR_SHAPES(MK_SET_SMEM)
+#undef MK_SET_SMEM
         const char *e2 = getenv("MKSNAP_SHA_FMA"); // tuning knob: 0 = plain adds in the chunk SHA-256 kernel
         if (e2 && e2[0] == '0')
             h->sha_fma = false;

@@ -381,7 +381,11 @@ template <int GEAR_GROUPS, int TW = 8, int ST = 4> struct GearCfg {
     __device__ static uint32_t stage_addr(uint32_t s0, uint32_t s) { return s < N_A ? s0 + s * TILE_BYTES : B0_ABS + (s - N_A) * TILE_BYTES; }
 };
 
-template <int GEAR_GROUPS, int TW, int ST>
+// RS ("register staging"): a consumer copies its whole 128-byte row into registers (8 LDS.128) and hands the stage back
+// to the producer BEFORE hashing it, so a stage is occupied for ~200 cycles instead of the ~6000 its tile takes to hash
+// and nearly all STAGES are in flight from HBM (ncu, round 2: without it only STAGES - GROUPS stages were, consumers
+// spent ~15 % of their issue slots polling the full barrier).  Costs 32 registers per thread: fewer consumer warps fit.
+template <int GEAR_GROUPS, int TW, int ST, bool RS>
 __global__ void __launch_bounds__((GEAR_GROUPS * TW + 1) * 32, 1)
 k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
             uint32_t n_tiles, const uint32_t *__restrict__ gear, uint32_t strict_lim, uint32_t loose_lim,
@@ -471,9 +475,18 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
         uint32_t L[32];                           // states of positions 0..31 (need the carry)
         uint32_t mL0 = 0, mL1 = 0, mL2 = 0, mL3 = 0; // loose candidates, bit p of the row
         uint32_t mS0 = 0, mS1 = 0, mS2 = 0, mS3 = 0; // strict candidates
+        uint4 rowreg[RS ? 8 : 1];
+        if (RS) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                rowreg[c] = lds_u128(ra + ((uint32_t)(c << 4) ^ swz));
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(bar_empty + s * 8);
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const uint4 w = lds_u128(ra + ((uint32_t)(c << 4) ^ swz));
+            const uint4 w = RS ? rowreg[c] : lds_u128(ra + ((uint32_t)(c << 4) ^ swz));
             uint32_t hv[16];
             MK_GEAR_BYTES(w.x, 0) MK_GEAR_BYTES(w.y, 4) MK_GEAR_BYTES(w.z, 8) MK_GEAR_BYTES(w.w, 12)
             if (c < 2) {
@@ -507,9 +520,11 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
             }
         }
         // the stage is consumed: hand it back to the producer before the tail work
-        __syncwarp();
-        if (lane == 0)
-            mbar_arrive(bar_empty + s * 8);
+        if (!RS) {
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(bar_empty + s * 8);
+        }
 
         // positions 0..30 need the carry A = previous lane's final state
         {
