@@ -296,7 +296,13 @@ int sort_unique_root(mksnap *h, const uint8_t *src, uint64_t n, cudaStream_t s)
         }
         k_gather_digests<<<(uint32_t)((2 * n + tb - 1) / tb), tb, 0, s>>>(src, h->d_idx[cur], n, h->d_sorted);
         LAUNCH_OK(h);
-        k_fix_ties<<<(uint32_t)((n + tb - 1) / tb), tb, 0, s>>>(h->d_keys[cur], n, h->d_sorted, 64 - SORT_KEY_BITS);
+        // long runs (duplicates) are listed in the idle flag buffer and handled by whole CTAs
+        uint2 *long_runs = reinterpret_cast<uint2 *>(h->d_hist); // sized for FIX_LONG_CAP entries in alloc_table_buffers
+        uint32_t *n_long = h->d_pos;
+        CK(h, cudaMemsetAsync(n_long, 0, 4, s));
+        k_fix_ties<<<(uint32_t)((n + tb - 1) / tb), tb, 0, s>>>(h->d_keys[cur], n, h->d_sorted, 64 - SORT_KEY_BITS, long_runs, n_long);
+        LAUNCH_OK(h);
+        k_fix_long_runs<<<h->sm_count, 256, 0, s>>>(h->d_sorted, long_runs, n_long);
         LAUNCH_OK(h);
         k_unique_flags<<<(uint32_t)((n + tb - 1) / tb), tb, 0, s>>>(h->d_sorted, n, h->d_flags);
         LAUNCH_OK(h);
@@ -401,7 +407,7 @@ static int alloc_table_buffers(mksnap *h, uint64_t rows)
     CK(h, cudaMalloc(&h->d_table, rows * 32));
     CK(h, cudaMalloc(&h->d_flags, rows * 4));
     CK(h, cudaMalloc(&h->d_pos, rows * 4));
-    const uint64_t hist_words = 256ull * ((rows + SORT_TILE - 1) / SORT_TILE + 1);
+    const uint64_t hist_words = std::max<uint64_t>(256ull * ((rows + SORT_TILE - 1) / SORT_TILE + 1), 2ull * FIX_LONG_CAP + 64); // also holds k_fix_ties' long-run list
     CK(h, cudaMalloc(&h->d_hist, hist_words * 4));
     const uint64_t merkle_rows = rows / 256 + 2;
     CK(h, cudaMalloc(&h->d_merkle[0], merkle_rows * 32));

@@ -1561,18 +1561,17 @@ __device__ __forceinline__ int digest_cmp(const uint8_t *a, const uint8_t *b)
     return 0;
 }
 
-// runs of equal 64-bit prefix: insertion sort on the full digest (linear when the run is all duplicates)
-__global__ void k_fix_ties(const uint64_t *__restrict__ keys, uint64_t n, uint8_t *__restrict__ d, int shift)
+// Runs of equal radix prefix are put in full 256-bit order.  SHA-256 output is uniform, so between DISTINCT digests a
+// run is a handful of rows and one thread's insertion sort is the cheapest thing to do.  Long runs are duplicates: an
+// all-zero context is one max-size chunk repeated (a 50 GiB zero context = 400 k identical rows), which one thread
+// would walk for tens of milliseconds.  Runs longer than FIX_SHORT rows go to a list instead and k_fix_long_runs
+// checks each of them with a whole CTA: all rows equal (the only case seen in practice) => nothing to do; otherwise
+// (distinct digests sharing 32 bits AND a long run of duplicates, ~n/2^32 likely) thread 0 insertion-sorts it.
+constexpr uint32_t FIX_SHORT = 64;
+constexpr uint32_t FIX_LONG_CAP = 8192; // list entries; a further long run is sorted by its own thread
+
+__device__ __forceinline__ void fix_insertion_sort(uint8_t *__restrict__ d, uint64_t i, uint64_t e)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n)
-        return;
-    const uint64_t ki = keys[i] >> shift; // only the bits the radix passes sorted on
-    if (i > 0 && (keys[i - 1] >> shift) == ki)
-        return; // not a run start
-    uint64_t e = i + 1;
-    while (e < n && (keys[e] >> shift) == ki)
-        ++e;
     for (uint64_t j = i + 1; j < e; ++j) {
         uint64_t k = j;
         while (k > i && digest_cmp(d + (k - 1) * 32, d + k * 32) > 0) {
@@ -1582,6 +1581,60 @@ __global__ void k_fix_ties(const uint64_t *__restrict__ keys, uint64_t n, uint8_
             b[0] = t0; b[1] = t1;
             --k;
         }
+    }
+}
+
+__global__ void k_fix_ties(const uint64_t *__restrict__ keys, uint64_t n, uint8_t *__restrict__ d, int shift,
+                           uint2 *__restrict__ long_runs, uint32_t *__restrict__ n_long)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const uint64_t ki = keys[i] >> shift; // only the bits the radix passes sorted on
+    if (i > 0 && (keys[i - 1] >> shift) == ki)
+        return; // not a run start
+    if (i + 1 >= n || (keys[i + 1] >> shift) != ki)
+        return; // a run of one
+    // run end: gallop, then binary search (keys are sorted on these bits)
+    uint64_t lo = i + 1, step = 1;
+    while (lo + step < n && (keys[lo + step] >> shift) == ki) {
+        lo += step;
+        step <<= 1;
+    }
+    uint64_t hi = lo + step < n ? lo + step : n; // keys[lo] is in the run, keys[hi] (if any) is not
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if ((keys[mid] >> shift) == ki)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const uint64_t e = hi;
+    if (e - i > FIX_SHORT && e <= 0xFFFFFFFFull) {
+        const uint32_t slot = atomicAdd(n_long, 1u);
+        if (slot < FIX_LONG_CAP) {
+            long_runs[slot] = make_uint2((uint32_t)i, (uint32_t)e);
+            return;
+        }
+    }
+    fix_insertion_sort(d, i, e);
+}
+
+__global__ void __launch_bounds__(256) k_fix_long_runs(uint8_t *__restrict__ d, const uint2 *__restrict__ long_runs,
+                                                       const uint32_t *__restrict__ n_long)
+{
+    const uint32_t total = *n_long < FIX_LONG_CAP ? *n_long : FIX_LONG_CAP;
+    for (uint32_t r = blockIdx.x; r < total; r += gridDim.x) {
+        const uint64_t i = long_runs[r].x, e = long_runs[r].y;
+        const uint4 f0 = reinterpret_cast<const uint4 *>(d + i * 32)[0], f1 = reinterpret_cast<const uint4 *>(d + i * 32)[1];
+        int differs = 0;
+        for (uint64_t j = i + 1 + threadIdx.x; j < e; j += blockDim.x) {
+            const uint4 a = reinterpret_cast<const uint4 *>(d + j * 32)[0], b = reinterpret_cast<const uint4 *>(d + j * 32)[1];
+            differs |= (a.x ^ f0.x) | (a.y ^ f0.y) | (a.z ^ f0.z) | (a.w ^ f0.w) | (b.x ^ f1.x) | (b.y ^ f1.y) | (b.z ^ f1.z) | (b.w ^ f1.w);
+        }
+        if (__syncthreads_or(differs) && threadIdx.x == 0)
+            fix_insertion_sort(d, i, e);
+        __syncthreads();
     }
 }
 

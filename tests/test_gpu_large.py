@@ -222,3 +222,46 @@ def test_big_file_selection_paths(oracle_lib, params):
         ends, digs = e.get_chunks(res.n_chunks)
         np.testing.assert_array_equal(ends, want["ends"])
         np.testing.assert_array_equal(digs, want["digests"])
+
+
+def test_config1_exact_1k_files_of_1MiB(oracle_lib):
+    """BASELINE configs[1] exactly: synthetic 1k files x 1 MiB on one B200, every cut point, every chunk digest, the
+    sorted-unique table and the root diffed bit-exact against the oracle, plus the cacheID CRC against zlib."""
+    import zlib
+    from makisu_b200.abi import Engine
+    n, fb = 1000, 1 << 20
+    with Engine(device=0, device_arena_bytes=(n * fb) + (1 << 20), max_extents=2 * n + 16) as e:
+        e.begin()
+        e.synth_fill(0, 0, n * fb, 0xC2)
+        arena = e.device_download(0, 0, n * fb)
+        np.testing.assert_array_equal(arena[:4096], oracle_lib.synth_fill(0, 4096, 0xC2))   # same generator on both sides
+        offs, lens = [i * fb for i in range(n)], [fb] * n
+        ext, total = crc_extents(offs, lens, list(range(n)))
+        for x in ext:
+            x.flags |= 2  # MKSNAP_X_CDC
+        e.device_submit(0, n * fb, ext)
+        res = e.finish()
+        want = oracle_lib.chunk_table(arena, offs, lens)
+        assert (res.n_chunks, res.n_unique, bytes(res.root)) == (want["n_chunks"], want["n_unique"], want["root"])
+        ends, dig = e.get_chunks(res.n_chunks)
+        np.testing.assert_array_equal(ends, want["ends"])
+        np.testing.assert_array_equal(dig, want["digests"])
+        np.testing.assert_array_equal(e.get_table(res.n_unique), want["table"])
+        assert e.ctx_crc32(res) == zlib.crc32(arena.tobytes()) and res.crc_bytes == n * fb
+
+
+def test_all_zero_context_has_one_long_run_of_duplicates(oracle_lib):
+    """2 GiB of zeros: every chunk is the same max-size chunk, i.e. one run of ~16 k identical digests for the tie
+    fix-up after the radix sort (k_fix_ties hands runs longer than 64 rows to k_fix_long_runs: a whole CTA checks that
+    they are duplicates instead of one thread walking them).  Table = 1 row (+ the tail chunk), root vs the oracle."""
+    from makisu_b200.abi import Engine
+    n, fb = 64, 32 << 20
+    with Engine(device=0, device_arena_bytes=n * fb, max_extents=n + 16) as e:
+        e.begin()
+        e.memset(0, 0, n * fb, 0)
+        e.device_submit(0, n * fb, cdc_extents([i * fb for i in range(n)], [fb] * n))
+        res = e.finish()
+        small = np.zeros(fb, dtype=np.uint8)
+        want = oracle_lib.chunk_table(small, [0], [fb])     # one file is enough: all files are identical
+        assert res.n_chunks == n * want["n_chunks"] and res.n_unique == want["n_unique"] == 1
+        assert bytes(res.root) == want["root"]
