@@ -142,7 +142,9 @@ size_t mkhost_memfs_describe_scan(mkhost_memfs *m, int64_t now_unix, char *out, 
  * out->tar_digest = SHA-256 of every byte read up to EOF (the layer's DiffID: compare with the image config to
  * verify the pulled blob, lib/docker/image/digest.go:42-50), out->root / n_chunks / n_unique = chunk table of the
  * regular-file members (so base layers join the chunk-granular dedup), out->n_entries = headers merged (the
- * count the reference logs).  flags: MKHOST_NO_TAR_DIGEST.  A member (header + padded body) must fit one arena. */
+ * count the reference logs).  flags: MKHOST_NO_TAR_DIGEST, MKHOST_FILE_DIGESTS, MKHOST_UNTAR.  A regular-file member
+ * larger than one arena travels in pieces (MKSNAP_X_MORE / MKSNAP_X_CONT); only MKHOST_UNTAR, which writes a member
+ * from one contiguous body, still needs every member to fit an arena. */
 int mkhost_memfs_update_from_tar(mkhost_memfs *m, mksnap_t *eng, int64_t now_unix, int tar_fd, uint32_t flags,
                                  mkhost_layer_result *out, char *err, size_t errlen);
 /* the same merge without a GPU: merged layer as text (format below) */

@@ -342,6 +342,7 @@ int mkhost_memfs_update_from_tar(mkhost_memfs *m, mksnap_t *eng, int64_t now_uni
         const bool file_digests = (flags & MKHOST_FILE_DIGESTS) != 0;
         ArenaTarSource src(eng, tar_fd, want_digest, file_digests);
         const bool untar = (flags & MKHOST_UNTAR) != 0;
+        src.allow_split = !untar; // untarOneItem writes a member from one contiguous body
         MemFS::Untar u;
         const std::vector<TarMember> members =
             untar ? read_tar(src, [&](const TarMember &mem, const uint8_t *body) { m->fs.untar_member(u, mem, body); }) // files written from the arena

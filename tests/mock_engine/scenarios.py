@@ -463,3 +463,46 @@ def batch_of_layers_in_one_session(make_engine, tmp):
         raise AssertionError("expected a capacity error")
     except host.HostError as e:
         assert "exceeds the arena" in str(e)
+
+
+def ingest_member_larger_than_the_arena(make_engine, tmp):
+    """mkhost_memfs_update_from_tar with members of 3.2 MB and 1.1 MB through 1 MiB arenas: the bodies travel in pieces
+    (MKSNAP_X_MORE / MKSNAP_X_CONT), DiffID, chunk table and per-file digests equal those of the undivided archive;
+    MKHOST_UNTAR, which needs a contiguous body, refuses loudly."""
+    rng = np.random.default_rng(12)
+    bodies = {"big/one.bin": rng.integers(0, 256, 3_200_001, dtype=np.uint8).tobytes(),
+              "big/two.bin": bytes(700_000) + rng.integers(0, 256, 400_123, dtype=np.uint8).tobytes(),
+              "small.txt": b"hello"}
+    buf = io.BytesIO()
+    with tarfile.open(fileobj=buf, mode="w", format=tarfile.PAX_FORMAT) as tf:
+        d = tarfile.TarInfo("big/")
+        d.type, d.mode, d.mtime = tarfile.DIRTYPE, 0o755, T
+        tf.addfile(d)
+        for name, data in bodies.items():
+            ti = tarfile.TarInfo(name)
+            ti.size, ti.mode, ti.mtime = len(data), 0o644, T
+            tf.addfile(ti, io.BytesIO(data))
+    data = buf.getvalue()
+    path = os.path.join(tmp, "big.tar")
+    open(path, "wb").write(data)
+    members = [m for m in lt.read_tar(data) if m.hdr.typeflag == lt.TYPE_REG and m.data_len]
+    want = olib.chunk_table(np.frombuffer(data, dtype=np.uint8), [m.data_off for m in members], [m.data_len for m in members])
+    root = os.path.join(tmp, "r")
+    os.mkdir(root)
+    for arena in (1 << 20, 8 << 20):
+        eng = make_engine(arena)
+        h = host.MemFS(root)
+        with open(path, "rb") as f:
+            got = h.update_from_tar(eng, NOW, f.fileno(), flags=host.MKHOST_FILE_DIGESTS)
+        assert got["tar_digest"] == "sha256:" + hashlib.sha256(data).hexdigest() and got["tar_bytes"] == len(data), arena
+        assert (got["n_chunks"], got["n_unique"], got["root"]) == (want["n_chunks"], want["n_unique"], want["root"]), arena
+        for name, body in bodies.items():
+            assert h.file_digest("/" + name) == hashlib.sha256(body).digest(), (arena, name)
+        h.close()
+    assert make_engine(1 << 20).submits() == 0
+    try:
+        with open(path, "rb") as f:
+            host.MemFS(root).update_from_tar(make_engine(1 << 20), NOW, f.fileno(), flags=host.MKHOST_UNTAR)
+        raise AssertionError("expected a capacity error")
+    except host.HostError as e:
+        assert "exceeds the arena" in str(e)

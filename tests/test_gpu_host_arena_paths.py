@@ -197,3 +197,28 @@ def test_failed_packers_give_their_arena_back(tmp_path):
         eng.arena_release(aid)
         with pytest.raises(Exception):
             eng.arena_release(aid)
+
+
+def test_ingest_member_larger_than_the_arena(tmp_path):
+    """mkhost_memfs_update_from_tar on the GPU with members of 3.2 MB / 1.1 MB through 1 MiB pinned arenas: bodies in
+    pieces (MKSNAP_X_MORE / MKSNAP_X_CONT + continued streams) give the DiffID, chunk table and per-file digests of the
+    undivided archive (same scenario as the CPU mock: tests/mock_engine/scenarios.py)."""
+    from makisu_b200.abi import Engine
+    from tests.mock_engine import scenarios
+
+    class RealEngineFactory:
+        def __init__(self):
+            self.made = []
+
+        def __call__(self, host_arena_bytes, n_host_arenas=2, max_extents=1 << 12):
+            e = Engine(device=0, device_arena_bytes=host_arena_bytes, n_host_arenas=n_host_arenas,
+                       host_arena_bytes=host_arena_bytes, max_extents=max_extents)
+            e.submits = lambda: 0
+            self.made.append(e)
+            return e
+    f = RealEngineFactory()
+    try:
+        scenarios.ingest_member_larger_than_the_arena(f, str(tmp_path))
+    finally:
+        for e in f.made:
+            e.close()

@@ -26,7 +26,8 @@ def mock_so(tmp_path_factory):
 @pytest.mark.skipif(os.geteuid() != 0, reason="chown needs root")
 @pytest.mark.parametrize("scenario", ["cache_id_and_commit", "ingest_untar_and_file_digests", "content_aware_scan",
                                       "materialize_from_the_arena", "random_trees_small_arenas",
-                                      "table_limits_and_arena_leases", "batch_of_layers_in_one_session"])
+                                      "table_limits_and_arena_leases", "batch_of_layers_in_one_session",
+                                      "ingest_member_larger_than_the_arena"])
 def test_host_packers_against_the_mock_engine(mock_so, tmp_path, scenario):
     r = subprocess.run([sys.executable, "-m", "tests.mock_engine.run", mock_so, scenario, str(tmp_path)], cwd=ROOT,
                        capture_output=True, text=True, timeout=600)
