@@ -70,6 +70,29 @@ int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, c
                          const char *const *from_paths, size_t n_paths, int n_threads, uint32_t *crc_out,
                          uint64_t *stream_len_out, char *err, size_t errlen);
 
+/* Incremental cacheID.  CRC-32 is linear: the context value is the XOR over its segments of pure(segment) shifted to
+ * the segment's place, so pure(file content) -- 32 bits -- remembered from an earlier build lets an UNCHANGED file be
+ * folded in on the host (mksnap_crc_add): no read, no copy to the device, no kernel.  "Unchanged" = same device, inode,
+ * size, mtime and ctime (nanoseconds) as when the value was remembered -- stricter than the reference's own notion of an
+ * unchanged file (tario.IsSimilarHeader: mtime to the second + size, lib/tario/compare.go:104-120).  Path strings,
+ * link targets and the prefix are always streamed (tiny).  The result is bit-identical to mkhost_context_crc32 /
+ * addCopyStep.SetCacheID whenever the remembered values are current; a cold cache degrades to the full computation and
+ * fills itself.  The cache object belongs to the caller (one per build context); save/load keep it between processes. */
+typedef struct mkhost_crc_cache mkhost_crc_cache;
+typedef struct {
+    uint64_t files_total, files_reused; /* regular files in the stream / folded from the cache */
+    uint64_t bytes_total, bytes_sent;   /* file bytes in the stream / file bytes that travelled to the device */
+} mkhost_crc_cache_stats;
+mkhost_crc_cache *mkhost_crc_cache_new(void);
+void mkhost_crc_cache_free(mkhost_crc_cache *c);
+uint64_t mkhost_crc_cache_size(const mkhost_crc_cache *c);
+int mkhost_crc_cache_save(const mkhost_crc_cache *c, const char *path, char *err, size_t errlen);
+int mkhost_crc_cache_load(mkhost_crc_cache *c, const char *path, char *err, size_t errlen);
+int mkhost_context_crc32_cached(mksnap_t *eng, mkhost_crc_cache *cache, const void *prefix, size_t prefix_len,
+                                const char *context_dir, const char *const *from_paths, size_t n_paths, int n_threads,
+                                uint32_t *crc_out, uint64_t *stream_len_out, mkhost_crc_cache_stats *stats, char *err,
+                                size_t errlen);
+
 /* Commit one layer from copy operations against an EMPTY MemFS rooted at root_dir (FROM scratch): packs
  * the sorted entries as a tar stream into one arena, digests it (TarDigest) and chunks every regular
  * file (chunk table).  now_unix = clk.Now() for synthesized ancestors (mem_fs.go:562). */

@@ -206,6 +206,18 @@ int mksnap_finish(mksnap_t *h, mksnap_result *out);
  * accumulator is res->crc_pure. */
 uint32_t mksnap_ctx_crc32(const mksnap_result *res);
 
+/* ---- incremental cacheID: CRC-32 is linear, so a file's contribution can be reused without its bytes ----
+ * With pure(M) = M(x) * x^32 mod P (what the engine accumulates), the context stream's value is the XOR over its
+ * segments of pure(segment) * x^(8 * bytes after the segment).  mksnap_get_extent_crcs returns pure(extent) for every
+ * MKSNAP_X_CRC extent of the finished session, in submission order; a caller that remembers pure(file content) per
+ * file (keyed like MemFS keys a file: size + mtime, lib/tario/compare.go:104-120) folds an UNCHANGED file into a later
+ * session with mksnap_crc_add -- no read, no H2D copy, no kernel -- and only changed files travel.  The cacheID is
+ * bit-identical to the full computation (add_copy_step.go:102-122) as long as the remembered values are current.
+ * mksnap_crc_concat joins the values of two adjacent pieces: pure(A||B) from pure(A), pure(B), len(B). */
+int mksnap_crc_add(mksnap_t *h, uint32_t pure, uint64_t len, uint64_t crc_suffix); /* between begin and finish */
+uint32_t mksnap_crc_concat(uint32_t pure_a, uint32_t pure_b, uint64_t len_b);
+int mksnap_get_extent_crcs(mksnap_t *h, uint32_t *pure, uint64_t capacity, uint64_t *n_out);
+
 /* ---- result tables (valid after mksnap_finish, until the next begin) ---- */
 /* chunk END offsets (exclusive; position in the concatenation of all submitted
  * arenas) and digests, in (submit, extent, position) order. */

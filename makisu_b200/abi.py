@@ -87,6 +87,9 @@ SYMBOLS = [
     ("mksnap_device_submit", C.c_int, [_P, C.c_uint32, C.c_uint64, C.POINTER(Extent), C.c_uint64, C.POINTER(Range), C.c_uint64]),
     ("mksnap_finish", C.c_int, [_P, C.POINTER(Result)]),
     ("mksnap_ctx_crc32", C.c_uint32, [C.POINTER(Result)]),
+    ("mksnap_crc_add", C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint64]),
+    ("mksnap_crc_concat", C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint64]),
+    ("mksnap_get_extent_crcs", C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("mksnap_get_chunks", C.c_int, [_P, _P, _P, C.c_uint64]),
     ("mksnap_get_table", C.c_int, [_P, _P, C.c_uint64]),
     ("mksnap_get_stream_digests", C.c_int, [_P, _P, C.c_uint64]),
@@ -190,6 +193,17 @@ class Engine:
         ptr, cap, aid = _P(), C.c_uint64(), C.c_int32()
         self._ck(self.lib.mksnap_arena_acquire(self.h, C.byref(ptr), C.byref(cap), C.byref(aid)), "mksnap_arena_acquire")
         return ptr.value, cap.value, aid.value
+
+    def crc_add(self, pure: int, length: int, crc_suffix: int):
+        self._ck(self.lib.mksnap_crc_add(self.h, pure, length, crc_suffix), "mksnap_crc_add")
+
+    def get_extent_crcs(self):
+        import numpy as np
+        n = C.c_uint64()
+        self.lib.mksnap_get_extent_crcs(self.h, None, 0, C.byref(n))
+        out = np.empty(max(1, n.value), dtype=np.uint32)
+        self._ck(self.lib.mksnap_get_extent_crcs(self.h, out.ctypes.data, out.size, C.byref(n)), "mksnap_get_extent_crcs")
+        return out[:n.value]
 
     def arena_release(self, arena_id: int):
         self._ck(self.lib.mksnap_arena_release(self.h, arena_id), "mksnap_arena_release")

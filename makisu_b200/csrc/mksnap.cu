@@ -42,6 +42,7 @@ struct MetaSet {
     // device mirrors
     CrcExtent *d_crc = nullptr;
     uint32_t *d_piece_base = nullptr;
+    uint32_t *d_ext_pure = nullptr; // pure(extent) of this submit's CRC extents
     CdcFile *d_files = nullptr;
     uint64_t *d_rstart = nullptr, *d_rlen = nullptr;
     uint32_t *d_rstream = nullptr, *d_rflags = nullptr;
@@ -120,6 +121,10 @@ struct mksnap {
     uint64_t n_streams = 0;
     uint64_t stream_base = 0; // bytes of arenas submitted before the current one
     uint64_t crc_bytes = 0;
+    uint32_t *d_crc_session = nullptr; // pure(extent) of every CRC extent of the session, submission order
+    uint64_t crc_session_cap = 0, crc_session_n = 0;
+    uint32_t crc_host_acc = 0;         // contributions folded on the host (mksnap_crc_add)
+    uint64_t crc_host_bytes = 0;
     bool open_file = false;      // the last submit ended with a MKSNAP_X_MORE extent: the next must start with its continuation
     uint8_t *d_carry = nullptr;  // open chunk of that file (k_carry_out -> k_carry_in)
     uint64_t carry_cap = 0;
@@ -503,6 +508,7 @@ static int create_impl(mksnap *h)
         CK(h, cudaHostAlloc(&m.h_rflags, mx * 4, cudaHostAllocDefault));
         CK(h, cudaMalloc(&m.d_crc, mx * sizeof(CrcExtent)));
         CK(h, cudaMalloc(&m.d_piece_base, (mx + 1) * 4));
+        CK(h, cudaMalloc(&m.d_ext_pure, mx * 4));
         CK(h, cudaMalloc(&m.d_files, mx * sizeof(CdcFile)));
         CK(h, cudaMalloc(&m.d_rstart, mx * 8));
         CK(h, cudaMalloc(&m.d_rlen, mx * 8));
@@ -563,6 +569,8 @@ static int create_impl(mksnap *h)
     h->pool_cap = (uint32_t)pc;
     CK(h, cudaMalloc(&h->d_pool, (uint64_t)h->pool_cap * 4));
     CK(h, cudaMalloc(&h->d_pool_count, 4));
+    h->crc_session_cap = std::max<uint64_t>(4 * mx, 1ull << 20);
+    CK(h, cudaMalloc(&h->d_crc_session, h->crc_session_cap * 4));
     h->carry_cap = ((uint64_t)h->prm.max_size + 511) / 512 * 512;
     CK(h, cudaMalloc(&h->d_carry, h->carry_cap));
     CK(h, cudaMalloc(&h->d_counts, mx * 4));
@@ -661,12 +669,14 @@ void mksnap_destroy(mksnap_t *h)
         cudaFreeHost(m.h_crc); cudaFreeHost(m.h_piece_base); cudaFreeHost(m.h_files);
         cudaFreeHost(m.h_rstart); cudaFreeHost(m.h_rlen); cudaFreeHost(m.h_rstream); cudaFreeHost(m.h_rflags);
         cudaFree(m.d_rstream); cudaFree(m.d_rflags);
+        cudaFree(m.d_ext_pure);
         cudaFree(m.d_crc); cudaFree(m.d_piece_base); cudaFree(m.d_files); cudaFree(m.d_rstart); cudaFree(m.d_rlen);
         if (m.ev_done)
             cudaEventDestroy(m.ev_done);
     }
     cudaFree(h->d_consts); cudaFree(h->d_gear); cudaFree(h->d_sc); cudaFreeHost(h->h_sc);
     cudaFree(h->d_carry);
+    cudaFree(h->d_crc_session);
     cudaFree(h->d_tiles); cudaFree(h->d_pool); cudaFree(h->d_pool_count); cudaFree(h->d_counts); cudaFree(h->d_bases);
     cudaFree(h->d_scan_tmp);
     cudaFree(h->d_order); cudaFree(h->d_chunk_start); cudaFree(h->d_chunk_len); cudaFree(h->d_chunk_end); cudaFree(h->d_digests);
@@ -695,6 +705,9 @@ int mksnap_begin(mksnap_t *h)
     h->n_streams = 0;
     h->stream_base = 0;
     h->crc_bytes = 0;
+    h->crc_session_n = 0;
+    h->crc_host_acc = 0;
+    h->crc_host_bytes = 0;
     h->open_file = false;
     h->n_unique = 0;
     h->finished = false;
@@ -893,9 +906,19 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     CK(h, cudaEventRecord(h->ev[0], sk));
     if (n_crc && pieces) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>(h->sm_count, (pieces + 31) / 32);
+        CK(h, cudaMemsetAsync(m.d_ext_pure, 0, n_crc * 4, sk));
         k_crc32_extents<<<grid, CRC_THREADS, CRC_SMEM, sk>>>(d_arena, m.d_crc, m.d_piece_base, (uint32_t)n_crc,
-                                                            (uint32_t)pieces, h->d_consts, &h->d_sc->crc_acc);
+                                                            (uint32_t)pieces, h->d_consts, m.d_ext_pure);
         LAUNCH_OK(h);
+    }
+    if (n_crc) { // every extent to its place in the stream (zero-length extents included: they keep their table slot)
+        if (!pieces)
+            CK(h, cudaMemsetAsync(m.d_ext_pure, 0, n_crc * 4, sk));
+        k_crc32_fold<<<(uint32_t)std::min<uint64_t>(h->sm_count * 4, (n_crc + 7) / 8), 256, 0, sk>>>(
+            m.d_crc, m.d_ext_pure, (uint32_t)n_crc, h->d_consts, &h->d_sc->crc_acc, h->d_crc_session, h->crc_session_n,
+            h->crc_session_cap);
+        LAUNCH_OK(h);
+        h->crc_session_n += n_crc;
     }
     CK(h, cudaEventRecord(h->ev[1], sk));
     if (n_files) {
@@ -1116,8 +1139,8 @@ int mksnap_finish(mksnap_t *h, mksnap_result *out)
     CK(h, cudaStreamSynchronize(s));
     h->have_fin_times = true;
     memset(out, 0, sizeof *out);
-    out->crc_pure = h->h_sc->crc_acc;
-    out->crc_bytes = h->crc_bytes;
+    out->crc_pure = h->h_sc->crc_acc ^ h->crc_host_acc;
+    out->crc_bytes = h->crc_bytes + h->crc_host_bytes;
     out->cdc_bytes = h->h_sc->cdc_bytes;
     out->n_files = h->h_sc->n_files;
     out->n_chunks = n;
@@ -1135,6 +1158,41 @@ uint32_t mksnap_ctx_crc32(const mksnap_result *res)
     const uint64_t M = 0xFFFFFFFFull;
     const uint64_t bits = ((res->crc_bytes % M) * 8ull) % M;
     return res->crc_pure ^ crc_mulmod(0xFFFFFFFFu, xpow_bits(bits)) ^ 0xFFFFFFFFu;
+}
+
+int mksnap_crc_add(mksnap_t *h, uint32_t pure, uint64_t len, uint64_t crc_suffix)
+{
+    if (!h)
+        return MKSNAP_E_INVAL;
+    if (!h->in_session || h->finished)
+        return fail(h, MKSNAP_E_STATE, "crc_add outside begin/finish");
+    const uint64_t M = 0xFFFFFFFFull;
+    h->crc_host_acc ^= crc_mulmod(pure, xpow_bits(((crc_suffix % M) * 8ull) % M));
+    h->crc_host_bytes += len;
+    return 0;
+}
+
+uint32_t mksnap_crc_concat(uint32_t pure_a, uint32_t pure_b, uint64_t len_b)
+{
+    const uint64_t M = 0xFFFFFFFFull;
+    return crc_mulmod(pure_a, xpow_bits(((len_b % M) * 8ull) % M)) ^ pure_b;
+}
+
+int mksnap_get_extent_crcs(mksnap_t *h, uint32_t *pure, uint64_t capacity, uint64_t *n_out)
+{
+    if (!h || !h->finished || !n_out)
+        return h ? fail(h, MKSNAP_E_STATE, "get_extent_crcs before finish") : MKSNAP_E_INVAL;
+    CK(h, cudaSetDevice(h->cfg.device));
+    *n_out = h->crc_session_n;
+    if (h->crc_session_n > h->crc_session_cap)
+        return fail(h, MKSNAP_E_CAPACITY, "the session submitted %llu CRC extents, the per-extent table keeps %llu",
+                    (unsigned long long)h->crc_session_n, (unsigned long long)h->crc_session_cap);
+    if (!pure || h->crc_session_n > capacity)
+        return fail(h, MKSNAP_E_CAPACITY, "need %llu entries", (unsigned long long)h->crc_session_n);
+    if (h->crc_session_n)
+        CK(h, cudaMemcpy(pure, h->d_crc_session, h->crc_session_n * 4, cudaMemcpyDeviceToHost));
+    h->stats.d2h_bytes += h->crc_session_n * 4;
+    return 0;
 }
 
 int mksnap_get_chunks(mksnap_t *h, uint64_t *ends, uint8_t *digests, uint64_t capacity)

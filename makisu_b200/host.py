@@ -26,6 +26,10 @@ class CopyOp(C.Structure):
                 ("work_dir", C.c_char_p), ("dst", C.c_char_p), ("uid", C.c_int32), ("gid", C.c_int32)]
 
 
+class CrcCacheStats(C.Structure):
+    _fields_ = [("files_total", C.c_uint64), ("files_reused", C.c_uint64), ("bytes_total", C.c_uint64), ("bytes_sent", C.c_uint64)]
+
+
 class LayerSpec(C.Structure):
     _fields_ = [("ops", C.POINTER(CopyOp)), ("n_ops", C.c_size_t), ("tar_fd", C.c_int)]
 
@@ -40,6 +44,14 @@ SYMBOLS = [
     ("mkhost_encode_tar_header", C.c_size_t, [C.POINTER(TarHeader), _P, C.c_size_t]),
     ("mkhost_context_crc32", C.c_int, [_P, _P, C.c_size_t, C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_int,
                                        C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t]),
+    ("mkhost_crc_cache_new", _P, []),
+    ("mkhost_crc_cache_free", None, [_P]),
+    ("mkhost_crc_cache_size", C.c_uint64, [_P]),
+    ("mkhost_crc_cache_save", C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_size_t]),
+    ("mkhost_crc_cache_load", C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_size_t]),
+    ("mkhost_context_crc32_cached", C.c_int, [_P, _P, _P, C.c_size_t, C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_int,
+                                              C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(CrcCacheStats), C.c_char_p,
+                                              C.c_size_t]),
     ("mkhost_commit_copy_ops", C.c_int, [_P, C.c_char_p, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_int,
                                          C.POINTER(LayerResult), C.c_char_p, C.c_size_t]),
     ("mkhost_commit_copy_ops_to_fd", C.c_int, [_P, C.c_char_p, C.c_int64, C.POINTER(CopyOp), C.c_size_t, C.c_int, C.c_int,
@@ -342,3 +354,40 @@ def eval_symlinks(path: str, src_root: str) -> str:
     if n == 0 or n > len(buf):
         raise HostError(err.value.decode() or "path too long")
     return os.fsdecode(buf.value)
+
+
+class CrcCache:
+    """pure(file content) per context file, remembered between builds: unchanged files are folded into the cacheID on
+    the host, only changed files travel to the device (include/mkhost.h, "Incremental cacheID")."""
+
+    def __init__(self, path: Optional[str] = None):
+        self.h = load().mkhost_crc_cache_new()
+        if path is not None and os.path.exists(path):
+            err = C.create_string_buffer(512)
+            if load().mkhost_crc_cache_load(self.h, os.fsencode(path), err, len(err)):
+                raise HostError(err.value.decode())
+
+    def __len__(self):
+        return int(load().mkhost_crc_cache_size(self.h))
+
+    def save(self, path: str):
+        err = C.create_string_buffer(512)
+        if load().mkhost_crc_cache_save(self.h, os.fsencode(path), err, len(err)):
+            raise HostError(err.value.decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            load().mkhost_crc_cache_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def context_crc32(self, eng: abi.Engine, prefix: bytes, context_dir: str, from_paths: Sequence[str], n_threads: int = 0):
+        """-> (crc32 as checksum.Sum32() returns it, stream length, stats dict)."""
+        err = C.create_string_buffer(1024)
+        crc, slen, st = C.c_uint32(), C.c_uint64(), CrcCacheStats()
+        rc = load().mkhost_context_crc32_cached(eng.h, self.h, prefix, len(prefix), os.fsencode(context_dir), _strs(from_paths),
+                                                len(from_paths), n_threads, C.byref(crc), C.byref(slen), C.byref(st), err, len(err))
+        if rc:
+            raise HostError(err.value.decode())
+        return crc.value, slen.value, {k: getattr(st, k) for k, _ in CrcCacheStats._fields_}

@@ -12,6 +12,8 @@
 #include <dirent.h>
 #include <errno.h>
 #include <fcntl.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -51,6 +53,16 @@ std::string errno_str(const std::string &what, const std::string &path)
 #include "packer.inc"
 
 } // namespace
+
+// pure(file content) per context file, remembered between builds (incremental cacheID, include/mkhost.h)
+struct mkhost_crc_cache {
+    struct Entry {
+        uint64_t dev, ino, size;
+        int64_t mtime_ns, ctime_ns;
+        uint32_t pure;
+    };
+    std::map<std::string, Entry> files; // key: absolute path
+};
 
 // persistent snapshot.MemFS mirror (layers accumulate in the merged tree, like context.BuildContext.MemFS)
 struct mkhost_memfs {
@@ -446,9 +458,9 @@ int mkhost_cache_chunk_entry_parse(const char *entry, uint8_t root[32], uint64_t
     return 0;
 }
 
-int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, const char *context_dir,
-                         const char *const *from_paths, size_t n_paths, int n_threads, uint32_t *crc_out,
-                         uint64_t *stream_len_out, char *err, size_t errlen)
+static int context_crc32_impl(mksnap_t *eng, mkhost_crc_cache *cache, mkhost_crc_cache_stats *stats, const void *prefix,
+                              size_t prefix_len, const char *context_dir, const char *const *from_paths, size_t n_paths,
+                              int n_threads, uint32_t *crc_out, uint64_t *stream_len_out, char *err, size_t errlen)
 {
     try {
         std::vector<Seg> segs = context_segments(go_clean(context_dir), from_paths, n_paths);
@@ -478,6 +490,14 @@ int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, c
         };
         acquire();
         uint64_t after = total; // stream bytes not yet placed
+        uint64_t n_crc_ext = 0; // CRC extents submitted so far in this session (index into mksnap_get_extent_crcs)
+        struct Sent {           // a file that travelled: its extents [first, first + pieces) and their lengths
+            const Seg *seg;
+            uint64_t first;
+            std::vector<uint64_t> piece_len;
+        };
+        std::vector<Sent> sent;
+        mkhost_crc_cache_stats st{};
         auto put_bytes = [&](const void *p, size_t n) {
             if (n == 0)
                 return;
@@ -493,6 +513,7 @@ int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, c
             memcpy((uint8_t *)hp + o, p, n);
             after -= n;
             ext.push_back(mksnap_extent{o, n, after, MKSNAP_X_CRC, 0});
+            ++n_crc_ext;
             pos = o + n;
         };
         put_bytes(prefix, prefix_len);
@@ -501,6 +522,21 @@ int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, c
                 put_bytes(g.bytes.data(), g.bytes.size());
                 continue;
             }
+            ++st.files_total;
+            st.bytes_total += g.size;
+            if (cache) { // unchanged since a build that remembered it: fold pure(content) in, send nothing
+                auto it = cache->files.find(g.path);
+                if (it != cache->files.end() && it->second.dev == g.dev && it->second.ino == g.ino && it->second.size == g.size &&
+                    it->second.mtime_ns == g.mtime_ns && it->second.ctime_ns == g.ctime_ns) {
+                    after -= g.size;
+                    ck(eng, mksnap_crc_add(eng, it->second.pure, g.size, after), "crc add");
+                    ++st.files_reused;
+                    continue;
+                }
+            }
+            st.bytes_sent += g.size;
+            if (cache)
+                sent.push_back(Sent{&g, n_crc_ext, {}});
             uint64_t done = 0; // CRC is linear: a file may be split across arenas at any 16-byte boundary
             while (done < g.size) {
                 uint64_t o = align_up(pos, 512);
@@ -513,6 +549,9 @@ int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, c
                 jobs.push_back(ReadJob{g.path, done, n, (uint8_t *)hp + o});
                 after -= n;
                 ext.push_back(mksnap_extent{o, n, after, MKSNAP_X_CRC, 0});
+                ++n_crc_ext;
+                if (cache)
+                    sent.back().piece_len.push_back(n);
                 pos = o + n;
                 done += n;
             }
@@ -525,11 +564,101 @@ int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, c
         *crc_out = mksnap_ctx_crc32(&res);
         if (stream_len_out)
             *stream_len_out = total;
+        if (cache) { // remember pure(content) of every file that travelled (pieces joined: pure(A||B) = pure(A) x^(8|B|) ^ pure(B))
+            std::vector<uint32_t> pure(std::max<uint64_t>(1, n_crc_ext));
+            uint64_t n_got = 0;
+            ck(eng, mksnap_get_extent_crcs(eng, pure.data(), pure.size(), &n_got), "extent crcs");
+            if (n_got != n_crc_ext)
+                throw HostError("internal: extent count mismatch");
+            for (const Sent &f : sent) {
+                uint32_t v = 0; // pure of the empty string
+                for (size_t k = 0; k < f.piece_len.size(); ++k)
+                    v = mksnap_crc_concat(v, pure[f.first + k], f.piece_len[k]);
+                cache->files[f.seg->path] =
+                    mkhost_crc_cache::Entry{f.seg->dev, f.seg->ino, f.seg->size, f.seg->mtime_ns, f.seg->ctime_ns, v};
+            }
+        }
+        if (stats)
+            *stats = st;
         return 0;
     } catch (const std::exception &e) {
         set_err(err, errlen, std::string("hash context sources: ") + e.what());
         return -1;
     }
+}
+
+int mkhost_context_crc32(mksnap_t *eng, const void *prefix, size_t prefix_len, const char *context_dir,
+                         const char *const *from_paths, size_t n_paths, int n_threads, uint32_t *crc_out,
+                         uint64_t *stream_len_out, char *err, size_t errlen)
+{
+    return context_crc32_impl(eng, nullptr, nullptr, prefix, prefix_len, context_dir, from_paths, n_paths, n_threads, crc_out,
+                              stream_len_out, err, errlen);
+}
+
+mkhost_crc_cache *mkhost_crc_cache_new(void) { return new mkhost_crc_cache; }
+void mkhost_crc_cache_free(mkhost_crc_cache *c) { delete c; }
+uint64_t mkhost_crc_cache_size(const mkhost_crc_cache *c) { return c ? c->files.size() : 0; }
+
+int mkhost_crc_cache_save(const mkhost_crc_cache *c, const char *path, char *err, size_t errlen)
+{
+    FILE *f = c && path ? fopen(path, "w") : nullptr;
+    if (!f) {
+        set_err(err, errlen, std::string("save crc cache: ") + strerror(errno));
+        return -1;
+    }
+    fprintf(f, "mkhost-crc-cache 1\n");
+    for (const auto &kv : c->files) // path last: it may hold spaces (newlines in file names are not cached)
+        if (kv.first.find('\n') == std::string::npos)
+            fprintf(f, "%llu %llu %llu %lld %lld %08x %s\n", (unsigned long long)kv.second.dev, (unsigned long long)kv.second.ino,
+                    (unsigned long long)kv.second.size, (long long)kv.second.mtime_ns, (long long)kv.second.ctime_ns, kv.second.pure,
+                    kv.first.c_str());
+    const bool ok = fclose(f) == 0;
+    if (!ok)
+        set_err(err, errlen, std::string("save crc cache: ") + strerror(errno));
+    return ok ? 0 : -1;
+}
+
+int mkhost_crc_cache_load(mkhost_crc_cache *c, const char *path, char *err, size_t errlen)
+{
+    FILE *f = c && path ? fopen(path, "r") : nullptr;
+    if (!f) {
+        set_err(err, errlen, std::string("load crc cache: ") + strerror(errno));
+        return -1;
+    }
+    char *line = nullptr;
+    size_t cap = 0;
+    ssize_t n = getline(&line, &cap, f);
+    bool ok = n > 0 && strncmp(line, "mkhost-crc-cache 1", 18) == 0;
+    while (ok && (n = getline(&line, &cap, f)) > 0) {
+        if (line[n - 1] == '\n')
+            line[--n] = 0;
+        unsigned long long dev, ino, size;
+        long long mt, ct;
+        unsigned pure;
+        int used = 0;
+        if (sscanf(line, "%llu %llu %llu %lld %lld %x %n", &dev, &ino, &size, &mt, &ct, &pure, &used) != 6 || used <= 0 || used >= n) {
+            ok = false;
+            break;
+        }
+        c->files[line + used] = mkhost_crc_cache::Entry{dev, ino, size, mt, ct, (uint32_t)pure};
+    }
+    free(line);
+    fclose(f);
+    if (!ok)
+        set_err(err, errlen, "load crc cache: not a mkhost-crc-cache file");
+    return ok ? 0 : -1;
+}
+
+int mkhost_context_crc32_cached(mksnap_t *eng, mkhost_crc_cache *cache, const void *prefix, size_t prefix_len,
+                                const char *context_dir, const char *const *from_paths, size_t n_paths, int n_threads,
+                                uint32_t *crc_out, uint64_t *stream_len_out, mkhost_crc_cache_stats *stats, char *err, size_t errlen)
+{
+    if (!cache) {
+        set_err(err, errlen, "hash context sources: no cache object");
+        return -1;
+    }
+    return context_crc32_impl(eng, cache, stats, prefix, prefix_len, context_dir, from_paths, n_paths, n_threads, crc_out,
+                              stream_len_out, err, errlen);
 }
 
 int mkhost_commit_copy_ops(mksnap_t *eng, const char *root_dir, int64_t now_unix, const mkhost_copy_op *ops, size_t n_ops,

@@ -35,6 +35,9 @@ struct mksnap {
     std::map<uint32_t, std::vector<uint8_t>> stream_digest;
     mksnap_result last;
     uint64_t submits = 0;
+    std::vector<uint32_t> ext_pure;    // pure(extent) of every CRC extent of the session
+    uint32_t host_acc = 0;             // mksnap_crc_add contributions
+    uint64_t host_bytes = 0;
     bool file_open = false;            // MKSNAP_X_MORE seen: the next submit must start with the continuation
     uint64_t open_follow = 0;
     std::vector<uint8_t> open_bytes;   // pieces of the file that spans submits
@@ -84,6 +87,9 @@ int mksnap_begin(mksnap_t *h)
     h->stream_digest.clear();
     h->file_open = false;
     h->open_bytes.clear();
+    h->ext_pure.clear();
+    h->host_acc = 0;
+    h->host_bytes = 0;
     std::fill(h->acquired.begin(), h->acquired.end(), false);
     return 0;
 }
@@ -153,7 +159,9 @@ int mksnap_arena_submit(mksnap_t *h, int32_t arena_id, uint64_t used, const mksn
         if (e.arena_off % 16 || e.arena_off + e.len > used)
             return fail(h, MKSNAP_E_INVAL, "extent outside the submitted bytes or not 16-byte aligned");
         if (e.flags & MKSNAP_X_CRC) {
-            h->crc_pure ^= mko_crc32_mulmod(mko_crc32_pure(a + e.arena_off, e.len), mko_crc32_xpow8n(e.crc_suffix));
+            const uint32_t pv = mko_crc32_pure(a + e.arena_off, e.len);
+            h->ext_pure.push_back(pv);
+            h->crc_pure ^= mko_crc32_mulmod(pv, mko_crc32_xpow8n(e.crc_suffix));
             h->crc_bytes += e.len;
         }
         if (e.flags & MKSNAP_X_CDC) {
@@ -245,8 +253,8 @@ int mksnap_finish(mksnap_t *h, mksnap_result *out)
     if (h->file_open)
         return fail(h, MKSNAP_E_STATE, "a file was left open (MKSNAP_X_MORE without its continuation)");
     memset(out, 0, sizeof *out);
-    out->crc_pure = h->crc_pure;
-    out->crc_bytes = h->crc_bytes;
+    out->crc_pure = h->crc_pure ^ h->host_acc;
+    out->crc_bytes = h->crc_bytes + h->host_bytes;
     out->cdc_bytes = h->cdc_bytes;
     out->n_files = h->n_files;
     out->n_chunks = h->digests.size() / 32;
@@ -279,6 +287,29 @@ int mksnap_get_stream_digests(mksnap_t *h, uint8_t *digests, uint64_t capacity)
         else
             memset(digests + 32 * s, 0xEE, 32); // never-written slot: garbage, like device memory
     }
+    return 0;
+}
+
+int mksnap_crc_add(mksnap_t *h, uint32_t pure, uint64_t len, uint64_t crc_suffix)
+{
+    if (!h || !h->in_session)
+        return MKSNAP_E_STATE;
+    h->host_acc ^= mko_crc32_mulmod(pure, mko_crc32_xpow8n(crc_suffix));
+    h->host_bytes += len;
+    return 0;
+}
+
+uint32_t mksnap_crc_concat(uint32_t pure_a, uint32_t pure_b, uint64_t len_b) { return mko_crc32_mulmod(pure_a, mko_crc32_xpow8n(len_b)) ^ pure_b; }
+
+int mksnap_get_extent_crcs(mksnap_t *h, uint32_t *pure, uint64_t capacity, uint64_t *n_out)
+{
+    if (!h || !n_out)
+        return MKSNAP_E_INVAL;
+    *n_out = h->ext_pure.size();
+    if (!pure || capacity < h->ext_pure.size())
+        return fail(h, MKSNAP_E_CAPACITY, "need more entries");
+    if (!h->ext_pure.empty())
+        memcpy(pure, h->ext_pure.data(), h->ext_pure.size() * 4);
     return 0;
 }
 

@@ -506,3 +506,60 @@ def ingest_member_larger_than_the_arena(make_engine, tmp):
         raise AssertionError("expected a capacity error")
     except host.HostError as e:
         assert "exceeds the arena" in str(e)
+
+
+def incremental_cache_id(make_engine, tmp):
+    """mkhost_context_crc32_cached: the first build fills the cache (every file travels), the second build of the
+    unchanged context sends NO file bytes and returns the identical cacheID, an edit re-sends exactly the edited file;
+    the value always equals the oracle's full computation (zlib over the reference's byte order), also through small
+    arenas that split files into several extents and through a saved + reloaded cache."""
+    ctx = _ctx(tmp)
+    seed = ctx_crc.from_step_cache_id(ctx_crc.plan_seed(True, False), "scratch")
+    prefix = (seed + "COPY" + ". /app/").encode()
+
+    def want():
+        return int(ctx_crc.copy_step_cache_id(seed, "COPY", ". /app/", ctx, ["."]), 16)
+    regular = [os.path.join(d, f) for d, _, fs in os.walk(ctx) for f in fs if not os.path.islink(os.path.join(d, f))]
+    n_files, total = len(regular), sum(os.path.getsize(p) for p in regular)
+    eng = make_engine(1 << 20)                                    # big.bin (1.5 MB) is split over two arenas
+    cache = host.CrcCache()
+    crc, slen, st = cache.context_crc32(eng, prefix, ctx, ["."])
+    assert crc == want() and st == {"files_total": n_files, "files_reused": 0, "bytes_total": total, "bytes_sent": total}
+    assert len(cache) == n_files
+    before = eng.submits()
+    crc2, slen2, st2 = cache.context_crc32(eng, prefix, ctx, ["."])
+    assert (crc2, slen2) == (crc, slen) and st2["files_reused"] == n_files and st2["bytes_sent"] == 0
+    assert eng.submits() - before == 1                            # one arena of path strings, no file bytes
+    assert host.context_crc32(eng, prefix, ctx, ["."])[0] == crc  # the uncached entry point agrees
+    # a different prefix (seed / directive / args) reuses the same per-file values: they are position independent
+    crc3, _, st3 = cache.context_crc32(eng, b"other" + prefix, ctx, ["."])
+    assert st3["bytes_sent"] == 0 and "%x" % crc3 == ctx_crc.copy_step_cache_id("other" + seed, "COPY", ". /app/", ctx, ["."])
+    # edit one file (same size): exactly that file travels again
+    p = os.path.join(ctx, "d1", "f003.bin")
+    size = os.path.getsize(p)
+    with open(p, "r+b") as f:
+        f.write(b"EDIT")
+    crc4, _, st4 = cache.context_crc32(eng, prefix, ctx, ["."])
+    assert crc4 == want() != crc and st4["files_reused"] == n_files - 1 and st4["bytes_sent"] == size
+    # grow big.bin (split across arenas): its pieces are joined into one remembered value
+    with open(os.path.join(ctx, "big.bin"), "ab") as f:
+        f.write(b"tail" * 1000)
+    crc5, _, st5 = cache.context_crc32(eng, prefix, ctx, ["."])
+    assert crc5 == want() and st5["files_reused"] == n_files - 1
+    crc6, _, st6 = cache.context_crc32(eng, prefix, ctx, ["."])
+    assert crc6 == crc5 and st6["bytes_sent"] == 0
+    # save / load: a later process starts warm; a stale entry (file replaced: new inode) is not trusted
+    path = os.path.join(tmp, "crc.cache")
+    cache.save(path)
+    warm = host.CrcCache(path)
+    assert len(warm) == len(cache)
+    q = os.path.join(ctx, "d0", "f001.bin")
+    data = open(q, "rb").read()
+    stq = os.stat(q)
+    os.rename(q, q + ".old")
+    with open(q, "wb") as f:
+        f.write(data[::-1])
+    os.utime(q, ns=(stq.st_atime_ns, stq.st_mtime_ns))
+    os.remove(q + ".old")
+    crc7, _, st7 = warm.context_crc32(make_engine(8 << 20), prefix, ctx, ["."])
+    assert crc7 == want() and st7["files_reused"] == n_files - 1 and st7["bytes_sent"] == len(data)

@@ -199,26 +199,67 @@ def test_failed_packers_give_their_arena_back(tmp_path):
             eng.arena_release(aid)
 
 
+class _RealEngineFactory:
+    """scenario driver for tests/mock_engine/scenarios.py with real engines (the GPU twin of the CPU mock runs)"""
+
+    def __init__(self):
+        self.made = []
+
+    def __call__(self, host_arena_bytes, n_host_arenas=2, max_extents=1 << 12):
+        from makisu_b200.abi import Engine
+        e = Engine(device=0, device_arena_bytes=host_arena_bytes, n_host_arenas=n_host_arenas,
+                   host_arena_bytes=host_arena_bytes, max_extents=max_extents)
+        self.made.append(e)
+        return e
+
+    def close(self):
+        for e in self.made:
+            e.close()
+
+
+def test_incremental_cache_id_on_the_gpu(tmp_path):
+    """mkhost_context_crc32_cached on a B200: K0 keeps pure(extent) per CRC extent (k_crc32_fold), unchanged files are
+    folded on the host (mksnap_crc_add) -- second build sends no file bytes, edits re-send one file, value == zlib."""
+    from makisu_b200 import host
+    from oracle import ctx_crc
+    from tests.mock_engine import scenarios
+    c = scenarios._ctx(str(tmp_path))
+    seed = ctx_crc.from_step_cache_id(ctx_crc.plan_seed(True, False), "scratch")
+    prefix = (seed + "COPY" + ". /app/").encode()
+    f = _RealEngineFactory()
+    try:
+        eng = f(1 << 20)
+        cache = host.CrcCache()
+        want = int(ctx_crc.copy_step_cache_id(seed, "COPY", ". /app/", c, ["."]), 16)
+        crc, slen, st = cache.context_crc32(eng, prefix, c, ["."])
+        assert crc == want and st["files_reused"] == 0 and st["bytes_sent"] == st["bytes_total"] > 0
+        h2d0 = eng.stats().h2d_bytes
+        crc2, _, st2 = cache.context_crc32(eng, prefix, c, ["."])
+        assert crc2 == want and st2["bytes_sent"] == 0 and st2["files_reused"] == st["files_total"]
+        assert eng.stats().h2d_bytes - h2d0 < st["bytes_total"] // 100      # < 1 % of the bytes move on the second build
+        with open(os.path.join(c, "d2", "f001.bin"), "r+b") as fh:
+            fh.write(b"changed!")
+        crc3, _, st3 = cache.context_crc32(eng, prefix, c, ["."])
+        assert crc3 == int(ctx_crc.copy_step_cache_id(seed, "COPY", ". /app/", c, ["."]), 16) != want
+        assert st3["files_reused"] == st["files_total"] - 1
+        assert host.context_crc32(eng, prefix, c, ["."])[0] == crc3
+    finally:
+        f.close()
+
+
 def test_ingest_member_larger_than_the_arena(tmp_path):
     """mkhost_memfs_update_from_tar on the GPU with members of 3.2 MB / 1.1 MB through 1 MiB pinned arenas: bodies in
     pieces (MKSNAP_X_MORE / MKSNAP_X_CONT + continued streams) give the DiffID, chunk table and per-file digests of the
     undivided archive (same scenario as the CPU mock: tests/mock_engine/scenarios.py)."""
-    from makisu_b200.abi import Engine
     from tests.mock_engine import scenarios
-
-    class RealEngineFactory:
-        def __init__(self):
-            self.made = []
-
-        def __call__(self, host_arena_bytes, n_host_arenas=2, max_extents=1 << 12):
-            e = Engine(device=0, device_arena_bytes=host_arena_bytes, n_host_arenas=n_host_arenas,
-                       host_arena_bytes=host_arena_bytes, max_extents=max_extents)
-            e.submits = lambda: 0
-            self.made.append(e)
-            return e
-    f = RealEngineFactory()
+    f = _RealEngineFactory()
     try:
-        scenarios.ingest_member_larger_than_the_arena(f, str(tmp_path))
+        orig = f.__call__
+
+        def make(host_arena_bytes, **kw):
+            e = orig(host_arena_bytes, **kw)
+            e.submits = lambda: 0
+            return e
+        scenarios.ingest_member_larger_than_the_arena(make, str(tmp_path))
     finally:
-        for e in f.made:
-            e.close()
+        f.close()

@@ -27,7 +27,7 @@ def mock_so(tmp_path_factory):
 @pytest.mark.parametrize("scenario", ["cache_id_and_commit", "ingest_untar_and_file_digests", "content_aware_scan",
                                       "materialize_from_the_arena", "random_trees_small_arenas",
                                       "table_limits_and_arena_leases", "batch_of_layers_in_one_session",
-                                      "ingest_member_larger_than_the_arena"])
+                                      "ingest_member_larger_than_the_arena", "incremental_cache_id"])
 def test_host_packers_against_the_mock_engine(mock_so, tmp_path, scenario):
     r = subprocess.run([sys.executable, "-m", "tests.mock_engine.run", mock_so, scenario, str(tmp_path)], cwd=ROOT,
                        capture_output=True, text=True, timeout=600)
