@@ -551,6 +551,11 @@ def run_reference_arm(args, emit):
         tot += last["bytes"]
         dt += last["s_total"]
     v = tot / GiB / dt
+    try:  # the same passes with scalar SHA-256 (Go 1.14 had no SHA-extension path): lower bracket of the reference
+        sc = cpu_reference_extras(file_bytes, 1)["sha256_scalar_GiBps"]
+        v_scalar = last["bytes"] / GiB / (last["s_crc"] + last["bytes"] / GiB / sc)
+    except Exception:  # noqa: BLE001
+        sc, v_scalar = None, None
     line = {
         "impl": "reference", "metric": "snapshot_hash_throughput", "value": v, "unit": "GiB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
@@ -559,7 +564,10 @@ def run_reference_arm(args, emit):
                                f"{sample_mib} MiB bounded sample of it", "path": "crc32 context pass + tar SHA-256 pass"},
         "cpu_baseline": {"value": v, "unit": "GiB/s", "cores": 1, "kind": "port",
                          "sample": f"{sample_mib} MiB/step, oracle/mkoracle.c (slicing-8 CRC-32, {last['sha_impl']} SHA-256), single "
-                                   f"thread like the reference's goroutine; crc {last['s_crc']:.2f}s sha {last['s_sha']:.2f}s"},
+                                   f"thread like the reference's goroutine; crc {last['s_crc']:.2f}s sha {last['s_sha']:.2f}s",
+                         "value_without_sha_extensions": v_scalar, "sha256_scalar_GiBps": sc,
+                         "note": "value uses SHA-NI (generous to the reference: Go 1.14 has no SHA-extension path); "
+                                 "value_without_sha_extensions is the lower bracket"},
         "e2e": {"value": v, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -1036,6 +1044,12 @@ def main():
                "host_cpus": os.cpu_count()}
         try:
             cpu["extras"] = cpu_reference_extras(file_bytes, max(1, min(len(os.sched_getaffinity(0)), 64)))
+            # Go 1.14's crypto/sha256 has no SHA-extension path (AVX2 assembly, ~0.4-0.5 GB/s): the same two passes with
+            # the scalar SHA-256 figure bracket the reference from below, `value` (SHA-NI) from above
+            sc = cpu["extras"]["sha256_scalar_GiBps"]
+            cpu["value_without_sha_extensions"] = c["bytes"] / GiB / (c["s_crc"] + c["bytes"] / GiB / sc)
+            cpu["note"] = "value uses the x86 SHA extensions (generous to the reference); value_without_sha_extensions = same CRC pass + " \
+                          "scalar SHA-256 (%.3f GiB/s): Go 1.14's AVX2 assembly sits between the two" % sc
         except Exception as ex:  # noqa: BLE001
             cpu["extras"] = {"unavailable": repr(ex)}
         try:  # honesty figure: all host threads doing what the GPU step does (not the reference's algorithm)
