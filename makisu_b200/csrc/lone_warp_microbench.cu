@@ -28,6 +28,13 @@ template <int OP> __global__ void __launch_bounds__(32, 1) bench(uint32_t *out, 
                 if (OP == 4) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));                                   // whatever ptxas picks for add
                 if (OP == 5) { if (i & 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));                      // alternate SHF / add
                                else asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(a[i])); }
+                if (OP == 6) asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(a[0]));                                   // ONE dependent chain
+                if (OP == 7) { if (i % 3 == 0) asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(a[0]));                 // SHF -> LOP3 -> add chain
+                               else if (i % 3 == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[0]) : "r"(b), "r"(c));
+                               else asm volatile("add.u32 %0, %0, %1;" : "+r"(a[0]) : "r"(b)); }
+                if (OP == 8) { if (i % 3 == 0) asm volatile("shf.r.wrap.b32 %0, %0, %0, 7;" : "+r"(a[0]));                 // SHF -> LOP3 -> IMAD chain
+                               else if (i % 3 == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[0]) : "r"(b), "r"(c));
+                               else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[0]) : "r"(one), "r"(c)); }
             }
     }
     unsigned long long t1 = clock64();
@@ -60,5 +67,8 @@ int main()
     run<2>("SHF, IMAD alternating (ALU + FMA)");
     run<4>("add.u32 only (IADD3 / IMAD.IADD, ptxas's pick)");
     run<5>("SHF, add.u32 alternating");
+    run<6>("SHF, ONE dependent chain (latency)");
+    run<7>("SHF -> LOP3 -> add, one dependent chain");
+    run<8>("SHF -> LOP3 -> IMAD, one dependent chain");
     return 0;
 }
