@@ -771,9 +771,12 @@ def main():
             k["frac_of_hbm_peak"] = k["algorithmic_GBps"] / peak
         k["share_of_step"] = k["ms"] / ms_step if ms_step else None
     traffic, traffic_src = None, None
-    try:  # DRAM bytes per launch from the committed ncu capture, scaled to this launch's algorithmic bytes
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_gear_scan"]
-        traffic, traffic_src = tj["ratio"] * ctx_bytes, tj["source"]
+    try:  # DRAM bytes of the launch from the committed ncu capture of the FULL-SIZE launch (scaled only when --files differs)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["k_gear_scan"]
+        if ctx_bytes == tj["algorithmic_bytes"]:
+            traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+        else:
+            traffic, traffic_src = tj["ratio"] * ctx_bytes, tj["source"] + " [scaled by algorithmic bytes]"
     except Exception:
         pass
     roofline = {"kernel": "k_gear_scan (north_star's rolling-hash kernel)", "bound": "hbm",

@@ -99,7 +99,6 @@ struct mksnap {
     TileRec *d_tiles = nullptr;
     CUtensorMap tm_main[MAX_SLOTS][3], tm_halo[MAX_SLOTS]; // per slot: arena viewed as [rows][128 B]
     int gear_cfg = 0; // index into GEAR_SHAPES
-    uint32_t gear_pf = 0; // L2 prefetch distance of k_gear_scan in tiles (MKSNAP_GEAR_PF)
     bool sha_fma = true;                                    // chunk SHA-256: additions on the FMA pipe                                       // index into the k_gear_scan instantiations
     uint32_t *d_pool = nullptr;
     uint32_t pool_cap = 0;
@@ -431,7 +430,7 @@ template <int GROUPS, int TW, int ST, bool RS> static int launch_gear(mksnap *h,
     const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)h->sm_count);
     k_gear_scan<GROUPS, TW, ST, RS><<<grid, Cfg::THREADS, Cfg::SMEM, sk>>>(h->tm_main[slot][0], h->tm_halo[slot], n_tiles, h->d_gear,
                                                                           h->prm.strict_lim, h->prm.loose_lim, h->d_tiles, h->d_pool,
-                                                                          h->pool_cap, h->d_pool_count, &h->d_sc->err, h->gear_pf);
+                                                                          h->pool_cap, h->d_pool_count, &h->d_sc->err);
     LAUNCH_OK(h);
     return 0;
 }
@@ -542,9 +541,6 @@ static int create_impl(mksnap *h)
         const char *e = getenv("MKSNAP_GEAR_CFG"); // tuning knob: index into GEAR_SHAPES (0 = default)
         if (e && e[0] >= '0' && e[0] < '0' + N_GEAR_SHAPES && !e[1])
             h->gear_cfg = e[0] - '0';
-        const char *epf = getenv("MKSNAP_GEAR_PF"); // tuning knob: L2 prefetch distance in tiles
-        if (epf && epf[0] >= '0' && epf[0] <= '9')
-            h->gear_pf = (uint32_t)atoi(epf);
         const uint64_t n_rows = (c.device_arena_bytes + SLOT_SLACK) / 128;
         const uint32_t box_rows = (uint32_t)GEAR_SHAPES[h->gear_cfg].tile_warps * 32u;
         for (uint32_t s = 0; s < h->n_slots; s++) {

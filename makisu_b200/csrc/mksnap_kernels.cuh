@@ -336,12 +336,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, int3
                  ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(bar)
                  : "memory");
 }
-// L2 prefetch of a tile that will be loaded PF iterations later: the data crosses HBM -> L2 without occupying a
-// shared-memory stage, so the number of stages no longer bounds the bytes in flight from DRAM
-__device__ __forceinline__ void tma_prefetch_2d(const void *tmap, int32_t x, int32_t y)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(x), "r"(y) : "memory");
-}
 __device__ __forceinline__ uint4 lds_u128(uint32_t addr)
 {
     uint4 v;
@@ -423,7 +417,7 @@ __global__ void __launch_bounds__((GEAR_GROUPS * TW + 1) * 32, 1)
 k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
             uint32_t n_tiles, const uint32_t *__restrict__ gear, uint32_t strict_lim, uint32_t loose_lim,
             TileRec *__restrict__ tiles, uint32_t *__restrict__ pool, uint32_t pool_cap,
-            uint32_t *__restrict__ pool_count, uint32_t *__restrict__ err_flag, uint32_t pf_tiles /* L2 prefetch distance, 0 = off */)
+            uint32_t *__restrict__ pool_count, uint32_t *__restrict__ err_flag)
 {
     using Cfg = GearCfg<GEAR_GROUPS, TW, ST>;
     constexpr uint32_t GEAR_STAGES = Cfg::STAGES;
@@ -454,17 +448,7 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
         // ------------------------- TMA producer -------------------------
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint32_t k = 0; k < pf_tiles; ++k) { // warm the L2 for the first tiles of this CTA
-                const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)k * gridDim.x;
-                if (t < n_tiles)
-                    tma_prefetch_2d(&tm_main, 0, (int32_t)(t * Cfg::ROWS));
-            }
             for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                if (pf_tiles) {
-                    const uint64_t t = (uint64_t)tile + (uint64_t)pf_tiles * gridDim.x;
-                    if (t < n_tiles)
-                        tma_prefetch_2d(&tm_main, 0, (int32_t)(t * Cfg::ROWS));
-                }
                 const uint32_t s = it % GEAR_STAGES;
                 if (it >= GEAR_STAGES)
                     mbar_wait(bar_empty + s * 8, ((it / GEAR_STAGES) & 1u) ^ 1u);
