@@ -332,10 +332,13 @@ int merkle_from(mksnap *h, const uint8_t *cur, uint64_t cur_n, cudaStream_t s)
     int which = 0;
     for (;;) {
         const uint64_t next_n = cur_n == 0 ? 1 : (cur_n + 255) / 256;
+        // a Merkle group is one 8 KiB serial SHA-256: the warp-pair stream kernel (next block prefetched, rounds and
+        // schedule on separate warps) does a level in ~0.14 ms where one lane per group of the chunk kernel, waiting
+        // for its un-prefetched loads with a handful of warps per SM, took ~0.8 ms
         CK(h, cudaMemsetAsync(&h->d_sc->work, 0, 4, s));
-        k_sha256_ranges<true><<<sha_grid(h), SHA_THREADS, 0, s>>>(cur, nullptr, nullptr, nullptr, next_n, nullptr, 0,
-                                                            8192, cur_n * 32, h->d_merkle[which], &h->d_sc->work,
-                                                            nullptr, 1u, nullptr, nullptr, nullptr, nullptr);
+        k_sha256_streams<<<(uint32_t)std::min<uint64_t>((next_n + 31) / 32, (uint64_t)h->sm_count * 4), SS_THREADS, 0, s>>>(
+            cur, nullptr, nullptr, (uint32_t)next_n, nullptr, nullptr, nullptr, h->d_merkle[which], &h->d_sc->work, 32u, 1u, 8192,
+            cur_n * 32);
         LAUNCH_OK(h);
         cur = h->d_merkle[which];
         cur_n = next_n;

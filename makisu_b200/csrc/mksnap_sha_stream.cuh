@@ -94,7 +94,9 @@ __global__ void __launch_bounds__(SS_THREADS)
 k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ start, const uint64_t *__restrict__ len,
                  uint32_t n, const uint32_t *__restrict__ rng_stream, const uint32_t *__restrict__ rng_flags,
                  StreamState *__restrict__ sstate, uint8_t *__restrict__ out, uint32_t *__restrict__ work_counter,
-                 uint32_t max_lanes, const uint32_t one /* = 1, see ss_add */)
+                 uint32_t max_lanes, const uint32_t one /* = 1, see ss_add */,
+                 uint64_t uni_len = 0, uint64_t uni_total = 0 /* start == nullptr: piece i = [i*uni_len, ...) of `data`, row i
+                                                                   of `out` (Merkle levels: 8 KiB groups of a digest table) */)
 {
     __shared__ SsShared sh;
     const uint32_t lane = threadIdx.x & 31;
@@ -243,15 +245,23 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
             if (phase == 0 && !exhausted) {
                 const uint32_t idx = basei + __popc(need & ((1u << lane) - 1u));
                 if (idx < n) {
-                    p = data + start[idx];
-                    total = len[idx];
-                    sid = rng_stream[idx];
-                    more = (rng_flags[idx] & 1u) != 0;
+                    if (start) {
+                        p = data + start[idx];
+                        total = len[idx];
+                        sid = rng_stream[idx];
+                        more = (rng_flags[idx] & 1u) != 0;
+                    } else {
+                        const uint64_t o = (uint64_t)idx * uni_len;
+                        p = data + o;
+                        total = uni_total - o < uni_len ? uni_total - o : uni_len;
+                        sid = idx;
+                        more = false;
+                    }
                     done = 0;
                     prior = 0;
                     first = true;
                     phase = 1;
-                    if (sstate[sid].open)
+                    if (start && sstate[sid].open)
                         prior = sstate[sid].bytes | (1ull << 63); // bit 63: resume the parked midstate
 #ifdef SS_PROFILE
                     if (ss_dbg != 1)
@@ -340,7 +350,7 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
                 ctrl |= SS_FINAL;
                 phase = 0;
             }
-            if (ctrl & SS_FINAL)
+            if ((ctrl & SS_FINAL) && start)
                 sstate[sid].open = 0;
         }
         if (phase == 1) { // a full data block was taken (rem >= 64)
