@@ -67,7 +67,7 @@ typedef struct {
     uint32_t n_device_slots;     /* 0 = auto (2 if host arenas are used, else 1)      */
     uint32_t reserved0;
     uint64_t max_extents;        /* per submit                                        */
-    uint64_t max_chunks;         /* per session; 0 = device_arena_bytes/min_size+max_extents */
+    uint64_t max_chunks;         /* per session; 0 = device_arena_bytes/min_size + 3*max_extents + 64 */
     mksnap_cdc_params cdc;       /* all-zero = defaults                               */
 } mksnap_config;
 

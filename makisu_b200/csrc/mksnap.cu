@@ -579,7 +579,8 @@ static int create_impl(mksnap *h)
     CK(h, cudaMalloc(&h->d_counts, mx * 4));
     CK(h, cudaMalloc(&h->d_bases, mx * 4));
 
-    h->max_chunks = c.max_chunks ? c.max_chunks : c.device_arena_bytes / h->prm.min_size + mx;
+    // default: every byte in min-size chunks, plus per file the end-of-file chunk and the two spare cut-list slots of the big-file path
+    h->max_chunks = c.max_chunks ? c.max_chunks : c.device_arena_bytes / h->prm.min_size + 3 * mx + 64;
     const uint64_t mc = h->max_chunks;
     CK(h, cudaMalloc(&h->d_chunk_start, mc * 8));
     CK(h, cudaMalloc(&h->d_chunk_len, mc * 8));

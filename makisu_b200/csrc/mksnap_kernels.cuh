@@ -732,24 +732,39 @@ k_select_cuts(const CdcFile *__restrict__ files, uint32_t n_files, CdcParamsDev 
     if (PASS == 1)
         out = sc->n_chunks + bases[f];
     uint32_t n = 0;
-    while (prev < end) {
-        const uint64_t cut = select_one_cut(prev, end, fl.more_after, prm, tiles, pool);
-        if (cut == CUT_OPEN) { // the file continues in the next submit: [prev, end) travels with it
+    if (fl.more_after == 0) { // the common case, kept free of the continuation logic (literal 0: the compiler drops it)
+        while (prev < end) {
+            const uint64_t cut = select_one_cut(prev, end, 0u, prm, tiles, pool);
             if (PASS == 1) {
-                sc->carry_off = prev;
-                sc->carry_len = end - prev;
+                if (out + n < max_chunks) {
+                    chunk_start[out + n] = prev;
+                    chunk_len[out + n] = cut - prev;
+                    chunk_end_out[out + n] = stream_base + cut;
+                }
             }
-            break;
+            ++n;
+            prev = cut;
         }
-        if (PASS == 1) {
-            if (out + n < max_chunks) {
-                chunk_start[out + n] = prev;
-                chunk_len[out + n] = cut - prev;
-                chunk_end_out[out + n] = stream_base + cut;
+    } else {
+        while (prev < end) {
+            const uint64_t cut = select_one_cut(prev, end, fl.more_after, prm, tiles, pool);
+            if (cut == CUT_OPEN) { // the file continues in the next submit: [prev, end) travels with it
+                if (PASS == 1) {
+                    sc->carry_off = prev;
+                    sc->carry_len = end - prev;
+                }
+                break;
             }
+            if (PASS == 1) {
+                if (out + n < max_chunks) {
+                    chunk_start[out + n] = prev;
+                    chunk_len[out + n] = cut - prev;
+                    chunk_end_out[out + n] = stream_base + cut;
+                }
+            }
+            ++n;
+            prev = cut;
         }
-        ++n;
-        prev = cut;
     }
     if (PASS == 0)
         counts[f] = n;
