@@ -263,3 +263,63 @@ func (fs *MemFS) UpdateFromTar(e *Engine, now int64, tarIn *os.File, untar bool,
 	}
 	return toResult(&r), nil
 }
+
+// CrcCache remembers pure(file content) per context file between builds (include/mkhost.h, "Incremental cacheID"):
+// unchanged files (same device, inode, size, mtime, ctime) are folded into the cacheID on the host, only changed files
+// travel to the device.  One cache per build context; Save/Load keep it between makisu invocations.
+type CrcCache struct{ c *C.mkhost_crc_cache }
+
+// NewCrcCache loads `path` when it exists ("" = start cold).
+func NewCrcCache(path string) (*CrcCache, error) {
+	cc := &CrcCache{c: C.mkhost_crc_cache_new()}
+	runtime.SetFinalizer(cc, func(cc *CrcCache) { C.mkhost_crc_cache_free(cc.c) })
+	if path == "" {
+		return cc, nil
+	}
+	if _, err := os.Stat(path); err != nil {
+		return cc, nil
+	}
+	errBuf := (*C.char)(C.malloc(errLen))
+	defer C.free(unsafe.Pointer(errBuf))
+	cpath := C.CString(path)
+	defer C.free(unsafe.Pointer(cpath))
+	if C.mkhost_crc_cache_load(cc.c, cpath, errBuf, errLen) != 0 {
+		return nil, fmt.Errorf("%s", C.GoString(errBuf))
+	}
+	return cc, nil
+}
+
+// Save writes the cache next to the build context (or into makisu's storage dir).
+func (cc *CrcCache) Save(path string) error {
+	errBuf := (*C.char)(C.malloc(errLen))
+	defer C.free(unsafe.Pointer(errBuf))
+	cpath := C.CString(path)
+	defer C.free(unsafe.Pointer(cpath))
+	if C.mkhost_crc_cache_save(cc.c, cpath, errBuf, errLen) != 0 {
+		return fmt.Errorf("%s", C.GoString(errBuf))
+	}
+	return nil
+}
+
+// ContextCRC32Cached is ContextCRC32 with the cache in the loop; sent = file bytes that travelled to the device.
+func (e *Engine) ContextCRC32Cached(cc *CrcCache, prefix []byte, contextDir string, fromPaths []string, threads int) (crc uint32, sent uint64, err error) {
+	var c C.uint32_t
+	var n C.uint64_t
+	var st C.mkhost_crc_cache_stats
+	errBuf := (*C.char)(C.malloc(errLen))
+	defer C.free(unsafe.Pointer(errBuf))
+	cdir := C.CString(contextDir)
+	defer C.free(unsafe.Pointer(cdir))
+	paths, free := cStrings(fromPaths)
+	defer free()
+	var p unsafe.Pointer
+	if len(prefix) > 0 {
+		p = C.CBytes(prefix)
+		defer C.free(p)
+	}
+	if rc := C.mkhost_context_crc32_cached(e.h, cc.c, p, C.size_t(len(prefix)), cdir, paths, C.size_t(len(fromPaths)),
+		C.int(threads), &c, &n, &st, errBuf, errLen); rc != 0 {
+		return 0, 0, fmt.Errorf("%s", C.GoString(errBuf))
+	}
+	return uint32(c), uint64(st.bytes_sent), nil
+}
