@@ -13,6 +13,8 @@
 """
 import os
 
+import numpy as np
+
 import pytest
 
 from makisu_b200 import host
@@ -240,3 +242,66 @@ def test_get_ancestors_fill_nonexistent_and_inclusive(tmp_path, payload_ctx):  #
     ents = _copy_both(o, h, payload_ctx, "/nonexistent1/nonexistent2/")
     assert ents == [("5", "/nonexistent1"), ("5", "/nonexistent1/nonexistent2"), ("0", "/nonexistent1/nonexistent2/p.txt")]
     h.close()
+
+
+# ---- random contexts full of symlinks: the C++ layer builder against the oracle ------------------------------------
+def _random_linked_tree(root, rng):
+    """files, directories and symlinks (relative, absolute-inside-the-root, chains, dangling, escaping) under root;
+    returns every path (relative, with a leading slash) that exists as a name -- usable as a COPY source."""
+    names, dirs = [], [""]
+    for i in range(int(rng.integers(6, 14))):
+        parent = dirs[int(rng.integers(0, len(dirs)))]
+        nm = parent + "/" + "".join(rng.choice(list("abXY01_"), size=int(rng.integers(1, 5)))) + str(i)
+        kind = rng.random()
+        p = root + nm
+        if os.path.lexists(p):
+            continue
+        if kind < 0.3:
+            os.mkdir(p)
+            dirs.append(nm)
+        elif kind < 0.6 or len(names) < 2:
+            with open(p, "wb") as f:
+                f.write(bytes(rng.integers(0, 256, int(rng.integers(0, 300)), dtype=np.uint8)))
+        else:
+            target = names[int(rng.integers(0, len(names)))]
+            form = rng.random()
+            if form < 0.45:
+                os.symlink(os.path.relpath(root + target, os.path.dirname(p)), p)      # relative
+            elif form < 0.8:
+                os.symlink(root + target, p)                                           # absolute, inside the root
+            elif form < 0.9:
+                os.symlink("nowhere/at/all", p)                                        # dangling
+            else:
+                os.symlink("/etc/hostname", p)                                         # escapes the root
+        names.append(nm)
+    for d, _, _ in os.walk(root):
+        os.utime(d, (T0, T0))
+    return names
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_symlinked_sources_layer_matches_oracle(tmp_path, seed):
+    """COPY <any name of a random symlink-ridden context> <dst>: the layer the C++ side builds (entries, header fields,
+    source paths, or the error) equals the oracle's -- both now resolve sources like mem_fs.go:380 does."""
+    rng = np.random.default_rng(1000 + seed)
+    ctx = str(tmp_path / "ctx")
+    os.mkdir(ctx)
+    names = _random_linked_tree(ctx, rng)
+    root = tmp_path / "root"
+    root.mkdir()
+    for k in range(6):
+        src = names[int(rng.integers(0, len(names)))]
+        dst = ["/out%d/" % k, "/out%d/sub/" % k, "/file%d" % k][int(rng.integers(0, 3))]
+        try:
+            want = _desc_from_oracle(lt.MemFS(lambda: NOW, str(root)).add_layer_by_copy_ops(
+                [lt.CopyOperation.new([src], ctx, "/", dst, uid=1, gid=2)]))
+            werr = None
+        except (OSError, ValueError) as e:
+            want, werr = None, e
+        try:
+            got = host.describe_layer(str(root), NOW, [host.CopyOperation([src], ctx, "/", dst, 1, 2)])
+            gerr = None
+        except host.HostError as e:
+            got, gerr = None, e
+        assert (werr is None) == (gerr is None), (src, dst, werr, gerr)
+        assert got == want, (src, dst)
