@@ -265,3 +265,43 @@ def test_all_zero_context_has_one_long_run_of_duplicates(oracle_lib):
         want = oracle_lib.chunk_table(small, [0], [fb])     # one file is enough: all files are identical
         assert res.n_chunks == n * want["n_chunks"] and res.n_unique == want["n_unique"] == 1
         assert bytes(res.root) == want["root"]
+
+
+def test_one_gib_file_through_256_mib_arenas(oracle_lib):
+    """BASELINE configs[3] has 1 GiB files; the e2e path uses arenas far smaller than that.  One 1 GiB file (content from
+    the device generator, with a 6 MiB zero run across an arena boundary) travels through 256 MiB pinned arenas in five
+    pieces (MKSNAP_X_MORE / MKSNAP_X_CONT) next to small neighbours; chunk count, every digest, table and root equal the
+    oracle's over the undivided file (lib/tario/write.go:45: io.CopyN of any size)."""
+    from makisu_b200.abi import Engine
+    from tests.test_gpu_parity import _split_submit
+    big_n = 1 << 30
+    arena = 256 << 20
+    with Engine(device=0, device_arena_bytes=arena, n_host_arenas=2, host_arena_bytes=arena, max_extents=64,
+                max_chunks=(big_n >> 12) + 4096) as e:
+        carry = e.limits().carry_bytes
+        # content: generator output fetched in slices (the engine's own slot is only 256 MiB)
+        big = np.empty(big_n, dtype=np.uint8)
+        e.begin()
+        for o in range(0, big_n, arena):
+            e.synth_fill(0, 0, arena, 0xB16 + o)
+            big[o:o + arena] = e.device_download(0, 0, arena)
+        e.finish()
+        first = arena - 4096 - (1 << 20)                       # first piece: what is left of arena 0 behind a 1 MiB neighbour
+        big[first - (3 << 20):first + (3 << 20)] = 0            # zero run straddling the first boundary: forced cuts across it
+        per = (arena - carry) // 512 * 512
+        pieces, left = [first], big_n - first
+        while left:
+            n = min(per, left)
+            pieces.append(n)
+            left -= n
+        small1 = oracle_lib.synth_fill(0, 1 << 20, 7)
+        small2 = oracle_lib.synth_fill(0, 300_001, 8)
+        files = [small1, big, small2]
+        res = _split_submit(e, files, [[len(small1)], pieces, [len(small2)]], carry, True)
+        offs = [0, 1 << 20, (1 << 20) + big_n]
+        whole = np.concatenate([small1, big, small2])
+        want = oracle_lib.chunk_table(whole, offs, [len(f) for f in files])
+        assert (res.n_chunks, res.n_unique, bytes(res.root)) == (want["n_chunks"], want["n_unique"], want["root"])
+        assert res.n_files == 3 and res.cdc_bytes == whole.size
+        _, dig = e.get_chunks(res.n_chunks)
+        np.testing.assert_array_equal(dig, want["digests"])
