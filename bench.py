@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--fs-files", type=int, default=16384, help="files of the e2e_fs leg (real files on tmpfs); 0 = skip")
     ap.add_argument("--fs-dir", default="/dev/shm")
     ap.add_argument("--fs-threads", type=int, default=32)
+    ap.add_argument("--fs-arena-mib", type=int, default=1024)
+    ap.add_argument("--fs-only", action="store_true", help="run only the e2e_fs leg and print its object (tuning aid, not the bench line)")
     ap.add_argument("--strong", action="store_true", help="run the strong-scaling legs at N=1 too (always run at N>1)")
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-deliverables", action="store_true", help="skip the {cacheID, TarDigest} same-deliverables leg")
@@ -474,12 +476,12 @@ def fs_leg(args, local, rank):
         os.makedirs(os.path.join(ctx, "d%03d" % d))
     total = n_files * fb
     threads = max(1, min(len(os.sched_getaffinity(0)), args.fs_threads))
-    arena = 1 << 30
+    arena = args.fs_arena_mib << 20
     t_create = time.perf_counter()
-    with Engine(device=local, device_arena_bytes=arena, n_host_arenas=4, host_arena_bytes=arena, n_device_slots=2,
+    with Engine(device=local, device_arena_bytes=arena, n_host_arenas=max(4, (4 << 30) // arena), host_arena_bytes=arena, n_device_slots=2,
                 max_extents=1 << 16, max_chunks=total // 4096 + n_files + (1 << 16)) as eng:
         # content: device generator -> host -> files (written by a few threads; tmpfs)
-        per = (arena // fb)
+        per = max(1, arena // fb)
         def write_one(args_):
             path, buf = args_
             with open(path, "wb") as f:
@@ -590,6 +592,12 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args, emit)
+        return
+    if args.fs_only:
+        import torch
+        torch.cuda.set_device(0)
+        bind_to_gpu_numa_node(0)
+        emit(fs_leg(args, 0, 0))
         return
 
     import torch
