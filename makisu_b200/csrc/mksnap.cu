@@ -912,16 +912,15 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
         const uint32_t grid = (uint32_t)std::min<uint64_t>(h->sm_count, (pieces + 31) / 32);
         CK(h, cudaMemsetAsync(m.d_ext_pure, 0, n_crc * 4, sk));
         k_crc32_extents<<<grid, CRC_THREADS, CRC_SMEM, sk>>>(d_arena, m.d_crc, m.d_piece_base, (uint32_t)n_crc,
-                                                            (uint32_t)pieces, h->d_consts, m.d_ext_pure);
+                                                            (uint32_t)pieces, h->d_consts, m.d_ext_pure, &h->d_sc->crc_acc);
         LAUNCH_OK(h);
     }
-    if (n_crc) { // every extent to its place in the stream (zero-length extents included: they keep their table slot)
+    if (n_crc) { // pure(extent) of this submit's extents joins the session table (zero-length extents keep their slot)
         if (!pieces)
             CK(h, cudaMemsetAsync(m.d_ext_pure, 0, n_crc * 4, sk));
-        k_crc32_fold<<<(uint32_t)std::min<uint64_t>(h->sm_count * 4, (n_crc + 7) / 8), 256, 0, sk>>>(
-            m.d_crc, m.d_ext_pure, (uint32_t)n_crc, h->d_consts, &h->d_sc->crc_acc, h->d_crc_session, h->crc_session_n,
-            h->crc_session_cap);
-        LAUNCH_OK(h);
+        if (h->crc_session_n < h->crc_session_cap)
+            CK(h, cudaMemcpyAsync(h->d_crc_session + h->crc_session_n, m.d_ext_pure,
+                                  std::min<uint64_t>(n_crc, h->crc_session_cap - h->crc_session_n) * 4, cudaMemcpyDeviceToDevice, sk));
         h->crc_session_n += n_crc;
     }
     CK(h, cudaEventRecord(h->ev[1], sk));
