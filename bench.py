@@ -579,6 +579,9 @@ def run_reference_arm(args, emit):
 # ----------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    if os.environ.get("MKSNAP_BENCH_WATCHDOG"):  # debugging aid: dump every thread's Python stack if the run is still alive after N s
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["MKSNAP_BENCH_WATCHDOG"]), repeat=True, file=sys.stderr)
     # stdout carries exactly ONE JSON line: libraries (NCCL prints its version there) get stderr until the end
     sys.stdout.flush()
     real_stdout = os.dup(1)
