@@ -59,8 +59,75 @@ template <int OP> void run(const char *name)
     cudaFree(out); cudaFree(cyc);
 }
 
+// ---- one SHA-256 round chain per lane, rotates as SHF (ALU pipe) or as IMAD.WIDE by 2^(32-n) (FMA pipe: hi ^ lo of the
+// 64-bit product IS the rotation, the two halves have disjoint bits) ----
+__device__ __forceinline__ uint32_t rot_shf(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+__device__ __forceinline__ void rot_mul(uint32_t x, int n, uint32_t &lo, uint32_t &hi)
+{
+    asm("{ .reg .b64 p; mul.wide.u32 p, %2, %3; mov.b64 {%0, %1}, p; }" : "=r"(lo), "=r"(hi) : "r"(x), "r"(1u << (32 - n)));
+}
+__device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b, uint32_t c) { asm("" : "+r"(a)); return (a + b) + c; }
+__device__ __forceinline__ uint32_t addsub(uint32_t a, uint32_t b, uint32_t c) { asm("" : "+r"(a)); return (a + b) - c; }
+// NMUL = how many of the three rotates of each big sigma go through the multiplier
+template <int NMUL> __device__ __forceinline__ uint32_t big_sigma(uint32_t x, int r0, int r1, int r2)
+{
+    if (NMUL == 0) return rot_shf(x, r0) ^ rot_shf(x, r1) ^ rot_shf(x, r2);
+    uint32_t l0, h0, l1, h1, l2, h2;
+    if (NMUL == 1) { rot_mul(x, r2, l2, h2); return (rot_shf(x, r0) ^ rot_shf(x, r1)) ^ (l2 ^ h2); }
+    if (NMUL == 2) { rot_mul(x, r1, l1, h1); rot_mul(x, r2, l2, h2); return (rot_shf(x, r0) ^ l1 ^ h1) ^ (l2 ^ h2); }
+    rot_mul(x, r0, l0, h0); rot_mul(x, r1, l1, h1); rot_mul(x, r2, l2, h2);
+    return (l0 ^ h0 ^ l1) ^ (h1 ^ l2 ^ h2);
+}
+template <int N1, int N0> __global__ void __launch_bounds__(32, 1) bench_round(uint32_t *out, uint32_t seed, unsigned long long *cycles)
+{
+    uint32_t a = seed + threadIdx.x, b = a * 3u, c = a * 5u, d = a * 7u, e = a * 11u, f = a * 13u, g = a * 17u, h = a * 19u;
+    uint32_t kw[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) kw[i] = seed * (2 * i + 1);
+    unsigned long long t0 = clock64();
+    for (int it = 0; it < 512; it++) {
+#pragma unroll
+        for (int t = 0; t < 64; t++) {
+            const uint32_t y = add3(h, kw[t & 15], d);
+            const uint32_t S1 = big_sigma<N1>(e, 6, 11, 25);
+            const uint32_t ch = (e & f) ^ (~e & g);
+            const uint32_t S0 = big_sigma<N0>(a, 2, 13, 22);
+            const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+            const uint32_t w_ = addsub(S0, mj, d);
+            h = g; g = f; f = e; e = add3(S1, ch, y);
+            d = c; c = b; b = a; a = e + w_;
+        }
+    }
+    unsigned long long t1 = clock64();
+    out[blockIdx.x * 32 + threadIdx.x] = a ^ b ^ c ^ d ^ e ^ f ^ g ^ h;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+template <int N1, int N0> void run_round(const char *name)
+{
+    uint32_t *out; unsigned long long *cyc;
+    cudaMalloc(&out, 148 * 32 * 4); cudaMalloc(&cyc, 148 * 8);
+    bench_round<N1, N0><<<148, 32>>>(out, 12345, cyc);
+    cudaDeviceSynchronize();
+    bench_round<N1, N0><<<148, 32>>>(out, 12345, cyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    unsigned long long h[148]; cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
+    uint32_t o0; cudaMemcpy(&o0, out, 4, cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < 148; i++) avg += h[i]; avg /= 148;
+    printf("%-44s %6.2f cycles per round, %6.0f per 64-byte block  out %08x (%s)\n", name, avg / (64.0 * 512), avg / 512, o0, cudaGetErrorString(e));
+    cudaFree(out); cudaFree(cyc);
+}
+
 int main()
 {
+    run_round<0, 0>("SHA round, 6 SHF rotates");
+    run_round<1, 1>("SHA round, 4 SHF + 2 IMAD.WIDE rotates");
+    run_round<2, 1>("SHA round, 3 SHF + 3 IMAD.WIDE rotates");
+    run_round<2, 2>("SHA round, 2 SHF + 4 IMAD.WIDE rotates");
+    run_round<3, 2>("SHA round, 1 SHF + 5 IMAD.WIDE rotates");
+    run_round<3, 3>("SHA round, 6 IMAD.WIDE rotates");
+    run_round<1, 0>("SHA round, S1 one IMAD.WIDE, S0 all SHF");
+    run_round<2, 0>("SHA round, S1 two IMAD.WIDE, S0 all SHF");
+
     run<0>("SHF only (ALU pipe)");
     run<3>("LOP3 only (ALU pipe)");
     run<1>("IMAD only (FMA pipe)");

@@ -218,7 +218,7 @@ class _RealEngineFactory:
 
 
 def test_incremental_cache_id_on_the_gpu(tmp_path):
-    """mkhost_context_crc32_cached on a B200: K0 keeps pure(extent) per CRC extent (k_crc32_fold), unchanged files are
+    """mkhost_context_crc32_cached on a B200: K0 keeps pure(extent) per CRC extent (k_crc32_extents), unchanged files are
     folded on the host (mksnap_crc_add) -- second build sends no file bytes, edits re-send one file, value == zlib."""
     from makisu_b200 import host
     from oracle import ctx_crc
