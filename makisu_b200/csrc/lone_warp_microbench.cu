@@ -117,8 +117,91 @@ template <int N1, int N0> void run_round(const char *name)
     cudaFree(out); cudaFree(cyc);
 }
 
+// ---- does a second warp with its OWN large straight-line body (the schedule warp) slow the rounds warp down?
+// warp 0: 64 unrolled rounds (ADDM 0: IADD3-friendly adds, 1: every add as IMAD on the FMA pipe);
+// warp 1 (if `second`): 3 x 16 unrolled message-schedule words per iteration, as the real schedule warp does.
+__device__ __forceinline__ uint32_t madd(uint32_t a, uint32_t b, uint32_t one)
+{
+    uint32_t d; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b)); return d;
+}
+template <int ADDM, int UNROLL> __global__ void __launch_bounds__(64, 1)
+bench_pair(uint32_t *out, uint32_t seed, uint32_t one, int second, unsigned long long *cycles)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    if (threadIdx.x >= 32) {
+        if (!second) return;
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = seed * (2 * i + 3) + lane;
+        uint32_t acc = 0;
+        for (int it = 0; it < 512; it++) {
+#pragma unroll
+            for (int t = 0; t < 64; t++) {
+                const uint32_t w15 = w[(t + 1) & 15], w2 = w[(t + 14) & 15];
+                const uint32_t s0 = rot_shf(w15, 7) ^ rot_shf(w15, 18) ^ (w15 >> 3);
+                const uint32_t s1 = rot_shf(w2, 17) ^ rot_shf(w2, 19) ^ (w2 >> 10);
+                w[t & 15] = add3(w[t & 15], s0, w[(t + 9) & 15]) + s1;
+                acc += w[t & 15] + t * 0x9E3779B9u;
+            }
+        }
+        out[blockIdx.x * 64 + threadIdx.x] = acc;
+        return;
+    }
+    uint32_t a = seed + lane, b = a * 3u, c = a * 5u, d = a * 7u, e = a * 11u, f = a * 13u, g = a * 17u, h = a * 19u;
+    uint32_t kw[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) kw[i] = seed * (2 * i + 1);
+    unsigned long long t0 = clock64();
+    for (int it = 0; it < 512 * (64 / UNROLL); it++) {
+#pragma unroll
+        for (int t = 0; t < UNROLL; t++) {
+            const uint32_t S1 = big_sigma<0>(e, 6, 11, 25);
+            const uint32_t ch = (e & f) ^ (~e & g);
+            const uint32_t S0 = big_sigma<0>(a, 2, 13, 22);
+            const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+            if (ADDM == 0) {
+                const uint32_t y = add3(h, kw[t & 15], d);
+                const uint32_t w_ = addsub(S0, mj, d);
+                h = g; g = f; f = e; e = add3(S1, ch, y);
+                d = c; c = b; b = a; a = e + w_;
+            } else {
+                const uint32_t y = madd(madd(h, kw[t & 15], one), d, one);
+                const uint32_t w_ = madd(madd(S0, mj, one), 0u - d, one);
+                h = g; g = f; f = e; e = madd(madd(ch, y, one), S1, one);
+                d = c; c = b; b = a; a = madd(e, w_, one);
+            }
+        }
+    }
+    unsigned long long t1 = clock64();
+    out[blockIdx.x * 64 + threadIdx.x] = a ^ b ^ c ^ d ^ e ^ f ^ g ^ h;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+template <int ADDM, int UNROLL> void run_pair(const char *name, int second)
+{
+    uint32_t *out; unsigned long long *cyc;
+    cudaMalloc(&out, 148 * 64 * 4); cudaMalloc(&cyc, 148 * 8);
+    bench_pair<ADDM, UNROLL><<<148, 64>>>(out, 12345, 1, second, cyc);
+    cudaDeviceSynchronize();
+    bench_pair<ADDM, UNROLL><<<148, 64>>>(out, 12345, 1, second, cyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    unsigned long long h[148]; cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
+    uint32_t o0; cudaMemcpy(&o0, out, 4, cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < 148; i++) avg += h[i]; avg /= 148;
+    printf("%-58s %6.2f cycles per round, %6.0f per block  out %08x (%s)\n", name, avg / (64.0 * 512), avg / 512, o0, cudaGetErrorString(e));
+    cudaFree(out); cudaFree(cyc);
+}
+
 int main()
 {
+    run_pair<0, 64>("rounds warp alone, IADD3 adds, 64 rounds unrolled", 0);
+    run_pair<0, 64>("  + schedule-like warp on the next sub-partition", 1);
+    run_pair<1, 64>("rounds warp alone, IMAD adds, 64 rounds unrolled", 0);
+    run_pair<1, 64>("  + schedule-like warp", 1);
+    run_pair<0, 8>("rounds warp alone, IADD3 adds, 8 rounds unrolled", 0);
+    run_pair<0, 8>("  + schedule-like warp", 1);
+    run_pair<1, 8>("rounds warp alone, IMAD adds, 8 rounds unrolled", 0);
+    run_pair<1, 8>("  + schedule-like warp", 1);
+
     run_round<0, 0>("SHA round, 6 SHF rotates");
     run_round<1, 1>("SHA round, 4 SHF + 2 IMAD.WIDE rotates");
     run_round<2, 1>("SHA round, 3 SHF + 3 IMAD.WIDE rotates");

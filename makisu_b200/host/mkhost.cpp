@@ -27,6 +27,7 @@
 #include <memory>
 #include <mutex>
 #include <stdexcept>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -98,7 +99,7 @@ size_t mkhost_describe_context_stream(const char *context_dir, const char *const
 {
     try {
         std::string s;
-        for (const auto &g : context_segments(go_clean(context_dir), from_paths, n_paths)) {
+        for (const auto &g : context_segments(go_clean(context_dir), from_paths, n_paths, 4)) { // 4: the parallel walk is what the parity tests see
             if (g.kind == 'F')
                 s += "F " + std::to_string(g.size) + " " + g.path + "\n";
             else
@@ -463,7 +464,14 @@ static int context_crc32_impl(mksnap_t *eng, mkhost_crc_cache *cache, mkhost_crc
                               int n_threads, uint32_t *crc_out, uint64_t *stream_len_out, char *err, size_t errlen)
 {
     try {
-        std::vector<Seg> segs = context_segments(go_clean(context_dir), from_paths, n_paths);
+        const bool trace = getenv("MKHOST_TRACE") != nullptr; // phase times on stderr
+        const auto t_start = std::chrono::steady_clock::now();
+        auto ms_since = [&](std::chrono::steady_clock::time_point t) {
+            return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+        };
+        double ms_reads = 0, ms_submit = 0, ms_acquire = 0;
+        std::vector<Seg> segs = context_segments(go_clean(context_dir), from_paths, n_paths, n_threads);
+        const double ms_walk = ms_since(t_start);
         uint64_t total = prefix_len;
         for (const auto &g : segs)
             total += g.kind == 'F' ? g.size : g.bytes.size();
@@ -478,14 +486,20 @@ static int context_crc32_impl(mksnap_t *eng, mkhost_crc_cache *cache, mkhost_crc
         std::vector<mksnap_extent> ext;
         std::vector<ReadJob> jobs;
         auto acquire = [&]() {
+            const auto t = std::chrono::steady_clock::now();
             ck(eng, mksnap_arena_acquire(eng, &hp, &cap, &aid), "arena acquire");
+            ms_acquire += ms_since(t);
             pos = 0;
             ext.clear();
             jobs.clear();
         };
         auto flush = [&]() {
+            auto t = std::chrono::steady_clock::now();
             run_reads(jobs, n_threads);
+            ms_reads += ms_since(t);
+            t = std::chrono::steady_clock::now();
             ck(eng, mksnap_arena_submit(eng, aid, pos, ext.data(), ext.size(), nullptr, 0), "arena submit");
+            ms_submit += ms_since(t);
             aid = -1;
         };
         acquire();
@@ -558,7 +572,12 @@ static int context_crc32_impl(mksnap_t *eng, mkhost_crc_cache *cache, mkhost_crc
         }
         flush();
         mksnap_result res;
+        const auto t_fin = std::chrono::steady_clock::now();
         ck(eng, mksnap_finish(eng, &res), "finish");
+        if (trace)
+            fprintf(stderr, "[mkhost] context crc32: %zu segments, %.1f MiB; walk %.2f ms, reads %.2f, acquire waits %.2f, submit %.2f, "
+                            "finish %.2f, total %.2f ms\n",
+                    segs.size(), (double)total / 1048576.0, ms_walk, ms_reads, ms_acquire, ms_submit, ms_since(t_fin), ms_since(t_start));
         if (res.crc_bytes != total)
             throw HostError("internal: stream length mismatch");
         *crc_out = mksnap_ctx_crc32(&res);
