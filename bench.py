@@ -7,7 +7,7 @@
   python bench.py --impl reference --gpus 1 --steps 3 --warmup 1  (reference arm: oracle port on host cores)
 
 A "step" = one pass of the hot path over one build context per GPU:
-  CRC-32 context fingerprint (cacheID, bit-exact reference arithmetic) + Gear-32 CDC + per-chunk SHA-256
+  CRC-32 context fingerprint (cacheID, bit-exact reference arithmetic) + Roll-32 CDC + per-chunk SHA-256
   + sort/unique + Merkle root [+ the NCCL table exchange when N > 1: range-partitioned all-to-all by default
   (checked untimed against the all-gather merge first, fallback to it on disagreement), --merge allgather for the other].
 Workload = BASELINE.json configs[2]: 100k files x 512 KiB (48.83 GiB) synthetic, per GPU (weak scaling:
@@ -747,7 +747,7 @@ def main():
     th = threading.Thread(target=clocks_sampler, args=(local, stop, rows), daemon=True)
     if rank == 0:
         th.start()
-    kern = {k: 0.0 for k in ["ms_crc", "ms_gear", "ms_select", "ms_sha", "ms_sort", "ms_root", "ms_gather"]}
+    kern = {k: 0.0 for k in ["ms_crc", "ms_scan", "ms_select", "ms_sha", "ms_sort", "ms_root", "ms_gather"]}
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -769,7 +769,7 @@ def main():
     peak, peak_src = measured_peak()
     gbs = lambda ms: (ctx_bytes / 1e9) / (ms / 1e3) if ms > 0 else None  # noqa: E731
     kernels = [
-        {"name": "K1 k_gear_scan", "bound": "hbm", "ms": kern["ms_gear"], "algorithmic_GBps": gbs(kern["ms_gear"])},
+        {"name": "K1 k_roll_scan", "bound": "hbm", "ms": kern["ms_scan"], "algorithmic_GBps": gbs(kern["ms_scan"])},
         {"name": "K0 k_crc32_extents", "bound": "hbm", "ms": kern["ms_crc"], "algorithmic_GBps": gbs(kern["ms_crc"])},
         {"name": "K2 k_sha256_ranges(chunks)", "bound": "int-alu", "ms": kern["ms_sha"], "algorithmic_GBps": gbs(kern["ms_sha"])},
         {"name": "K1b k_select_cuts+scan", "bound": "latency", "ms": kern["ms_select"]},
@@ -790,9 +790,9 @@ def main():
             traffic, traffic_src = tj["ratio"] * ctx_bytes, tj["source"] + " [scaled by algorithmic bytes]"
     except Exception:
         pass
-    roofline = {"kernel": "k_gear_scan (north_star's rolling-hash kernel)", "bound": "hbm",
-                "achieved": gbs(kern["ms_gear"]), "peak": peak, "unit": "GB/s",
-                "frac": (gbs(kern["ms_gear"]) or 0) / peak, "traffic": traffic, "traffic_source": traffic_src,
+    roofline = {"kernel": "k_roll_scan (north_star's rolling-hash kernel)", "bound": "hbm",
+                "achieved": gbs(kern["ms_scan"]), "peak": peak, "unit": "GB/s",
+                "frac": (gbs(kern["ms_scan"]) or 0) / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ctx_bytes,
                 "note": "dominant kernel BY TIME is K2 (SHA-256, integer-ALU bound, not HBM): see kernels[]"}
@@ -1024,7 +1024,7 @@ def main():
                    "n_chunks": int(sr.n_chunks), "n_unique": int(sr.n_unique),
                    "dedup_ratio_unique_over_total": int(sr.n_unique) / int(sr.n_chunks) if sr.n_chunks else None,
                    "cache_id": "%x" % se.ctx_crc32(sr), "root": bytes(sr.root).hex(),
-                   "rank0_ms": {"crc": sst.ms_crc, "gear": sst.ms_gear, "select": sst.ms_select, "sha": sst.ms_sha,
+                   "rank0_ms": {"crc": sst.ms_crc, "scan": sst.ms_scan, "select": sst.ms_select, "sha": sst.ms_sha,
                                 "sort": sst.ms_sort, "root": sst.ms_root, "exchange": sst.ms_gather}}
             strong["runs"][kind] = run
             se.close()
@@ -1070,7 +1070,7 @@ def main():
             nt = max(1, min(len(os.sched_getaffinity(0)), 64))
             b = cpu_same_work_pass(file_bytes, nt)
             cpu_best = {"value": b["bytes"] / GiB / b["s"], "unit": "GiB/s", "cores": nt, "kind": "port",
-                        "sample": f"{b['n_files']} files x {args.file_kib} KiB ({b['bytes'] / GiB:.2f} GiB): crc32 (slicing-8) + gear32 CDC + "
+                        "sample": f"{b['n_files']} files x {args.file_kib} KiB ({b['bytes'] / GiB:.2f} GiB): crc32 (slicing-8) + roll32 CDC + "
                                   f"chunk SHA-256 ({b['sha_impl']}) per file on {nt} threads, {b['chunks']} chunks; sort/unique/root excluded"}
         except Exception as ex:  # noqa: BLE001
             cpu_best = {"unavailable": repr(ex)}
@@ -1101,7 +1101,7 @@ def main():
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{args.files} files x {args.file_kib} KiB ({ctx_bytes / GiB:.2f} GiB) per GPU, "
                                    f"{args.dirs} dirs, BASELINE configs[2]",
-                       "per_step": "crc32 cacheID + gear32 CDC + chunk SHA-256 + sort/unique + merkle root"
+                       "per_step": "crc32 cacheID + roll32 CDC + chunk SHA-256 + sort/unique + merkle root"
                                    + ((" + nccl " + merge["mode"] + " of the tables" + (" [" + merge["note"] + "]" if "note" in merge else ""))
                                       if world > 1 else ""),
                        "l2": "inputs (48.8 GiB) >> L2 (126 MB): no flush needed", "sharding": f"files by rank, dp{world}",

@@ -55,7 +55,7 @@ typedef struct {
     uint32_t min_size;    /* default 4096   (must be >= 64)                     */
     uint32_t normal_size; /* default 16384  (strict mask below, loose at/after) */
     uint32_t max_size;    /* default 131072                                     */
-    uint32_t strict_bits; /* default 16: candidate iff gear32 < 2^(32-bits)     */
+    uint32_t strict_bits; /* default 16: candidate iff the top bits of roll32 are all ones */
     uint32_t loose_bits;  /* default 12                                         */
 } mksnap_cdc_params;
 
@@ -126,7 +126,7 @@ typedef struct {
     /* device time of the most recent submit, CUDA events on the compute stream */
     float ms_total;
     float ms_crc;     /* K0  crc32 extents          */
-    float ms_gear;    /* K1  gear candidate scan    */
+    float ms_scan;    /* K1  rolling-hash candidate scan */
     float ms_select;  /* K1b cut selection          */
     float ms_sha;     /* K2  per-chunk SHA-256      */
     float ms_stream;  /* K4  serial-stream SHA-256  */
@@ -268,8 +268,9 @@ int mksnap_device_download(mksnap_t *h, uint32_t slot, uint64_t src_off, void *d
 int mksnap_sync(mksnap_t *h);
 int mksnap_stats(mksnap_t *h, mksnap_stats_t *out);
 void mksnap_default_cdc(mksnap_cdc_params *p);
-/* the frozen Gear-32 table (for cross-checking against the oracle) */
-void mksnap_gear_table(uint32_t out[256]);
+/* the multiplier M of the frozen rolling hash h_i = h_{i-1}*M + (LE word ending at byte i) (for cross-checking against
+ * the oracle) */
+uint32_t mksnap_roll_multiplier(void);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,7 @@ class Result(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("ms_total", C.c_float), ("ms_crc", C.c_float), ("ms_gear", C.c_float), ("ms_select", C.c_float),
+    _fields_ = [("ms_total", C.c_float), ("ms_crc", C.c_float), ("ms_scan", C.c_float), ("ms_select", C.c_float),
                 ("ms_sha", C.c_float), ("ms_stream", C.c_float), ("ms_h2d", C.c_float), ("ms_sort", C.c_float),
                 ("ms_root", C.c_float), ("ms_gather", C.c_float), ("kernel_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
@@ -106,7 +106,7 @@ SYMBOLS = [
     ("mksnap_sync", C.c_int, [_P]),
     ("mksnap_stats", C.c_int, [_P, C.POINTER(Stats)]),
     ("mksnap_default_cdc", None, [C.POINTER(CdcParams)]),
-    ("mksnap_gear_table", None, [_P]),
+    ("mksnap_roll_multiplier", C.c_uint32, []),
 ]
 
 _lib = None
@@ -332,8 +332,5 @@ def exchange_plan(rows_per_rank, rank: int) -> dict:
     return dict(zip(["U", "g0", "lead", "full", "tail_own", "borrowed", "groups"], [int(v) for v in out]))
 
 
-def gear_table():
-    import numpy as np
-    g = np.empty(256, dtype=np.uint32)
-    load().mksnap_gear_table(g.ctypes.data)
-    return g
+def roll_multiplier() -> int:
+    return int(load().mksnap_roll_multiplier())

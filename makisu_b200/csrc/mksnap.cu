@@ -92,14 +92,13 @@ struct mksnap {
     uint64_t submit_idx = 0;
 
     CrcConsts *d_consts = nullptr;
-    uint32_t *d_gear = nullptr;
     SessionCounters *d_sc = nullptr;
     SessionCounters *h_sc = nullptr; // pinned
 
     TileRec *d_tiles = nullptr;
-    CUtensorMap tm_main[MAX_SLOTS][3], tm_halo[MAX_SLOTS]; // per slot: arena viewed as [rows][128 B]
-    int gear_cfg = 0; // index into GEAR_SHAPES
-    bool sha_fma = true;                                    // chunk SHA-256: additions on the FMA pipe                                       // index into the k_gear_scan instantiations
+    CUtensorMap tm_main[MAX_SLOTS]; // per slot: arena viewed as [rows][128 B]
+    int scan_cfg = 0; // index into SCAN_SHAPES
+    bool sha_fma = true; // chunk SHA-256: additions on the FMA pipe
     uint32_t *d_pool = nullptr;
     uint32_t pool_cap = 0;
     uint32_t *d_pool_count = nullptr;
@@ -198,12 +197,6 @@ int fail(mksnap *h, int code, const char *fmt, ...)
                         cudaGetErrorString(e__));                                                     \
         (h)->stats.kernel_launches++;                                                                 \
     } while (0)
-
-void gear_table_host(uint32_t out[256])
-{
-    for (uint64_t b = 0; b < 256; b++)
-        out[b] = (uint32_t)(mix64(0x6D616B697375ull + (b + 1) * MK_GOLDEN64) >> 32);
-}
 
 uint32_t xpow_bits(uint64_t bits) // x^bits mod P, reflected
 {
@@ -368,7 +361,7 @@ void mksnap_default_cdc(mksnap_cdc_params *p)
     p->loose_bits = 12;
 }
 
-void mksnap_gear_table(uint32_t out[256]) { gear_table_host(out); }
+uint32_t mksnap_roll_multiplier(void) { return ROLL_MULT; }
 
 const char *mksnap_last_error(const mksnap_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -426,41 +419,36 @@ static int alloc_table_buffers(mksnap *h, uint64_t rows)
     return 0;
 }
 
-template <int GROUPS, int TW, int ST, bool RS> static int launch_gear(mksnap *h, uint32_t slot, uint32_t n_regions, cudaStream_t sk)
+template <int GROUPS, int TW, int ST> static int launch_scan(mksnap *h, uint32_t slot, uint32_t n_regions, cudaStream_t sk)
 {
-    using Cfg = GearCfg<GROUPS, TW, ST>;
+    using Cfg = ScanCfg<GROUPS, TW, ST>;
     const uint32_t n_tiles = (n_regions + Cfg::TILE_WARPS - 1) / Cfg::TILE_WARPS;
     const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)h->sm_count);
-    k_gear_scan<GROUPS, TW, ST, RS><<<grid, Cfg::THREADS, Cfg::SMEM, sk>>>(h->tm_main[slot][0], h->tm_halo[slot], n_tiles, h->d_gear,
-                                                                          h->prm.strict_lim, h->prm.loose_lim, h->d_tiles, h->d_pool,
-                                                                          h->pool_cap, h->d_pool_count, &h->d_sc->err);
+    k_roll_scan<GROUPS, TW, ST><<<grid, Cfg::THREADS, Cfg::SMEM, sk>>>(h->tm_main[slot], n_tiles, h->prm.strict_lim, h->prm.loose_lim,
+                                                                     h->d_tiles, h->d_pool, h->pool_cap, h->d_pool_count, &h->d_sc->err);
     LAUNCH_OK(h);
     return 0;
 }
 
-// the k_gear_scan shapes that are compiled in: {groups, warps per tile, stages, register staging}; MKSNAP_GEAR_CFG picks one
-struct GearShape {
-    int groups, tile_warps, stages, rs;
+// the k_roll_scan shapes that are compiled in: {groups, warps per tile, stages}; MKSNAP_SCAN_CFG picks one (0 = default)
+struct ScanShape {
+    int groups, tile_warps, stages;
 };
-static const GearShape GEAR_SHAPES[] = {{4, 6, 6, 0}, {3, 8, 4, 0}, {2, 8, 4, 0}, {3, 7, 5, 0}, {6, 4, 9, 0},
-                                        {4, 4, 9, 1}, {5, 4, 9, 1}, {3, 6, 6, 1}, {4, 5, 7, 1}};
-constexpr int N_GEAR_SHAPES = 9;
+#define MK_SCAN_SHAPES(X) X(0, 4, 6, 8) X(1, 3, 6, 8) X(2, 2, 6, 8) X(3, 4, 4, 12) X(4, 3, 4, 12) X(5, 2, 4, 12) X(6, 3, 7, 7) X(7, 2, 7, 7) \
+    X(8, 4, 3, 16) X(9, 6, 4, 12)
+#define MK_SHAPE_ROW(I, G, T, S) {G, T, S},
+static const ScanShape SCAN_SHAPES[] = {MK_SCAN_SHAPES(MK_SHAPE_ROW)};
+#undef MK_SHAPE_ROW
+constexpr int N_SCAN_SHAPES = (int)(sizeof(SCAN_SHAPES) / sizeof(SCAN_SHAPES[0]));
 
-#define MK_GEAR_SHAPES(X) X(4, 6, 6, false) X(3, 8, 4, false) X(2, 8, 4, false) X(3, 7, 5, false) X(6, 4, 9, false) \
-    X(4, 4, 9, true) X(5, 4, 9, true) X(3, 6, 6, true) X(4, 5, 7, true)
-
-static int launch_gear_cfg(mksnap *h, uint32_t slot, uint32_t n_regions, cudaStream_t sk)
+static int launch_scan_cfg(mksnap *h, uint32_t slot, uint32_t n_regions, cudaStream_t sk)
 {
-    switch (h->gear_cfg) {
-    case 1: return launch_gear<3, 8, 4, false>(h, slot, n_regions, sk);
-    case 2: return launch_gear<2, 8, 4, false>(h, slot, n_regions, sk);
-    case 3: return launch_gear<3, 7, 5, false>(h, slot, n_regions, sk);
-    case 4: return launch_gear<6, 4, 9, false>(h, slot, n_regions, sk);
-    case 5: return launch_gear<4, 4, 9, true>(h, slot, n_regions, sk);
-    case 6: return launch_gear<5, 4, 9, true>(h, slot, n_regions, sk);
-    case 7: return launch_gear<3, 6, 6, true>(h, slot, n_regions, sk);
-    case 8: return launch_gear<4, 5, 7, true>(h, slot, n_regions, sk);
-    default: return launch_gear<4, 6, 6, false>(h, slot, n_regions, sk);
+    switch (h->scan_cfg) {
+#define MK_SHAPE_CASE(I, G, T, S) \
+    case I: return launch_scan<G, T, S>(h, slot, n_regions, sk);
+        MK_SCAN_SHAPES(MK_SHAPE_CASE)
+#undef MK_SHAPE_CASE
+    default: return launch_scan<4, 6, 8>(h, slot, n_regions, sk);
     }
 }
 
@@ -525,15 +513,11 @@ static int create_impl(mksnap *h)
     CK(h, cudaMalloc(&h->d_consts, sizeof(CrcConsts)));
     CK(h, cudaMemcpy(h->d_consts, hc, sizeof(CrcConsts), cudaMemcpyHostToDevice));
     delete hc;
-    uint32_t g[256];
-    gear_table_host(g);
-    CK(h, cudaMalloc(&h->d_gear, sizeof g));
-    CK(h, cudaMemcpy(h->d_gear, g, sizeof g, cudaMemcpyHostToDevice));
     CK(h, cudaMalloc(&h->d_sc, sizeof(SessionCounters)));
     CK(h, cudaMemset(h->d_sc, 0, sizeof(SessionCounters)));
     CK(h, cudaHostAlloc(&h->h_sc, sizeof(SessionCounters), cudaHostAllocDefault));
 
-    const uint64_t n_tiles = c.device_arena_bytes / GEAR_TILE + 128; // one TileRec per 4 KiB region (+ tile round-up)
+    const uint64_t n_tiles = c.device_arena_bytes / SCAN_TILE + 128; // one TileRec per 4 KiB region (+ tile round-up)
     CK(h, cudaMalloc(&h->d_tiles, n_tiles * sizeof(TileRec)));
     {
         EncodeTiledFn enc = nullptr;
@@ -541,20 +525,19 @@ static int create_impl(mksnap *h)
         CK(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&enc, cudaEnableDefault, &qres));
         if (!enc || qres != cudaDriverEntryPointSuccess)
             return fail(h, MKSNAP_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-        const char *e = getenv("MKSNAP_GEAR_CFG"); // tuning knob: index into GEAR_SHAPES (0 = default)
-        if (e && e[0] >= '0' && e[0] < '0' + N_GEAR_SHAPES && !e[1])
-            h->gear_cfg = e[0] - '0';
+        const char *e = getenv("MKSNAP_SCAN_CFG"); // tuning knob: index into SCAN_SHAPES (0 = default)
+        if (e && e[0] >= '0' && e[0] < '0' + N_SCAN_SHAPES && !e[1])
+            h->scan_cfg = e[0] - '0';
         const uint64_t n_rows = (c.device_arena_bytes + SLOT_SLACK) / 128;
-        const uint32_t box_rows = (uint32_t)GEAR_SHAPES[h->gear_cfg].tile_warps * 32u;
+        const uint32_t box_rows = (uint32_t)SCAN_SHAPES[h->scan_cfg].tile_warps * 32u + 1u; // the row above the tile travels with it
         for (uint32_t s = 0; s < h->n_slots; s++) {
             int rc;
-            if ((rc = make_row_map(h, enc, &h->tm_main[s][0], h->d_slot[s], n_rows, box_rows)) ||
-                (rc = make_row_map(h, enc, &h->tm_halo[s], h->d_slot[s], n_rows, 1)))
+            if ((rc = make_row_map(h, enc, &h->tm_main[s], h->d_slot[s], n_rows, box_rows)))
                 return rc;
         }
-#define MK_SET_SMEM(G, T, S, R) \
-    CK(h, cudaFuncSetAttribute(k_gear_scan<G, T, S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GearCfg<G, T, S>::SMEM));
-        MK_GEAR_SHAPES(MK_SET_SMEM)
+#define MK_SET_SMEM(I, G, T, S) \
+    CK(h, cudaFuncSetAttribute(k_roll_scan<G, T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScanCfg<G, T, S>::SMEM));
+        MK_SCAN_SHAPES(MK_SET_SMEM)
 #undef MK_SET_SMEM
         const char *e2 = getenv("MKSNAP_SHA_FMA"); // tuning knob: 0 = plain adds in the chunk SHA-256 kernel
         if (e2 && e2[0] == '0')
@@ -564,9 +547,9 @@ static int create_impl(mksnap *h)
             h->sha_order = false;
     }
     // expected candidates = bytes >> loose_bits; 8x headroom (32x at the default 12 bits would be wasteful for
-    // dense parameter sets), plus one private block per resident gear warp (x2)
+    // dense parameter sets), plus one private block per resident scan warp (x2)
     uint64_t pc = std::max<uint64_t>(1u << 20, (c.device_arena_bytes >> h->cfg.cdc.loose_bits) * 8) +
-                  2ull * h->sm_count * 32 * GEAR_POOL_BLOCK;
+                  2ull * h->sm_count * 32 * SCAN_POOL_BLOCK;
     if (pc > 0xFFFFFFF0ull)
         pc = 0xFFFFFFF0ull;
     h->pool_cap = (uint32_t)pc;
@@ -678,7 +661,7 @@ void mksnap_destroy(mksnap_t *h)
         if (m.ev_done)
             cudaEventDestroy(m.ev_done);
     }
-    cudaFree(h->d_consts); cudaFree(h->d_gear); cudaFree(h->d_sc); cudaFreeHost(h->h_sc);
+    cudaFree(h->d_consts); cudaFree(h->d_sc); cudaFreeHost(h->h_sc);
     cudaFree(h->d_carry);
     cudaFree(h->d_crc_session);
     cudaFree(h->d_tiles); cudaFree(h->d_pool); cudaFree(h->d_pool_count); cudaFree(h->d_counts); cudaFree(h->d_bases);
@@ -925,9 +908,9 @@ static int submit_common(mksnap *h, uint32_t slot, uint64_t used, const mksnap_e
     }
     CK(h, cudaEventRecord(h->ev[1], sk));
     if (n_files) {
-        const uint32_t n_regions = (uint32_t)((used + GEAR_TILE - 1) / GEAR_TILE);
+        const uint32_t n_regions = (uint32_t)((used + SCAN_TILE - 1) / SCAN_TILE);
         CK(h, cudaMemsetAsync(h->d_pool_count, 0, 4, sk));
-        int rc = launch_gear_cfg(h, slot, n_regions, sk);
+        int rc = launch_scan_cfg(h, slot, n_regions, sk);
         if (rc)
             return rc;
     }
@@ -1114,7 +1097,7 @@ int mksnap_finish(mksnap_t *h, mksnap_result *out)
     CK(h, cudaStreamSynchronize(s));
     h->stats.d2h_bytes += sizeof(SessionCounters);
     if (h->h_sc->err & 1u)
-        return fail(h, MKSNAP_E_CAPACITY, "gear candidate pool overflow (capacity %u entries): pathologically dense candidates", h->pool_cap);
+        return fail(h, MKSNAP_E_CAPACITY, "candidate pool overflow (capacity %u entries): pathologically dense candidates", h->pool_cap);
     if (h->h_sc->err & 4u)
         return fail(h, MKSNAP_E_CUDA, "k_gear_scan: dynamic shared memory does not start where the layout plan assumes");
     if (h->h_sc->err & 8u)
@@ -1255,7 +1238,7 @@ int mksnap_stats(mksnap_t *h, mksnap_stats_t *out)
         for (int i = 0; i < 5; i++)
             CK(h, cudaEventElapsedTime(&t[i], h->ev[i], h->ev[i + 1]));
         h->stats.ms_crc = t[0];
-        h->stats.ms_gear = t[1];
+        h->stats.ms_scan = t[1];
         h->stats.ms_select = t[2];
         h->stats.ms_sha = t[3];
         h->stats.ms_stream = t[4];

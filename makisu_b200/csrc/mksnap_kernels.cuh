@@ -1,7 +1,7 @@
 // mksnap_kernels.cuh — hand-written sm_100a kernels of the snapshot+hash path.
 //
 //   K0  k_crc32_extents   CRC-32/IEEE of the context stream      (HBM-read bound)
-//   K1  k_gear_scan       Gear-32 candidate scan                 (HBM-read bound)
+//   K1  k_roll_scan       Roll-32 candidate scan                 (HBM-read bound)
 //   K1b k_select_cuts     min/normal/max cut selection per file  (latency, tiny)
 //   K2  k_sha256_ranges   SHA-256 of many byte ranges            (int-ALU bound)
 //       (the same kernel digests the serial layer-tar streams, K4, and the
@@ -262,28 +262,29 @@ k_crc32_extents(const uint8_t *__restrict__ arena, const CrcExtent *__restrict__
 }
 
 // ------------------------------------------------------------------------
-// K1: Gear-32 candidate scan.
-//   h_i = sum_{k<32} G[b_{i-k}] << k  (mod 2^32);  candidate iff h_i < 2^(32-bits)
+// K1: Roll-32 candidate scan.
+//   u_i = little-endian 32-bit word that ENDS at byte i;  h_i = h_{i-1}*M + u_i (mod 2^32), M = 2*odd, so
+//   h_i = sum_{k<32} u_{i-k} * M^k: a 32-position (35-byte) window and NO table.
+//   candidate iff the top `bits` bits of h_i are all ones (h_i >= 2^32 - 2^(32-bits)).
+// Per byte that is one funnel shift (ALU pipe; none for the aligned position of each word), one IMAD (FMA pipe) and
+// half a VIMNMX3 for the test -- 2.25 issue slots per byte and not one shared-memory lookup, so the kernel is bounded
+// by HBM and nothing else.  (The round-1/2 kernel hashed with a 256-entry Gear table: PRMT + LDS + IMAD per byte kept
+// the LSU at 72 % and issue at 79 % of their peaks, and it stalled at 73 % of the HBM peak.)
 //
-// Data path: the arena is viewed as a [rows][128 B] tensor.  A producer warp streams
-// tiles of GEAR_WARPS*32 rows into shared memory with TMA (cp.async.bulk.tensor.2d,
-// SWIZZLE_128B) through a GEAR_STAGES-deep full/empty mbarrier ring; a second one-row
-// TMA brings the 128 bytes that precede the tile (the rolling-hash halo).
-// Each consumer thread owns ONE 128-byte row: it reads it with eight conflict-free
-// LDS.128 (chunk c of row r sits at c ^ (r&7)), and rolls the hash over its 128
-// bytes from state 0.  The update h' = 2h + G[b] is linear in h, so the state the
-// thread should have started from -- A = hash of the 32 bytes before its row, i.e.
-// the previous lane's final state, one warp shuffle away -- is added afterwards as
-// h_i += A << (i+1), which only matters for the first 31 positions.  A warp is
-// fully autonomous (its lane-0 carry comes from a 32-lane cooperative hash of the
-// preceding 32 bytes), so there is no block-level synchronisation at all.
-// Candidates are rare (2^-12 per byte): they are collected in per-lane register
-// bitmasks (lane l's mask = its own row), compacted in position order with one
-// warp scan, and bump-allocated into the pool: one TileRec per 4 KiB warp region,
-// pool entry = pos_in_region | strict<<31.
+// Data path: the arena is viewed as a [rows][128 B] tensor.  A producer warp streams tiles of TILE_WARPS*32 rows PLUS
+// the row in front of them (one cp.async.bulk.tensor.2d, SWIZZLE_128B, box = ROWS+1 rows starting at row0-1; the row
+// before the arena is out of bounds and arrives as zeros) through a STAGES-deep full/empty mbarrier ring.
+// Each consumer thread owns ONE 128-byte row.  It warms the hash up over the last 32 positions of the row above it
+// (two LDS.128 + one LDS.32 from that row: after 32 positions the state no longer depends on where it started), then
+// rolls it over its own 128 bytes, eight conflict-free LDS.128 (chunk c of row r sits at c ^ (r & 7)).  No carry
+// between lanes, no block-level synchronisation: a thread needs nothing but its two rows.
+// Candidates are rare (2^-12 per byte): they are collected in per-lane register bitmasks (lane l's mask = its own
+// row), compacted in position order with one warp scan, and bump-allocated into the pool: one TileRec per 4 KiB warp
+// region, pool entry = pos_in_region | strict<<31.
 // ------------------------------------------------------------------------
-constexpr uint32_t GEAR_TILE = 4096; // bytes per TileRec region (= one warp x 32 rows x 128 B)
-constexpr uint32_t GEAR_POOL_BLOCK = 256; // pool entries a warp reserves per global atomic
+constexpr uint32_t SCAN_TILE = 4096; // bytes per TileRec region (= one warp x 32 rows x 128 B)
+constexpr uint32_t SCAN_POOL_BLOCK = 256; // pool entries a warp reserves per global atomic
+constexpr uint32_t ROLL_MULT = 0x9E3779BAu; // M = 2 * 0x4F1BBCDD (oracle/mkoracle.c ROLL_MULT)
 
 struct TileRec {
     uint32_t base;  // first pool entry of this region
@@ -307,8 +308,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     uint32_t ok;
     do {
         // the suspend-time hint lets the hardware park the warp instead of re-issuing the probe: a spinning warp
-        // steals issue slots from the warps that have data (ncu, round 2: 20 % of all issued instructions were
-        // YIELD/SYNCS/BRA of this loop)
+        // steals issue slots from the warps that have data
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok)
                      : "r"(bar), "r"(parity), "r"(200000u)
@@ -327,101 +327,73 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr)
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
 
-// roll 4 bytes of `word` into h, keeping every intermediate state in hv[k0..k0+3]
-// address of G[byte K of word] for this lane: one PRMT -> {G.b3, G.b2, word.bK, G.b0}
-template <int K> __device__ __forceinline__ uint32_t gear_addr(uint32_t word, uint32_t G)
+// h*M + u on the FMA pipe
+__device__ __forceinline__ uint32_t roll_step(uint32_t h, uint32_t u)
 {
-    return __byte_perm(word, G, 0x7604 + (K << 4));
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(h), "n"(ROLL_MULT), "r"(u));
+    return d;
 }
-
-#define MK_GEAR_BYTES(word, k0)                                     \
+// the four positions that end in the bytes of `w` (`p` = the word before it), every intermediate state kept
+#define MK_ROLL_WORD(p, w, k0)                                      \
     {                                                               \
-        const uint32_t g0 = lds_u32(gear_addr<0>(word, G));         \
-        const uint32_t g1 = lds_u32(gear_addr<1>(word, G));         \
-        const uint32_t g2 = lds_u32(gear_addr<2>(word, G));         \
-        const uint32_t g3 = lds_u32(gear_addr<3>(word, G));         \
-        h = fma_2a_plus_b(h, g0);                                   \
+        h = roll_step(h, __funnelshift_r((p), (w), 8));             \
         hv[(k0)] = h;                                               \
-        h = fma_2a_plus_b(h, g1);                                   \
+        h = roll_step(h, __funnelshift_r((p), (w), 16));            \
         hv[(k0) + 1] = h;                                           \
-        h = fma_2a_plus_b(h, g2);                                   \
+        h = roll_step(h, __funnelshift_r((p), (w), 24));            \
         hv[(k0) + 2] = h;                                           \
-        h = fma_2a_plus_b(h, g3);                                   \
+        h = roll_step(h, (w));                                      \
         hv[(k0) + 3] = h;                                           \
     }
+// the same without keeping the states (warm-up over the row above)
+#define MK_ROLL_WARM(p, w)                                          \
+    {                                                               \
+        h = roll_step(h, __funnelshift_r((p), (w), 8));             \
+        h = roll_step(h, __funnelshift_r((p), (w), 16));            \
+        h = roll_step(h, __funnelshift_r((p), (w), 24));            \
+        h = roll_step(h, (w));                                      \
+    }
 
-// A tile is TILE_WARPS warps x 32 rows x 128 B (one TMA op); GROUPS groups of TILE_WARPS consumer warps take the
-// CTA's tiles round-robin, so the pipeline depth (STAGES) is independent of how many warps hide latency.  With G groups
-// consuming, STAGES - G stages are in flight from HBM: the round-1 shape (3 groups x 8 warps, 4 stages of 32 KiB)
-// left ONE 32 KiB stage in flight per SM -- 4.7 MB over the chip against the ~6.5 MB that 6.5 TB/s x ~1 us of loaded
-// latency needs -- and consumers spun on the full barrier; 4 groups x 6 warps with 6 stages of 24 KiB keeps the same 24
-// consumer warps and puts two stages (48 KiB per SM, 7.1 MB) in flight.
-// Shared-memory plan (ABSOLUTE shared-window addresses; the kernel has no static shared memory, so the dynamic
-// region starts at the architecture's reserved 1 KiB, s0 = 0x400):
-//   [0x400, 0x20000)       the first N_A stages
-//   [0x20000, 0x30000)     gear table, 256-byte stride: value v of lane l at 0x20000 + v*256 + l*4.  With the
-//                          table on a 64 KiB boundary ONE PRMT builds a lookup address
-//                          (bytes {lane*4, data byte, 0x02, 0x00}): no multiply/add per lookup.
-//   [0x30000, ...)         the remaining stages, then the halo rows (one 128 B row per stage) and the mbarriers
-template <int GEAR_GROUPS, int TW = 8, int ST = 4> struct GearCfg {
+// A tile is TILE_WARPS warps x 32 rows x 128 B plus the row above it (one TMA op); GROUPS groups of TILE_WARPS consumer
+// warps take the CTA's tiles round-robin, so the pipeline depth (STAGES) is independent of how many warps hide latency.
+// With G groups consuming, STAGES - G stages are in flight from HBM; the chip needs ~45 KiB per SM in flight to cover
+// 6.5 TB/s x ~1 us of loaded latency.  With no table in shared memory all 227 KiB hold stages.
+// Shared-memory plan (dynamic region, 1 KiB aligned): STAGES stages of PITCH bytes (box rounded up to whole swizzle
+// atoms), then the mbarriers.
+template <int SCAN_GROUPS, int TW = 6, int ST = 8> struct ScanCfg {
     static constexpr uint32_t STAGES = ST;
     static constexpr uint32_t TILE_WARPS = TW;
-    static constexpr uint32_t GROUPS = GEAR_GROUPS;
+    static constexpr uint32_t GROUPS = SCAN_GROUPS;
     static constexpr uint32_t ROWS = TILE_WARPS * 32;
-    static constexpr uint32_t TILE_BYTES = ROWS * 128;
-    static constexpr uint32_t BOX_ROWS = ROWS;
-    static constexpr uint32_t CONSUMER_WARPS = GEAR_GROUPS * TILE_WARPS;
+    static constexpr uint32_t BOX_ROWS = ROWS + 1;                 // the row above the tile travels with it
+    static constexpr uint32_t TILE_BYTES = BOX_ROWS * 128;         // bytes one TMA op delivers
+    static constexpr uint32_t PITCH = (TILE_BYTES + 1023) / 1024 * 1024;
+    static constexpr uint32_t CONSUMER_WARPS = SCAN_GROUPS * TILE_WARPS;
     static constexpr uint32_t THREADS = (CONSUMER_WARPS + 1) * 32;
-    static constexpr uint32_t A0_ABS = 0x400;
-    static constexpr uint32_t GEAR_ABS = 0x20000;
-    static constexpr uint32_t B0_ABS = 0x30000;
-    static constexpr uint32_t N_A = (GEAR_ABS - A0_ABS) / TILE_BYTES < STAGES ? (GEAR_ABS - A0_ABS) / TILE_BYTES : STAGES;
-    static constexpr uint32_t N_B = STAGES - N_A;
-    static constexpr uint32_t HALO_ABS = B0_ABS + N_B * TILE_BYTES;           // 1 KiB aligned (TILE_BYTES is)
-    static constexpr uint32_t BARS_ABS = HALO_ABS + ((STAGES * 128 + 1023) / 1024) * 1024;
-    static constexpr uint32_t END_ABS = BARS_ABS + 2 * STAGES * 8;
-    static constexpr uint32_t SMEM = END_ABS - 1024; // dynamic bytes to request when the region starts at 0x400
-    static_assert(TILE_BYTES % 1024 == 0 && ROWS <= 256, "tile = whole swizzle atoms, one TMA box");
-    static_assert(END_ABS <= 227 * 1024 + 1024, "exceeds the 227 KiB per-CTA limit");
-    __device__ static uint32_t stage_addr(uint32_t s0, uint32_t s) { return s < N_A ? s0 + s * TILE_BYTES : B0_ABS + (s - N_A) * TILE_BYTES; }
+    static constexpr uint32_t BARS_OFF = STAGES * PITCH;
+    static constexpr uint32_t SMEM = BARS_OFF + 2 * STAGES * 8 + 1024; // dynamic bytes to request, alignment slack included
+    static_assert(BOX_ROWS <= 256, "one TMA box");
+    static_assert(SMEM <= 227 * 1024, "exceeds the 227 KiB per-CTA limit");
 };
 
-// RS ("register staging"): a consumer copies its whole 128-byte row into registers (8 LDS.128) and hands the stage back
-// to the producer BEFORE hashing it, so a stage is occupied for ~200 cycles instead of the ~6000 its tile takes to hash
-// and nearly all STAGES are in flight from HBM (ncu, round 2: without it only STAGES - GROUPS stages were, consumers
-// spent ~15 % of their issue slots polling the full barrier).  Costs 32 registers per thread: fewer consumer warps fit.
-template <int GEAR_GROUPS, int TW, int ST, bool RS>
-__global__ void __launch_bounds__((GEAR_GROUPS * TW + 1) * 32, 1)
-k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_halo,
-            uint32_t n_tiles, const uint32_t *__restrict__ gear, uint32_t strict_lim, uint32_t loose_lim,
+template <int SCAN_GROUPS, int TW, int ST>
+__global__ void __launch_bounds__((SCAN_GROUPS * TW + 1) * 32, 1)
+k_roll_scan(const __grid_constant__ CUtensorMap tm_main, uint32_t n_tiles, uint32_t strict_lim, uint32_t loose_lim,
             TileRec *__restrict__ tiles, uint32_t *__restrict__ pool, uint32_t pool_cap,
             uint32_t *__restrict__ pool_count, uint32_t *__restrict__ err_flag)
 {
-    using Cfg = GearCfg<GEAR_GROUPS, TW, ST>;
-    constexpr uint32_t GEAR_STAGES = Cfg::STAGES;
+    using Cfg = ScanCfg<SCAN_GROUPS, TW, ST>;
+    constexpr uint32_t STAGES = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t s0 = smem_u32(smem_raw); // stages 0..2 live at the start of the dynamic region
+    const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u; // swizzle atoms are 1 KiB: align the stages ourselves
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t bar_full = Cfg::BARS_ABS, bar_empty = bar_full + GEAR_STAGES * 8;
-    const uint32_t halo_abs = Cfg::HALO_ABS;
-    if (s0 + Cfg::N_A * Cfg::TILE_BYTES > Cfg::GEAR_ABS || (s0 & 1023u)) { // layout assumption violated: fail loudly
-        if (threadIdx.x == 0)
-            atomicExch(err_flag, 4u);
-        return;
-    }
+    const uint32_t bar_full = s0 + Cfg::BARS_OFF, bar_empty = bar_full + STAGES * 8;
+    const uint32_t strict_thr = 0u - strict_lim, loose_thr = 0u - loose_lim; // top `bits` bits all ones
 
-    // lane-replicated gear table, 256-byte stride: value v of lane l at GEAR_ABS + v*256 + l*4
-    for (uint32_t i = threadIdx.x; i < 256u * 32u; i += blockDim.x)
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(Cfg::GEAR_ABS + (i >> 5) * 256u + (i & 31u) * 4u), "r"(__ldg(gear + (i >> 5))));
     if (threadIdx.x == 0) {
-        for (int s = 0; s < GEAR_STAGES; ++s) {
+        for (int s = 0; s < (int)STAGES; ++s) {
             mbar_init(bar_full + s * 8, 1);
             mbar_init(bar_empty + s * 8, Cfg::TILE_WARPS);
         }
@@ -434,134 +406,81 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
         if (lane == 0) {
             uint32_t it = 0;
             for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const uint32_t s = it % GEAR_STAGES;
-                if (it >= GEAR_STAGES)
-                    mbar_wait(bar_empty + s * 8, ((it / GEAR_STAGES) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(bar_full + s * 8, Cfg::TILE_BYTES + 128u);
-                const int32_t row0 = (int32_t)(tile * Cfg::ROWS);
-#pragma unroll
-                for (uint32_t b = 0; b < Cfg::ROWS / Cfg::BOX_ROWS; ++b)
-                    tma_load_2d(Cfg::stage_addr(s0, s) + b * Cfg::BOX_ROWS * 128u, &tm_main, 0,
-                                row0 + (int32_t)(b * Cfg::BOX_ROWS), bar_full + s * 8);
-                tma_load_2d(halo_abs + s * 128u, &tm_halo, 0, row0 - 1, bar_full + s * 8);
+                const uint32_t s = it % STAGES;
+                if (it >= STAGES)
+                    mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(bar_full + s * 8, Cfg::TILE_BYTES);
+                tma_load_2d(s0 + s * Cfg::PITCH, &tm_main, 0, (int32_t)(tile * Cfg::ROWS) - 1, bar_full + s * 8);
             }
         }
         return;
     }
 
     // ----------------------------- consumers -----------------------------
-    const uint32_t G = Cfg::GEAR_ABS + lane * 4u; // bytes {lane*4, 0x00, 0x02, 0x00}
     const uint32_t group = warp / Cfg::TILE_WARPS, wt = warp % Cfg::TILE_WARPS; // wt = warp within the tile
-    const uint32_t row = wt * 32u + lane;
-    const uint32_t swz = (row & 7u) << 4;
+    const uint32_t row = wt * 32u + lane;   // row of the tile; it sits at box row `row + 1`, the row above it at `row`
+    const uint32_t ra_off = (row + 1u) * 128u, swz = ((row + 1u) & 7u) << 4;
+    const uint32_t rp_off = row * 128u, swp = (row & 7u) << 4;
     uint32_t blk_next = 0, blk_end = 0; // this warp's private slice of the pool (warp-uniform)
     // CTA-local tile sequence it = 0,1,2,... (global tile = blockIdx.x + it*gridDim.x); group g takes it = g (mod GROUPS)
-    for (uint32_t it = group;; it += GEAR_GROUPS) {
+    for (uint32_t it = group;; it += SCAN_GROUPS) {
         const uint64_t tile64 = (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
         if (tile64 >= n_tiles)
             break;
         const uint32_t tile = (uint32_t)tile64;
-        const uint32_t s = it % GEAR_STAGES;
-        const uint32_t sb = Cfg::stage_addr(s0, s);
-        mbar_wait(bar_full + s * 8, (it / GEAR_STAGES) & 1u);
+        const uint32_t s = it % STAGES;
+        const uint32_t sb = s0 + s * Cfg::PITCH;
+        mbar_wait(bar_full + s * 8, (it / STAGES) & 1u);
 
-        // carry into lane 0: hash of the 32 bytes before the warp's first row, one byte per lane
-        uint32_t a_warp;
+        // warm-up: the 32 positions that end in bytes 96..127 of the row above (their words reach back to byte 93)
+        uint32_t h = 0, pw;
         {
-            uint32_t addr;
-            if (wt == 0) {
-                addr = halo_abs + s * 128u + (((6u + (lane >> 4)) ^ (s & 7u)) << 4) + (lane & 15u);
-            } else {
-                const uint32_t pr = wt * 32u - 1u; // previous row, chunks 6 and 7
-                addr = sb + pr * 128u + (((6u + (lane >> 4)) ^ (pr & 7u)) << 4) + (lane & 15u);
-            }
-            uint32_t v = lds_u32(gear_addr<0>(lds_u8(addr), G)) << (31u - lane);
-#pragma unroll
-            for (int sft = 16; sft; sft >>= 1)
-                v += __shfl_xor_sync(0xFFFFFFFFu, v, sft);
-            a_warp = v;
+            const uint32_t rp = sb + rp_off;
+            const uint32_t w5 = lds_u32(rp + ((5u << 4) ^ swp) + 12u); // bytes 92..95
+            const uint4 a = lds_u128(rp + ((6u << 4) ^ swp)), b = lds_u128(rp + ((7u << 4) ^ swp));
+            MK_ROLL_WARM(w5, a.x) MK_ROLL_WARM(a.x, a.y) MK_ROLL_WARM(a.y, a.z) MK_ROLL_WARM(a.z, a.w)
+            MK_ROLL_WARM(a.w, b.x) MK_ROLL_WARM(b.x, b.y) MK_ROLL_WARM(b.y, b.z) MK_ROLL_WARM(b.z, b.w)
+            pw = b.w;
         }
 
-        const uint32_t ra = sb + row * 128u;
-        uint32_t h = 0;
-        uint32_t L[32];                           // states of positions 0..31 (need the carry)
+        const uint32_t ra = sb + ra_off;
         uint32_t mL0 = 0, mL1 = 0, mL2 = 0, mL3 = 0; // loose candidates, bit p of the row
         uint32_t mS0 = 0, mS1 = 0, mS2 = 0, mS3 = 0; // strict candidates
-        uint4 rowreg[RS ? 8 : 1];
-        if (RS) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                rowreg[c] = lds_u128(ra + ((uint32_t)(c << 4) ^ swz));
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(bar_empty + s * 8);
-        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const uint4 w = RS ? rowreg[c] : lds_u128(ra + ((uint32_t)(c << 4) ^ swz));
+            const uint4 w = lds_u128(ra + ((uint32_t)(c << 4) ^ swz));
             uint32_t hv[16];
-            MK_GEAR_BYTES(w.x, 0) MK_GEAR_BYTES(w.y, 4) MK_GEAR_BYTES(w.z, 8) MK_GEAR_BYTES(w.w, 12)
-            if (c < 2) {
+            MK_ROLL_WORD(pw, w.x, 0) MK_ROLL_WORD(w.x, w.y, 4) MK_ROLL_WORD(w.y, w.z, 8) MK_ROLL_WORD(w.z, w.w, 12)
+            pw = w.w;
+            uint32_t m = hv[0];
+#pragma unroll
+            for (int i = 1; i < 16; ++i)
+                m = max(m, hv[i]);
+            // ~0.4 % of lane-chunks hold a candidate, so ~12 % of the time some lane of the warp does: the vote makes
+            // the branch warp-uniform (no BSSY/BSYNC pair around it on the 88 % path)
+            if (__any_sync(0xFFFFFFFFu, m >= loose_thr) && m >= loose_thr) {
+                uint32_t bl = 0, bs = 0;
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    L[c * 16 + i] = hv[i];
-            } else {
-                uint32_t m = hv[0];
-#pragma unroll
-                for (int i = 1; i < 16; ++i)
-                    m = min(m, hv[i]);
-                // ~0.4 % of lane-chunks hold a candidate, so ~12 % of the time some lane of the warp does: the vote makes
-                // the branch warp-uniform (no BSSY/BSYNC pair around it on the 88 % path)
-                if (__any_sync(0xFFFFFFFFu, m < loose_lim) && m < loose_lim) {
-                    uint32_t bl = 0, bs = 0;
+                    if (hv[i] >= loose_thr)
+                        bl |= 1u << i;
+                if (m >= strict_thr) { // 1/16 of those
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (hv[i] < loose_lim)
-                            bl |= 1u << i;
-                    if (m < strict_lim) { // 1/16 of those
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (hv[i] < strict_lim)
-                                bs |= 1u << i;
-                    }
-                    const uint32_t sh = (c & 1) * 16;
-                    if ((c >> 1) == 1) { mL1 |= bl << sh; mS1 |= bs << sh; }
-                    if ((c >> 1) == 2) { mL2 |= bl << sh; mS2 |= bs << sh; }
-                    if ((c >> 1) == 3) { mL3 |= bl << sh; mS3 |= bs << sh; }
+                        if (hv[i] >= strict_thr)
+                            bs |= 1u << i;
                 }
+                const uint32_t sh = (c & 1) * 16;
+                if ((c >> 1) == 0) { mL0 |= bl << sh; mS0 |= bs << sh; }
+                if ((c >> 1) == 1) { mL1 |= bl << sh; mS1 |= bs << sh; }
+                if ((c >> 1) == 2) { mL2 |= bl << sh; mS2 |= bs << sh; }
+                if ((c >> 1) == 3) { mL3 |= bl << sh; mS3 |= bs << sh; }
             }
         }
         // the stage is consumed: hand it back to the producer before the tail work
-        if (!RS) {
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(bar_empty + s * 8);
-        }
-
-        // positions 0..30 need the carry A = previous lane's final state
-        {
-            uint32_t A = __shfl_up_sync(0xFFFFFFFFu, h, 1);
-            if (lane == 0)
-                A = a_warp;
-            uint32_t m = L[31];
-#pragma unroll
-            for (int i = 0; i < 31; ++i) {
-                L[i] += A << (i + 1);
-                m = min(m, L[i]);
-            }
-            if (__any_sync(0xFFFFFFFFu, m < loose_lim) && m < loose_lim) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (L[i] < loose_lim)
-                        mL0 |= 1u << i;
-                if (m < strict_lim) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (L[i] < strict_lim)
-                            mS0 |= 1u << i;
-                }
-            }
-        }
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(bar_empty + s * 8);
 
         // ordered compaction: lane l's candidates precede lane l+1's
         const uint32_t cnt = __popc(mL0) + __popc(mL1) + __popc(mL2) + __popc(mL3);
@@ -582,10 +501,10 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
             }
             total = __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        if (total > blk_end - blk_next) { // refill: rare (every ~GEAR_POOL_BLOCK candidates)
+        if (total > blk_end - blk_next) { // refill: rare (every ~SCAN_POOL_BLOCK candidates)
             uint32_t nb = 0;
             if (lane == 0) {
-                const uint32_t want = total > GEAR_POOL_BLOCK ? total : GEAR_POOL_BLOCK;
+                const uint32_t want = total > SCAN_POOL_BLOCK ? total : SCAN_POOL_BLOCK;
                 nb = atomicAdd(pool_count, want);
                 if (nb + want > pool_cap || nb + want < nb) {
                     atomicExch(err_flag, 1u);
@@ -594,7 +513,7 @@ k_gear_scan(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__
             }
             nb = __shfl_sync(0xFFFFFFFFu, nb, 0);
             blk_next = nb;
-            blk_end = nb == 0xFFFFFFFFu ? nb : nb + (total > GEAR_POOL_BLOCK ? total : GEAR_POOL_BLOCK);
+            blk_end = nb == 0xFFFFFFFFu ? nb : nb + (total > SCAN_POOL_BLOCK ? total : SCAN_POOL_BLOCK);
         }
         const uint32_t base = blk_next;
         if (base != 0xFFFFFFFFu)
@@ -675,9 +594,9 @@ __device__ __forceinline__ uint64_t select_one_cut(uint64_t prev, uint64_t end, 
     const uint64_t scan_end = limit_end < end ? limit_end : end;
     const uint64_t lo = prev + prm.min_size - 1;
     const uint64_t normal_pos = prev + prm.normal_size - 1; // pos >= this: loose accepted
-    for (uint64_t t = lo / GEAR_TILE; t * GEAR_TILE < scan_end; ++t) {
+    for (uint64_t t = lo / SCAN_TILE; t * SCAN_TILE < scan_end; ++t) {
         const TileRec tr = tiles[t];
-        const uint64_t tb = t * GEAR_TILE;
+        const uint64_t tb = t * SCAN_TILE;
         for (uint32_t j = 0; j < tr.count; ++j) {
             const uint32_t ent = __ldg(pool + tr.base + j);
             const uint64_t pos = tb + (ent & 0x7FFFFFFFu);
@@ -860,8 +779,8 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
         if (prev0 >= end)
             break;
         // ---- 1. stage the window that starts at the region holding `prev` ----
-        const uint64_t t0 = prev0 / GEAR_TILE;
-        const uint64_t t_last = (end - 1) / GEAR_TILE;
+        const uint64_t t0 = prev0 / SCAN_TILE;
+        const uint64_t t_last = (end - 1) / SCAN_TILE;
         const uint32_t want = (uint32_t)((t_last - t0 + 1 < SELB_REGIONS) ? (t_last - t0 + 1) : SELB_REGIONS);
         constexpr uint32_t PER = SELB_REGIONS / SELB_THREADS;
         uint32_t cnt[PER], bs[PER], mine = 0;
@@ -899,7 +818,7 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
             if (o + cnt[k] <= SELB_CANDS) {
                 for (uint32_t j = 0; j < cnt[k]; ++j) {
                     const uint32_t ent = __ldg(pool + bs[k] + j);
-                    s_cand[o + j] = (r * GEAR_TILE + (ent & 0x7FFFFFFFu)) | (ent & 0x80000000u);
+                    s_cand[o + j] = (r * SCAN_TILE + (ent & 0x7FFFFFFFu)) | (ent & 0x80000000u);
                 }
             }
             o += cnt[k];
@@ -910,11 +829,11 @@ k_select_cuts_big(const CdcFile *__restrict__ files, uint32_t n_files, CdcParams
         uint32_t nreg = want; // regions whose candidates all fit in s_cand (same value in every thread)
         while (nreg > 0 && s_off[nreg] > SELB_CANDS)
             --nreg;
-        const uint64_t wbase = t0 * GEAR_TILE;
+        const uint64_t wbase = t0 * SCAN_TILE;
         SelWin w;
         w.cand = s_cand;
         w.ncand = s_off[nreg];
-        w.wend = nreg * GEAR_TILE;
+        w.wend = nreg * SCAN_TILE;
         // a piece whose file continues (more_after) has no file end in sight: the chain stops with NX_OUT near the
         // piece end and the exact rule (select_one_cut with more_after) finishes from global memory
         w.fend = (wbase + w.wend >= end && !fl.more_after) ? (uint32_t)(end - wbase) : 0xFFFFFFFFu;

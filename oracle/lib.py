@@ -43,8 +43,8 @@ def L():
         l.mko_crc32_combine.restype = u32; l.mko_crc32_combine.argtypes = [u32, u32, u64]
         l.mko_sha256.restype = None; l.mko_sha256.argtypes = [vp, sz, vp]
         l.mko_cdc_default_params.restype = None; l.mko_cdc_default_params.argtypes = [C.POINTER(CdcParams)]
-        l.mko_gear_table.restype = None; l.mko_gear_table.argtypes = [vp]
-        l.mko_gear_at.restype = u32; l.mko_gear_at.argtypes = [vp, sz]
+        l.mko_roll_multiplier.restype = u32; l.mko_roll_multiplier.argtypes = []
+        l.mko_roll_at.restype = u32; l.mko_roll_at.argtypes = [vp, sz]
         l.mko_cdc_cuts.restype = sz; l.mko_cdc_cuts.argtypes = [vp, sz, C.POINTER(CdcParams), vp, sz]
         l.mko_sort_unique_digests.restype = sz; l.mko_sort_unique_digests.argtypes = [vp, sz]
         l.mko_merkle_root.restype = None; l.mko_merkle_root.argtypes = [vp, sz, vp]
@@ -85,10 +85,13 @@ def default_params() -> CdcParams:
     return p
 
 
-def gear_table() -> np.ndarray:
-    g = np.empty(256, dtype=np.uint32)
-    L().mko_gear_table(g.ctypes.data)
-    return g
+def roll_multiplier() -> int:
+    return int(L().mko_roll_multiplier())
+
+
+def roll_at(data, i: int) -> int:
+    a = _buf(data)
+    return int(L().mko_roll_at(a.ctypes.data, i))
 
 
 def cdc_cuts(data, params: CdcParams | None = None) -> np.ndarray:

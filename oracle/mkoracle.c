@@ -12,7 +12,7 @@
  * algorithms (reflected CRC-32 poly 0xEDB88320; FIPS 180-4) are restated and
  * pinned against the reference's own fixtures in tests/test_oracle_golden.py.
  *
- * Gear-32 CDC / chunk table / Merkle root: no reference counterpart
+ * Roll-32 CDC / chunk table / Merkle root: no reference counterpart
  * ("parity unpinned"); this file is the normative statement of DESIGN.md section 3.
  */
 #include "mkoracle.h"
@@ -216,24 +216,27 @@ void mko_sha256(const uint8_t *p, size_t n, uint8_t out[32])
 }
 
 /* ======================================================================= */
-/* Gear-32 CDC (no reference counterpart)                   */
+/* Roll-32 CDC (no reference counterpart)                   */
 /* ======================================================================= */
+/* Rabin-Karp style polynomial rolling hash over the little-endian 32-bit word that ENDS at each byte:
+ *   u_i = b[i-3] | b[i-2]<<8 | b[i-1]<<16 | b[i]<<24
+ *   h_i = h_{i-1} * M + u_i   (mod 2^32),   M = 2 * (odd)  =>  M^32 = 0 (mod 2^32):
+ *   h_i = sum_{k<32} u_{i-k} * M^k  -- a window of 32 positions = 35 bytes, no table.
+ * Candidate at byte i iff the top `bits` bits of h_i are all ONES (h_i >= 2^32 - 2^(32-bits)); a run of zero bytes
+ * hashes to 0 and is therefore never a candidate. */
 
+#define ROLL_MULT 0x9E3779BAu /* 2 * 0x4F1BBCDD */
+
+/* splitmix64 finaliser: the synthetic-content generator below (mko_synth_fill) */
 static inline uint64_t mix64(uint64_t z)
 {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
 }
-
 #define GOLDEN64 0x9E3779B97F4A7C15ull
-#define GEAR_SEED 0x6D616B697375ull /* "makisu" */
 
-void mko_gear_table(uint32_t out[256])
-{
-    for (uint64_t b = 0; b < 256; b++)
-        out[b] = (uint32_t)(mix64(GEAR_SEED + (b + 1) * GOLDEN64) >> 32);
-}
+uint32_t mko_roll_multiplier(void) { return ROLL_MULT; }
 
 void mko_cdc_default_params(mko_cdc_params *p)
 {
@@ -244,24 +247,30 @@ void mko_cdc_default_params(mko_cdc_params *p)
     p->loose_bits = 12;
 }
 
-uint32_t mko_gear_at(const uint8_t *data, size_t i)
+static inline uint32_t word_ending_at(const uint8_t *data, size_t k)
 {
-    uint32_t g[256];
-    mko_gear_table(g);
+    /* bytes before data[0] do not exist for the callers below except in mko_roll_at, which treats them as absent (0) */
+    uint32_t u = (uint32_t)data[k] << 24;
+    if (k >= 1) u |= (uint32_t)data[k - 1] << 16;
+    if (k >= 2) u |= (uint32_t)data[k - 2] << 8;
+    if (k >= 3) u |= (uint32_t)data[k - 3];
+    return u;
+}
+
+uint32_t mko_roll_at(const uint8_t *data, size_t i)
+{
     size_t start = i >= 31 ? i - 31 : 0;
     uint32_t h = 0;
     for (size_t k = start; k <= i; k++)
-        h = (h << 1) + g[data[k]];
+        h = h * ROLL_MULT + word_ending_at(data, k);
     return h;
 }
 
 size_t mko_cdc_cuts(const uint8_t *data, size_t len, const mko_cdc_params *p,
                     uint64_t *ends, size_t cap)
 {
-    uint32_t g[256];
-    mko_gear_table(g);
-    const uint32_t strict_lim = 1u << (32 - p->strict_bits);
-    const uint32_t loose_lim = 1u << (32 - p->loose_bits);
+    const uint32_t strict_thr = 0u - (1u << (32 - p->strict_bits));
+    const uint32_t loose_thr = 0u - (1u << (32 - p->loose_bits));
     size_t n = 0, prev = 0;
     while (prev < len) {
         size_t rem = len - prev;
@@ -270,21 +279,22 @@ size_t mko_cdc_cuts(const uint8_t *data, size_t len, const mko_cdc_params *p,
             cut = len;
         } else {
             size_t limit = rem < p->max_size ? rem : p->max_size;
-            /* window of 32 bytes ending at the last byte of a min-size chunk */
+            /* window of 32 positions (35 bytes) ending at the last byte of a min-size chunk: min_size >= 64, so it
+             * lies inside the chunk */
             uint32_t h = 0;
             for (size_t k = prev + p->min_size - 32; k < prev + p->min_size; k++)
-                h = (h << 1) + g[data[k]];
+                h = h * ROLL_MULT + word_ending_at(data + prev, k - prev);
             size_t L = p->min_size;
             cut = 0;
             for (;;) {
-                uint32_t lim = L < p->normal_size ? strict_lim : loose_lim;
-                if (h < lim) {
+                uint32_t thr = L < p->normal_size ? strict_thr : loose_thr;
+                if (h >= thr) {
                     cut = prev + L;
                     break;
                 }
                 if (L == limit)
                     break;
-                h = (h << 1) + g[data[prev + L]];
+                h = h * ROLL_MULT + word_ending_at(data + prev, L);
                 L++;
             }
             if (!cut)
@@ -388,7 +398,7 @@ int mko_chunk_table(const uint8_t *arena, const uint64_t *offs, const uint64_t *
 }
 
 /* Baseline timing only (bench.py cpu_best_effort): the work of one GPU step over a slice of files -- CRC-32 of every
- * file, Gear CDC, SHA-256 of every chunk through the SHA-NI path when the CPU has it.  Thread safe (no shared
+ * file, Roll-32 CDC, SHA-256 of every chunk through the SHA-NI path when the CPU has it.  Thread safe (no shared
  * state): bench.py runs one call per host thread on disjoint slices.  Returns the number of chunks; digests may be
  * NULL (then the last digest is folded into *sink so the work cannot be optimised away). */
 size_t mko_step_same_work(const uint8_t *arena, const uint64_t *offs, const uint64_t *lens, size_t n_files,

@@ -16,7 +16,7 @@
  *   - SHA-256 (FIPS 180-4) as Go's crypto/sha256 computes it for
  *     reference lib/builder/step/common.go:44-45 (tarDigester/gzipDigester)
  *     and lib/docker/image/digester.go:35-55.
- *   - The chunk-table spec frozen in DESIGN.md section 3 (Gear-32 CDC, per-chunk
+ *   - The chunk-table spec frozen in DESIGN.md section 3 (Roll-32 CDC, per-chunk
  *     SHA-256, sorted-unique table, fan-out-256 Merkle root).  This part has
  *     NO reference counterpart => "parity unpinned": it is
  *     pinned only by this restatement and the golden vectors in tests/golden.
@@ -59,19 +59,20 @@ void mko_sha256(const uint8_t *p, size_t n, uint8_t out[32]);
 int mko_have_sha_ni(void);
 void mko_sha256_update_fast(mko_sha256_ctx *c, const uint8_t *p, size_t n);
 
-/* ---- Gear-32 content-defined chunking ------------------ */
+/* ---- Roll-32 content-defined chunking ------------------ */
 typedef struct {
     uint32_t min_size;     /* 4096   */
     uint32_t normal_size;  /* 16384: strict mask below, loose mask at/after */
     uint32_t max_size;     /* 131072 */
-    uint32_t strict_bits;  /* 16: candidate iff h < 2^(32-strict_bits) */
+    uint32_t strict_bits;  /* 16: candidate iff the top strict_bits bits of h are all ones */
     uint32_t loose_bits;   /* 12 */
 } mko_cdc_params;
 void mko_cdc_default_params(mko_cdc_params *p);
-void mko_gear_table(uint32_t out[256]);
-/* Gear hash of the 32-byte window ending at data[i] (bytes before the start
- * of the buffer count as absent, i.e. state starts at 0 at data[0]). */
-uint32_t mko_gear_at(const uint8_t *data, size_t i);
+/* the multiplier M of h_i = h_{i-1}*M + u_i (u_i = little-endian 32-bit word ending at byte i) */
+uint32_t mko_roll_multiplier(void);
+/* Rolling hash of the 32-position (35-byte) window ending at data[i] (bytes before the start
+ * of the buffer count as absent, i.e. state starts at 0 at data[0] and missing bytes read as 0). */
+uint32_t mko_roll_at(const uint8_t *data, size_t i);
 /* Chunk one file.  Writes chunk END offsets (exclusive, relative to data)
  * into ends[0..cap); returns the number of chunks (may exceed cap: call
  * again with a larger buffer).  An empty file has 0 chunks. */
@@ -102,7 +103,7 @@ int mko_chunk_table(const uint8_t *arena, const uint64_t *offs,
                     uint8_t *digests, uint8_t *table, size_t cap,
                     mko_table_summary *summary);
 
-/* baseline timing (bench.py): CRC-32 + Gear CDC + per-chunk SHA-256 (fast path) of a slice of files; thread safe */
+/* baseline timing (bench.py): CRC-32 + Roll-32 CDC + per-chunk SHA-256 (fast path) of a slice of files; thread safe */
 size_t mko_step_same_work(const uint8_t *arena, const uint64_t *offs, const uint64_t *lens, size_t n_files,
                           const mko_cdc_params *p, uint32_t *crcs, uint8_t *digests, size_t cap, uint32_t *sink);
 

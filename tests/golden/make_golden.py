@@ -8,7 +8,7 @@
   re-encoding test has something to chew on without the 1.3 MB tarball.
 - build_context_cacheids.json: cacheIDs of every testdata/build-context/* directory under `COPY . /app/`,
   computed with Python's zlib.crc32 (independent of oracle/mkoracle.c) in the reference byte order.
-- cdc_vectors.json: Gear-32 table / cut points / table roots of seeded inputs (our frozen spec).
+- cdc_vectors.json: Roll-32 multiplier / cut points / table roots of seeded inputs (our frozen spec).
 """
 import base64
 import gzip
@@ -68,8 +68,9 @@ def main():
     json.dump({"plan_seed": seed0, "from_scratch": seed1, "contexts": ids},
               open(f"{HERE}/build_context_cacheids.json", "w"), indent=1, sort_keys=True)
 
-    vec = {"gear_table_sha256": hashlib.sha256(olib.gear_table().tobytes()).hexdigest(),
-           "gear_table_first8": [int(x) for x in olib.gear_table()[:8]], "cases": []}
+    probe = olib.synth_fill(0, 4096, 99)
+    vec = {"roll_multiplier": olib.roll_multiplier(),
+           "roll_probe_seed99": [olib.roll_at(probe, i) for i in (0, 1, 2, 3, 30, 31, 32, 1000, 4095)], "cases": []}
     for seed, n in [(1, 0), (2, 100), (3, 4096), (4, 4097), (5, 100000), (6, 1 << 20), (7, 3000001)]:
         d = olib.synth_fill(0, (n + 7) // 8 * 8, seed)[:n]
         t = olib.chunk_table(d, [0], [n])

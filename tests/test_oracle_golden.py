@@ -150,9 +150,14 @@ def test_build_context_cacheids_via_c_oracle():
 
 def test_cdc_vectors():
     v = json.load(open(f"{HERE}/golden/cdc_vectors.json"))
-    g = olib.gear_table()
-    assert hashlib.sha256(g.tobytes()).hexdigest() == v["gear_table_sha256"]
-    assert [int(x) for x in g[:8]] == v["gear_table_first8"]
+    m = olib.roll_multiplier()
+    assert m == v["roll_multiplier"] and m % 4 == 2  # exactly one factor of two: M^32 = 0 (mod 2^32), M^31 != 0
+    assert pow(m, 32, 1 << 32) == 0 and pow(m, 31, 1 << 32) != 0
+    probe = olib.synth_fill(0, 4096, 99)
+    assert [olib.roll_at(probe, i) for i in (0, 1, 2, 3, 30, 31, 32, 1000, 4095)] == v["roll_probe_seed99"]
+    # no window of one repeated byte is a (loose) candidate: runs give forced max-size cuts, not a cut per byte
+    T = sum(pow(m, k, 1 << 32) for k in range(32)) & 0xFFFFFFFF
+    assert all(((b * 0x01010101 * T) & 0xFFFFFFFF) < 0xFFF00000 for b in range(256))
     for c in v["cases"]:
         n = c["len"]
         d = olib.synth_fill(0, (n + 7) // 8 * 8, c["seed"])[:n]
@@ -183,17 +188,17 @@ def test_cdc_vectors():
 
 
 def test_cdc_cut_rule_bruteforce():
-    """Cut selection re-derived from the windowed definition (hash of the 32 bytes ending at i), independent
-    of the rolling implementation in mkoracle.c."""
-    g = olib.gear_table().astype(np.uint64)
+    """Cut selection re-derived from the windowed definition (sum over the 32 words ending at i-k, k < 32, of
+    word * M^k), independent of the rolling implementation in mkoracle.c."""
+    M = olib.roll_multiplier()
     rng = np.random.default_rng(4)
     d = rng.integers(0, 256, 400000, dtype=np.uint8)
-    # windowed hash at every position via 32 shifted adds
-    gv = g[d]
+    # windowed hash at every position via 32 multiply-adds of the shifted word sequence
+    pz = np.concatenate([np.zeros(3, np.uint8), d]).astype(np.uint64)
+    u = pz[:d.size] | (pz[1:d.size + 1] << np.uint64(8)) | (pz[2:d.size + 2] << np.uint64(16)) | (pz[3:d.size + 3] << np.uint64(24))
     h = np.zeros(d.size, dtype=np.uint64)
     for k in range(32):
-        h[k:] += gv[:d.size - k] << np.uint64(k)
-    h &= np.uint64(0xFFFFFFFF)
+        h[k:] = (h[k:] + u[:d.size - k] * np.uint64(pow(M, k, 1 << 32))) & np.uint64(0xFFFFFFFF)
     p = olib.default_params()
     ends, prev = [], 0
     while prev < d.size:
@@ -204,14 +209,14 @@ def test_cdc_cut_rule_bruteforce():
             limit = min(rem, p.max_size)
             cut = prev + limit
             for L in range(p.min_size, limit + 1):
-                lim = (1 << (32 - p.strict_bits)) if L < p.normal_size else (1 << (32 - p.loose_bits))
-                if h[prev + L - 1] < lim:
+                thr = (1 << 32) - ((1 << (32 - p.strict_bits)) if L < p.normal_size else (1 << (32 - p.loose_bits)))
+                if h[prev + L - 1] >= thr:
                     cut = prev + L
                     break
         ends.append(cut)
         prev = cut
     assert [int(x) for x in olib.cdc_cuts(d)] == ends
-    assert olib.L().mko_gear_at(d.ctypes.data, 1000) == int(h[1000])
+    assert olib.roll_at(d, 1000) == int(h[1000]) and olib.roll_at(d, 2) == int(h[2])
 
 
 def test_sha_ni_baseline_path_matches_scalar():
