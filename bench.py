@@ -20,7 +20,7 @@ e2e    : same work through mksnap_arena_acquire/submit with PINNED HOST arenas: 
          context host->device in batches (overlapped with compute) and reads the result struct back.
 TarDigest (serial SHA-256 per layer stream) is reported separately in "tar_digest" (DESIGN.md section 5).
 cpu_baseline    : the reference-equivalent CPU path (single thread like the reference's goroutines) on a bounded sample.
-cpu_best_effort : all host threads doing the SAME work as the GPU step (CRC-32 + Gear CDC + SHA-NI chunk SHA-256).
+cpu_best_effort : all host threads doing the SAME work as the GPU step (CRC-32 + Roll-32 CDC + SHA-NI chunk SHA-256).
 """
 from __future__ import annotations
 
@@ -426,7 +426,7 @@ def cpu_reference_extras(file_bytes: int, threads: int):
 
 
 def cpu_same_work_pass(file_bytes: int, threads: int, files_per_thread: int = 192):
-    """Best-effort CPU figure: the SAME work as one GPU step -- CRC-32 of every file, Gear CDC, SHA-256
+    """Best-effort CPU figure: the SAME work as one GPU step -- CRC-32 of every file, Roll-32 CDC, SHA-256
     of every chunk (SHA-NI when present) -- on `threads` host threads over disjoint slices of files
     (oracle/mkoracle.c mko_step_same_work; ctypes releases the GIL).  Sort/unique/root are left out (tiny)."""
     import oracle.lib as o
@@ -783,7 +783,7 @@ def main():
         k["share_of_step"] = k["ms"] / ms_step if ms_step else None
     traffic, traffic_src = None, None
     try:  # DRAM bytes of the launch from the committed ncu capture of the FULL-SIZE launch (scaled only when --files differs)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["k_gear_scan"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2b_traffic.json")))["k_roll_scan"]
         if ctx_bytes == tj["algorithmic_bytes"]:
             traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
         else:

@@ -45,13 +45,13 @@ template <int OP> __global__ void __launch_bounds__(32, 1) bench(uint32_t *out, 
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
-template <int OP> void run(const char *name)
+template <int OP> void run(const char *name, int threads = 32)
 {
     uint32_t *out; unsigned long long *cyc;
     cudaMalloc(&out, 148 * 32 * 4); cudaMalloc(&cyc, 148 * 8);
-    bench<OP><<<148, 32>>>(out, 12345, 1, cyc);
+    bench<OP><<<148, threads>>>(out, 12345, 1, cyc);
     cudaDeviceSynchronize();
-    bench<OP><<<148, 32>>>(out, 12345, 1, cyc);
+    bench<OP><<<148, threads>>>(out, 12345, 1, cyc);
     cudaError_t e = cudaDeviceSynchronize();
     unsigned long long h[148]; cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
     double avg = 0; for (int i = 0; i < 148; i++) avg += h[i]; avg /= 148;
@@ -102,13 +102,13 @@ template <int N1, int N0> __global__ void __launch_bounds__(32, 1) bench_round(u
     out[blockIdx.x * 32 + threadIdx.x] = a ^ b ^ c ^ d ^ e ^ f ^ g ^ h;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
-template <int N1, int N0> void run_round(const char *name)
+template <int N1, int N0> void run_round(const char *name, int threads = 32)
 {
     uint32_t *out; unsigned long long *cyc;
     cudaMalloc(&out, 148 * 32 * 4); cudaMalloc(&cyc, 148 * 8);
-    bench_round<N1, N0><<<148, 32>>>(out, 12345, cyc);
+    bench_round<N1, N0><<<148, threads>>>(out, 12345, cyc);
     cudaDeviceSynchronize();
-    bench_round<N1, N0><<<148, 32>>>(out, 12345, cyc);
+    bench_round<N1, N0><<<148, threads>>>(out, 12345, cyc);
     cudaError_t e = cudaDeviceSynchronize();
     unsigned long long h[148]; cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
     uint32_t o0; cudaMemcpy(&o0, out, 4, cudaMemcpyDeviceToHost);
@@ -191,8 +191,21 @@ template <int ADDM, int UNROLL> void run_pair(const char *name, int second)
     cudaFree(out); cudaFree(cyc);
 }
 
-int main()
+int main(int argc, char **argv)
 {
+    if (argc > 1) { // does a warp with fewer ACTIVE lanes issue faster?  (it does not, if the pipe takes two passes per warp anyway)
+        run<0>("SHF only, 32 lanes", 32);
+        run<0>("SHF only, 16 lanes (half warp launched)", 16);
+        run<0>("SHF only, 8 lanes", 8);
+        run<0>("SHF only, 1 lane", 1);
+        run<1>("IMAD only, 16 lanes", 16);
+        run<2>("SHF, IMAD alternating, 16 lanes", 16);
+        run<4>("add.u32 only, 16 lanes", 16);
+        run_round<0, 0>("SHA round, 6 SHF rotates, 32 lanes", 32);
+        run_round<0, 0>("SHA round, 6 SHF rotates, 16 lanes", 16);
+        run_round<0, 0>("SHA round, 6 SHF rotates, 1 lane", 1);
+        return 0;
+    }
     run_pair<0, 64>("rounds warp alone, IADD3 adds, 64 rounds unrolled", 0);
     run_pair<0, 64>("  + schedule-like warp on the next sub-partition", 1);
     run_pair<1, 64>("rounds warp alone, IMAD adds, 64 rounds unrolled", 0);

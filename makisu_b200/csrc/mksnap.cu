@@ -435,7 +435,7 @@ struct ScanShape {
     int groups, tile_warps, stages;
 };
 #define MK_SCAN_SHAPES(X) X(0, 4, 6, 8) X(1, 3, 6, 8) X(2, 2, 6, 8) X(3, 4, 4, 12) X(4, 3, 4, 12) X(5, 2, 4, 12) X(6, 3, 7, 7) X(7, 2, 7, 7) \
-    X(8, 4, 3, 16) X(9, 6, 4, 12)
+    X(8, 4, 3, 16) X(9, 6, 4, 12) X(10, 4, 7, 7) X(11, 5, 5, 9)
 #define MK_SHAPE_ROW(I, G, T, S) {G, T, S},
 static const ScanShape SCAN_SHAPES[] = {MK_SCAN_SHAPES(MK_SHAPE_ROW)};
 #undef MK_SHAPE_ROW
@@ -526,8 +526,8 @@ static int create_impl(mksnap *h)
         if (!enc || qres != cudaDriverEntryPointSuccess)
             return fail(h, MKSNAP_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
         const char *e = getenv("MKSNAP_SCAN_CFG"); // tuning knob: index into SCAN_SHAPES (0 = default)
-        if (e && e[0] >= '0' && e[0] < '0' + N_SCAN_SHAPES && !e[1])
-            h->scan_cfg = e[0] - '0';
+        if (e && e[0] >= '0' && e[0] <= '9' && atoi(e) < N_SCAN_SHAPES)
+            h->scan_cfg = atoi(e);
         const uint64_t n_rows = (c.device_arena_bytes + SLOT_SLACK) / 128;
         const uint32_t box_rows = (uint32_t)SCAN_SHAPES[h->scan_cfg].tile_warps * 32u + 1u; // the row above the tile travels with it
         for (uint32_t s = 0; s < h->n_slots; s++) {

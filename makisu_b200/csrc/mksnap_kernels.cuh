@@ -275,7 +275,7 @@ k_crc32_extents(const uint8_t *__restrict__ arena, const CrcExtent *__restrict__
 // the row in front of them (one cp.async.bulk.tensor.2d, SWIZZLE_128B, box = ROWS+1 rows starting at row0-1; the row
 // before the arena is out of bounds and arrives as zeros) through a STAGES-deep full/empty mbarrier ring.
 // Each consumer thread owns ONE 128-byte row.  It warms the hash up over the last 32 positions of the row above it
-// (two LDS.128 + one LDS.32 from that row: after 32 positions the state no longer depends on where it started), then
+// (three LDS.128 from that row: after 32 positions the state no longer depends on where it started), then
 // rolls it over its own 128 bytes, eight conflict-free LDS.128 (chunk c of row r sits at c ^ (r & 7)).  No carry
 // between lanes, no block-level synchronisation: a thread needs nothing but its two rows.
 // Candidates are rare (2^-12 per byte): they are collected in per-lane register bitmasks (lane l's mask = its own
@@ -436,7 +436,9 @@ k_roll_scan(const __grid_constant__ CUtensorMap tm_main, uint32_t n_tiles, uint3
         uint32_t h = 0, pw;
         {
             const uint32_t rp = sb + rp_off;
-            const uint32_t w5 = lds_u32(rp + ((5u << 4) ^ swp) + 12u); // bytes 92..95
+            // bytes 92..95: the whole 16-byte chunk is read (a 4-byte read of its last word is a 4-way bank conflict:
+            // the 32 rows of a warp put that word in only 8 banks)
+            const uint32_t w5 = lds_u128(rp + ((5u << 4) ^ swp)).w;
             const uint4 a = lds_u128(rp + ((6u << 4) ^ swp)), b = lds_u128(rp + ((7u << 4) ^ swp));
             MK_ROLL_WARM(w5, a.x) MK_ROLL_WARM(a.x, a.y) MK_ROLL_WARM(a.y, a.z) MK_ROLL_WARM(a.z, a.w)
             MK_ROLL_WARM(a.w, b.x) MK_ROLL_WARM(b.x, b.y) MK_ROLL_WARM(b.y, b.z) MK_ROLL_WARM(b.z, b.w)
