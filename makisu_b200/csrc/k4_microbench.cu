@@ -83,12 +83,12 @@ int main(int argc, char **argv)
     const int ns[] = {1, 32, 256, 1024, 4736, 9472, 20000};
     const int lanes[] = {32};
     printf("schedule warp = warp %d of the CTA (%d threads)\n", SS_SCHED_WARP, SS_THREADS);
-    for (int dbg = 0; dbg < 3; ++dbg)
+    for (int dbg = 0; dbg < 4; ++dbg)
     for (int max_lanes : lanes)
         for (int n : ns) {
             if (dbg && n != 32) continue;
             CK(cudaMemcpyToSymbol(mk::ss_dbg, &dbg, sizeof dbg));
-            if (dbg) printf("debug mode %d (1 = no global loads in the schedule warp, 2 = no rounds in the rounds warp): digests will not match\n", dbg);
+            if (dbg) printf("debug mode %d (1 = no global loads in the schedule warp, 2 = no rounds in the rounds warp, 3 = no expansion in the schedule warp): digests will not match\n", dbg);
             // ragged lengths around L, L chosen so the run takes a few ms
             uint64_t L = n <= 64 ? (1u << 20) : (n <= 1024 ? (256u << 10) : (48u << 10));
             std::vector<uint64_t> start(n), len(n);

@@ -191,8 +191,69 @@ template <int ADDM, int UNROLL> void run_pair(const char *name, int second)
     cudaFree(out); cudaFree(cyc);
 }
 
+
+// ---- the split-rounds step of mksnap_sha_stream.cuh MODE 1 (two lanes per stream) on registers only.
+// XCH 0: no exchange (the word a lane needs is faked from its own), 1: one butterfly shuffle per step, consumed DELAY steps later
+template <int XCH, int DELAY> __global__ void __launch_bounds__(32, 1) bench_split(uint32_t *out, uint32_t seed, unsigned long long *cycles)
+{
+    const uint32_t lane = threadIdx.x & 31, half = lane >> 4;
+    uint32_t n1 = half ? 2u : 6u, n2 = half ? 13u : 11u, n3 = half ? 22u : 25u, nmask = half ? 0xFFFFFFFFu : 0u, sg = half ? 0xFFFFFFFFu : 1u;
+    asm volatile("" : "+r"(n1), "+r"(n2), "+r"(n3), "+r"(nmask), "+r"(sg));
+    uint32_t x0 = seed + lane, x1 = x0 * 3u, x2 = x0 * 5u, x3 = x0 * 7u;
+    uint32_t kw[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) kw[i] = seed * (2 * i + 1);
+    uint32_t r[4] = {x3, x2, x1, x0};
+    unsigned long long t0 = clock64();
+    for (int it = 0; it < 512; it++) {
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            uint32_t r1, r2, r3, S, p, F, u;
+            asm("shf.r.wrap.b32 %0, %1, %1, %2;" : "=r"(r1) : "r"(x0), "r"(n1));
+            asm("shf.r.wrap.b32 %0, %1, %1, %2;" : "=r"(r2) : "r"(x0), "r"(n2));
+            asm("shf.r.wrap.b32 %0, %1, %1, %2;" : "=r"(r3) : "r"(x0), "r"(n3));
+            asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(S) : "r"(r1), "r"(r2), "r"(r3));
+            asm("lop3.b32 %0, %1, %2, %3, 0xD2;" : "=r"(p) : "r"(x0), "r"(x1), "r"(nmask));
+            asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(F) : "r"(p), "r"(x1), "r"(x2));
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(u) : "r"(x3), "r"(sg), "r"(kw[k & 15]));
+            const uint32_t Y = u + r[0];
+            uint32_t a = S;
+            asm("" : "+r"(a));
+            const uint32_t nx = (a + F) + Y;
+#pragma unroll
+            for (int j = 0; j < DELAY - 1; ++j) r[j] = r[j + 1];
+            r[DELAY - 1] = XCH ? __shfl_xor_sync(0xFFFFFFFFu, nx, 16) : (nx ^ nmask);
+            x3 = x2; x2 = x1; x1 = x0; x0 = nx;
+        }
+    }
+    unsigned long long t1 = clock64();
+    out[blockIdx.x * 32 + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+template <int XCH, int DELAY> void run_split(const char *name)
+{
+    uint32_t *out; unsigned long long *cyc;
+    cudaMalloc(&out, 148 * 32 * 4); cudaMalloc(&cyc, 148 * 8);
+    bench_split<XCH, DELAY><<<148, 32>>>(out, 12345, cyc);
+    cudaDeviceSynchronize();
+    bench_split<XCH, DELAY><<<148, 32>>>(out, 12345, cyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    unsigned long long h[148]; cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < 148; i++) avg += h[i]; avg /= 148;
+    printf("%-64s %6.2f cycles per step, %6.0f per 66-step block (%s)\n", name, avg / (64.0 * 512), avg / 512 / 64 * 66, cudaGetErrorString(e));
+    cudaFree(out); cudaFree(cyc);
+}
+
 int main(int argc, char **argv)
 {
+    if (argc > 1 && argv[1][0] == 's') {
+        run_split<0, 2>("split step, no exchange (own word, 2 steps old)");
+        run_split<1, 2>("split step, SHFL.BFLY per step, consumed 2 steps later");
+        run_split<1, 3>("split step, SHFL.BFLY per step, consumed 3 steps later");
+        run_split<1, 4>("split step, SHFL.BFLY per step, consumed 4 steps later");
+        run_split<1, 1>("split step, SHFL.BFLY per step, consumed in the NEXT step");
+        return 0;
+    }
     if (argc > 1) { // does a warp with fewer ACTIVE lanes issue faster?  (it does not, if the pipe takes two passes per warp anyway)
         run<0>("SHF only, 32 lanes", 32);
         run<0>("SHF only, 16 lanes (half warp launched)", 16);

@@ -59,7 +59,7 @@ struct SsShared {
 // microbenchmark only (k4_microbench.cu): [0] rounds-warp cycles, [1] of which waiting for a full buffer,
 // [2] schedule-warp cycles, [3] of which waiting for an empty buffer, [4] blocks; CTA 0 only
 __device__ unsigned long long ss_prof[8];
-__device__ int ss_dbg; // 1: the schedule warp skips its global loads; 2: the rounds warp skips the rounds (timing only)
+__device__ int ss_dbg; // 1: the schedule warp skips its global loads; 2: the rounds warp skips the rounds; 3: the schedule warp skips the expansion (timing only)
 #endif
 __device__ __forceinline__ void ss_bar_sync(uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void ss_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
@@ -86,6 +86,16 @@ __device__ __forceinline__ uint4 ss_ldg(const uint4 *p)
     return r;
 }
 
+
+__constant__ uint32_t SS_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
 
 // One piece per (start[i], len[i], stream[i], flags[i]); start multiple of 16.  Digest of a finished stream goes to
 // row stream[i] of `out`; a piece with flag bit 0 (MKSNAP_R_MORE, len multiple of 64) parks the midstate in
@@ -377,42 +387,46 @@ k_sha256_streams(const uint8_t *__restrict__ data, const uint64_t *__restrict__ 
         sh.sid[b][lane] = sid;
 
         // ---- message schedule: W[t] + K[t] for the 64 rounds ----
-        constexpr uint32_t K[64] = {
-            0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
-            0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
-            0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
-            0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
-            0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
-            0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
-            0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
-            0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+        // Rolled: 16 words are copied, then 3 x 16 are expanded by ONE unrolled body (the ring index t & 15 is static
+        // inside it, K[t] comes from constant memory).  Fully unrolled, this loop was 11 KB of code running beside the
+        // rounds warp's 15 KB and the rounds warp -- the one that bounds a stream -- needed 2219 cycles per block; with
+        // the rolled loop it needs 2022 although this warp itself got slower (1484 -> 1863 cycles alone, it has the
+        // slack): the two warps compete for instruction fetch, not for a pipe (profiles/r2b_k4_microbench.txt).
         const uint32_t kbase = (uint32_t)__cvta_generic_to_shared(&sh.kw[b][lane * (SS_LANE_WORDS / 4)]);
-        uint32_t o4[4];
+#ifdef SS_PROFILE
+        if (ss_dbg != 3)
+#endif
+        {
+            uint32_t o4[4];
 #pragma unroll
-        for (int t = 0; t < 64; ++t) {
-            uint32_t wt;
-            if (t < 16) {
-                wt = w[t];
-            } else {
-                const uint32_t w15 = w[(t + 1) & 15], w2 = w[(t + 14) & 15];
-                const uint32_t s0 = ss_rotr(w15, 7) ^ ss_rotr(w15, 18) ^ (w15 >> 3);
-                const uint32_t s1 = ss_rotr(w2, 17) ^ ss_rotr(w2, 19) ^ (w2 >> 10);
-#if SS_ADD_MODE == 1
-                wt = ss_add(ss_add(w[t & 15], s0, one), ss_add(w[(t + 9) & 15], s1, one), one);
-#else
-                wt = ss_add3(ss_add3(w[t & 15], s0, w[(t + 9) & 15]), s1, 0u);
-#endif
-                w[t & 15] = wt;
+            for (int t = 0; t < 16; ++t) {
+                o4[t & 3] = w[t] + SS_K[t];
+                if ((t & 3) == 3)
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(kbase + 4u * (t - 3)), "r"(o4[0]), "r"(o4[1]), "r"(o4[2]),
+                                 "r"(o4[3])
+                                 : "memory");
             }
+#pragma unroll 1
+            for (int q = 1; q < 4; ++q) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+                    const uint32_t s0 = ss_rotr(w15, 7) ^ ss_rotr(w15, 18) ^ (w15 >> 3);
+                    const uint32_t s1 = ss_rotr(w2, 17) ^ ss_rotr(w2, 19) ^ (w2 >> 10);
 #if SS_ADD_MODE == 1
-            o4[t & 3] = ss_add(wt, K[t], one);
+                    const uint32_t wt = ss_add(ss_add(w[i], s0, one), ss_add(w[(i + 9) & 15], s1, one), one);
+                    o4[i & 3] = ss_add(wt, SS_K[16 * q + i], one);
 #else
-            o4[t & 3] = wt + K[t];
+                    const uint32_t wt = ss_add3(ss_add3(w[i], s0, w[(i + 9) & 15]), s1, 0u);
+                    o4[i & 3] = wt + SS_K[16 * q + i];
 #endif
-            if ((t & 3) == 3)
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(kbase + 4u * (t - 3)), "r"(o4[0]), "r"(o4[1]), "r"(o4[2]),
-                             "r"(o4[3])
-                             : "memory");
+                    w[i] = wt;
+                    if ((i & 3) == 3)
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(kbase + 4u * (16 * q + i - 3)), "r"(o4[0]), "r"(o4[1]),
+                                     "r"(o4[2]), "r"(o4[3])
+                                     : "memory");
+                }
+            }
         }
         ss_bar_arrive(1 + b);
     }
