@@ -66,7 +66,7 @@ def parse():
     ap.add_argument("--tar-files", type=int, default=256, help="files in the TarDigest side measurement")
     ap.add_argument("--fs-files", type=int, default=16384, help="files of the e2e_fs leg (real files on tmpfs); 0 = skip")
     ap.add_argument("--fs-dir", default="/dev/shm")
-    ap.add_argument("--fs-threads", type=int, default=32)
+    ap.add_argument("--fs-threads", type=int, default=16, help="reader threads of the e2e_fs leg (16 measured best on the 2-socket box: profiles/r2b_fs_threads.txt)")
     ap.add_argument("--fs-arena-mib", type=int, default=1024)
     ap.add_argument("--fs-only", action="store_true", help="run only the e2e_fs leg and print its object (tuning aid, not the bench line)")
     ap.add_argument("--strong", action="store_true", help="run the strong-scaling legs at N=1 too (always run at N>1)")
