@@ -219,6 +219,35 @@ def test_cdc_cut_rule_bruteforce():
     assert olib.roll_at(d, 1000) == int(h[1000]) and olib.roll_at(d, 2) == int(h[2])
 
 
+def test_cdc_is_content_defined():
+    """The property the chunk table exists for: cut points follow the CONTENT.  Bytes inserted in front shift every later
+    cut by the same amount once the chunker has resynchronised (a candidate depends on the 35 bytes before it only), so
+    all chunks behind the first common cut keep their digests; and a run of one repeated byte has no candidates (forced
+    max-size cuts, not a cut per byte)."""
+    rng = np.random.default_rng(11)
+    d = rng.integers(0, 256, 1_500_000, dtype=np.uint8)
+    base = [int(x) for x in olib.cdc_cuts(d)]
+    for ins in (1, 3, 4, 511, 4097):
+        e = np.concatenate([rng.integers(0, 256, ins, dtype=np.uint8), d])
+        cuts = [int(x) for x in olib.cdc_cuts(e)]
+        shifted = {c - ins for c in cuts}
+        common = [c for c in base if c in shifted]
+        assert common, ins
+        first = common[0]
+        # resynchronised within a few chunks, and IDENTICAL from there on
+        assert first <= 8 * olib.default_params().max_size, (ins, first)
+        assert [c for c in base if c >= first] == sorted(c for c in shifted if c >= first), ins
+    for b in (0x00, 0x20, 0x41, 0xFF):
+        z = np.full(300_000, b, dtype=np.uint8)
+        assert [int(x) for x in olib.cdc_cuts(z)] == [131072, 262144, 300000], b
+    # low-entropy text: candidates keep their design rate within a factor of two (chunks average between min and max)
+    words = [b"layer", b"cache", b"makisu", b"digest", b"COPY", b"FROM", b"RUN", b"/usr/lib", b"\n", b" ", b"=", b"0123456789"]
+    t = b"".join(words[i] for i in rng.integers(0, len(words), 400_000))
+    tc = olib.cdc_cuts(np.frombuffer(t, dtype=np.uint8))
+    mean = len(t) / len(tc)
+    assert 8192 < mean < 65536, mean
+
+
 def test_sha_ni_baseline_path_matches_scalar():
     import ctypes
     L = olib.L()
