@@ -81,6 +81,17 @@ def main():
     t = olib.chunk_table(z, [0], [z.size])
     vec["zeros_300000"] = {"ends": [int(x) for x in t["ends"]], "n_unique": t["n_unique"], "root": t["root"].hex()}
     json.dump(vec, open(f"{HERE}/cdc_vectors.json", "w"), indent=1, sort_keys=True)
+
+    # BASELINE configs[1] exactly (1k files x 1 MiB, device generator seed 0xC2): what the GPU test diffs against
+    n, fb = 1000, 1 << 20
+    arena = olib.synth_fill(0, n * fb, 0xC2)
+    t = olib.chunk_table(arena, [i * fb for i in range(n)], [fb] * n)
+    c1 = {"files": n, "file_bytes": fb, "seed": 0xC2, "n_chunks": t["n_chunks"], "n_unique": t["n_unique"], "root": t["root"].hex(),
+          "crc32_of_content": zlib.crc32(arena.tobytes()),
+          "sha256_of_chunk_ends_u64le": hashlib.sha256(np.asarray(t["ends"], dtype=np.uint64).tobytes()).hexdigest(),
+          "sha256_of_chunk_digests": hashlib.sha256(np.ascontiguousarray(t["digests"]).tobytes()).hexdigest(),
+          "first_ends": [int(x) for x in t["ends"][:4]]}
+    json.dump(c1, open(f"{HERE}/config1_1k_x_1MiB.json", "w"), indent=1, sort_keys=True)
     print("wrote", os.listdir(HERE))
 
 

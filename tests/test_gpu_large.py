@@ -248,6 +248,13 @@ def test_config1_exact_1k_files_of_1MiB(oracle_lib):
         np.testing.assert_array_equal(dig, want["digests"])
         np.testing.assert_array_equal(e.get_table(res.n_unique), want["table"])
         assert e.ctx_crc32(res) == zlib.crc32(arena.tobytes()) and res.crc_bytes == n * fb
+        # ... and against the committed fingerprint (tests/golden/config1_1k_x_1MiB.json, written by make_golden.py)
+        import json
+        import os
+        from tests.util import table_fingerprint
+        g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_1k_x_1MiB.json")))
+        got = table_fingerprint(res.n_chunks, res.n_unique, bytes(res.root), ends, dig, e.ctx_crc32(res))
+        assert got == {k: g[k] for k in got}
 
 
 def test_all_zero_context_has_one_long_run_of_duplicates(oracle_lib):

@@ -248,6 +248,19 @@ def test_cdc_is_content_defined():
     assert 8192 < mean < 65536, mean
 
 
+def test_config1_golden():
+    """BASELINE configs[1] (1k files x 1 MiB, generator seed 0xC2): the oracle reproduces the committed fingerprint
+    (tests/golden/config1_1k_x_1MiB.json) that the GPU test holds the engine to."""
+    import zlib
+    from tests.util import table_fingerprint
+    g = json.load(open(f"{HERE}/golden/config1_1k_x_1MiB.json"))
+    n, fb = g["files"], g["file_bytes"]
+    arena = olib.synth_fill(0, n * fb, g["seed"])
+    t = olib.chunk_table(arena, [i * fb for i in range(n)], [fb] * n)
+    got = table_fingerprint(t["n_chunks"], t["n_unique"], t["root"], t["ends"], t["digests"], zlib.crc32(arena.tobytes()))
+    assert got == {k: g[k] for k in got}
+
+
 def test_sha_ni_baseline_path_matches_scalar():
     import ctypes
     L = olib.L()

@@ -54,3 +54,12 @@ def ranges(offs, lens):
         r.arena_off, r.len, r.stream, r.flags = o, l, i, 0
         out.append(r)
     return out
+
+
+def table_fingerprint(n_chunks, n_unique, root, ends, digests, crc):
+    """What tests/golden/config1_1k_x_1MiB.json pins (same code for the oracle on the CPU and the engine on the GPU)."""
+    import hashlib
+    return {"n_chunks": int(n_chunks), "n_unique": int(n_unique), "root": bytes(root).hex(), "crc32_of_content": int(crc),
+            "sha256_of_chunk_ends_u64le": hashlib.sha256(np.ascontiguousarray(ends, dtype=np.uint64).tobytes()).hexdigest(),
+            "sha256_of_chunk_digests": hashlib.sha256(np.ascontiguousarray(digests, dtype=np.uint8).tobytes()).hexdigest(),
+            "first_ends": [int(x) for x in ends[:4]]}
