@@ -187,19 +187,18 @@ def test_cdc_vectors():
     assert [int(x) for x in z["ends"]] == v["zeros_300000"]["ends"] == [131072, 262144, 300000]
 
 
-def test_cdc_cut_rule_bruteforce():
-    """Cut selection re-derived from the windowed definition (sum over the 32 words ending at i-k, k < 32, of
-    word * M^k), independent of the rolling implementation in mkoracle.c."""
+def _windowed_hash(d):
+    """h_i = sum over k < 32 of (LE word ending at i-k) * M^k, straight from the definition"""
     M = olib.roll_multiplier()
-    rng = np.random.default_rng(4)
-    d = rng.integers(0, 256, 400000, dtype=np.uint8)
-    # windowed hash at every position via 32 multiply-adds of the shifted word sequence
     pz = np.concatenate([np.zeros(3, np.uint8), d]).astype(np.uint64)
     u = pz[:d.size] | (pz[1:d.size + 1] << np.uint64(8)) | (pz[2:d.size + 2] << np.uint64(16)) | (pz[3:d.size + 3] << np.uint64(24))
     h = np.zeros(d.size, dtype=np.uint64)
     for k in range(32):
         h[k:] = (h[k:] + u[:d.size - k] * np.uint64(pow(M, k, 1 << 32))) & np.uint64(0xFFFFFFFF)
-    p = olib.default_params()
+    return h
+
+
+def _bruteforce_cuts(d, h, p):
     ends, prev = [], 0
     while prev < d.size:
         rem = d.size - prev
@@ -215,8 +214,30 @@ def test_cdc_cut_rule_bruteforce():
                     break
         ends.append(cut)
         prev = cut
-    assert [int(x) for x in olib.cdc_cuts(d)] == ends
+    return ends
+
+
+def test_cdc_cut_rule_bruteforce():
+    """Cut selection re-derived from the windowed definition (sum over the 32 words ending at i-k, k < 32, of
+    word * M^k), independent of the rolling implementation in mkoracle.c."""
+    rng = np.random.default_rng(4)
+    d = rng.integers(0, 256, 400000, dtype=np.uint8)
+    h = _windowed_hash(d)
+    assert [int(x) for x in olib.cdc_cuts(d)] == _bruteforce_cuts(d, h, olib.default_params())
     assert olib.roll_at(d, 1000) == int(h[1000]) and olib.roll_at(d, 2) == int(h[2])
+
+
+@pytest.mark.parametrize("mn,nm,mx,sb,lb", [(64, 256, 1024, 10, 6), (64, 64, 64, 8, 8), (100, 1000, 5000, 12, 9),
+                                            (4096, 8192, 65536, 14, 11), (512, 512, 100000, 31, 1)])
+def test_cdc_cut_rule_bruteforce_other_parameters(mn, nm, mx, sb, lb):
+    """The same for parameter sets the C-ABI accepts besides the default (min >= 64, strict >= loose): dense candidates,
+    min = normal = max (fixed-size chunks), a strict mask that never fires, a loose mask that nearly always does."""
+    rng = np.random.default_rng(mn + sb)
+    d = rng.integers(0, 256, 150000, dtype=np.uint8)
+    d[5000:9000] = 0          # a run without candidates inside random content
+    d[60000:60100] = 0xFF
+    p = olib.CdcParams(mn, nm, mx, sb, lb)
+    assert [int(x) for x in olib.cdc_cuts(d, p)] == _bruteforce_cuts(d, _windowed_hash(d), p)
 
 
 def test_cdc_is_content_defined():
